@@ -1,0 +1,117 @@
+"""ctypes binding of libd3p_b200.so — the C ABI declared in include/d3p_b200.h.
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+MAX_LEAVES = 16
+
+OK = 0
+FAMILY_LOGREG, FAMILY_GAUSS = 0, 1
+LINK_EXP, LINK_SOFTPLUS = 0, 1
+OPT_NONE, OPT_SGD, OPT_ADAM = 0, 1, 2
+
+
+class MeanfieldDesc(C.Structure):
+    _fields_ = [("family", C.c_int32), ("link", C.c_int32), ("joint_site", C.c_int32), ("d", C.c_uint32),
+                ("n_params", C.c_uint32), ("loc_off", C.c_uint32), ("rho_off", C.c_uint32),
+                ("b_loc_off", C.c_uint32), ("b_rho_off", C.c_uint32), ("num_obs_total", C.c_float),
+                ("lik_scale", C.c_float)]
+
+
+class LeafTable(C.Structure):
+    _fields_ = [("n_leaves", C.c_uint32), ("leaf_off", C.c_uint32 * MAX_LEAVES),
+                ("leaf_len", C.c_uint32 * MAX_LEAVES), ("site_state", (C.c_uint32 * 16) * MAX_LEAVES)]
+
+
+class OptimDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("step_size", C.c_float), ("b1", C.c_float), ("b2", C.c_float),
+                ("eps", C.c_float), ("step", C.c_int32)]
+
+
+_u32p = C.POINTER(C.c_uint32)
+_vp = C.c_void_p
+
+_SIGNATURES = {
+    "d3p_abi_version": (C.c_int32, []),
+    "d3p_error_string": (C.c_char_p, [C.c_int32]),
+    "d3p_chacha_key_from_seed_h": (C.c_int32, [_vp, C.c_size_t, _u32p]),
+    "d3p_chacha_fold_in_h": (C.c_int32, [_u32p, C.c_uint32, _u32p]),
+    "d3p_chacha_split_h": (C.c_int32, [_u32p, C.c_int32, _u32p]),
+    "d3p_chacha_random_bits_h": (C.c_int32, [_u32p, C.c_uint64, _u32p, C.c_size_t]),
+    "d3p_chacha_random_bits": (C.c_int32, [_u32p, C.c_uint64, _vp, C.c_size_t, _vp]),
+    "d3p_chacha_uniform_f32": (C.c_int32, [_u32p, C.c_uint64, C.c_float, C.c_float, _vp, C.c_size_t, _vp]),
+    "d3p_chacha_normal_f32": (C.c_int32, [_u32p, C.c_uint64, _vp, C.c_size_t, _vp]),
+    "d3p_chacha_randint_round_u32": (C.c_int32, [_u32p, C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, _vp, _vp]),
+    "d3p_randint_finish_i32": (C.c_int32, [_vp, C.c_int32, _vp, C.c_size_t, _vp]),
+    "d3p_feistel_round_constants_h": (C.c_int32, [_u32p, _u32p]),
+    "d3p_feistel_sample": (C.c_int32, [_u32p, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "d3p_poisson_workspace_bytes": (C.c_size_t, [C.c_uint32]),
+    "d3p_poisson_sample": (C.c_int32, [_u32p, C.c_float, C.c_uint32, C.c_uint32, C.c_int32, _vp, _vp, _vp, _vp,
+                                       C.c_size_t, _vp]),
+    "d3p_gather_rows_masked": (C.c_int32, [_vp, C.c_size_t, _vp, _vp, C.c_uint32, _vp, _vp]),
+    "d3p_clip_rows_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_float, _vp, _vp]),
+    "d3p_clip_and_sum_workspace_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32]),
+    "d3p_clip_and_sum_f32": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_float, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_meanfield_workspace_bytes": (C.c_size_t, [C.POINTER(MeanfieldDesc), _u32p]),
+    "d3p_dpsvi_step_meanfield": (C.c_int32, [C.POINTER(MeanfieldDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp,
+                                             C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_float, C.c_float,
+                                             _vp, _vp, _vp, _vp, C.c_size_t, _vp]),  # norms, grads, loss, ws
+    "d3p_perturb_finalize_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(LeafTable),
+                                             C.c_float, C.c_float, C.c_float, C.c_int32, _vp,
+                                             C.POINTER(OptimDesc), _vp, _vp, _vp, _vp,
+                                             C.POINTER(C.c_float), _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+_lib = None
+
+
+class D3PNativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libd3p_b200.so (once).  Raises if it has not been built — there is no CPU fallback."""
+    global _lib
+    if _lib is None:
+        path = _build.lib_path()
+        if not os.path.exists(path):
+            raise D3PNativeError(
+                f"{path} is missing: build it with `python -m d3p_b200._build` "
+                "(d3p_b200 has no CPU fallback; the CUDA library is the product).")
+        handle = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != OK:
+        msg = lib().d3p_error_string(rc).decode()
+        raise D3PNativeError(f"{what or 'd3p_b200 call'} failed: {msg} (code {rc})")
+
+
+def u32(arr):
+    """numpy uint32 array (contiguous) -> ctypes pointer; keeps `arr` alive via the return pair."""
+    a = np.ascontiguousarray(arr, dtype=np.uint32)
+    return a, a.ctypes.data_as(_u32p)
+
+
+def ptr(t):
+    """device pointer of a torch CUDA tensor (or None)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,163 @@
+// Shared device/host helpers for the d3p_b200 hot path (sm_100a).
+// ChaCha20 (RFC 8439) block function, Threefry-2x32-20, the jax.random bits->float->normal
+// transform (d3p/random/__init__.py:76-81) and small warp utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/d3p_b200.h"
+
+#define D3P_HD __host__ __device__ __forceinline__
+#define D3P_D __device__ __forceinline__
+
+namespace d3p {
+
+struct ChaChaState { uint32_t w[16]; };
+
+D3P_HD uint32_t rotl32(uint32_t x, int n) {
+#ifdef __CUDA_ARCH__
+  return __funnelshift_l(x, x, n);
+#else
+  return (x << n) | (x >> (32 - n));
+#endif
+}
+
+#define D3P_QR(a, b, c, d)            \
+  a += b; d ^= a; d = rotl32(d, 16);  \
+  c += d; b ^= c; b = rotl32(b, 12);  \
+  a += b; d ^= a; d = rotl32(d, 8);   \
+  c += d; b ^= c; b = rotl32(b, 7);
+
+// RFC 8439 section 2.3: 10 double rounds + feed-forward. `counter` replaces word 12.
+D3P_HD void chacha20_block(const uint32_t (&in)[16], uint32_t counter, uint32_t (&out)[16]) {
+  uint32_t x0 = in[0], x1 = in[1], x2 = in[2], x3 = in[3], x4 = in[4], x5 = in[5], x6 = in[6],
+           x7 = in[7], x8 = in[8], x9 = in[9], x10 = in[10], x11 = in[11], x12 = counter,
+           x13 = in[13], x14 = in[14], x15 = in[15];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    D3P_QR(x0, x4, x8, x12) D3P_QR(x1, x5, x9, x13) D3P_QR(x2, x6, x10, x14) D3P_QR(x3, x7, x11, x15)
+    D3P_QR(x0, x5, x10, x15) D3P_QR(x1, x6, x11, x12) D3P_QR(x2, x7, x8, x13) D3P_QR(x3, x4, x9, x14)
+  }
+  out[0] = x0 + in[0]; out[1] = x1 + in[1]; out[2] = x2 + in[2]; out[3] = x3 + in[3];
+  out[4] = x4 + in[4]; out[5] = x5 + in[5]; out[6] = x6 + in[6]; out[7] = x7 + in[7];
+  out[8] = x8 + in[8]; out[9] = x9 + in[9]; out[10] = x10 + in[10]; out[11] = x11 + in[11];
+  out[12] = x12 + counter; out[13] = x13 + in[13]; out[14] = x14 + in[14]; out[15] = x15 + in[15];
+}
+
+// Threefry-2x32, 20 rounds (Random123), as used by jax.random (d3p/svi.py:290).
+struct TfKey {
+  uint32_t k0, k1, k2;
+  D3P_HD TfKey() : k0(0), k1(0), k2(0) {}
+  D3P_HD TfKey(uint32_t a, uint32_t b) : k0(a), k1(b), k2(a ^ b ^ 0x1BD11BDAu) {}
+};
+
+#define D3P_TF_ROUND(r) x0 += x1; x1 = rotl32(x1, r); x1 ^= x0;
+
+D3P_HD void threefry2x32(const TfKey& k, uint32_t c0, uint32_t c1, uint32_t& y0, uint32_t& y1) {
+  uint32_t x0 = c0 + k.k0, x1 = c1 + k.k1;
+  D3P_TF_ROUND(13) D3P_TF_ROUND(15) D3P_TF_ROUND(26) D3P_TF_ROUND(6)
+  x0 += k.k1; x1 += k.k2 + 1u;
+  D3P_TF_ROUND(17) D3P_TF_ROUND(29) D3P_TF_ROUND(16) D3P_TF_ROUND(24)
+  x0 += k.k2; x1 += k.k0 + 2u;
+  D3P_TF_ROUND(13) D3P_TF_ROUND(15) D3P_TF_ROUND(26) D3P_TF_ROUND(6)
+  x0 += k.k0; x1 += k.k1 + 3u;
+  D3P_TF_ROUND(17) D3P_TF_ROUND(29) D3P_TF_ROUND(16) D3P_TF_ROUND(24)
+  x0 += k.k1; x1 += k.k2 + 4u;
+  D3P_TF_ROUND(13) D3P_TF_ROUND(15) D3P_TF_ROUND(26) D3P_TF_ROUND(6)
+  x0 += k.k2; x1 += k.k0 + 5u;
+  y0 = x0; y1 = x1;
+}
+
+// jax.random.split(key, 2): counts iota(4) -> calls (0,2),(1,3); child0=(a.y0,b.y0), child1=(a.y1,b.y1)
+D3P_HD void tf_split2(const TfKey& k, TfKey& child0, TfKey& child1) {
+  uint32_t a0, a1, b0, b1;
+  threefry2x32(k, 0u, 2u, a0, a1);
+  threefry2x32(k, 1u, 3u, b0, b1);
+  child0 = TfKey(a0, b0);
+  child1 = TfKey(a1, b1);
+}
+
+// word m of jax.random.split(K, B) flattened ([B,2] row-major): counts iota(2B) halves.
+D3P_HD uint32_t tf_split_word(const TfKey& K, uint32_t B, uint32_t m) {
+  uint32_t y0, y1;
+  if (m < B) { threefry2x32(K, m, m + B, y0, y1); return y0; }
+  threefry2x32(K, m - B, m, y0, y1);
+  return y1;
+}
+
+D3P_HD TfKey tf_example_key(const TfKey& K, uint32_t B, uint32_t p) {
+  return TfKey(tf_split_word(K, B, 2u * p), tf_split_word(K, B, 2u * p + 1u));
+}
+
+// ---- bits -> uniform -> normal (jax.random._uniform / _normal_real) -------------------------
+D3P_HD float bits_to_unit_float(uint32_t bits) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+#else
+  union { uint32_t u; float f; } v; v.u = (bits >> 9) | 0x3F800000u; return v.f - 1.0f;
+#endif
+}
+
+// Giles' single-precision erfinv polynomial as lowered by XLA for f32 (lax.erf_inv).
+// kFast: w = -log(1 - x*x) through MUFU.LG2 (abs error ~4e-7 in w, <2e-7 relative in the
+// result); otherwise log1pf as XLA does.
+template <bool kFast>
+D3P_D float erfinv_f32(float x) {
+  float w;
+  if (kFast) w = -__logf(fmaf(-x, x, 1.0f));
+  else w = -log1pf(-x * x);
+  float p;
+  if (w < 5.0f) {
+    w = w - 2.5f;
+    p = 2.81022636e-08f;
+    p = fmaf(p, w, 3.43273939e-07f);
+    p = fmaf(p, w, -3.5233877e-06f);
+    p = fmaf(p, w, -4.39150654e-06f);
+    p = fmaf(p, w, 0.00021858087f);
+    p = fmaf(p, w, -0.00125372503f);
+    p = fmaf(p, w, -0.00417768164f);
+    p = fmaf(p, w, 0.246640727f);
+    p = fmaf(p, w, 1.50140941f);
+  } else {
+    w = (kFast ? __fsqrt_rn(w) : sqrtf(w)) - 3.0f;
+    p = -0.000200214257f;
+    p = fmaf(p, w, 0.000100950558f);
+    p = fmaf(p, w, 0.00134934322f);
+    p = fmaf(p, w, -0.00367342844f);
+    p = fmaf(p, w, 0.00573950773f);
+    p = fmaf(p, w, -0.0076224613f);
+    p = fmaf(p, w, 0.00943887047f);
+    p = fmaf(p, w, 1.00167406f);
+    p = fmaf(p, w, 2.83297682f);
+  }
+  return (fabsf(x) == 1.0f) ? x * __int_as_float(0x7F800000) : p * x;
+}
+
+#define D3P_NORMAL_LO (-0.99999994f)   // nextafter(-1, 0) in float32
+#define D3P_SQRT2 1.41421354f          // float32(sqrt(2))
+
+template <bool kFast>
+D3P_D float bits_to_normal(uint32_t bits) {
+  float f = bits_to_unit_float(bits);
+  // (hi - lo) rounds to exactly 2.0f in float32, so f*(hi-lo)+lo == fma(f, 2, lo) exactly
+  float u = fmaxf(D3P_NORMAL_LO, fmaf(f, 2.0f, D3P_NORMAL_LO));
+  return D3P_SQRT2 * erfinv_f32<kFast>(u);
+}
+
+D3P_D float bits_to_uniform(uint32_t bits, float lo, float hi) {
+  float f = bits_to_unit_float(bits);
+  return fmaxf(lo, __fadd_rn(__fmul_rn(f, hi - lo), lo));
+}
+
+// ---- warp helpers ---------------------------------------------------------------------------
+template <int W>
+D3P_D float group_sum(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+D3P_D float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+D3P_D float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace d3p

@@ -1,0 +1,166 @@
+// K8: fixed-order reduction of the per-CTA partial sums + mean + ChaCha20 Gaussian perturbation
+// + rescale + optimizer step, in one launch.  Replaces DPSVI._combine_gradients
+// (d3p/svi.py:327-348), _perturb_and_reassemble_gradients (:350-377), perturbation_function
+// (:470-498) and _apply_gradient (:379-393) with numpyro.optim.SGD / Adam.
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace d3p {
+
+struct LeafTable {
+  uint32_t n_leaves;
+  uint32_t off[D3P_MAX_LEAVES];
+  uint32_t len[D3P_MAX_LEAVES];
+};
+
+struct FinalizeArgs {
+  const float* partials;
+  uint32_t n_partials, P, B;
+  float dp_scale, C, obs_scale;
+  int add_noise;
+  float* grad_out;
+  int opt_kind;
+  float step_size, b1, b2, eps;
+  int step;
+  float* params;
+  float* m;
+  float* v;
+  float* stats;
+  int use_override;
+  float n_override, f_override;
+};
+
+constexpr int kFinThreads = 128;
+
+// site states live in constant-bank kernel parameters next to the leaf table
+struct SiteStates { uint32_t w[D3P_MAX_LEAVES][16]; };
+
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites) {
+  __shared__ float red[2][kFinThreads / 32];
+  __shared__ float s_n, s_loss;
+  const uint32_t stride = a.P + 2;
+  // every CTA reduces the (count, loss) columns itself: n_partials is a few hundred at most
+  float cnt = 0.f, loss = 0.f;
+  for (uint32_t p = threadIdx.x; p < a.n_partials; p += kFinThreads) {
+    loss += a.partials[(size_t)p * stride + a.P];
+    cnt += a.partials[(size_t)p * stride + a.P + 1];
+  }
+  cnt = group_sum<32>(cnt);
+  loss = group_sum<32>(loss);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = cnt; red[1][threadIdx.x >> 5] = loss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float c = 0.f, l = 0.f;
+#pragma unroll
+    for (int w = 0; w < kFinThreads / 32; ++w) { c += red[0][w]; l += red[1][w]; }
+    s_n = c; s_loss = l;
+  }
+  __syncthreads();
+  const float n = a.use_override ? a.n_override : s_n;
+  const float Bf = (float)a.B;
+  const float f = a.use_override ? a.f_override : ((n == 0.f) ? 0.f : __fdiv_rn(Bf, n));   // svi.py:305
+  const float sigma = __fmul_rn(a.dp_scale, __fdiv_rn(a.C, n));        // svi.py:365-366 (inf when n == 0)
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
+    a.stats[0] = __fmul_rn(__fdiv_rn(s_loss, Bf), f);                  // svi.py:306,342
+    a.stats[1] = n;
+    a.stats[2] = f;
+  }
+  // 32 columns per CTA; warp w adds partials w, w+4, ... and warp 0 combines them in fixed order
+  __shared__ float colred[kFinThreads / 32][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t j = blockIdx.x * 32 + lane;
+  float part = 0.f;
+  if (j < a.P) {
+    uint32_t p = warp;
+    for (; p + 3 * (kFinThreads / 32) < a.n_partials; p += 4 * (kFinThreads / 32)) {
+      float v0 = a.partials[(size_t)p * stride + j];
+      float v1 = a.partials[(size_t)(p + (kFinThreads / 32)) * stride + j];
+      float v2 = a.partials[(size_t)(p + 2 * (kFinThreads / 32)) * stride + j];
+      float v3 = a.partials[(size_t)(p + 3 * (kFinThreads / 32)) * stride + j];
+      part += v0; part += v1; part += v2; part += v3;
+    }
+    for (; p < a.n_partials; p += kFinThreads / 32) part += a.partials[(size_t)p * stride + j];
+  }
+  colred[warp][lane] = part;
+  __syncthreads();
+  if (warp != 0 || j >= a.P) return;
+  float sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < kFinThreads / 32; ++w) sum += colred[w][lane];
+  float g = __fdiv_rn(sum, Bf);                                        // mean over the padded batch size
+  if (a.add_noise) {
+    int leaf = -1;
+#pragma unroll 1
+    for (uint32_t l = 0; l < leaves.n_leaves; ++l)
+      if (j >= leaves.off[l] && j < leaves.off[l] + leaves.len[l]) leaf = (int)l;
+    if (leaf >= 0) {
+      uint32_t e = j - leaves.off[leaf];
+      uint32_t ks[16];
+      chacha20_block(sites.w[leaf], sites.w[leaf][12] + (e >> 4), ks);
+      uint32_t bits = ks[0];
+#pragma unroll
+      for (int i = 1; i < 16; ++i) bits = ((e & 15u) == (uint32_t)i) ? ks[i] : bits;
+      float xi = bits_to_normal<false>(bits);
+      g = __fadd_rn(g, __fmul_rn(xi, sigma));                          // svi.py:485-486
+    }
+  }
+  g = __fmul_rn(__fmul_rn(g, a.obs_scale), f);                         // svi.py:374-375
+  if (a.grad_out) a.grad_out[j] = g;
+  if (a.opt_kind == D3P_OPT_SGD) {
+    a.params[j] = a.params[j] - a.step_size * g;
+  } else if (a.opt_kind == D3P_OPT_ADAM) {
+    float m = (1.0f - a.b1) * g + a.b1 * a.m[j];
+    float v = (1.0f - a.b2) * (g * g) + a.b2 * a.v[j];
+    float t = (float)(a.step + 1);
+    float mhat = m / (1.0f - powf(a.b1, t));
+    float vhat = v / (1.0f - powf(a.b2, t));
+    a.params[j] = a.params[j] - a.step_size * mhat / (sqrtf(vhat) + a.eps);
+    a.m[j] = m;
+    a.v[j] = v;
+  }
+}
+
+}  // namespace d3p
+
+using namespace d3p;
+
+extern "C" int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
+                                            const d3p_leaf_table* leaves_h, float dp_scale, float C, float obs_scale,
+                                            int32_t add_noise, float* grad_out_d, const d3p_optim_desc* optim_h,
+                                            float* params_d, float* m_d, float* v_d, float* stats_d,
+                                            const float* nf_override_h, void* stream) {
+  if (!partials_d || n_partials == 0 || B == 0) return D3P_ERR_INVALID_ARGUMENT;
+  if (add_noise && !leaves_h) return D3P_ERR_INVALID_ARGUMENT;
+  if (leaves_h && leaves_h->n_leaves > D3P_MAX_LEAVES) return D3P_ERR_UNSUPPORTED;
+  FinalizeArgs a;
+  a.partials = partials_d; a.n_partials = n_partials; a.P = P; a.B = B;
+  a.dp_scale = dp_scale; a.C = C; a.obs_scale = obs_scale; a.add_noise = add_noise;
+  a.grad_out = grad_out_d;
+  a.opt_kind = optim_h ? optim_h->kind : D3P_OPT_NONE;
+  a.step_size = optim_h ? optim_h->step_size : 0.f;
+  a.b1 = optim_h ? optim_h->b1 : 0.f; a.b2 = optim_h ? optim_h->b2 : 0.f; a.eps = optim_h ? optim_h->eps : 0.f;
+  a.step = optim_h ? optim_h->step : 0;
+  a.params = params_d; a.m = m_d; a.v = v_d; a.stats = stats_d;
+  a.use_override = nf_override_h ? 1 : 0;
+  a.n_override = nf_override_h ? nf_override_h[0] : 0.f;
+  a.f_override = nf_override_h ? nf_override_h[1] : 0.f;
+  if (a.opt_kind != D3P_OPT_NONE && !params_d) return D3P_ERR_INVALID_ARGUMENT;
+  if (a.opt_kind == D3P_OPT_ADAM && (!m_d || !v_d)) return D3P_ERR_INVALID_ARGUMENT;
+  if (a.opt_kind != D3P_OPT_NONE && a.opt_kind != D3P_OPT_SGD && a.opt_kind != D3P_OPT_ADAM) return D3P_ERR_UNSUPPORTED;
+  LeafTable lt;
+  SiteStates ss;
+  memset(&lt, 0, sizeof(lt));
+  memset(&ss, 0, sizeof(ss));
+  if (leaves_h) {
+    lt.n_leaves = leaves_h->n_leaves;
+    for (uint32_t l = 0; l < lt.n_leaves; ++l) {
+      lt.off[l] = leaves_h->leaf_off[l];
+      lt.len[l] = leaves_h->leaf_len[l];
+      if ((uint64_t)lt.off[l] + lt.len[l] > P) return D3P_ERR_INVALID_ARGUMENT;
+      for (int i = 0; i < 16; ++i) ss.w[l][i] = leaves_h->site_state[l][i];
+    }
+  }
+  unsigned grid = P ? (P + 31) / 32 : 1;
+  finalize_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(a, lt, ss);
+  return check_launch();
+}

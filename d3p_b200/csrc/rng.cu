@@ -1,0 +1,201 @@
+// K1: ChaCha20 keystream kernels (+ uniform / normal transforms, randint round) and the
+// host-side key plumbing of the rng suite.  Replaces jax-chacha-prng behind
+// d3p/random/__init__.py:28-155.
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace d3p {
+
+enum { kBits = 0, kUniform = 1, kNormal = 2 };
+
+// One thread per 64-byte block; a warp writes 32 consecutive blocks.  Each lane owns 16
+// consecutive words, stored as four 16-byte vectors (each lane writes a full 64 B line half).
+template <int kMode>
+__global__ void __launch_bounds__(256) chacha_stream_kernel(ChaChaState st, uint32_t first_block, void* out,
+                                                            size_t n_words, float lo, float hi) {
+  size_t n_blocks = (n_words + 15) / 16;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks;
+       b += (size_t)gridDim.x * blockDim.x) {
+    uint32_t ks[16];
+    chacha20_block(st.w, st.w[12] + first_block + (uint32_t)b, ks);
+    uint32_t vals[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (kMode == kBits) vals[i] = ks[i];
+      else if (kMode == kUniform) vals[i] = __float_as_uint(bits_to_uniform(ks[i], lo, hi));
+      else vals[i] = __float_as_uint(bits_to_normal<false>(ks[i]));
+    }
+    size_t base = b * 16;
+    uint32_t* o = reinterpret_cast<uint32_t*>(out);
+    if (base + 16 <= n_words && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      uint4* o4 = reinterpret_cast<uint4*>(o + base);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o4[i] = make_uint4(vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (base + i < n_words) o[base + i] = vals[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) randint_round_kernel(ChaChaState st, uint32_t bitmask, uint32_t delta,
+                                                            int first, uint32_t* vals, size_t n, int* pending) {
+  size_t n_blocks = (n + 15) / 16;
+  int local = 0;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks;
+       b += (size_t)gridDim.x * blockDim.x) {
+    uint32_t ks[16];
+    chacha20_block(st.w, st.w[12] + (uint32_t)b, ks);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      size_t e = b * 16 + i;
+      if (e < n) {
+        uint32_t v = first ? 0xFFFFFFFFu : vals[e];
+        if (first || v > delta) v = ks[i] & bitmask;
+        vals[e] = v;
+        local += (v > delta);
+      }
+    }
+  }
+  local = __reduce_add_sync(0xffffffffu, local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(pending, local);
+}
+
+__global__ void randint_finish_kernel(const uint32_t* vals, int32_t minval, int32_t* out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (int32_t)vals[i] + minval;
+}
+
+static ChaChaState load_state(const uint32_t* s) {
+  ChaChaState st;
+  for (int i = 0; i < 16; ++i) st.w[i] = s[i];
+  return st;
+}
+
+// The single key-derivation rule of this build (DESIGN.md "ChaCha key derivation"; mirrored by
+// oracle/chacha.py:derive_key).  [parity unpinned: jax-chacha-prng's rule is not in the reference tree]
+static void derive_key(const uint32_t in[16], uint32_t data, uint32_t out[16]) {
+  uint32_t tmp[16], blk[16];
+  for (int i = 0; i < 16; ++i) tmp[i] = in[i];
+  tmp[15] ^= 0x80000000u;
+  chacha20_block(tmp, data, blk);
+  out[0] = 0x61707865u; out[1] = 0x3320646Eu; out[2] = 0x79622D32u; out[3] = 0x6B206574u;
+  for (int i = 0; i < 8; ++i) out[4 + i] = blk[i];
+  out[12] = 0;
+  out[13] = in[13]; out[14] = in[14]; out[15] = in[15];
+}
+
+template <int kMode>
+static int32_t launch_stream(const uint32_t* state_h, uint64_t first_block, void* out_d, size_t n, float lo,
+                             float hi, void* stream) {
+  if (!state_h || (!out_d && n)) return D3P_ERR_INVALID_ARGUMENT;
+  if (n == 0) return D3P_OK;
+  size_t n_blocks = (n + 15) / 16;
+  if (first_block + n_blocks > 0x100000000ull) return D3P_ERR_INVALID_ARGUMENT;  // 32-bit block counter
+  int threads = 256;
+  size_t grid = (n_blocks + threads - 1) / threads;
+  if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
+  chacha_stream_kernel<kMode><<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(
+      load_state(state_h), (uint32_t)first_block, out_d, n, lo, hi);
+  return check_launch();
+}
+
+}  // namespace d3p
+
+using namespace d3p;
+
+extern "C" {
+
+int32_t d3p_abi_version(void) { return 1; }
+
+const char* d3p_error_string(int32_t code) {
+  switch (code) {
+    case D3P_OK: return "ok";
+    case D3P_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case D3P_ERR_CUDA: return "CUDA error (kernel launch failed)";
+    case D3P_ERR_UNSUPPORTED: return "unsupported configuration";
+    case D3P_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown error";
+  }
+}
+
+int32_t d3p_chacha_key_from_seed_h(const uint8_t* seed_h, size_t len, uint32_t out_h[16]) {
+  if (!out_h || (!seed_h && len) || len > 32) return D3P_ERR_INVALID_ARGUMENT;
+  uint8_t buf[32] = {0};
+  for (size_t i = 0; i < len; ++i) buf[i] = seed_h[i];
+  out_h[0] = 0x61707865u; out_h[1] = 0x3320646Eu; out_h[2] = 0x79622D32u; out_h[3] = 0x6B206574u;
+  for (int i = 0; i < 8; ++i)
+    out_h[4 + i] = (uint32_t)buf[4 * i] | ((uint32_t)buf[4 * i + 1] << 8) | ((uint32_t)buf[4 * i + 2] << 16) |
+                   ((uint32_t)buf[4 * i + 3] << 24);
+  out_h[12] = out_h[13] = out_h[14] = out_h[15] = 0;
+  return D3P_OK;
+}
+
+int32_t d3p_chacha_fold_in_h(const uint32_t in_h[16], uint32_t data, uint32_t out_h[16]) {
+  if (!in_h || !out_h) return D3P_ERR_INVALID_ARGUMENT;
+  uint32_t tmp[16];
+  derive_key(in_h, data, tmp);
+  for (int i = 0; i < 16; ++i) out_h[i] = tmp[i];
+  return D3P_OK;
+}
+
+int32_t d3p_chacha_split_h(const uint32_t in_h[16], int32_t num, uint32_t* out_h) {
+  if (!in_h || num < 0 || (!out_h && num)) return D3P_ERR_INVALID_ARGUMENT;
+  uint32_t src[16];
+  for (int i = 0; i < 16; ++i) src[i] = in_h[i];
+  for (int32_t k = 0; k < num; ++k) derive_key(src, (uint32_t)k, out_h + 16 * (size_t)k);
+  return D3P_OK;
+}
+
+int32_t d3p_chacha_random_bits_h(const uint32_t state_h[16], uint64_t first_block, uint32_t* out_h,
+                                 size_t n_words) {
+  if (!state_h || (!out_h && n_words)) return D3P_ERR_INVALID_ARGUMENT;
+  uint32_t st[16], blk[16];
+  for (int i = 0; i < 16; ++i) st[i] = state_h[i];
+  for (size_t b = 0; b * 16 < n_words; ++b) {
+    chacha20_block(st, st[12] + (uint32_t)first_block + (uint32_t)b, blk);
+    for (int i = 0; i < 16 && b * 16 + i < n_words; ++i) out_h[b * 16 + i] = blk[i];
+  }
+  return D3P_OK;
+}
+
+int32_t d3p_chacha_random_bits(const uint32_t state_h[16], uint64_t first_block, uint32_t* out_d,
+                               size_t n_words, void* stream) {
+  return launch_stream<kBits>(state_h, first_block, out_d, n_words, 0.f, 1.f, stream);
+}
+
+int32_t d3p_chacha_uniform_f32(const uint32_t state_h[16], uint64_t first_block, float lo, float hi,
+                               float* out_d, size_t n, void* stream) {
+  return launch_stream<kUniform>(state_h, first_block, out_d, n, lo, hi, stream);
+}
+
+int32_t d3p_chacha_normal_f32(const uint32_t state_h[16], uint64_t first_block, float* out_d, size_t n,
+                              void* stream) {
+  return launch_stream<kNormal>(state_h, first_block, out_d, n, 0.f, 1.f, stream);
+}
+
+int32_t d3p_chacha_randint_round_u32(const uint32_t round_state_h[16], uint32_t bitmask, uint32_t delta,
+                                     int32_t first, uint32_t* vals_d, size_t n, int32_t* pending_d,
+                                     void* stream) {
+  if (!round_state_h || !pending_d || (!vals_d && n)) return D3P_ERR_INVALID_ARGUMENT;
+  cudaMemsetAsync(pending_d, 0, sizeof(int32_t), (cudaStream_t)stream);
+  if (n == 0) return check_launch();
+  size_t n_blocks = (n + 15) / 16;
+  size_t grid = (n_blocks + 255) / 256;
+  if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
+  randint_round_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(load_state(round_state_h), bitmask, delta,
+                                                                         first, vals_d, n, pending_d);
+  return check_launch();
+}
+
+int32_t d3p_randint_finish_i32(const uint32_t* vals_d, int32_t minval, int32_t* out_d, size_t n, void* stream) {
+  if ((!vals_d || !out_d) && n) return D3P_ERR_INVALID_ARGUMENT;
+  if (n == 0) return D3P_OK;
+  size_t grid = (n + 255) / 256;
+  if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
+  randint_finish_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(vals_d, minval, out_d, n);
+  return check_launch();
+}
+
+}  // extern "C"

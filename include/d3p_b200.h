@@ -1,0 +1,203 @@
+/* d3p_b200 — C ABI of the B200-native DP-VI update path.
+ *
+ * This is the drop-in boundary for the hot path of DPBayes/d3p (reference paths are relative
+ * to the d3p repository root).  Every entry point
+ *   - is `extern "C"`, takes plain pointers and sizes (no torch / jax types),
+ *   - returns D3P_OK (0) or a negative D3P_ERR_* code, never throws,
+ *   - never allocates device memory and never synchronises the device (pointer arguments
+ *     with suffix `_d` are DEVICE pointers, suffix `_h` HOST pointers; scratch space comes
+ *     from the caller, sized by the matching `*_workspace_bytes` query),
+ *   - enqueues its kernels on `stream` (a `cudaStream_t` passed as `void*`; NULL = default),
+ *   - keeps no global mutable state and is re-entrant across streams and threads.
+ * One process per GPU; the caller selects the device with cudaSetDevice before calling.
+ *
+ * ChaCha states are 16 x uint32 in RFC 8439 layout (constants | 8 key words | counter |
+ * 3 nonce words), i.e. jax-chacha-prng's 4x4 `RNGState` flattened row-major.
+ */
+#ifndef D3P_B200_H_
+#define D3P_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3P_OK 0
+#define D3P_ERR_INVALID_ARGUMENT (-1)
+#define D3P_ERR_CUDA (-2)
+#define D3P_ERR_UNSUPPORTED (-3)
+#define D3P_ERR_WORKSPACE (-4)
+
+#define D3P_MAX_LEAVES 16
+
+/* Library / build identification. */
+int32_t d3p_abi_version(void);
+const char* d3p_error_string(int32_t code);
+
+/* ------------------------------------------------------------------------------------------
+ * ChaCha20 rng suite — replaces jax-chacha-prng behind d3p/random/__init__.py:28-32.
+ * ------------------------------------------------------------------------------------------ */
+
+/* d3p.random.PRNGKey (d3p/random/__init__.py:35-47): <=32 seed bytes, zero padded. */
+int32_t d3p_chacha_key_from_seed_h(const uint8_t* seed_h, size_t len, uint32_t out_h[16]);
+/* rng_suite.fold_in (d3p/random/__init__.py:30; call sites d3p/minibatch.py:115,207,230). */
+int32_t d3p_chacha_fold_in_h(const uint32_t in_h[16], uint32_t data, uint32_t out_h[16]);
+/* rng_suite.split (d3p/random/__init__.py:29; call sites d3p/svi.py:210,447,491). out = num x 16. */
+int32_t d3p_chacha_split_h(const uint32_t in_h[16], int32_t num, uint32_t* out_h);
+/* Host keystream (few words): rng_suite.random_bits for tiny outputs, e.g.
+ * convert_to_jax_rng_key (d3p/random/__init__.py:149-155) and the Feistel round constants
+ * (d3p/util.py:240-246). */
+int32_t d3p_chacha_random_bits_h(const uint32_t state_h[16], uint64_t first_block, uint32_t* out_h,
+                                 size_t n_words);
+/* Device keystream: rng_suite.random_bits(key, 32, shape) (d3p/random/__init__.py:31). */
+int32_t d3p_chacha_random_bits(const uint32_t state_h[16], uint64_t first_block, uint32_t* out_d,
+                               size_t n_words, void* stream);
+/* rng_suite.uniform(key, shape, float32, lo, hi) (d3p/random/__init__.py:32). */
+int32_t d3p_chacha_uniform_f32(const uint32_t state_h[16], uint64_t first_block, float lo, float hi,
+                               float* out_d, size_t n, void* stream);
+/* d3p.random.normal (d3p/random/__init__.py:50-81): sqrt(2) * erf_inv(uniform(lo=-1+ulp, hi=1)). */
+int32_t d3p_chacha_normal_f32(const uint32_t state_h[16], uint64_t first_block, float* out_d, size_t n,
+                              void* stream);
+/* One rejection round of d3p.random._randint (d3p/random/__init__.py:128-143) for 32-bit
+ * outputs: vals[i] = (first || vals[i] > delta) ? bits(round_key)[i] & bitmask : vals[i];
+ * *pending_d = number of lanes still > delta afterwards. */
+int32_t d3p_chacha_randint_round_u32(const uint32_t round_state_h[16], uint32_t bitmask, uint32_t delta,
+                                     int32_t first, uint32_t* vals_d, size_t n, int32_t* pending_d,
+                                     void* stream);
+/* vals -> int32 indices: idx = int32(vals) + minval. */
+int32_t d3p_randint_finish_i32(const uint32_t* vals_d, int32_t minval, int32_t* out_d, size_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Minibatch samplers — replace d3p/util.py:216-301 and d3p/minibatch.py:29-39,103-131,217-237.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Round constants of sample_from_array (d3p/util.py:240-246): 30 keystream words, rc[3j] |= 1. */
+int32_t d3p_feistel_round_constants_h(const uint32_t state_h[16], uint32_t rc_h[30]);
+/* idx[p - first_pos] = walk(pi_rc(p)) for p in [first_pos, first_pos + n) (d3p/util.py:249-299). */
+int32_t d3p_feistel_sample(const uint32_t rc_h[30], uint32_t capacity, uint32_t first_pos, uint32_t n,
+                           int32_t* idx_d, void* stream);
+
+/* poisson_sample_idxs + truncate/suppress + mask (d3p/minibatch.py:29-39,115-124).
+ * idx_d[max_b]: selected indices in DESCENDING order, then unselected indices descending.
+ * counts_d[0] = raw number selected, counts_d[1] = effective count after truncate / suppress.
+ * mask_d[max_b] (may be NULL) = arange(max_b) < counts_d[1].
+ * Multi-GPU: every rank runs the (cheap, ALU-only) sampler on the replicated key, so the
+ * index list is bit-identical on all ranks without any collective. */
+size_t d3p_poisson_workspace_bytes(uint32_t n_records);
+int32_t d3p_poisson_sample(const uint32_t state_h[16], float q, uint32_t n_records, uint32_t max_b,
+                           int32_t suppress, int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d,
+                           size_t ws_bytes, void* stream);
+
+/* mask * take(a, idxs, axis=0) (d3p/minibatch.py:126-131,210,233,306).
+ * dst[r, :] = (num_valid_d == NULL || r < *num_valid_d) ? src[idx[r], :] : 0 ; row_bytes % 4 == 0. */
+int32_t d3p_gather_rows_masked(const void* src_d, size_t row_bytes, const int32_t* idx_d,
+                               const int32_t* num_valid_d, uint32_t b, void* dst_d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-example clipping on materialised gradients — replace d3p/svi.py:68-124,310-348.
+ * px_grads is [B, P] row-major float32: the concatenation of the ravelled leaves per example.
+ * ------------------------------------------------------------------------------------------ */
+
+/* DPSVI._clip_gradients (d3p/svi.py:310-325): rows scaled in place by 1/max(1, norm/C).
+ * norms_d (may be NULL) receives the pre-clip L2 norms (full_norm, d3p/svi.py:68-87). */
+int32_t d3p_clip_rows_f32(float* px_grads_d, uint32_t B, uint32_t P, float C, float* norms_d, void* stream);
+/* Fused clip + sum over examples (d3p/svi.py:310-348 without the [B,P] round trip):
+ * sum_d[P + 2] = { sum_i m_i c_i g_i , sum_i m_i loss_i (px_loss_d may be NULL), sum_i m_i }. */
+size_t d3p_clip_and_sum_workspace_bytes(uint32_t B, uint32_t P);
+int32_t d3p_clip_and_sum_f32(const float* px_grads_d, const float* px_loss_d, const uint8_t* mask_d,
+                             uint32_t B, uint32_t P, float C, float* sum_d, void* ws_d, size_t ws_bytes,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused per-example gradient + clip + sum for mean-field Normal guides — replaces
+ * d3p/svi.py:238-348 for the model/guide pairs of examples/logistic_regression.py:49-86 and
+ * examples/simple_gaussian_posterior.py:50-83 (and their AutoDiagonalNormal variants,
+ * README.md:81,102).  No [B, P] tensor is materialised.
+ * ------------------------------------------------------------------------------------------ */
+#define D3P_FAMILY_LOGREG 0 /* Bernoulli(logits = x.w + b), N(0,1) priors          */
+#define D3P_FAMILY_GAUSS 1  /* x ~ N(mu, lik_scale) per dimension, N(0,1) prior on mu */
+#define D3P_LINK_EXP 0      /* scale = exp(rho)       (examples' hand-written guides) */
+#define D3P_LINK_SOFTPLUS 1 /* scale = softplus(rho)  (AutoDiagonalNormal)            */
+
+typedef struct {
+  int32_t family;       /* D3P_FAMILY_*                                                    */
+  int32_t link;         /* D3P_LINK_*                                                      */
+  int32_t joint_site;   /* 0: one guide sample site per latent (w, then intercept);        */
+                        /* 1: a single `_auto_latent` site holding [w..., intercept]        */
+  uint32_t d;           /* data columns                                                    */
+  uint32_t n_params;    /* P: length of the flat parameter vector                          */
+  uint32_t loc_off;     /* offset of the d weight/mean location params in the flat vector  */
+  uint32_t rho_off;     /* offset of the d unconstrained scale params                      */
+  uint32_t b_loc_off;   /* LOGREG only: offset of the intercept location                   */
+  uint32_t b_rho_off;   /* LOGREG only: offset of the intercept unconstrained scale        */
+  float num_obs_total;  /* plate size N  (static kwarg `num_obs_total`)                    */
+  float lik_scale;      /* GAUSS only: likelihood standard deviation                       */
+} d3p_meanfield_desc;
+
+/* Rows per row of the partial-sum workspace: P + 2 (grad sum | loss sum | valid count). */
+size_t d3p_meanfield_workspace_bytes(const d3p_meanfield_desc* desc, uint32_t* n_partials_out);
+
+/* One pass over a batch: for every position p < B with (mask_d == NULL || mask_d[p]) and
+ * (num_valid_d == NULL || p < *num_valid_d):
+ *     row = idx_d ? idx_d[p] : p ;  key_p = jax.random.split(threefry_key, B)[p]
+ *     eps  = numpyro seed/Normal.sample plumbing ; g_p = grad of (1/obs_scale) * (-ELBO_p)
+ *     c_p  = 1 / max(1, ||g_p|| / C)
+ * and writes per-CTA partial sums of { c_p g_p , obs_scale * loss_p , 1 } to ws_d
+ * ([n_partials, P + 2]); they are reduced in a fixed order by d3p_perturb_finalize_f32.
+ * `pos_begin/pos_end` restrict the positions handled by this rank (sharded batch).
+ * px_norms_d[B] (may be NULL) receives the pre-clip norms; px_grads_d[B, P] / px_loss_d[B] (may
+ * be NULL) receive the UNCLIPPED per-example gradients and obs_scale * loss_p — the stage-method
+ * form DPSVI._compute_per_example_gradients (d3p/svi.py:238-308).  Masked positions are not
+ * written (the caller zero-fills). */
+int32_t d3p_dpsvi_step_meanfield(const d3p_meanfield_desc* desc, const float* params_d, const float* x_d,
+                                 size_t x_row_stride /* floats */, const int32_t* y_d, const int32_t* idx_d,
+                                 const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                                 uint32_t pos_begin, uint32_t pos_end, const uint32_t threefry_key_h[2],
+                                 float obs_scale, float C, float* px_norms_d, float* px_grads_d, float* px_loss_d,
+                                 void* ws_d, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Reduce + perturb + rescale (+ optimizer) — replaces d3p/svi.py:327-393,470-498.
+ * ------------------------------------------------------------------------------------------ */
+#define D3P_OPT_NONE 0
+#define D3P_OPT_SGD 1
+#define D3P_OPT_ADAM 2
+
+typedef struct {
+  uint32_t n_leaves;
+  uint32_t leaf_off[D3P_MAX_LEAVES]; /* offset of each leaf in the flat vector (pytree order) */
+  uint32_t leaf_len[D3P_MAX_LEAVES];
+  uint32_t site_state[D3P_MAX_LEAVES][16]; /* rng_suite.split(k_noise, n_leaves) (d3p/svi.py:491) */
+} d3p_leaf_table;
+
+typedef struct {
+  int32_t kind;       /* D3P_OPT_*                               */
+  float step_size;
+  float b1, b2, eps;  /* Adam                                     */
+  int32_t step;       /* numpyro optimizer step counter i (>= 0)  */
+} d3p_optim_desc;
+
+/* partials_d is [n_partials, P + 2] (grad sum | loss sum | count).  With n = total count,
+ * f = (n == 0 ? 0 : B / n):
+ *   grad = ((sum / B) + dp_scale * (C / n) * xi) * obs_scale * f     (d3p/svi.py:342-375)
+ *   loss = (loss_sum / B) * f                                          (d3p/svi.py:306,342)
+ * xi ~ N(0, 1) from the ChaCha stream of the leaf's site state (counter from 0).
+ * grad_out_d[P] (may be NULL) receives grad; if optim->kind != NONE, params_d / m_d / v_d are
+ * updated in place (numpyro.optim.SGD / Adam, d3p/svi.py:379-393).
+ * stats_d[3] (may be NULL) = { loss, n, f }.
+ * nf_override_h (may be NULL) = { n, f } supplied by the caller instead of the counts in the
+ * partials — the stage-method form DPSVI._perturb_and_reassemble_gradients(state, key,
+ * avg_clipped_grads, num_elements, batch_mask_scaling_factor) (d3p/svi.py:350-377), called with
+ * partials = the averaged gradients, n_partials = 1, B = 1. */
+int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
+                                 const d3p_leaf_table* leaves_h, float dp_scale, float C, float obs_scale,
+                                 int32_t add_noise, float* grad_out_d, const d3p_optim_desc* optim_h,
+                                 float* params_d, float* m_d, float* v_d, float* stats_d,
+                                 const float* nf_override_h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3P_B200_H_ */
