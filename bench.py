@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — DPSVI.update examples/sec on the BASELINE.json workload.
+
+Workload (config.workload = "c2"): synthetic logistic regression, N = 10M records x d = 1024
+float32 (41 GB resident in HBM, >> L2), Poisson sampling q = 0.01 (max_batch_size = the 0.99
+Poisson quantile = 100736), hand-written mean-field guide, Adam(1e-3), C = 1, dp_scale = 1.
+
+A "step" = sample indices (Poisson sampler kernels) + fused gather / per-example gradient / clip /
+sum kernel + (NCCL all-reduce at N > 1) + reduce / ChaCha noise / rescale / Adam kernel, i.e.
+`get_batch(i, state)` followed by `DPSVI.update(state, *batch, mask=mask)`.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); the batch is sharded over the ranks
+(strong scaling: the global batch is fixed by the config).  `--impl reference` times the CPU
+oracle port of the same step on the host cores (the reference itself needs jax/numpyro/
+jax-chacha-prng, none of which can be installed here — see DESIGN.md).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, d, q, family)
+    "c2": dict(N=10_000_000, d=1024, q=0.01, family="logreg", C=1.0),
+    "c3": dict(N=50_000_000, d=256, q=0.01, family="gauss", C=1.0),
+    "c1": dict(N=10_000, d=8, q=0.02, family="logreg", C=1.0),
+}
+ALGO_BYTES_PER_EXAMPLE = {"c2": 4 * (1024 + 1), "c3": 4 * 256, "c1": 4 * (8 + 1)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the benchmark runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def max_batch_size(N, q):
+    import scipy.stats
+    return int(scipy.stats.poisson(N * q).ppf(.99))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port (oracle) — the cpu_baseline leg and `--impl reference`
+# ------------------------------------------------------------------------------------------------
+def cpu_port_throughput(cfg, steps, warmup, sample_examples, threads):
+    import torch
+    from oracle import chacha, families, svi as osvi
+    torch.set_num_threads(threads)
+    d, N = cfg["d"], cfg["N"]
+    rs = np.random.RandomState(123)
+    B = sample_examples
+    if cfg["family"] == "logreg":
+        fam = families.LogisticRegression(d, N)
+        X = rs.randn(B, d).astype(np.float32)
+        y = (rs.rand(B) < .5).astype(np.int32)
+        args = (X, y)
+    else:
+        fam = families.GaussianMean(d, N)
+        args = ((1 + .1 * rs.randn(B, d)).astype(np.float32),)
+    s = osvi.DPSVI(fam, None, osvi.Adam(1e-3), None, cfg["C"], 1.0)
+    st = s.init(chacha.PRNGKey(0), *args)
+    mask = np.ones(B, dtype=bool)
+    for _ in range(warmup):
+        st, _ = s.update(st, *args, mask=mask)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st, _ = s.update(st, *args, mask=mask)
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps * 1e3
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 4096 if cfg["d"] >= 256 else 8192
+    steps = max(1, min(args.steps, 8))
+    warmup = min(args.warmup, 1)
+    value, ms = cpu_port_throughput(cfg, steps, warmup, sample, threads)
+    line = {
+        "impl": "reference", "metric": "DPSVI.update examples/sec", "value": value, "unit": "examples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, cfg),
+        "cpu_baseline": {"value": value, "unit": "examples/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} steps of {sample} examples (d={cfg['d']}) through the oracle port of "
+                                   "DPSVI.update (numpy Threefry/ChaCha + torch.func vmap(grad) + clip + noise + Adam); "
+                                   "the reference's JAX path cannot be installed here"},
+        "e2e": {"value": value, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(name, cfg):
+    return {"workload": f"{name}: synthetic {cfg['family']} N={cfg['N']} d={cfg['d']} Poisson q={cfg['q']} "
+                        f"max_batch_size={max_batch_size(cfg['N'], cfg['q'])}",
+            "l2_policy": "inputs larger than L2 (dataset resident in HBM, rows gathered at random)",
+            "optimizer": "Adam(1e-3)", "clipping_threshold": cfg["C"], "dp_scale": 1.0}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def make_dataset(cfg, device):
+    """Synthetic data of the named shape, generated on the device with the build's own ChaCha
+    kernels (reproducible without JAX): X ~ N(0, 1); y ~ Bernoulli(sigmoid(X w* + b*))."""
+    import torch
+    import d3p_b200.random as rng
+    N, d = cfg["N"], cfg["d"]
+    kx, kw, ky = rng.split(rng.PRNGKey(123), 3)
+    X = rng.normal(kx, (N, d))
+    if cfg["family"] == "gauss":
+        X.mul_(0.1).add_(1.0)
+        return (X,)
+    w = rng.normal(kw, (d + 1,))
+    logits = torch.mv(X, w[:d]) + w[d]
+    y = (rng.uniform(ky, (N,)) < torch.sigmoid(logits)).to(torch.int32)
+    return (X, y)
+
+
+def run_b200(args, cfg):
+    import torch
+    import torch.distributed as dist
+    import d3p_b200.random as rng
+    from d3p_b200 import minibatch as mb, models, optimizers, parallel, svi as dsvi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    N, d, q = cfg["N"], cfg["d"], cfg["q"]
+    dataset = make_dataset(cfg, device)
+    fam = models.LogisticRegression(d) if cfg["family"] == "logreg" else models.GaussianMean(d)
+    svi = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), cfg["C"], 1.0,
+                     num_obs_total=N)
+    svi.donate_state = True
+    if world > 1:
+        parallel.shard_dpsvi(svi, rank, world)
+    init, get_batch = mb.poisson_batchify_data(dataset, q, .99)
+    key = rng.PRNGKey(0)
+    key, k_init, k_fetch = rng.split(key, 3)
+    _, bstate = init(k_fetch)
+    batch, mask = get_batch(0, bstate)
+    max_b = len(batch[0])
+    state = svi.init(k_init, *batch)
+
+    kernel_events = []
+
+    def hook(tag):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        kernel_events.append(ev)
+
+    def one_step(i, state):
+        batch, mask = get_batch(i, bstate)
+        state, loss = svi.update(state, *batch, mask=mask)
+        return state, loss, batch[0].num_valid
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for i in range(args.warmup):
+        state, loss, _ = one_step(i, state)
+    sync_all()
+    svi.event_hook = hook
+    counts = []
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for i in range(args.steps):
+        state, loss, nv = one_step(args.warmup + i, state)
+        counts.append(nv)
+    t_end.record()
+    sync_all()
+    svi.event_hook = None
+    clocks = sampler.stop()
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    n_examples = int(torch.stack([c.reshape(()) for c in counts]).sum().item())
+    value = n_examples / (elapsed_ms * 1e-3)
+    kern_ms = [kernel_events[2 * i].elapsed_time(kernel_events[2 * i + 1]) for i in range(len(kernel_events) // 2)]
+    kern_ms_avg = float(np.mean(kern_ms))
+    if not np.isfinite(float(loss)):
+        raise RuntimeError("bench produced a non-finite loss")
+
+    # ---- end to end through the public API with HOST buffers (rank-local shard at N > 1) -----------
+    e2e = None
+    if args.e2e:
+        Xb = batch[0].tensor()
+        host = [torch.empty(t_.shape, dtype=t_.dtype).pin_memory() for t_ in (Xb,) + tuple(b.tensor() for b in batch[1:])]
+        for h, src in zip(host, (Xb,) + tuple(b.tensor() for b in batch[1:])):
+            h.copy_(src)
+        host_mask = torch.empty(mask.shape, dtype=torch.bool).pin_memory()
+        host_mask.copy_(mask)
+        n_valid_host = int(mask.sum().item())
+        dev_bufs = [[torch.empty_like(h, device=device) for h in host] + [torch.empty_like(host_mask, device=device)]
+                    for _ in range(2)]
+        loss_host = torch.empty(args.steps + args.warmup, dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        h2d_bytes = sum(h.numel() * h.element_size() for h in host) + host_mask.numel()
+
+        def e2e_loop(n_steps, state, base):
+            main = torch.cuda.current_stream()
+            for i in range(n_steps):
+                slot = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[slot])
+                    for dst, src in zip(dev_bufs[slot], host + [host_mask]):
+                        dst.copy_(src, non_blocking=True)
+                    ready[slot].record(copy_stream)
+                main.wait_event(ready[slot])
+                state, loss = svi.update(state, *dev_bufs[slot][:-1], mask=dev_bufs[slot][-1])
+                consumed[slot].record(main)
+                loss_host[base + i:base + i + 1].copy_(loss.reshape(1), non_blocking=True)
+            return state
+
+        for ev in consumed:
+            ev.record()
+        state = e2e_loop(args.warmup, state, 0)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        state = e2e_loop(args.steps, state, args.warmup)
+        e1.record()
+        sync_all()
+        e_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([e_ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": n_valid_host * args.steps / (e_ms * 1e-3), "unit": "examples/s",
+               "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
+               "note": "DPSVI.update(state, X_batch, y_batch, mask) with the batch in pinned HOST memory: "
+                       "H2D copy of the padded batch + update + loss read-back every step (double-buffered)"}
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        algo_bytes = ALGO_BYTES_PER_EXAMPLE[args.workload] * (n_examples / args.steps) / world
+        achieved = algo_bytes / (kern_ms_avg * 1e-3) / 1e9
+        line = {
+            "metric": "DPSVI.update examples/sec", "value": value, "unit": "examples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.workload, cfg),
+            "clocks": clocks, "gpu_launches": 5 * args.steps + (1 if world > 1 else 0) * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "meanfield_step_kernel", "achieved": achieved,
+                         "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "kernel_ms": kern_ms_avg, "kernel_share_of_step": kern_ms_avg / (elapsed_ms / args.steps),
+                         "note": "ALU co-bound: one Threefry normal per data float (SURVEY.md 8d)"},
+            "examples_per_step": n_examples / args.steps, "max_batch_size": max_b,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and args.cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = 2048
+            v, ms = cpu_port_throughput(cfg, 3, 1, sample, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "examples/s", "cores": threads, "kind": "port",
+                                    "sample": f"3 steps of {sample} examples (d={d}) through the oracle port"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=None, help="override N (development only)")
+    ap.add_argument("--no-e2e", dest="e2e", action="store_false")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    cfg = dict(WORKLOADS[args.workload])
+    if args.rows:
+        cfg["N"] = args.rows
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_b200(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,7 @@ _SIGNATURES = {
                                              C.c_float, C.c_float, C.c_float, C.c_int32, _vp,
                                              C.POINTER(OptimDesc), _vp, _vp, _vp, _vp,
                                              C.POINTER(C.c_float), _vp]),
+    "d3p_reduce_partials_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -120,9 +120,38 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
   }
 }
 
+// out[j] = sum_p partials[p][j] for j < row_len, fixed order (warp w adds rows w, w+4, ...).
+__global__ void __launch_bounds__(kFinThreads) reduce_partials_kernel(const float* __restrict__ partials,
+                                                                      uint32_t n_partials, uint32_t row_len,
+                                                                      float* __restrict__ out) {
+  __shared__ float colred[kFinThreads / 32][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t j = blockIdx.x * 32 + lane;
+  float part = 0.f;
+  if (j < row_len)
+    for (uint32_t p = warp; p < n_partials; p += kFinThreads / 32) part += partials[(size_t)p * row_len + j];
+  colred[warp][lane] = part;
+  __syncthreads();
+  if (warp == 0 && j < row_len) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < kFinThreads / 32; ++w) sum += colred[w][lane];
+    out[j] = sum;
+  }
+}
+
 }  // namespace d3p
 
 using namespace d3p;
+
+extern "C" int32_t d3p_reduce_partials_f32(const float* partials_d, uint32_t n_partials, uint32_t P, float* out_d,
+                                           void* stream) {
+  if (!partials_d || !out_d || n_partials == 0) return D3P_ERR_INVALID_ARGUMENT;
+  uint32_t row_len = P + 2;
+  reduce_partials_kernel<<<(row_len + 31) / 32, kFinThreads, 0, (cudaStream_t)stream>>>(partials_d, n_partials, row_len,
+                                                                                        out_d);
+  return check_launch();
+}
 
 extern "C" int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
                                             const d3p_leaf_table* leaves_h, float dp_scale, float C, float obs_scale,

@@ -156,6 +156,7 @@ class DPSVI:
         self.donate_state = False
         self._ws = None
         self.shard = None   # (rank, world_size, reduce_fn) set by d3p_b200.parallel.shard_dpsvi
+        self.event_hook = None   # optional callable(tag) around the step kernel launch (bench instrumentation)
 
     # ---- state plumbing (svi.py:192-211) -----------------------------------------------------------
     @staticmethod
@@ -269,11 +270,15 @@ class DPSVI:
             per = (B + world - 1) // world
             pos_begin, pos_end = min(B, rank * per), min(B, (rank + 1) * per)
         flat = state.optim_state.flat
+        if self.event_hook is not None:
+            self.event_hook("step_begin")
         _n.check(_n.lib().d3p_dpsvi_step_meanfield(
             C.byref(desc), _n.ptr(flat), _n.ptr(Xsrc), stride, _n.ptr(ysrc), _n.ptr(idx), _n.ptr(mask_t), None,
             B, pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
             float(self._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_grads), _n.ptr(px_loss), _n.ptr(ws), need,
             _n.stream_ptr()), "dpsvi_step_meanfield")
+        if self.event_hook is not None:
+            self.event_hook("step_end")
         return ws, n_part, B, desc
 
     def _leaf_table(self, layout, rng_key):

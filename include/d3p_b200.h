@@ -197,6 +197,13 @@ int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_partials, u
                                  float* params_d, float* m_d, float* v_d, float* stats_d,
                                  const float* nf_override_h, void* stream);
 
+/* Multi-GPU (new; the reference is single-device): out_d[P + 2] = sum over the n_partials rows of
+ * a step workspace, in a fixed order.  The caller all-reduces out_d over the ranks that share a
+ * batch (ncclAllReduce, sum) and passes it to d3p_perturb_finalize_f32 with n_partials = 1; every
+ * rank then draws the SAME noise from the replicated ChaCha state, so the mechanism is unchanged. */
+int32_t d3p_reduce_partials_f32(const float* partials_d, uint32_t n_partials, uint32_t P, float* out_d,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -231,10 +231,10 @@ def test_generic_clip_and_combine_vs_oracle(cuda):
 def test_gradient_manipulators(cuda):
     # tests/test_gradient_manipulators.py
     from d3p_b200 import svi
-    tree = (torch.arange(1., 4., device=cuda), {"a": torch.arange(4., 6., device=cuda),
-                                                "b": torch.tensor([[6., 7.], [8., 9.]], device=cuda)})
-    assert np.isclose(float(svi.full_norm(tree)), 16.613247)
-    assert svi.full_norm([]) == 0.
+    tree = (torch.ones(17, 2, 3, device=cuda), torch.ones(2, 54, device=cuda),
+            (torch.ones(2, 3, device=cuda), torch.ones(3, 4, 5, device=cuda)), ())
+    assert np.allclose(16.613247, float(svi.full_norm(tree)))
+    assert svi.full_norm([]) == 0. and svi.full_norm(None) == 0. and svi.full_norm(()) == 0.
     g = (torch.tensor([3., 4.], device=cuda), torch.tensor([[12.]], device=cuda))
     out = svi.clip_gradient(g, 26.)
     assert np.allclose(_np(out[0]), [3., 4.]) and np.allclose(_np(out[1]), [[12.]])
