@@ -144,6 +144,63 @@ D3P_D float bits_to_normal(uint32_t bits) {
   return D3P_SQRT2 * erfinv_f32<kFast>(u);
 }
 
+// ---- fast path for the in-kernel guide noise (Threefry normals) --------------------------------
+// Same function as bits_to_normal, restructured for throughput:
+//   * u = fma(f, 2, lo) already satisfies u >= lo and |u| < 1, so the max() and the |x| == 1 test
+//     of the reference transform are no-ops and are dropped (bit-identical);
+//   * w - 2.5 = fma(lg2(1 - u*u), -ln2, -2.5) through MUFU.LG2 (absolute error ~4e-7 in w);
+//   * sqrt(2) is folded into the polynomial coefficients (<= 1 ulp difference);
+//   * the |u| > 0.9966 tail (0.34 % of the variates) is not evaluated here: the caller checks
+//     `needs_tail` for a whole group of variates with one warp-uniform branch and patches them
+//     with normal_tail(), which keeps the common path branch-free (ILP across variates).
+struct FastNormal { float value; float w; };
+
+D3P_D float unit_to_u(uint32_t bits) {
+  return fmaf(bits_to_unit_float(bits), 2.0f, D3P_NORMAL_LO);
+}
+
+D3P_D float normal_central(float u, float& w_out) {
+  const float l2 = __log2f(fmaf(-u, u, 1.0f));
+  w_out = l2;                                            // w = -ln2 * l2 ; tail iff w >= 5
+  const float w = fmaf(l2, -0.693147182f, -2.5f);
+  float p = 2.81022636e-08f * D3P_SQRT2;
+  p = fmaf(p, w, 3.43273939e-07f * D3P_SQRT2);
+  p = fmaf(p, w, -3.5233877e-06f * D3P_SQRT2);
+  p = fmaf(p, w, -4.39150654e-06f * D3P_SQRT2);
+  p = fmaf(p, w, 0.00021858087f * D3P_SQRT2);
+  p = fmaf(p, w, -0.00125372503f * D3P_SQRT2);
+  p = fmaf(p, w, -0.00417768164f * D3P_SQRT2);
+  p = fmaf(p, w, 0.246640727f * D3P_SQRT2);
+  p = fmaf(p, w, 1.50140941f * D3P_SQRT2);
+  return p * u;
+}
+
+// lg2(1 - u^2) <= -5 / ln2  <=>  w >= 5
+#define D3P_TAIL_L2 (-7.21347523f)
+
+D3P_D float normal_tail(float u, float l2) {
+  const float w = __fsqrt_rn(l2 * -0.693147182f) - 3.0f;
+  float p = -0.000200214257f * D3P_SQRT2;
+  p = fmaf(p, w, 0.000100950558f * D3P_SQRT2);
+  p = fmaf(p, w, 0.00134934322f * D3P_SQRT2);
+  p = fmaf(p, w, -0.00367342844f * D3P_SQRT2);
+  p = fmaf(p, w, 0.00573950773f * D3P_SQRT2);
+  p = fmaf(p, w, -0.0076224613f * D3P_SQRT2);
+  p = fmaf(p, w, 0.00943887047f * D3P_SQRT2);
+  p = fmaf(p, w, 1.00167406f * D3P_SQRT2);
+  p = fmaf(p, w, 2.83297682f * D3P_SQRT2);
+  return p * u;
+}
+
+// scalar convenience form (per-variate branch): used by the generic kernel
+D3P_D float bits_to_normal_fast(uint32_t bits) {
+  const float u = unit_to_u(bits);
+  float l2;
+  float r = normal_central(u, l2);
+  if (l2 <= D3P_TAIL_L2) r = normal_tail(u, l2);
+  return r;
+}
+
 D3P_D float bits_to_uniform(uint32_t bits, float lo, float hi) {
   float f = bits_to_unit_float(bits);
   return fmaxf(lo, __fadd_rn(__fmul_rn(f, hi - lo), lo));

@@ -15,52 +15,9 @@
 //   gs_e = d loss / d rho_e = gl_e * eps_e * s'_e - (1/S) * s'_e / s_e
 #include "common.cuh"
 #include "launch.cuh"
+#include "meanfield_common.cuh"
 
 namespace d3p {
-
-constexpr int kStepThreads = 256;
-constexpr int kStepWarps = kStepThreads / 32;
-
-struct StepArgs {
-  const float* params;
-  const float* x;
-  size_t x_stride;
-  const int32_t* y;
-  const int32_t* idx;
-  const uint8_t* mask;
-  const int32_t* num_valid;
-  uint32_t B, pos_begin, pos_end;
-  uint32_t k0, k1;
-  float inv_S, L, C, N;
-  float inv_var, log_norm_lik;
-  uint32_t d, n_main, half, P, loc_off, rho_off, b_loc_off, b_rho_off;
-  int has_b;
-  float* px_norms;
-  float* px_grads;
-  float* px_loss;
-  float* partials;
-};
-
-template <int LINK>
-D3P_D void link_terms(float rho, float inv_S, float& s, float& a, float& bt, float& log_s) {
-  if (LINK == D3P_LINK_EXP) {
-    s = expf(rho); a = s; bt = inv_S; log_s = rho;
-  } else {
-    s = softplus_f(rho); a = sigmoid_f(rho); bt = inv_S * a / s; log_s = logf(s);
-  }
-}
-
-template <int G>
-D3P_D unsigned group_mask(int lane) {
-  return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-}
-
-template <int G>
-D3P_D float gsum(float v, unsigned m) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
-  return v;
-}
 
 template <int FAMILY, int LINK, int G, int NQ>
 __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArgs a) {
@@ -147,7 +104,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
         tf_split2(rng, rng2, k_b);                       // second latent site (intercept)
         uint32_t y0, y1;
         threefry2x32(k_b, 0u, 0u, y0, y1);               // random_bits(k, 32, ()) -> counts [0, pad 0]
-        my_eb = bits_to_normal<true>(y0);
+        my_eb = bits_to_normal_fast(y0);
       }
       my_row = a.idx ? (uint32_t)a.idx[my_p] : my_p;
       if (FAMILY == D3P_FAMILY_LOGREG) my_y = (float)a.y[my_row];
@@ -177,8 +134,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
         if ((vmask >> (2 * k)) & 1u) {
           uint32_t y0, y1;
           threefry2x32(km, e0, (e1 < a.n_main) ? e1 : 0u, y0, y1);
-          ev[2 * k] = bits_to_normal<true>(y0);
-          if ((vmask >> (2 * k + 1)) & 1u) ev[2 * k + 1] = bits_to_normal<true>(y1);
+          ev[2 * k] = bits_to_normal_fast(y0);
+          if ((vmask >> (2 * k + 1)) & 1u) ev[2 * k + 1] = bits_to_normal_fast(y1);
         }
       }
       // ---- pass 1: theta, sums -----------------------------------------------------------------
@@ -311,6 +268,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
   for (uint32_t j = threadIdx.x; j < a.P + 2; j += kStepThreads) out[j] = s_acc[j];
 }
 
+int32_t launch_meanfield_vec(int family, int link, const StepArgs& a, unsigned grid, cudaStream_t s);
+
 struct Shape { int G, NQ; };
 
 static bool pick_shape(uint32_t half, Shape& sh) {
@@ -402,6 +361,10 @@ int32_t d3p_dpsvi_step_meanfield(const d3p_meanfield_desc* desc, const float* pa
   a.loc_off = desc->loc_off; a.rho_off = desc->rho_off; a.b_loc_off = desc->b_loc_off; a.b_rho_off = desc->b_rho_off;
   a.has_b = (desc->family == D3P_FAMILY_LOGREG && !desc->joint_site) ? 1 : 0;
   a.px_norms = px_norms_d; a.px_grads = px_grads_d; a.px_loss = px_loss_d; a.partials = reinterpret_cast<float*>(ws_d);
+  {
+    int32_t rc = launch_meanfield_vec(desc->family, desc->link, a, n_partials, (cudaStream_t)stream);
+    if (rc != D3P_ERR_UNSUPPORTED) return rc;
+  }
   Shape sh;
   if (!pick_shape(a.half, sh)) return D3P_ERR_UNSUPPORTED;
   size_t smem = step_smem_bytes(desc, sh);

@@ -1,0 +1,299 @@
+// K5a/K5b fast path: the fused mean-field step for "full" shapes d = 64 * NQ (256, 512, 1024),
+// one warp per example, 4 consecutive latent elements per lane and float4 everywhere
+// (LDG.128 row loads, LDS.128 parameter reads).  Same math and same random streams as the generic
+// kernel in meanfield_step.cu (that file documents the algebra); this one removes the per-slot
+// predicates, keeps the Gaussian transform branch-free (one warp-uniform tail fix-up per 4
+// variates) and exposes 4-8 independent Threefry / erf_inv chains per lane to the scheduler.
+#include "common.cuh"
+#include "launch.cuh"
+#include "meanfield_common.cuh"
+
+namespace d3p {
+
+D3P_D float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+D3P_D float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+#define D3P_F4_FOREACH(OP) OP(x) OP(y) OP(z) OP(w)
+
+// 4 Threefry calls (q, q + HALF), q = q0..q0+3 -> normals for the low and the high half.
+D3P_D void normals8(const TfKey& km, uint32_t q0, uint32_t half, float4& lo, float4& hi) {
+  uint32_t a0, b0, a1, b1, a2, b2, a3, b3;
+  threefry2x32(km, q0 + 0u, q0 + 0u + half, a0, b0);
+  threefry2x32(km, q0 + 1u, q0 + 1u + half, a1, b1);
+  threefry2x32(km, q0 + 2u, q0 + 2u + half, a2, b2);
+  threefry2x32(km, q0 + 3u, q0 + 3u + half, a3, b3);
+  float4 ul = make_float4(unit_to_u(a0), unit_to_u(a1), unit_to_u(a2), unit_to_u(a3));
+  float4 uh = make_float4(unit_to_u(b0), unit_to_u(b1), unit_to_u(b2), unit_to_u(b3));
+  float4 wl, wh;
+#define D3P_CENTRAL(c) lo.c = normal_central(ul.c, wl.c); hi.c = normal_central(uh.c, wh.c);
+  D3P_F4_FOREACH(D3P_CENTRAL)
+#undef D3P_CENTRAL
+  const float wmin = fminf(fminf(fminf(wl.x, wl.y), fminf(wl.z, wl.w)), fminf(fminf(wh.x, wh.y), fminf(wh.z, wh.w)));
+  if (__any_sync(0xffffffffu, wmin <= D3P_TAIL_L2)) {        // warp-uniform, ~58 % of the groups
+#define D3P_TAIL(c)                                              \
+    if (wl.c <= D3P_TAIL_L2) lo.c = normal_tail(ul.c, wl.c);     \
+    if (wh.c <= D3P_TAIL_L2) hi.c = normal_tail(uh.c, wh.c);
+    D3P_F4_FOREACH(D3P_TAIL)
+#undef D3P_TAIL
+  }
+}
+
+template <int FAMILY, int LINK, int NQ>
+__global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_vec_kernel(StepArgs a) {
+  static_assert(NQ % 4 == 0, "NQ must be a multiple of 4");
+  constexpr int NCH = NQ / 4;          // float4 chunks per half per lane
+  constexpr int HALF = 32 * NQ;        // d / 2
+  constexpr int D = 2 * HALF;
+  constexpr int TILE = 8;
+  constexpr bool kExp = LINK == D3P_LINK_EXP;
+  extern __shared__ __align__(16) float smem[];
+  float* s_loc = smem;
+  float* s_scl = s_loc + D;
+  float* s_a = s_scl + D;                       // softplus only
+  float* s_sa = s_a + (kExp ? 0 : D);
+  float* s_bt = s_sa + (kExp ? 0 : D);
+  float* s_acc = s_bt + (kExp ? 0 : D);         // [P + 2]
+  __shared__ float s_red[kStepWarps];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  float log_s_part = 0.f;
+  for (int e = threadIdx.x; e < D; e += kStepThreads) {
+    float s, aa, bt, ls;
+    link_terms<LINK>(a.params[a.rho_off + e], a.inv_S, s, aa, bt, ls);
+    s_loc[e] = a.params[a.loc_off + e];
+    s_scl[e] = s;
+    if (!kExp) { s_a[e] = aa; s_sa[e] = s / aa; s_bt[e] = bt; }
+    log_s_part += ls;
+  }
+  float b_loc = 0.f, b_s = 0.f, b_a = 0.f, b_bt = 0.f;
+  if (a.has_b) {
+    float ls;
+    b_loc = a.params[a.b_loc_off];
+    link_terms<LINK>(a.params[a.b_rho_off], a.inv_S, b_s, b_a, b_bt, ls);
+    if (threadIdx.x == 0) log_s_part += ls;
+  }
+  log_s_part = gsum<32>(log_s_part, 0xffffffffu);
+  if (lane == 0) s_red[warp] = log_s_part;
+  for (uint32_t j = threadIdx.x; j < a.P + 2; j += kStepThreads) s_acc[j] = 0.f;
+  __syncthreads();
+  float sum_log_s = 0.f;
+#pragma unroll
+  for (int w = 0; w < kStepWarps; ++w) sum_log_s += s_red[w];
+
+  float4 accL[2 * NCH], accR[2 * NCH];
+#pragma unroll
+  for (int i = 0; i < 2 * NCH; ++i) { accL[i] = make_float4(0.f, 0.f, 0.f, 0.f); accR[i] = accL[i]; }
+  float acc_bloc = 0.f, acc_brho = 0.f, acc_loss = 0.f, acc_cnt = 0.f;
+
+  const TfKey K(a.k0, a.k1);
+  const uint32_t npos = a.pos_end - a.pos_begin;
+  const uint32_t nv = a.num_valid ? (uint32_t)max(*a.num_valid, 0) : 0xffffffffu;
+  const uint32_t total_warps = gridDim.x * kStepWarps;
+  const float Linv = a.L * a.inv_var;
+
+  for (uint32_t wt = blockIdx.x * kStepWarps + warp; (uint64_t)wt * TILE < npos; wt += total_warps) {
+    const uint32_t base = a.pos_begin + wt * TILE;
+    const uint32_t my_p = base + lane;
+    bool my_valid = (lane < TILE) && (my_p < a.pos_end) && (my_p < nv) && (!a.mask || a.mask[my_p]);
+    uint32_t my_k0 = 0, my_k1 = 0, my_row = 0;
+    float my_eb = 0.f, my_y = 0.f;
+    if (my_valid) {
+      TfKey kp = tf_example_key(K, a.B, my_p);
+      TfKey model_seed, guide_seed, rng, k_main;
+      tf_split2(kp, model_seed, guide_seed);
+      tf_split2(guide_seed, rng, k_main);
+      my_k0 = k_main.k0; my_k1 = k_main.k1;
+      if (a.has_b) {
+        TfKey rng2, k_b;
+        tf_split2(rng, rng2, k_b);
+        uint32_t y0, y1;
+        threefry2x32(k_b, 0u, 0u, y0, y1);
+        my_eb = bits_to_normal_fast(y0);
+      }
+      my_row = a.idx ? (uint32_t)a.idx[my_p] : my_p;
+      if (FAMILY == D3P_FAMILY_LOGREG) my_y = (float)a.y[my_row];
+    }
+    const unsigned valid_bits = __ballot_sync(0xffffffffu, my_valid);
+#pragma unroll 1
+    for (int t = 0; t < TILE; ++t) {
+      if (!((valid_bits >> t) & 1u)) continue;           // warp-uniform
+      const TfKey km(__shfl_sync(0xffffffffu, my_k0, t), __shfl_sync(0xffffffffu, my_k1, t));
+      const uint32_t row = __shfl_sync(0xffffffffu, my_row, t);
+      const float eb = __shfl_sync(0xffffffffu, my_eb, t);
+      const float yv = __shfl_sync(0xffffffffu, my_y, t);
+      const float* __restrict__ xr = a.x + (size_t)row * a.x_stride;
+
+      float4 xv[2 * NCH], ev[2 * NCH];
+#pragma unroll
+      for (int kk = 0; kk < NCH; ++kk) {
+        const int q0 = 4 * (lane + 32 * kk);
+        xv[2 * kk] = ldg4(xr + q0);
+        xv[2 * kk + 1] = ldg4(xr + HALF + q0);
+      }
+#pragma unroll
+      for (int kk = 0; kk < NCH; ++kk)
+        normals8(km, 4u * (lane + 32u * kk), HALF, ev[2 * kk], ev[2 * kk + 1]);
+
+      // ---- pass 1 ------------------------------------------------------------------------------
+      float zdot = 0.f, s_th2 = 0.f, s_e2 = 0.f, s_res2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2 * NCH; ++i) {
+        const int e0 = (i & 1) * HALF + 4 * (lane + 32 * (i >> 1));
+        const float4 loc = ld4(s_loc + e0), sc = ld4(s_scl + e0);
+        float4 aa = sc;
+        if (!kExp) aa = ld4(s_a + e0);
+#define D3P_P1(c)                                                        \
+        {                                                                \
+          const float th = fmaf(ev[i].c, sc.c, loc.c);                   \
+          s_e2 = fmaf(ev[i].c, ev[i].c, s_e2);                           \
+          s_th2 = fmaf(th, th, s_th2);                                   \
+          if (FAMILY == D3P_FAMILY_LOGREG) zdot = fmaf(xv[i].c, th, zdot); \
+          else { const float r = xv[i].c - th; s_res2 = fmaf(r, r, s_res2); } \
+          ev[i].c = ev[i].c * aa.c;                                      \
+        }
+        D3P_F4_FOREACH(D3P_P1)
+#undef D3P_P1
+      }
+      if (FAMILY == D3P_FAMILY_LOGREG) zdot = gsum<32>(zdot, 0xffffffffu);
+      else s_res2 = gsum<32>(s_res2, 0xffffffffu);
+      s_th2 = gsum<32>(s_th2, 0xffffffffu);
+      s_e2 = gsum<32>(s_e2, 0xffffffffu);
+
+      float th_b = 0.f, Lr = 0.f, loglik;
+      if (a.has_b) { th_b = fmaf(eb, b_s, b_loc); s_th2 = fmaf(th_b, th_b, s_th2); s_e2 = fmaf(eb, eb, s_e2); }
+      if (FAMILY == D3P_FAMILY_LOGREG) {
+        const float z = zdot + th_b;
+        const float sp = fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
+        loglik = -(sp - z * yv);
+        Lr = a.L * (sigmoid_f(z) - yv);
+      } else {
+        loglik = -0.5f * s_res2 * a.inv_var - (float)D * a.log_norm_lik;
+      }
+      const float loss_i = 0.5f * s_th2 - 0.5f * s_e2 - sum_log_s - a.N * loglik;
+
+      // ---- pass 2: gl overwrites xv --------------------------------------------------------------
+      float nrm = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2 * NCH; ++i) {
+        const int e0 = (i & 1) * HALF + 4 * (lane + 32 * (i >> 1));
+        const float4 loc = ld4(s_loc + e0);
+        float4 sa = loc, bt = loc;
+        if (!kExp) { sa = ld4(s_sa + e0); bt = ld4(s_bt + e0); }
+#define D3P_P2(c)                                                                              \
+        {                                                                                      \
+          const float th = kExp ? (loc.c + ev[i].c) : fmaf(ev[i].c, sa.c, loc.c);              \
+          const float h = (FAMILY == D3P_FAMILY_LOGREG) ? Lr * xv[i].c : Linv * (th - xv[i].c); \
+          const float gl = fmaf(th, a.inv_S, h);                                               \
+          const float gs = fmaf(gl, ev[i].c, -(kExp ? a.inv_S : bt.c));                        \
+          xv[i].c = gl;                                                                        \
+          nrm = fmaf(gl, gl, fmaf(gs, gs, nrm));                                               \
+        }
+        D3P_F4_FOREACH(D3P_P2)
+#undef D3P_P2
+        if (a.px_grads) {
+          float* pg = a.px_grads + (size_t)(base + t) * a.P;
+#define D3P_PG(c, k)                                                                           \
+          pg[a.loc_off + e0 + k] = xv[i].c;                                                    \
+          pg[a.rho_off + e0 + k] = fmaf(xv[i].c, ev[i].c, -(kExp ? a.inv_S : bt.c));
+          D3P_PG(x, 0) D3P_PG(y, 1) D3P_PG(z, 2) D3P_PG(w, 3)
+#undef D3P_PG
+        }
+      }
+      nrm = gsum<32>(nrm, 0xffffffffu);
+      float glb = 0.f, gsb = 0.f;
+      if (a.has_b) {
+        glb = fmaf(th_b, a.inv_S, Lr);
+        gsb = fmaf(glb, eb * b_a, -b_bt);
+        nrm = fmaf(glb, glb, fmaf(gsb, gsb, nrm));
+      }
+      const float norm = sqrtf(nrm);
+      const float c = 1.0f / fmaxf(1.0f, norm / a.C);
+
+      // ---- pass 3 ------------------------------------------------------------------------------
+#pragma unroll
+      for (int i = 0; i < 2 * NCH; ++i) {
+        float4 bt = make_float4(a.inv_S, a.inv_S, a.inv_S, a.inv_S);
+        if (!kExp) bt = ld4(s_bt + (i & 1) * HALF + 4 * (lane + 32 * (i >> 1)));
+#define D3P_P3(c)                                                        \
+        accL[i].c = fmaf(c_, xv[i].c, accL[i].c);                        \
+        accR[i].c = fmaf(c_, fmaf(xv[i].c, ev[i].c, -bt.c), accR[i].c);
+        const float c_ = c;
+        D3P_F4_FOREACH(D3P_P3)
+#undef D3P_P3
+      }
+      if (lane == 0) {
+        acc_bloc = fmaf(c, glb, acc_bloc);
+        acc_brho = fmaf(c, gsb, acc_brho);
+        acc_loss += loss_i;
+        acc_cnt += 1.0f;
+        if (a.px_norms) a.px_norms[base + t] = norm;
+        if (a.px_loss) a.px_loss[base + t] = loss_i;
+        if (a.px_grads && a.has_b) {
+          float* pg = a.px_grads + (size_t)(base + t) * a.P;
+          pg[a.b_loc_off] = glb;
+          pg[a.b_rho_off] = gsb;
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: warps add into the CTA partial in a fixed order ----------------------------------
+  for (int w = 0; w < kStepWarps; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int i = 0; i < 2 * NCH; ++i) {
+        const int e0 = (i & 1) * HALF + 4 * (lane + 32 * (i >> 1));
+        float* pl = s_acc + a.loc_off + e0;
+        float* pr = s_acc + a.rho_off + e0;
+        pl[0] += accL[i].x; pl[1] += accL[i].y; pl[2] += accL[i].z; pl[3] += accL[i].w;
+        pr[0] += accR[i].x; pr[1] += accR[i].y; pr[2] += accR[i].z; pr[3] += accR[i].w;
+      }
+      if (lane == 0) {
+        if (a.has_b) { s_acc[a.b_loc_off] += acc_bloc; s_acc[a.b_rho_off] += acc_brho; }
+        s_acc[a.P] += acc_loss;
+        s_acc[a.P + 1] += acc_cnt;
+      }
+    }
+    __syncthreads();
+  }
+  float* out = a.partials + (size_t)blockIdx.x * (a.P + 2);
+  for (uint32_t j = threadIdx.x; j < a.P + 2; j += kStepThreads) out[j] = s_acc[j];
+}
+
+template <int FAMILY, int LINK, int NQ>
+static int32_t launch_vec_one(const StepArgs& a, unsigned grid, cudaStream_t s) {
+  constexpr int D = 64 * NQ;
+  size_t smem = ((LINK == D3P_LINK_EXP ? 2 : 5) * (size_t)D + a.P + 2) * sizeof(float);
+  auto kern = meanfield_step_vec_kernel<FAMILY, LINK, NQ>;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return D3P_ERR_CUDA;
+  kern<<<grid, kStepThreads, smem, s>>>(a);
+  return check_launch();
+}
+
+template <int FAMILY, int LINK>
+static int32_t launch_vec_nq(const StepArgs& a, unsigned grid, cudaStream_t s) {
+  switch (a.d) {
+    case 256: return launch_vec_one<FAMILY, LINK, 4>(a, grid, s);
+    case 512: return launch_vec_one<FAMILY, LINK, 8>(a, grid, s);
+    case 1024: return launch_vec_one<FAMILY, LINK, 16>(a, grid, s);
+    default: return D3P_ERR_UNSUPPORTED;
+  }
+}
+
+// Eligibility: full shape (single main site of exactly d = 256/512/1024 elements) and 16-byte
+// aligned rows.  Returns D3P_ERR_UNSUPPORTED when the generic kernel has to be used.
+int32_t launch_meanfield_vec(int family, int link, const StepArgs& a, unsigned grid, cudaStream_t s) {
+  if (a.n_main != a.d || (a.d != 256 && a.d != 512 && a.d != 1024)) return D3P_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(a.x) & 15) || (a.x_stride & 3)) return D3P_ERR_UNSUPPORTED;
+  if (family == D3P_FAMILY_LOGREG) {
+    if (link == D3P_LINK_EXP) return launch_vec_nq<D3P_FAMILY_LOGREG, D3P_LINK_EXP>(a, grid, s);
+    return launch_vec_nq<D3P_FAMILY_LOGREG, D3P_LINK_SOFTPLUS>(a, grid, s);
+  }
+  if (link == D3P_LINK_EXP) return launch_vec_nq<D3P_FAMILY_GAUSS, D3P_LINK_EXP>(a, grid, s);
+  return launch_vec_nq<D3P_FAMILY_GAUSS, D3P_LINK_SOFTPLUS>(a, grid, s);
+}
+
+}  // namespace d3p
