@@ -328,7 +328,7 @@ extern "C" {
 
 size_t d3p_meanfield_workspace_bytes(const d3p_meanfield_desc* desc, uint32_t* n_partials_out) {
   if (!desc_ok(desc)) return 0;
-  uint32_t n_partials = (uint32_t)sm_count();
+  uint32_t n_partials = 2u * (uint32_t)sm_count();   // two resident CTAs per SM on the fast path
   if (n_partials_out) *n_partials_out = n_partials;
   return (size_t)n_partials * (desc->n_params + 2) * sizeof(float);
 }

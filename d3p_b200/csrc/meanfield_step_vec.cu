@@ -38,8 +38,18 @@ D3P_D void normals8(const TfKey& km, uint32_t q0, uint32_t half, float4& lo, flo
   }
 }
 
+D3P_D void cp_async16(float* smem_dst, const float* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+}
+D3P_D void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+// Per-warp staging in shared memory: the example's row x (later overwritten by gl) and the scaled
+// noise u.  Every lane only touches its own 16-byte slots, so no intra-warp synchronisation is
+// needed; the loops over chunks stay rolled, which keeps the hot loop inside the instruction cache
+// (the fully unrolled variant was fetch-bound: ncu `no_instruction` stalls, profiles/r1_*).
 template <int FAMILY, int LINK, int NQ>
-__global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_vec_kernel(StepArgs a) {
+__global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(StepArgs a) {
   static_assert(NQ % 4 == 0, "NQ must be a multiple of 4");
   constexpr int NCH = NQ / 4;          // float4 chunks per half per lane
   constexpr int HALF = 32 * NQ;        // d / 2
@@ -52,10 +62,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_vec_kernel(Ste
   float* s_a = s_scl + D;                       // softplus only
   float* s_sa = s_a + (kExp ? 0 : D);
   float* s_bt = s_sa + (kExp ? 0 : D);
-  float* s_acc = s_bt + (kExp ? 0 : D);         // [P + 2]
+  float* s_stage = s_bt + (kExp ? 0 : D);       // [kStepWarps][2 * D]
+  float* s_acc = s_stage + kStepWarps * 2 * D;  // [P + 2]
   __shared__ float s_red[kStepWarps];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* xs = s_stage + warp * 2 * D;           // x, then gl
+  float* us = xs + D;                           // u = eps * s'
 
   float log_s_part = 0.f;
   for (int e = threadIdx.x; e < D; e += kStepThreads) {
@@ -124,36 +137,43 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_vec_kernel(Ste
       const float yv = __shfl_sync(0xffffffffu, my_y, t);
       const float* __restrict__ xr = a.x + (size_t)row * a.x_stride;
 
-      float4 xv[2 * NCH], ev[2 * NCH];
-#pragma unroll
-      for (int kk = 0; kk < NCH; ++kk) {
-        const int q0 = 4 * (lane + 32 * kk);
-        xv[2 * kk] = ldg4(xr + q0);
-        xv[2 * kk + 1] = ldg4(xr + HALF + q0);
-      }
-#pragma unroll
-      for (int kk = 0; kk < NCH; ++kk)
-        normals8(km, 4u * (lane + 32u * kk), HALF, ev[2 * kk], ev[2 * kk + 1]);
-
-      // ---- pass 1 ------------------------------------------------------------------------------
-      float zdot = 0.f, s_th2 = 0.f, s_e2 = 0.f, s_res2 = 0.f;
+      // the row goes straight to this lane's staging slots (no register staging)
 #pragma unroll
       for (int i = 0; i < 2 * NCH; ++i) {
         const int e0 = (i & 1) * HALF + 4 * (lane + 32 * (i >> 1));
-        const float4 loc = ld4(s_loc + e0), sc = ld4(s_scl + e0);
-        float4 aa = sc;
-        if (!kExp) aa = ld4(s_a + e0);
-#define D3P_P1(c)                                                        \
-        {                                                                \
-          const float th = fmaf(ev[i].c, sc.c, loc.c);                   \
-          s_e2 = fmaf(ev[i].c, ev[i].c, s_e2);                           \
-          s_th2 = fmaf(th, th, s_th2);                                   \
-          if (FAMILY == D3P_FAMILY_LOGREG) zdot = fmaf(xv[i].c, th, zdot); \
-          else { const float r = xv[i].c - th; s_res2 = fmaf(r, r, s_res2); } \
-          ev[i].c = ev[i].c * aa.c;                                      \
-        }
-        D3P_F4_FOREACH(D3P_P1)
+        cp_async16(xs + e0, xr + e0);
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+
+      // ---- loop A: noise + pass 1 ----------------------------------------------------------------
+      float zdot = 0.f, s_th2 = 0.f, s_e2 = 0.f, s_res2 = 0.f;
+#pragma unroll 1
+      for (int kk = 0; kk < NCH; ++kk) {
+        const int q0 = 4 * (lane + 32 * kk);
+        float4 ev[2];
+        normals8(km, (uint32_t)q0, HALF, ev[0], ev[1]);
+        if (kk == 0) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e0 = h * HALF + q0;
+          const float4 xv = ld4(xs + e0);
+          const float4 loc = ld4(s_loc + e0), sc = ld4(s_scl + e0);
+          float4 aa = sc;
+          if (!kExp) aa = ld4(s_a + e0);
+          float4 u;
+#define D3P_P1(c)                                                      \
+          {                                                            \
+            const float th = fmaf(ev[h].c, sc.c, loc.c);               \
+            s_e2 = fmaf(ev[h].c, ev[h].c, s_e2);                       \
+            s_th2 = fmaf(th, th, s_th2);                               \
+            if (FAMILY == D3P_FAMILY_LOGREG) zdot = fmaf(xv.c, th, zdot); \
+            else { const float r = xv.c - th; s_res2 = fmaf(r, r, s_res2); } \
+            u.c = ev[h].c * aa.c;                                      \
+          }
+          D3P_F4_FOREACH(D3P_P1)
 #undef D3P_P1
+          st4(us + e0, u);
+        }
       }
       if (FAMILY == D3P_FAMILY_LOGREG) zdot = gsum<32>(zdot, 0xffffffffu);
       else s_res2 = gsum<32>(s_res2, 0xffffffffu);
@@ -172,30 +192,30 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_vec_kernel(Ste
       }
       const float loss_i = 0.5f * s_th2 - 0.5f * s_e2 - sum_log_s - a.N * loglik;
 
-      // ---- pass 2: gl overwrites xv --------------------------------------------------------------
+      // ---- loop B: gradient wrt loc (overwrites x in the staging buffer), norm ----------------
       float nrm = 0.f;
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < 2 * NCH; ++i) {
         const int e0 = (i & 1) * HALF + 4 * (lane + 32 * (i >> 1));
-        const float4 loc = ld4(s_loc + e0);
-        float4 sa = loc, bt = loc;
+        const float4 loc = ld4(s_loc + e0), xv = ld4(xs + e0), u = ld4(us + e0);
+        float4 sa = loc, bt = loc, gl;
         if (!kExp) { sa = ld4(s_sa + e0); bt = ld4(s_bt + e0); }
-#define D3P_P2(c)                                                                              \
-        {                                                                                      \
-          const float th = kExp ? (loc.c + ev[i].c) : fmaf(ev[i].c, sa.c, loc.c);              \
-          const float h = (FAMILY == D3P_FAMILY_LOGREG) ? Lr * xv[i].c : Linv * (th - xv[i].c); \
-          const float gl = fmaf(th, a.inv_S, h);                                               \
-          const float gs = fmaf(gl, ev[i].c, -(kExp ? a.inv_S : bt.c));                        \
-          xv[i].c = gl;                                                                        \
-          nrm = fmaf(gl, gl, fmaf(gs, gs, nrm));                                               \
+#define D3P_P2(c)                                                                            \
+        {                                                                                    \
+          const float th = kExp ? (loc.c + u.c) : fmaf(u.c, sa.c, loc.c);                    \
+          const float h = (FAMILY == D3P_FAMILY_LOGREG) ? Lr * xv.c : Linv * (th - xv.c);    \
+          gl.c = fmaf(th, a.inv_S, h);                                                       \
+          const float gs = fmaf(gl.c, u.c, -(kExp ? a.inv_S : bt.c));                        \
+          nrm = fmaf(gl.c, gl.c, fmaf(gs, gs, nrm));                                         \
         }
         D3P_F4_FOREACH(D3P_P2)
 #undef D3P_P2
+        st4(xs + e0, gl);
         if (a.px_grads) {
           float* pg = a.px_grads + (size_t)(base + t) * a.P;
-#define D3P_PG(c, k)                                                                           \
-          pg[a.loc_off + e0 + k] = xv[i].c;                                                    \
-          pg[a.rho_off + e0 + k] = fmaf(xv[i].c, ev[i].c, -(kExp ? a.inv_S : bt.c));
+#define D3P_PG(c, k)                                                                         \
+          pg[a.loc_off + e0 + k] = gl.c;                                                     \
+          pg[a.rho_off + e0 + k] = fmaf(gl.c, u.c, -(kExp ? a.inv_S : bt.c));
           D3P_PG(x, 0) D3P_PG(y, 1) D3P_PG(z, 2) D3P_PG(w, 3)
 #undef D3P_PG
         }
@@ -210,15 +230,16 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_vec_kernel(Ste
       const float norm = sqrtf(nrm);
       const float c = 1.0f / fmaxf(1.0f, norm / a.C);
 
-      // ---- pass 3 ------------------------------------------------------------------------------
+      // ---- loop C: clipped accumulation (unrolled: the accumulators live in registers) ---------
 #pragma unroll
       for (int i = 0; i < 2 * NCH; ++i) {
+        const int e0 = (i & 1) * HALF + 4 * (lane + 32 * (i >> 1));
+        const float4 gl = ld4(xs + e0), u = ld4(us + e0);
         float4 bt = make_float4(a.inv_S, a.inv_S, a.inv_S, a.inv_S);
-        if (!kExp) bt = ld4(s_bt + (i & 1) * HALF + 4 * (lane + 32 * (i >> 1)));
-#define D3P_P3(c)                                                        \
-        accL[i].c = fmaf(c_, xv[i].c, accL[i].c);                        \
-        accR[i].c = fmaf(c_, fmaf(xv[i].c, ev[i].c, -bt.c), accR[i].c);
-        const float c_ = c;
+        if (!kExp) bt = ld4(s_bt + e0);
+#define D3P_P3(c_)                                                     \
+        accL[i].c_ = fmaf(c, gl.c_, accL[i].c_);                       \
+        accR[i].c_ = fmaf(c, fmaf(gl.c_, u.c_, -bt.c_), accR[i].c_);
         D3P_F4_FOREACH(D3P_P3)
 #undef D3P_P3
       }
@@ -264,7 +285,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_vec_kernel(Ste
 template <int FAMILY, int LINK, int NQ>
 static int32_t launch_vec_one(const StepArgs& a, unsigned grid, cudaStream_t s) {
   constexpr int D = 64 * NQ;
-  size_t smem = ((LINK == D3P_LINK_EXP ? 2 : 5) * (size_t)D + a.P + 2) * sizeof(float);
+  size_t smem = ((LINK == D3P_LINK_EXP ? 2 : 5) * (size_t)D + (size_t)kStepWarps * 2 * D + a.P + 2) * sizeof(float);
   auto kern = meanfield_step_vec_kernel<FAMILY, LINK, NQ>;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
