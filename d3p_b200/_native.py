@@ -67,6 +67,10 @@ _SIGNATURES = {
                                              C.POINTER(OptimDesc), _vp, _vp, _vp, _vp,
                                              C.POINTER(C.c_float), _vp]),
     "d3p_reduce_partials_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "d3p_split_tf32": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_gemm_tf32x3": (C.c_int32, [_vp, _vp, C.c_int32, C.c_size_t, _vp, _vp, C.c_int32, C.c_size_t, C.c_uint32,
+                                    C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, C.c_size_t,
+                                    C.c_int32, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,0 +1,261 @@
+// 3xTF32 GEMM on the 5th-generation tensor cores:  D[M, N] = sum_k A[m, k] * B[n, k]  in fp32
+// accuracy, with A = a_hi + a_lo and B = b_hi + b_lo pre-split by the producing kernel
+// (a_hi = A with the 13 low mantissa bits cleared, exactly representable in TF32):
+//     D = a_hi*b_hi + a_hi*b_lo + a_lo*b_hi        (the a_lo*b_lo term is < 2^-22 relative)
+// Each term is one tcgen05.mma.kind::tf32 into the same TMEM accumulator.  An operand whose values
+// are exact in TF32 (e.g. binarised pixels) passes lo = NULL and its correction MMA is skipped.
+//
+// Structure (one CTA per 128 x BN output tile and K split, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of 32 fp32 (one 128 B swizzle span) into
+//               a STAGES-deep shared-memory ring, mbarrier complete_tx
+//   warp 1      MMA issuer (one thread): 4 k-steps of UMMA_K = 8 per 32-deep k-block, 1-3 MMAs each;
+//               tcgen05.commit releases the stage / publishes the accumulator
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> Epi::tile()
+// Operand major-ness (template): K-major = the contraction index is contiguous in memory,
+// MN-major = the M (or N) index is contiguous (needed for A^T * diag(c) * Delta, where the
+// contraction runs over the batch, the slow axis of both activations).
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace d3p {
+namespace tc {
+
+constexpr int kBM = 128;          // UMMA M
+constexpr int kKB = 32;           // fp32 per k-block = one 128-byte swizzle span
+constexpr int kUK = 8;            // UMMA K for tf32
+constexpr int kGemmThreads = 192;
+
+struct GemmMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo; };
+
+struct GemmShape {
+  uint32_t M, N, K;
+  uint32_t num_k_blocks;          // ceil(K / 32)
+  uint32_t split_k;               // gridDim.z
+  int has_a_lo, has_b_lo;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr uint32_t kABytes = kBM * 128;
+  static constexpr uint32_t kBBytes = BN * 128;
+  static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = (int)((220u * 1024u) / kStageBytes) > 4 ? 4 : (int)((220u * 1024u) / kStageBytes);
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32, 256]");
+  static_assert(kStages >= 2, "tile too large for a 2-stage pipeline");
+};
+
+template <bool A_MN, bool B_MN, int BN, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const typename Epi::Args ea) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_full[STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[STAGES];
+  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t m_tile = blockIdx.x, n_tile = blockIdx.y, split = blockIdx.z;
+  // balanced k-block ranges: the first (num_k_blocks % split_k) splits get one block more
+  const uint32_t base = g.num_k_blocks / g.split_k, rem = g.num_k_blocks % g.split_k;
+  const uint32_t kb_begin = split * base + (split < rem ? split : rem);
+  const uint32_t kb_end = kb_begin + base + (split < rem ? 1u : 0u);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a_hi);
+    tma_prefetch_desc(&maps.b_hi);
+    if (g.has_a_lo) tma_prefetch_desc(&maps.a_lo);
+    if (g.has_b_lo) tma_prefetch_desc(&maps.b_lo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+      mbar_init(&bar_acc, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::kTmemCols>(&tmem_base_s);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  auto stage_ptr = [&](int s, int which) -> uint8_t* {   // which: 0 a_hi, 1 a_lo, 2 b_hi, 3 b_lo
+    uint8_t* p = smem + (size_t)s * Cfg::kStageBytes;
+    if (which >= 1) p += Cfg::kABytes;
+    if (which >= 2) p += Cfg::kABytes;
+    if (which >= 3) p += Cfg::kBBytes;
+    return p;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = Cfg::kABytes * (1 + (g.has_a_lo ? 1 : 0)) + Cfg::kBBytes * (1 + (g.has_b_lo ? 1 : 0));
+      uint32_t it = 0;
+      for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(&bar_empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&bar_full[s], tx);
+        const int32_t k0 = (int32_t)(kb * kKB);
+        const int32_t m0 = (int32_t)(m_tile * kBM), n0 = (int32_t)(n_tile * BN);
+        if (!A_MN) {
+          tma_load_2d(&maps.a_hi, &bar_full[s], stage_ptr(s, 0), k0, m0);
+          if (g.has_a_lo) tma_load_2d(&maps.a_lo, &bar_full[s], stage_ptr(s, 1), k0, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < kBM / 32; ++c) {
+            tma_load_2d(&maps.a_hi, &bar_full[s], stage_ptr(s, 0) + c * 4096, m0 + c * 32, k0);
+            if (g.has_a_lo) tma_load_2d(&maps.a_lo, &bar_full[s], stage_ptr(s, 1) + c * 4096, m0 + c * 32, k0);
+          }
+        }
+        if (!B_MN) {
+          tma_load_2d(&maps.b_hi, &bar_full[s], stage_ptr(s, 2), k0, n0);
+          if (g.has_b_lo) tma_load_2d(&maps.b_lo, &bar_full[s], stage_ptr(s, 3), k0, n0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            tma_load_2d(&maps.b_hi, &bar_full[s], stage_ptr(s, 2) + c * 4096, n0 + c * 32, k0);
+            if (g.has_b_lo) tma_load_2d(&maps.b_lo, &bar_full[s], stage_ptr(s, 3) + c * 4096, n0 + c * 32, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, A_MN, B_MN);
+      constexpr uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
+      constexpr uint32_t a_step = A_MN ? 1024u : 32u, b_step = B_MN ? 1024u : 32u;
+      constexpr uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
+      constexpr uint32_t a_lt = A_MN ? kLayoutSw128Base32 : kLayoutSw128, b_lt = B_MN ? kLayoutSw128Base32 : kLayoutSw128;
+      uint32_t it = 0, accumulate = 0;
+      for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
+        const uint32_t b_hi = smem_u32(stage_ptr(s, 2)), b_lo = smem_u32(stage_ptr(s, 3));
+#pragma unroll
+        for (int ks = 0; ks < kKB / kUK; ++ks) {
+          const uint64_t da_hi = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
+          const uint64_t db_hi = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
+          umma_tf32(tmem_base, da_hi, db_hi, idesc, accumulate);
+          accumulate = 1;
+          if (g.has_b_lo) umma_tf32(tmem_base, da_hi, make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt), idesc, 1);
+          if (g.has_a_lo) umma_tf32(tmem_base, make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt), db_hi, idesc, 1);
+        }
+        umma_commit(&bar_empty[s]);     // frees the stage once these MMAs have read it
+      }
+      umma_commit(&bar_acc);            // accumulator complete
+    }
+  } else {
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after();
+    const uint32_t row = m_tile * kBM + q * 32 + lane;
+    typename Epi::RowState rs;
+    Epi::begin(ea, g, row, n_tile, split, rs);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      Epi::tile(ea, g, row, n_tile * BN + c * 32, split, v, rs);
+    }
+    Epi::end(ea, g, row, n_tile, split, rs);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ---- plain store epilogue: out[split][m, n] (or transposed) --------------------------------------
+struct EpiStore {
+  struct Args {
+    float* out;
+    size_t ldc;            // row stride of the stored matrix (floats)
+    size_t split_stride;   // floats between the outputs of consecutive K splits
+    int transpose;         // 0: out[m * ldc + n]; 1: out[n * ldc + m]
+  };
+  struct RowState {};
+  __device__ static void begin(const Args&, const GemmShape&, uint32_t, uint32_t, uint32_t, RowState&) {}
+  __device__ static void end(const Args&, const GemmShape&, uint32_t, uint32_t, uint32_t, RowState&) {}
+  __device__ static void tile(const Args& a, const GemmShape& g, uint32_t row, uint32_t col0, uint32_t split,
+                              const uint32_t (&v)[32], RowState&) {
+    float* out = a.out + (size_t)split * a.split_stride;
+    if (!a.transpose) {
+      if (row >= g.M) return;
+      float* p = out + (size_t)row * a.ldc + col0;
+      if (col0 + 32 <= g.N && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(p + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < g.N) p[j] = __uint_as_float(v[j]);
+      }
+    } else {
+      if (row >= g.M) return;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < g.N) out[(size_t)(col0 + j) * a.ldc + row] = __uint_as_float(v[j]);
+    }
+  }
+};
+
+// ---- host launcher ------------------------------------------------------------------------------------
+struct GemmOperand {
+  const float* hi;
+  const float* lo;     // may be NULL (operand exact in TF32)
+  int mn_major;        // 0: stored [rows = M or N, K] (K contiguous); 1: stored [K, M or N]
+  size_t ld;           // row stride in floats (multiple of 4)
+};
+
+template <bool A_MN, bool B_MN, int BN, class Epi>
+int32_t launch_tc_gemm(const GemmOperand& A, const GemmOperand& B, uint32_t M, uint32_t N, uint32_t K, uint32_t split_k,
+                       const typename Epi::Args& ea, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  if (!A.hi || !B.hi || M == 0 || N == 0 || K == 0 || split_k == 0) return D3P_ERR_INVALID_ARGUMENT;
+  if ((A.ld & 3) || (B.ld & 3) || (reinterpret_cast<uintptr_t>(A.hi) & 15) || (reinterpret_cast<uintptr_t>(B.hi) & 15) ||
+      (A.lo && (reinterpret_cast<uintptr_t>(A.lo) & 15)) || (B.lo && (reinterpret_cast<uintptr_t>(B.lo) & 15)))
+    return D3P_ERR_INVALID_ARGUMENT;
+  GemmShape g;
+  g.M = M; g.N = N; g.K = K;
+  g.num_k_blocks = (K + kKB - 1) / kKB;
+  g.split_k = split_k > g.num_k_blocks ? g.num_k_blocks : split_k;
+  g.has_a_lo = A.lo ? 1 : 0;
+  g.has_b_lo = B.lo ? 1 : 0;
+  GemmMaps maps;
+  bool ok = true;
+  if (!A_MN) {
+    ok = ok && make_map_2d(&maps.a_hi, A.hi, M, K, A.ld, kBM, false);
+    ok = ok && make_map_2d(&maps.a_lo, A.lo ? A.lo : A.hi, M, K, A.ld, kBM, false);
+  } else {
+    ok = ok && make_map_2d(&maps.a_hi, A.hi, K, M, A.ld, kKB, true);
+    ok = ok && make_map_2d(&maps.a_lo, A.lo ? A.lo : A.hi, K, M, A.ld, kKB, true);
+  }
+  if (!B_MN) {
+    ok = ok && make_map_2d(&maps.b_hi, B.hi, N, K, B.ld, BN, false);
+    ok = ok && make_map_2d(&maps.b_lo, B.lo ? B.lo : B.hi, N, K, B.ld, BN, false);
+  } else {
+    ok = ok && make_map_2d(&maps.b_hi, B.hi, K, N, B.ld, kKB, true);
+    ok = ok && make_map_2d(&maps.b_lo, B.lo ? B.lo : B.hi, K, N, B.ld, kKB, true);
+  }
+  if (!ok) return D3P_ERR_CUDA;
+  auto kern = tc_gemm_kernel<A_MN, B_MN, BN, Epi>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
+    return D3P_ERR_CUDA;
+  dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, g.split_k);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(maps, g, ea);
+  return cudaGetLastError() == cudaSuccess ? D3P_OK : D3P_ERR_CUDA;
+}
+
+}  // namespace tc
+}  // namespace d3p

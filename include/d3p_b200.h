@@ -204,6 +204,30 @@ int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_partials, u
 int32_t d3p_reduce_partials_f32(const float* partials_d, uint32_t n_partials, uint32_t P, float* out_d,
                                 void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core building blocks of the dense-layer (VAE) path — new; the reference leaves dense layers
+ * to XLA's cuBLAS calls (examples/vae.py:80-103) and clips materialised [B, P] gradients
+ * (d3p/svi.py:310-348).
+ * ------------------------------------------------------------------------------------------ */
+
+/* hi[i] = tf32_truncate(x[i] * s), lo[i] = x[i] * s - hi[i], s = row_scale_d ? row_scale_d[i / cols] : 1.
+ * lo_d may be NULL. */
+int32_t d3p_split_tf32(const float* x_d, const float* row_scale_d, uint32_t cols, float* hi_d, float* lo_d, size_t n,
+                       void* stream);
+
+/* out[split][m, n] = sum over the split's k range of A[m, k] * B[n, k] in 3xTF32 (fp32 accuracy) on
+ * tcgen05 tensor cores fed by TMA.  A = a_hi + a_lo, B = b_hi + b_lo (d3p_split_tf32); a lo pointer
+ * may be NULL when the operand is exact in TF32.  *_mn_major = 0: operand stored [M or N, K] with the
+ * contraction index contiguous; 1: stored [K, M or N] (the clipped-sum case A^T diag(c) Delta, where
+ * the contraction runs over the batch).  lda / ldb / ldc are row strides in floats (multiples of 4,
+ * 16-byte aligned bases).  tile_n is 128 or 224.  The split_k partial results are written
+ * split_stride floats apart (the caller reduces them in a fixed order); transpose_out stores
+ * out[n * ldc + m]. */
+int32_t d3p_gemm_tf32x3(const float* a_hi_d, const float* a_lo_d, int32_t a_mn_major, size_t lda, const float* b_hi_d,
+                        const float* b_lo_d, int32_t b_mn_major, size_t ldb, uint32_t M, uint32_t N, uint32_t K,
+                        uint32_t split_k, int32_t tile_n, float* out_d, size_t ldc, size_t split_stride,
+                        int32_t transpose_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,7 +149,10 @@ class DPSVI:
         p = self.model.init_params() if params is None else params
         optim_state = self.optim.init(p)
         # get_observations_scale (svi.py:43-65): plate(name, N, 1) on a one-element batch
-        observation_scale = float(self.model.num_obs_total) if self._clip_unscaled_observations else 1.0
+        observation_scale = 1.0
+        if self._clip_unscaled_observations:
+            # unique scale of the observed sites: N for a bare plate, N * (1/N) under vae.py's scale handler
+            observation_scale = float(getattr(self.model, "site_scale", self.model.num_obs_total))
         return DPSVIState(optim_state, rng_key, observation_scale)
 
     def get_params(self, state):
