@@ -24,6 +24,13 @@ class MeanfieldDesc(C.Structure):
                 ("lik_scale", C.c_float)]
 
 
+class VaeDesc(C.Structure):
+    _fields_ = [("out_dim", C.c_uint32), ("hidden_dim", C.c_uint32), ("z_dim", C.c_uint32), ("n_params", C.c_uint32),
+                ("off_w4", C.c_uint32), ("off_b4", C.c_uint32), ("off_w5", C.c_uint32), ("off_b5", C.c_uint32),
+                ("off_w1", C.c_uint32), ("off_b1", C.c_uint32), ("off_w2", C.c_uint32), ("off_b2", C.c_uint32),
+                ("off_w3", C.c_uint32), ("off_b3", C.c_uint32), ("site_scale", C.c_float)]
+
+
 class LeafTable(C.Structure):
     _fields_ = [("n_leaves", C.c_uint32), ("leaf_off", C.c_uint32 * MAX_LEAVES),
                 ("leaf_len", C.c_uint32 * MAX_LEAVES), ("site_state", (C.c_uint32 * 16) * MAX_LEAVES)]
@@ -67,6 +74,9 @@ _SIGNATURES = {
                                              C.POINTER(OptimDesc), _vp, _vp, _vp, _vp,
                                              C.POINTER(C.c_float), _vp]),
     "d3p_reduce_partials_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "d3p_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.c_uint32, _u32p]),
+    "d3p_dpsvi_step_vae": (C.c_int32, [C.POINTER(VaeDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),
     "d3p_split_tf32": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_size_t, _vp]),
     "d3p_gemm_tf32x3": (C.c_int32, [_vp, _vp, C.c_int32, C.c_size_t, _vp, _vp, C.c_int32, C.c_size_t, C.c_uint32,
                                     C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, C.c_size_t,

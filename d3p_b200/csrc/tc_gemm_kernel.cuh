@@ -32,6 +32,7 @@ struct GemmShape {
   uint32_t num_k_blocks;          // ceil(K / 32)
   uint32_t split_k;               // gridDim.z
   int has_a_lo, has_b_lo;
+  const int* a_lo_flag;           // optional device flag: 0 = a_lo is all zeros, skip its MMA (and its loads)
 };
 
 template <int BN>
@@ -64,12 +65,14 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
   const uint32_t base = g.num_k_blocks / g.split_k, rem = g.num_k_blocks % g.split_k;
   const uint32_t kb_begin = split * base + (split < rem ? split : rem);
   const uint32_t kb_end = kb_begin + base + (split < rem ? 1u : 0u);
+  const bool has_a_lo = g.has_a_lo && (g.a_lo_flag == nullptr || __ldg(g.a_lo_flag) != 0);
+  const bool has_b_lo = g.has_b_lo != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a_hi);
     tma_prefetch_desc(&maps.b_hi);
-    if (g.has_a_lo) tma_prefetch_desc(&maps.a_lo);
-    if (g.has_b_lo) tma_prefetch_desc(&maps.b_lo);
+    if (has_a_lo) tma_prefetch_desc(&maps.a_lo);
+    if (has_b_lo) tma_prefetch_desc(&maps.b_lo);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -95,7 +98,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx = Cfg::kABytes * (1 + (g.has_a_lo ? 1 : 0)) + Cfg::kBBytes * (1 + (g.has_b_lo ? 1 : 0));
+      const uint32_t tx = Cfg::kABytes * (1 + (has_a_lo ? 1 : 0)) + Cfg::kBBytes * (1 + (has_b_lo ? 1 : 0));
       uint32_t it = 0;
       for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++it) {
         const int s = it % STAGES;
@@ -106,22 +109,22 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
         const int32_t m0 = (int32_t)(m_tile * kBM), n0 = (int32_t)(n_tile * BN);
         if (!A_MN) {
           tma_load_2d(&maps.a_hi, &bar_full[s], stage_ptr(s, 0), k0, m0);
-          if (g.has_a_lo) tma_load_2d(&maps.a_lo, &bar_full[s], stage_ptr(s, 1), k0, m0);
+          if (has_a_lo) tma_load_2d(&maps.a_lo, &bar_full[s], stage_ptr(s, 1), k0, m0);
         } else {
 #pragma unroll
           for (int c = 0; c < kBM / 32; ++c) {
             tma_load_2d(&maps.a_hi, &bar_full[s], stage_ptr(s, 0) + c * 4096, m0 + c * 32, k0);
-            if (g.has_a_lo) tma_load_2d(&maps.a_lo, &bar_full[s], stage_ptr(s, 1) + c * 4096, m0 + c * 32, k0);
+            if (has_a_lo) tma_load_2d(&maps.a_lo, &bar_full[s], stage_ptr(s, 1) + c * 4096, m0 + c * 32, k0);
           }
         }
         if (!B_MN) {
           tma_load_2d(&maps.b_hi, &bar_full[s], stage_ptr(s, 2), k0, n0);
-          if (g.has_b_lo) tma_load_2d(&maps.b_lo, &bar_full[s], stage_ptr(s, 3), k0, n0);
+          if (has_b_lo) tma_load_2d(&maps.b_lo, &bar_full[s], stage_ptr(s, 3), k0, n0);
         } else {
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c) {
             tma_load_2d(&maps.b_hi, &bar_full[s], stage_ptr(s, 2) + c * 4096, n0 + c * 32, k0);
-            if (g.has_b_lo) tma_load_2d(&maps.b_lo, &bar_full[s], stage_ptr(s, 3) + c * 4096, n0 + c * 32, k0);
+            if (has_b_lo) tma_load_2d(&maps.b_lo, &bar_full[s], stage_ptr(s, 3) + c * 4096, n0 + c * 32, k0);
           }
         }
       }
@@ -147,8 +150,8 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
           const uint64_t db_hi = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
           umma_tf32(tmem_base, da_hi, db_hi, idesc, accumulate);
           accumulate = 1;
-          if (g.has_b_lo) umma_tf32(tmem_base, da_hi, make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt), idesc, 1);
-          if (g.has_a_lo) umma_tf32(tmem_base, make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt), db_hi, idesc, 1);
+          if (has_b_lo) umma_tf32(tmem_base, da_hi, make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt), idesc, 1);
+          if (has_a_lo) umma_tf32(tmem_base, make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt), db_hi, idesc, 1);
         }
         umma_commit(&bar_empty[s]);     // frees the stage once these MMAs have read it
       }
@@ -220,7 +223,7 @@ struct GemmOperand {
 
 template <bool A_MN, bool B_MN, int BN, class Epi>
 int32_t launch_tc_gemm(const GemmOperand& A, const GemmOperand& B, uint32_t M, uint32_t N, uint32_t K, uint32_t split_k,
-                       const typename Epi::Args& ea, cudaStream_t stream) {
+                       const typename Epi::Args& ea, cudaStream_t stream, const int* a_lo_flag = nullptr) {
   using Cfg = GemmCfg<BN>;
   if (!A.hi || !B.hi || M == 0 || N == 0 || K == 0 || split_k == 0) return D3P_ERR_INVALID_ARGUMENT;
   if ((A.ld & 3) || (B.ld & 3) || (reinterpret_cast<uintptr_t>(A.hi) & 15) || (reinterpret_cast<uintptr_t>(B.hi) & 15) ||
@@ -232,6 +235,7 @@ int32_t launch_tc_gemm(const GemmOperand& A, const GemmOperand& B, uint32_t M, u
   g.split_k = split_k > g.num_k_blocks ? g.num_k_blocks : split_k;
   g.has_a_lo = A.lo ? 1 : 0;
   g.has_b_lo = B.lo ? 1 : 0;
+  g.a_lo_flag = a_lo_flag;
   GemmMaps maps;
   bool ok = true;
   if (!A_MN) {

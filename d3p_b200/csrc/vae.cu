@@ -1,0 +1,697 @@
+// K7: fused DP-SVI step for the VAE of examples/vae.py:65-153 — per-example gradient, ghost norm,
+// clip and clipped sum (d3p/svi.py:238-348) without ever materialising the [B, P] per-example
+// gradients (10.7 GB at B = 4096, P = 652 824).
+//
+// A dense layer's per-example gradient is the outer product a_i (x) delta_i (+ delta_i for the bias):
+//     ||g_i||^2 = sum_layers (||a_i||^2 + 1) ||delta_i||^2          (ghost norm)
+//     sum_i c_i g_i = A^T diag(c) Delta                               (clipped sum)
+// Pipeline (one stream, no host sync; GEMMs = 3xTF32 tcgen05 kernels of tc_gemm_kernel.cuh):
+//   split W1, W5 -> hi/lo | prep X (gather, hi/lo, ||x||^2, ones column)
+//   G1  pre1 = X W1          epilogue: + b1, softplus -> H1 hi/lo, ||h1||^2
+//   S1  heads z_loc, log z_std (K = H, N = 2Z), eps (Threefry), z, KL part, pre4 = z W4, H2 hi/lo
+//   G5  logits = H2 W5       epilogue: + b5, sigmoid, Bernoulli loss, delta5 hi/lo, ||delta5||^2
+//   G5b dh2 = delta5 W5^T    epilogue: * softplus'(pre4) -> delta4, ||delta4||^2
+//   S2  delta_z, delta2/3, delta1, ghost norm, c_i; writes c*delta1 hi/lo, c*delta4, c*[delta2|delta3],
+//       [c*h2 | c] hi/lo
+//   GW1 [X | 1]^T (c delta1)        -> dW1, db1  (split over the batch, partial rows)
+//   GW5 delta5^T [c h2 | c]         -> dW5^T, db5
+//   S4  thin clipped sums dW4, db4, dW2, db2, dW3, db3, loss, count -> thin partials -> partial row 0
+// The partial rows [S, P + 2] are reduced in a fixed order by d3p_perturb_finalize_f32.
+#include "common.cuh"
+#include "launch.cuh"
+#include "tc_gemm_kernel.cuh"
+
+namespace d3p {
+
+constexpr int kVaeBN = 224;            // N tile of every VAE GEMM
+constexpr int kMidWarps = 8;
+constexpr int kMidE = 4;               // examples per warp iteration in the SIMT "middle" kernels
+constexpr uint32_t kThinSlabs = 64;
+constexpr float kF32Tiny = 1.17549435e-38f;
+constexpr float kF32OneMinusEps = 0.99999988079071044921875f;   // 1 - 2^-23
+
+// ---- epilogues ---------------------------------------------------------------------------------------
+struct EpiFwd1 {   // H1 = softplus(acc + b1)
+  struct Args { const float* bias; float* h_hi; float* h_lo; size_t ld; float* rowsq; uint32_t rows_ld; };
+  struct RowState { float sq; };
+  __device__ static void begin(const Args&, const tc::GemmShape&, uint32_t, uint32_t, uint32_t, RowState& rs) { rs.sq = 0.f; }
+  __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t,
+                              const uint32_t (&v)[32], RowState& rs) {
+    if (row >= g.M) return;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (col0 + j >= g.N) break;                 // N is a multiple of 4
+      float h[4], hi[4], lo[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        h[t] = softplus_f(__uint_as_float(v[j + t]) + __ldg(a.bias + col0 + j + t));
+        hi[t] = tc::tf32_hi(h[t]);
+        lo[t] = h[t] - hi[t];
+        rs.sq = fmaf(h[t], h[t], rs.sq);
+      }
+      *reinterpret_cast<float4*>(a.h_hi + (size_t)row * a.ld + col0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(a.h_lo + (size_t)row * a.ld + col0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  __device__ static void end(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t n_tile, uint32_t, RowState& rs) {
+    if (row < g.M) a.rowsq[(size_t)n_tile * a.rows_ld + row] = rs.sq;
+  }
+};
+
+struct EpiFwd5 {   // p = sigmoid(acc + b5); Bernoulli(probs) log-lik (numpyro clamp_probs); delta5 = p - x
+  struct Args {
+    const float* bias; const float* x_hi; const float* x_lo; size_t ldx;
+    float* d_hi; float* d_lo; size_t ld; float* rowsq; float* rowloss; uint32_t rows_ld;
+  };
+  struct RowState { float sq, loss; };
+  __device__ static void begin(const Args&, const tc::GemmShape&, uint32_t, uint32_t, uint32_t, RowState& rs) {
+    rs.sq = 0.f; rs.loss = 0.f;
+  }
+  __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t,
+                              const uint32_t (&v)[32], RowState& rs) {
+    if (row >= g.M) return;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (col0 + j >= g.N) break;
+      const float4 xh = *reinterpret_cast<const float4*>(a.x_hi + (size_t)row * a.ldx + col0 + j);
+      const float4 xl = *reinterpret_cast<const float4*>(a.x_lo + (size_t)row * a.ldx + col0 + j);
+      const float xs[4] = {xh.x + xl.x, xh.y + xl.y, xh.z + xl.z, xh.w + xl.w};
+      float hi[4], lo[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float logit = __uint_as_float(v[j + t]) + __ldg(a.bias + col0 + j + t);
+        const float p = 1.0f / (1.0f + expf(-logit));
+        // jnp.clip = minimum(maximum(p, tiny), 1 - eps): gradient 1 inside, 1/2 at a bound, 0 outside
+        const float wclip = (p > kF32Tiny ? 1.0f : (p == kF32Tiny ? 0.5f : 0.f)) *
+                            (p < kF32OneMinusEps ? 1.0f : (p == kF32OneMinusEps ? 0.5f : 0.f));
+        const float pc = fminf(fmaxf(p, kF32Tiny), kF32OneMinusEps);
+        rs.loss -= xs[t] * logf(pc) + (1.0f - xs[t]) * log1pf(-pc);
+        const float d = wclip * (p - xs[t]);
+        hi[t] = tc::tf32_hi(d);
+        lo[t] = d - hi[t];
+        rs.sq = fmaf(d, d, rs.sq);
+      }
+      *reinterpret_cast<float4*>(a.d_hi + (size_t)row * a.ld + col0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(a.d_lo + (size_t)row * a.ld + col0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  __device__ static void end(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t n_tile, uint32_t, RowState& rs) {
+    if (row < g.M) {
+      a.rowsq[(size_t)n_tile * a.rows_ld + row] = rs.sq;
+      a.rowloss[(size_t)n_tile * a.rows_ld + row] = rs.loss;
+    }
+  }
+};
+
+struct EpiBwd5 {   // delta4 = acc * softplus'(pre4) = acc * (1 - exp(-h2))
+  struct Args { const float* h_hi; const float* h_lo; size_t ld; float* d4; float* rowsq; uint32_t rows_ld; };
+  struct RowState { float sq; };
+  __device__ static void begin(const Args&, const tc::GemmShape&, uint32_t, uint32_t, uint32_t, RowState& rs) { rs.sq = 0.f; }
+  __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t,
+                              const uint32_t (&v)[32], RowState& rs) {
+    if (row >= g.M) return;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (col0 + j >= g.N) break;
+      const float4 hh = *reinterpret_cast<const float4*>(a.h_hi + (size_t)row * a.ld + col0 + j);
+      const float4 hl = *reinterpret_cast<const float4*>(a.h_lo + (size_t)row * a.ld + col0 + j);
+      const float hs[4] = {hh.x + hl.x, hh.y + hl.y, hh.z + hl.z, hh.w + hl.w};
+      float d[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        d[t] = __uint_as_float(v[j + t]) * (-expm1f(-hs[t]));
+        rs.sq = fmaf(d[t], d[t], rs.sq);
+      }
+      *reinterpret_cast<float4*>(a.d4 + (size_t)row * a.ld + col0 + j) = make_float4(d[0], d[1], d[2], d[3]);
+    }
+  }
+  __device__ static void end(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t n_tile, uint32_t, RowState& rs) {
+    if (row < g.M) a.rowsq[(size_t)n_tile * a.rows_ld + row] = rs.sq;
+  }
+};
+
+struct EpiGrad {   // clipped-sum tile -> partial row `split`: weight block + the bias row / column
+  struct Args {
+    float* partials; size_t row_stride;   // P + 2
+    uint32_t w_off, b_off;                // offsets of the weight matrix and of the bias in the flat vector
+    uint32_t w_ld;                        // row stride of the weight matrix
+    uint32_t main;                        // !transpose: rows < main are weights, row == main is the bias
+    int transpose;                        //  transpose: cols < main are weights (stored [col, row]), col == main the bias
+  };
+  struct RowState {};
+  __device__ static void begin(const Args&, const tc::GemmShape&, uint32_t, uint32_t, uint32_t, RowState&) {}
+  __device__ static void end(const Args&, const tc::GemmShape&, uint32_t, uint32_t, uint32_t, RowState&) {}
+  __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t split,
+                              const uint32_t (&v)[32], RowState&) {
+    if (row >= g.M) return;
+    float* out = a.partials + (size_t)split * a.row_stride;
+    if (!a.transpose) {
+      float* p = row < a.main ? out + a.w_off + (size_t)row * a.w_ld : out + a.b_off;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < g.N) p[col0 + j] = __uint_as_float(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t col = col0 + j;
+        if (col < a.main) out[a.w_off + (size_t)col * a.w_ld + row] = __uint_as_float(v[j]);
+        else if (col == a.main) out[a.b_off + row] = __uint_as_float(v[j]);
+      }
+    }
+  }
+};
+
+// ---- SIMT kernels ------------------------------------------------------------------------------------
+struct VaeArgs {
+  uint32_t D, H, Z, B, Bl, pos_begin;
+  size_t ldx, ldc2;                   // D + 4, H + 4
+  const float* params;
+  uint32_t off_w4, off_b4, off_w5, off_b5, off_w1, off_b1, off_w2, off_b2, off_w3, off_b3, P;
+  const float* x; size_t x_stride; const int32_t* idx; const uint8_t* mask; const int32_t* num_valid;
+  uint32_t k0, k1;
+  float site_scale, inv_S, C;
+  uint32_t nt_h, nt_d;                // N tiles over H and over D
+  uint32_t S;                         // partial rows
+  // workspace
+  float *x_hi, *x_lo; int* x_lo_flag;
+  float *h1_hi, *h1_lo, *h2_hi, *h2_lo, *ch2_hi, *ch2_lo, *d5_hi, *d5_lo, *d4, *cd1_hi, *cd1_lo;
+  float *z, *u, *cd23;
+  float *sq_x, *sq_h1, *sq_h2, *sq_z, *sq_d5, *loss_rec, *sq_d4, *loss_kl, *lossv, *cnt;
+  float* thin;                        // [kThinSlabs, T + 2]
+  float* partials;
+  float* px_norms; float* px_loss;
+};
+
+// X rows -> [X | 1 | 0 0 0] hi / lo (row stride D + 4), ||x||^2, "some lo != 0" flag.  One warp per row.
+__global__ void vae_prep_x_kernel(VaeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = (blockDim.x >> 5) * gridDim.x;
+  bool any_lo = false;
+  for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < a.Bl; r += warps) {
+    const uint32_t p = a.pos_begin + r;
+    const size_t src = (size_t)(a.idx ? (uint32_t)a.idx[p] : p) * a.x_stride;
+    float sq = 0.f;
+    for (uint32_t j = lane; j < a.D + 4; j += 32) {
+      float v = j < a.D ? a.x[src + j] : (j == a.D ? 1.0f : 0.0f);
+      const float hi = tc::tf32_hi(v), lo = v - hi;
+      a.x_hi[(size_t)r * a.ldx + j] = hi;
+      a.x_lo[(size_t)r * a.ldx + j] = lo;
+      if (j < a.D) sq = fmaf(v, v, sq);
+      any_lo |= (lo != 0.f);
+    }
+    sq = group_sum<32>(sq);
+    if (lane == 0) a.sq_x[r] = sq;
+  }
+  if (__any_sync(0xffffffffu, any_lo) && lane == 0) atomicOr(a.x_lo_flag, 1);
+}
+
+// S1: encoder heads, guide sample, KL part of the loss, decoder hidden layer.
+__global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t H = a.H, Z = a.Z;
+  float* h1s = smem + (size_t)warp * kMidE * (H + 3 * 64);      // [E][H]
+  float* zs = h1s + kMidE * H;                                  // [E][64]  (z_loc | log z_std)
+  float* es = zs + kMidE * 64;                                  // [E][64]  eps
+  float* zz = es + kMidE * 64;                                  // [E][64]  z
+  const float* W2 = a.params + a.off_w2; const float* W3 = a.params + a.off_w3;
+  const float* W4 = a.params + a.off_w4;
+  const TfKey K(a.k0, a.k1);
+  const uint32_t half = (Z + 1) / 2;
+  const uint32_t groups = (a.Bl + kMidE - 1) / kMidE;
+  for (uint32_t gidx = blockIdx.x * kMidWarps + warp; gidx < groups; gidx += gridDim.x * kMidWarps) {
+    const uint32_t r0 = gidx * kMidE;
+#pragma unroll
+    for (int e = 0; e < kMidE; ++e) {
+      const uint32_t r = r0 + e;
+      for (uint32_t k = lane; k < H; k += 32)
+        h1s[e * H + k] = r < a.Bl ? a.h1_hi[(size_t)r * H + k] + a.h1_lo[(size_t)r * H + k] : 0.f;
+      // guide noise: key_p -> (_, guide_seed) -> (rng, k_plate) -> (_, k_z); eps = normal(k_z, (Z,))
+      if (r < a.Bl) {
+        TfKey kp = tf_example_key(K, a.B, a.pos_begin + r);
+        TfKey model_seed, guide_seed, rng, k_plate, rng2, k_z;
+        tf_split2(kp, model_seed, guide_seed);
+        tf_split2(guide_seed, rng, k_plate);
+        tf_split2(rng, rng2, k_z);
+        for (uint32_t j = lane; j < half; j += 32) {
+          uint32_t y0, y1;
+          const uint32_t c1 = (j + half < Z) ? j + half : 0u;
+          threefry2x32(k_z, j, c1, y0, y1);
+          es[e * 64 + j] = bits_to_normal<false>(y0);
+          if (j + half < Z) es[e * 64 + j + half] = bits_to_normal<false>(y1);
+        }
+      }
+    }
+    __syncwarp();
+    // heads: output j < Z is z_loc_j (W2), Z <= j < 2Z is log z_std (W3); lane owns j = lane, lane + 32
+    float acc[kMidE][2];
+    const uint32_t j0 = lane, j1 = lane + 32;
+    const bool v0 = j0 < 2 * Z, v1 = j1 < 2 * Z;
+    const float* w0p = v0 ? (j0 < Z ? W2 + j0 : W3 + (j0 - Z)) : W2;
+    const float* w1p = v1 ? (j1 < Z ? W2 + j1 : W3 + (j1 - Z)) : W2;
+    const float bias0 = v0 ? (j0 < Z ? a.params[a.off_b2 + j0] : a.params[a.off_b3 + j0 - Z]) : 0.f;
+    const float bias1 = v1 ? (j1 < Z ? a.params[a.off_b2 + j1] : a.params[a.off_b3 + j1 - Z]) : 0.f;
+#pragma unroll
+    for (int e = 0; e < kMidE; ++e) { acc[e][0] = 0.f; acc[e][1] = 0.f; }
+    for (uint32_t k = 0; k < H; ++k) {
+      const float w0 = v0 ? __ldg(w0p + (size_t)k * Z) : 0.f;
+      const float w1 = v1 ? __ldg(w1p + (size_t)k * Z) : 0.f;
+#pragma unroll
+      for (int e = 0; e < kMidE; ++e) {
+        const float h = h1s[e * H + k];
+        acc[e][0] = fmaf(h, w0, acc[e][0]);
+        acc[e][1] = fmaf(h, w1, acc[e][1]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < kMidE; ++e) {
+      if (v0) zs[e * 64 + j0] = acc[e][0] + bias0;
+      if (v1) zs[e * 64 + j1] = acc[e][1] + bias1;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < kMidE; ++e) {
+      const uint32_t r = r0 + e;
+      float kl = 0.f, sqz = 0.f;
+      for (uint32_t j = lane; j < Z; j += 32) {
+        const float zl = zs[e * 64 + j], sr = zs[e * 64 + Z + j], eps = es[e * 64 + j];
+        const float u = expf(sr) * eps;
+        const float z = zl + u;
+        zz[e * 64 + j] = z;
+        if (r < a.Bl) { a.z[(size_t)r * Z + j] = z; a.u[(size_t)r * Z + j] = u; }
+        kl += 0.5f * z * z - 0.5f * eps * eps - sr;       // -log N(z;0,1) + log N(z; z_loc, z_std), constants cancel
+        sqz = fmaf(z, z, sqz);
+      }
+      kl = group_sum<32>(kl);
+      sqz = group_sum<32>(sqz);
+      if (lane == 0 && r < a.Bl) { a.loss_kl[r] = kl; a.sq_z[r] = sqz; }
+    }
+    __syncwarp();
+    // decoder hidden layer: h2 = softplus(z W4 + b4)
+    float sq2[kMidE];
+#pragma unroll
+    for (int e = 0; e < kMidE; ++e) sq2[e] = 0.f;
+    for (uint32_t h = lane; h < H; h += 32) {
+      float s[kMidE];
+      const float b = a.params[a.off_b4 + h];
+#pragma unroll
+      for (int e = 0; e < kMidE; ++e) s[e] = b;
+      for (uint32_t j = 0; j < Z; ++j) {
+        const float w = __ldg(W4 + (size_t)j * H + h);
+#pragma unroll
+        for (int e = 0; e < kMidE; ++e) s[e] = fmaf(zz[e * 64 + j], w, s[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < kMidE; ++e) {
+        const uint32_t r = r0 + e;
+        const float h2 = softplus_f(s[e]);
+        sq2[e] = fmaf(h2, h2, sq2[e]);
+        if (r < a.Bl) {
+          const float hi = tc::tf32_hi(h2);
+          a.h2_hi[(size_t)r * H + h] = hi;
+          a.h2_lo[(size_t)r * H + h] = h2 - hi;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < kMidE; ++e) {
+      const float s = group_sum<32>(sq2[e]);
+      if (lane == 0 && r0 + e < a.Bl) a.sq_h2[r0 + e] = s;
+    }
+    __syncwarp();
+  }
+}
+
+// S2: back-propagation through the z layer and the encoder heads, ghost norm, clip factor, scaled
+// operands of the clipped-sum GEMMs.
+__global__ void __launch_bounds__(kMidWarps * 32) vae_mid_bwd_kernel(VaeArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t H = a.H, Z = a.Z;
+  float* d4s = smem + (size_t)warp * kMidE * (2 * H + 2 * 64);  // [E][H]
+  float* d1s = d4s + kMidE * H;                                 // [E][H]
+  float* d23 = d1s + kMidE * H;                                 // [E][128]: delta2 at [0,64), delta3 at [64,128)
+  const float* W2 = a.params + a.off_w2; const float* W3 = a.params + a.off_w3;
+  const float* W4 = a.params + a.off_w4;
+  const uint32_t nv = a.num_valid ? (uint32_t)max(*a.num_valid, 0) : 0xffffffffu;
+  const float ratio = a.site_scale * a.inv_S;                   // (1 / obs_scale) * site scale
+  const uint32_t groups = (a.Bl + kMidE - 1) / kMidE;
+  for (uint32_t gidx = blockIdx.x * kMidWarps + warp; gidx < groups; gidx += gridDim.x * kMidWarps) {
+    const uint32_t r0 = gidx * kMidE;
+#pragma unroll
+    for (int e = 0; e < kMidE; ++e) {
+      const uint32_t r = r0 + e;
+      for (uint32_t h = lane; h < H; h += 32) d4s[e * H + h] = r < a.Bl ? a.d4[(size_t)r * H + h] : 0.f;
+    }
+    __syncwarp();
+    // delta_z_j = z_j + sum_h delta4_h W4[j, h]
+    float sq23[kMidE];
+#pragma unroll
+    for (int e = 0; e < kMidE; ++e) sq23[e] = 0.f;
+    for (uint32_t j = 0; j < Z; ++j) {
+      float part[kMidE];
+#pragma unroll
+      for (int e = 0; e < kMidE; ++e) part[e] = 0.f;
+      for (uint32_t h = lane; h < H; h += 32) {
+        const float w = __ldg(W4 + (size_t)j * H + h);
+#pragma unroll
+        for (int e = 0; e < kMidE; ++e) part[e] = fmaf(d4s[e * H + h], w, part[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < kMidE; ++e) {
+        const float s = group_sum<32>(part[e]);
+        const uint32_t r = r0 + e;
+        if (lane == 0) {
+          const float zj = r < a.Bl ? a.z[(size_t)r * Z + j] : 0.f;
+          const float uj = r < a.Bl ? a.u[(size_t)r * Z + j] : 0.f;
+          const float dz = s + zj;
+          const float d3 = fmaf(dz, uj, -1.0f);
+          d23[e * 128 + j] = dz;
+          d23[e * 128 + 64 + j] = d3;
+          sq23[e] = fmaf(dz, dz, fmaf(d3, d3, sq23[e]));
+        }
+      }
+    }
+    __syncwarp();
+    // delta_h1 = delta2 W2^T + delta3 W3^T ; delta1 = delta_h1 * softplus'(pre1)
+    float sq1[kMidE];
+#pragma unroll
+    for (int e = 0; e < kMidE; ++e) sq1[e] = 0.f;
+    for (uint32_t h = lane; h < H; h += 32) {
+      float s[kMidE];
+#pragma unroll
+      for (int e = 0; e < kMidE; ++e) s[e] = 0.f;
+      for (uint32_t j = 0; j < Z; ++j) {
+        const float w2 = __ldg(W2 + (size_t)h * Z + j), w3 = __ldg(W3 + (size_t)h * Z + j);
+#pragma unroll
+        for (int e = 0; e < kMidE; ++e) s[e] = fmaf(d23[e * 128 + j], w2, fmaf(d23[e * 128 + 64 + j], w3, s[e]));
+      }
+#pragma unroll
+      for (int e = 0; e < kMidE; ++e) {
+        const uint32_t r = r0 + e;
+        const float h1 = r < a.Bl ? a.h1_hi[(size_t)r * H + h] + a.h1_lo[(size_t)r * H + h] : 0.f;
+        const float d1 = s[e] * (-expm1f(-h1));
+        d1s[e * H + h] = d1;
+        sq1[e] = fmaf(d1, d1, sq1[e]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < kMidE; ++e) {
+      const uint32_t r = r0 + e;
+      if (r >= a.Bl) continue;                     // warp-uniform
+      const float s1 = group_sum<32>(sq1[e]);
+      const float s23 = __shfl_sync(0xffffffffu, sq23[e], 0);
+      float sq_h1 = 0.f, sq_d4 = 0.f, sq_d5 = 0.f, lrec = 0.f;
+      for (uint32_t t = 0; t < a.nt_h; ++t) { sq_h1 += a.sq_h1[(size_t)t * a.Bl + r]; sq_d4 += a.sq_d4[(size_t)t * a.Bl + r]; }
+      for (uint32_t t = 0; t < a.nt_d; ++t) { sq_d5 += a.sq_d5[(size_t)t * a.Bl + r]; lrec += a.loss_rec[(size_t)t * a.Bl + r]; }
+      const float n2 = (a.sq_h2[r] + 1.0f) * sq_d5 + (a.sq_z[r] + 1.0f) * sq_d4 + (sq_h1 + 1.0f) * s23 +
+                       (a.sq_x[r] + 1.0f) * s1;
+      const float norm = fabsf(ratio) * sqrtf(n2);
+      const uint32_t p = a.pos_begin + r;
+      const bool valid = (p < nv) && (!a.mask || a.mask[p]);
+      const float c = valid ? 1.0f / fmaxf(1.0f, norm / a.C) : 0.f;
+      const float cc = c * ratio;
+      const float loss_s = valid ? a.site_scale * (a.loss_kl[r] + lrec) : 0.f;   // = obs_scale * loss_i
+      if (lane == 0) {
+        a.lossv[r] = loss_s;
+        a.cnt[r] = valid ? 1.0f : 0.f;
+        if (a.px_norms) a.px_norms[p] = valid ? norm : 0.f;
+        if (a.px_loss) a.px_loss[p] = loss_s;
+      }
+      for (uint32_t h = lane; h < H; h += 32) {
+        const float v1 = cc * d1s[e * H + h];
+        const float hi1 = tc::tf32_hi(v1);
+        a.cd1_hi[(size_t)r * H + h] = hi1;
+        a.cd1_lo[(size_t)r * H + h] = v1 - hi1;
+        a.d4[(size_t)r * H + h] = cc * d4s[e * H + h];
+        const float v2 = cc * (a.h2_hi[(size_t)r * H + h] + a.h2_lo[(size_t)r * H + h]);
+        const float hi2 = tc::tf32_hi(v2);
+        a.ch2_hi[(size_t)r * a.ldc2 + h] = hi2;
+        a.ch2_lo[(size_t)r * a.ldc2 + h] = v2 - hi2;
+      }
+      if (lane < 4) {
+        const float v = lane == 0 ? cc : 0.f;
+        const float hi = tc::tf32_hi(v);
+        a.ch2_hi[(size_t)r * a.ldc2 + H + lane] = hi;
+        a.ch2_lo[(size_t)r * a.ldc2 + H + lane] = v - hi;
+      }
+      for (uint32_t j = lane; j < 2 * Z; j += 32)
+        a.cd23[(size_t)r * 2 * Z + j] = cc * (j < Z ? d23[e * 128 + j] : d23[e * 128 + 64 + j - Z]);
+    }
+    __syncwarp();
+  }
+}
+
+// S4: thin clipped sums.  Thin vector T = [dW4 (Z,H) | db4 (H) | dW2 (H,Z) | db2 (Z) | dW3 (H,Z) | db3 (Z) | loss | cnt].
+// grid (kThinSlabs, ceil(H / 128)); thread = one hidden unit h; slab = a contiguous range of examples.
+template <int ZP>
+__global__ void __launch_bounds__(128) vae_thin_kernel(VaeArgs a) {
+  constexpr int TI = 16;
+  __shared__ float zt[TI][ZP];
+  __shared__ float c2[TI][ZP];
+  __shared__ float c3[TI][ZP];
+  const uint32_t H = a.H, Z = a.Z;
+  const uint32_t T = 3 * Z * H + H + 2 * Z;
+  const uint32_t slab = blockIdx.x;
+  const uint32_t per = (a.Bl + kThinSlabs - 1) / kThinSlabs;
+  const uint32_t i0 = slab * per, i1 = min(a.Bl, i0 + per);
+  const uint32_t h = blockIdx.y * 128 + threadIdx.x;
+  const bool hv = h < H;
+  float w4[ZP], w2[ZP], w3[ZP], b4 = 0.f;
+#pragma unroll
+  for (int j = 0; j < ZP; ++j) { w4[j] = 0.f; w2[j] = 0.f; w3[j] = 0.f; }
+  float b23 = 0.f, ls = 0.f, cn = 0.f;       // blockIdx.y == 0: thread j < 2Z sums c*delta23[:, j]; thread 127 loss / count
+  for (uint32_t t0 = i0; t0 < i1; t0 += TI) {
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < TI * ZP; q += 128) {
+      const uint32_t i = t0 + q / ZP, j = q % ZP;
+      const bool ok = i < i1 && j < Z;
+      zt[q / ZP][j] = ok ? a.z[(size_t)i * Z + j] : 0.f;
+      c2[q / ZP][j] = ok ? a.cd23[(size_t)i * 2 * Z + j] : 0.f;
+      c3[q / ZP][j] = ok ? a.cd23[(size_t)i * 2 * Z + Z + j] : 0.f;
+    }
+    __syncthreads();
+    const uint32_t n = min((uint32_t)TI, i1 - t0);
+    for (uint32_t t = 0; t < n; ++t) {
+      const uint32_t i = t0 + t;
+      const float d4 = hv ? a.d4[(size_t)i * H + h] : 0.f;                                   // already c * delta4
+      const float h1 = hv ? a.h1_hi[(size_t)i * H + h] + a.h1_lo[(size_t)i * H + h] : 0.f;
+      b4 += d4;
+#pragma unroll
+      for (int j = 0; j < ZP; ++j) {
+        w4[j] = fmaf(zt[t][j], d4, w4[j]);
+        w2[j] = fmaf(h1, c2[t][j], w2[j]);
+        w3[j] = fmaf(h1, c3[t][j], w3[j]);
+      }
+      if (blockIdx.y == 0) {
+        if (threadIdx.x < 2 * Z) b23 += a.cd23[(size_t)i * 2 * Z + threadIdx.x];
+        if (threadIdx.x == 127) { ls += a.lossv[i]; cn += a.cnt[i]; }
+      }
+    }
+  }
+  float* out = a.thin + (size_t)slab * (T + 2);
+  if (hv) {
+#pragma unroll
+    for (int j = 0; j < ZP; ++j)
+      if ((uint32_t)j < Z) {
+        out[(size_t)j * H + h] = w4[j];
+        out[Z * H + H + (size_t)h * Z + j] = w2[j];
+        out[2 * Z * H + H + Z + (size_t)h * Z + j] = w3[j];
+      }
+    out[Z * H + h] = b4;
+  }
+  if (blockIdx.y == 0) {
+    if (threadIdx.x < Z) out[2 * Z * H + H + threadIdx.x] = b23;
+    else if (threadIdx.x < 2 * Z) out[3 * Z * H + H + Z + (threadIdx.x - Z)] = b23;
+    if (threadIdx.x == 127) { out[T] = ls; out[T + 1] = cn; }
+  }
+}
+
+// thin partials [kThinSlabs, T + 2] -> partial row 0 (fixed order), rows 1..S-1 zero at the thin offsets
+__global__ void vae_thin_reduce_kernel(VaeArgs a) {
+  const uint32_t H = a.H, Z = a.Z;
+  const uint32_t T = 3 * Z * H + H + 2 * Z;
+  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= T + 2) return;
+  float s = 0.f;
+  for (uint32_t k = 0; k < kThinSlabs; ++k) s += a.thin[(size_t)k * (T + 2) + col];
+  uint32_t dst;
+  if (col < Z * H) dst = a.off_w4 + col;
+  else if (col < Z * H + H) dst = a.off_b4 + (col - Z * H);
+  else if (col < 2 * Z * H + H) dst = a.off_w2 + (col - Z * H - H);
+  else if (col < 2 * Z * H + H + Z) dst = a.off_b2 + (col - 2 * Z * H - H);
+  else if (col < 3 * Z * H + H + Z) dst = a.off_w3 + (col - 2 * Z * H - H - Z);
+  else if (col < T) dst = a.off_b3 + (col - 3 * Z * H - H - Z);
+  else dst = a.P + (col - T);
+  a.partials[dst] = s;
+  for (uint32_t r = 1; r < a.S; ++r) a.partials[(size_t)r * (a.P + 2) + dst] = 0.f;
+}
+
+// ---- host --------------------------------------------------------------------------------------------
+struct VaeLayout {
+  size_t total;
+  size_t partials, w1_hi, w1_lo, w5_hi, w5_lo, x_hi, x_lo, flag, h1_hi, h1_lo, h2_hi, h2_lo, ch2_hi, ch2_lo, d5_hi, d5_lo,
+      d4, cd1_hi, cd1_lo, z, u, cd23, sq_x, sq_h1, sq_h2, sq_z, sq_d5, loss_rec, sq_d4, loss_kl, lossv, cnt, thin;
+  uint32_t S, nt_h, nt_d;
+};
+
+static uint32_t vae_splits(uint32_t Bl) {
+  uint32_t kb = (Bl + tc::kKB - 1) / tc::kKB;
+  return kb < 10 ? (kb ? kb : 1) : 10;
+}
+
+static VaeLayout vae_layout(const d3p_vae_desc* d, uint32_t Bl) {
+  VaeLayout L;
+  const size_t D = d->out_dim, H = d->hidden_dim, Z = d->z_dim, P = d->n_params;
+  L.S = vae_splits(Bl);
+  L.nt_h = (uint32_t)((H + kVaeBN - 1) / kVaeBN);
+  L.nt_d = (uint32_t)((D + kVaeBN - 1) / kVaeBN);
+  size_t off = 0;
+  auto take = [&](size_t floats) { size_t o = off; off += align_up(floats * sizeof(float), 256); return o; };
+  L.partials = take((size_t)L.S * (P + 2));
+  L.w1_hi = take(D * H); L.w1_lo = take(D * H); L.w5_hi = take(H * D); L.w5_lo = take(H * D);
+  L.x_hi = take((size_t)Bl * (D + 4)); L.x_lo = take((size_t)Bl * (D + 4)); L.flag = take(4);
+  L.h1_hi = take((size_t)Bl * H); L.h1_lo = take((size_t)Bl * H);
+  L.h2_hi = take((size_t)Bl * H); L.h2_lo = take((size_t)Bl * H);
+  L.ch2_hi = take((size_t)Bl * (H + 4)); L.ch2_lo = take((size_t)Bl * (H + 4));
+  L.d5_hi = take((size_t)Bl * D); L.d5_lo = take((size_t)Bl * D);
+  L.d4 = take((size_t)Bl * H); L.cd1_hi = take((size_t)Bl * H); L.cd1_lo = take((size_t)Bl * H);
+  L.z = take((size_t)Bl * Z); L.u = take((size_t)Bl * Z); L.cd23 = take((size_t)Bl * 2 * Z);
+  L.sq_x = take(Bl); L.sq_h1 = take((size_t)L.nt_h * Bl); L.sq_h2 = take(Bl); L.sq_z = take(Bl);
+  L.sq_d5 = take((size_t)L.nt_d * Bl); L.loss_rec = take((size_t)L.nt_d * Bl); L.sq_d4 = take((size_t)L.nt_h * Bl);
+  L.loss_kl = take(Bl); L.lossv = take(Bl); L.cnt = take(Bl);
+  L.thin = take((size_t)kThinSlabs * (3 * Z * H + H + 2 * Z + 2));
+  L.total = off;
+  return L;
+}
+
+static bool vae_supported(const d3p_vae_desc* d) {
+  return d && d->out_dim >= 4 && d->hidden_dim >= 4 && d->z_dim >= 1 && d->z_dim <= 32 && (d->out_dim % 4) == 0 &&
+         (d->hidden_dim % 4) == 0;
+}
+
+}  // namespace d3p
+
+using namespace d3p;
+
+extern "C" size_t d3p_vae_workspace_bytes(const d3p_vae_desc* desc, uint32_t batch_rows, uint32_t* n_partials_out) {
+  if (!vae_supported(desc) || batch_rows == 0) return 0;
+  VaeLayout L = vae_layout(desc, batch_rows);
+  if (n_partials_out) *n_partials_out = L.S;
+  return L.total;
+}
+
+extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* params_d, const float* x_d,
+                                      size_t x_row_stride, const int32_t* idx_d, const uint8_t* mask_d,
+                                      const int32_t* num_valid_d, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
+                                      const uint32_t threefry_key_h[2], float obs_scale, float C, float* px_norms_d,
+                                      float* px_loss_d, void* ws_d, size_t ws_bytes, void* stream) {
+  if (!desc || !params_d || !x_d || !threefry_key_h || !ws_d) return D3P_ERR_INVALID_ARGUMENT;
+  if (!vae_supported(desc)) return D3P_ERR_UNSUPPORTED;
+  if (pos_end > B || pos_begin >= pos_end || !(C > 0.f) || !(obs_scale != 0.f)) return D3P_ERR_INVALID_ARGUMENT;
+  if (reinterpret_cast<uintptr_t>(ws_d) & 255) return D3P_ERR_INVALID_ARGUMENT;
+  const uint32_t Bl = pos_end - pos_begin;
+  const VaeLayout L = vae_layout(desc, Bl);
+  if (ws_bytes < L.total) return D3P_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = static_cast<char*>(ws_d);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  const uint32_t D = desc->out_dim, H = desc->hidden_dim, Z = desc->z_dim, P = desc->n_params;
+
+  VaeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.D = D; a.H = H; a.Z = Z; a.B = B; a.Bl = Bl; a.pos_begin = pos_begin;
+  a.ldx = D + 4; a.ldc2 = H + 4;
+  a.params = params_d;
+  a.off_w4 = desc->off_w4; a.off_b4 = desc->off_b4; a.off_w5 = desc->off_w5; a.off_b5 = desc->off_b5;
+  a.off_w1 = desc->off_w1; a.off_b1 = desc->off_b1; a.off_w2 = desc->off_w2; a.off_b2 = desc->off_b2;
+  a.off_w3 = desc->off_w3; a.off_b3 = desc->off_b3; a.P = P;
+  a.x = x_d; a.x_stride = x_row_stride; a.idx = idx_d; a.mask = mask_d; a.num_valid = num_valid_d;
+  a.k0 = threefry_key_h[0]; a.k1 = threefry_key_h[1];
+  a.site_scale = desc->site_scale; a.inv_S = 1.0f / obs_scale; a.C = C;
+  a.nt_h = L.nt_h; a.nt_d = L.nt_d; a.S = L.S;
+  a.x_hi = F(L.x_hi); a.x_lo = F(L.x_lo); a.x_lo_flag = reinterpret_cast<int*>(ws + L.flag);
+  a.h1_hi = F(L.h1_hi); a.h1_lo = F(L.h1_lo); a.h2_hi = F(L.h2_hi); a.h2_lo = F(L.h2_lo);
+  a.ch2_hi = F(L.ch2_hi); a.ch2_lo = F(L.ch2_lo); a.d5_hi = F(L.d5_hi); a.d5_lo = F(L.d5_lo);
+  a.d4 = F(L.d4); a.cd1_hi = F(L.cd1_hi); a.cd1_lo = F(L.cd1_lo);
+  a.z = F(L.z); a.u = F(L.u); a.cd23 = F(L.cd23);
+  a.sq_x = F(L.sq_x); a.sq_h1 = F(L.sq_h1); a.sq_h2 = F(L.sq_h2); a.sq_z = F(L.sq_z); a.sq_d5 = F(L.sq_d5);
+  a.loss_rec = F(L.loss_rec); a.sq_d4 = F(L.sq_d4); a.loss_kl = F(L.loss_kl); a.lossv = F(L.lossv); a.cnt = F(L.cnt);
+  a.thin = F(L.thin); a.partials = F(L.partials);
+  a.px_norms = px_norms_d; a.px_loss = px_loss_d;
+  float* w1_hi = F(L.w1_hi); float* w1_lo = F(L.w1_lo); float* w5_hi = F(L.w5_hi); float* w5_lo = F(L.w5_lo);
+
+  const int sms = sm_count();
+  int32_t rc;
+  // parameter splits + X preparation
+  if ((rc = d3p_split_tf32(params_d + a.off_w1, nullptr, 0, w1_hi, w1_lo, (size_t)D * H, stream)) != D3P_OK) return rc;
+  if ((rc = d3p_split_tf32(params_d + a.off_w5, nullptr, 0, w5_hi, w5_lo, (size_t)H * D, stream)) != D3P_OK) return rc;
+  if (cudaMemsetAsync(a.x_lo_flag, 0, sizeof(int), s) != cudaSuccess) return D3P_ERR_CUDA;
+  {
+    unsigned grid = (Bl + 7) / 8;
+    if (grid > (unsigned)sms * 8) grid = sms * 8;
+    vae_prep_x_kernel<<<grid, 256, 0, s>>>(a);
+    if ((rc = check_launch()) != D3P_OK) return rc;
+  }
+  // G1: pre1 = X W1  (A = X K-major [Bl, D]; B = W1 stored [K = D, N = H])
+  {
+    tc::GemmOperand A{a.x_hi, a.x_lo, 0, a.ldx}, Bo{w1_hi, w1_lo, 1, H};
+    EpiFwd1::Args ea{params_d + a.off_b1, a.h1_hi, a.h1_lo, H, a.sq_h1, Bl};
+    if ((rc = tc::launch_tc_gemm<false, true, kVaeBN, EpiFwd1>(A, Bo, Bl, H, D, 1, ea, s, a.x_lo_flag)) != D3P_OK) return rc;
+  }
+  const size_t mid_fwd_smem = (size_t)kMidWarps * kMidE * (H + 3 * 64) * sizeof(float);
+  const size_t mid_bwd_smem = (size_t)kMidWarps * kMidE * (2 * H + 2 * 64) * sizeof(float);
+  if (mid_fwd_smem > 200 * 1024 || mid_bwd_smem > 200 * 1024) return D3P_ERR_UNSUPPORTED;
+  unsigned mid_grid = ((Bl + kMidE - 1) / kMidE + kMidWarps - 1) / kMidWarps;
+  if (mid_grid > (unsigned)sms) mid_grid = sms;
+  {
+    if (cudaFuncSetAttribute(vae_mid_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_fwd_smem) != cudaSuccess)
+      return D3P_ERR_CUDA;
+    vae_mid_fwd_kernel<<<mid_grid, kMidWarps * 32, mid_fwd_smem, s>>>(a);
+    if ((rc = check_launch()) != D3P_OK) return rc;
+  }
+  // G5: logits = H2 W5  (B = W5 stored [K = H, N = D])
+  {
+    tc::GemmOperand A{a.h2_hi, a.h2_lo, 0, H}, Bo{w5_hi, w5_lo, 1, D};
+    EpiFwd5::Args ea{params_d + a.off_b5, a.x_hi, a.x_lo, a.ldx, a.d5_hi, a.d5_lo, D, a.sq_d5, a.loss_rec, Bl};
+    if ((rc = tc::launch_tc_gemm<false, true, kVaeBN, EpiFwd5>(A, Bo, Bl, D, H, 1, ea, s, nullptr)) != D3P_OK) return rc;
+  }
+  // G5b: dh2 = delta5 W5^T  (B[n = h, k = d] = W5[h, d]: K-major)
+  {
+    tc::GemmOperand A{a.d5_hi, a.d5_lo, 0, D}, Bo{w5_hi, w5_lo, 0, D};
+    EpiBwd5::Args ea{a.h2_hi, a.h2_lo, H, a.d4, a.sq_d4, Bl};
+    if ((rc = tc::launch_tc_gemm<false, false, kVaeBN, EpiBwd5>(A, Bo, Bl, H, D, 1, ea, s, nullptr)) != D3P_OK) return rc;
+  }
+  {
+    if (cudaFuncSetAttribute(vae_mid_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_bwd_smem) != cudaSuccess)
+      return D3P_ERR_CUDA;
+    vae_mid_bwd_kernel<<<mid_grid, kMidWarps * 32, mid_bwd_smem, s>>>(a);
+    if ((rc = check_launch()) != D3P_OK) return rc;
+  }
+  // GW1: [X | 1]^T (c delta1) -> dW1 [D, H] and db1; contraction over the batch
+  {
+    tc::GemmOperand A{a.x_hi, a.x_lo, 1, a.ldx}, Bo{a.cd1_hi, a.cd1_lo, 1, H};
+    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w1, a.off_b1, H, D, 0};
+    if ((rc = tc::launch_tc_gemm<true, true, kVaeBN, EpiGrad>(A, Bo, D + 1, H, Bl, L.S, ea, s, a.x_lo_flag)) != D3P_OK) return rc;
+  }
+  // GW5: delta5^T [c h2 | c] -> dW5^T (stored [H, D]) and db5
+  {
+    tc::GemmOperand A{a.d5_hi, a.d5_lo, 1, D}, Bo{a.ch2_hi, a.ch2_lo, 1, a.ldc2};
+    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w5, a.off_b5, D, H, 1};
+    if ((rc = tc::launch_tc_gemm<true, true, kVaeBN, EpiGrad>(A, Bo, D, H + 1, Bl, L.S, ea, s, nullptr)) != D3P_OK) return rc;
+  }
+  // thin clipped sums
+  {
+    dim3 grid(kThinSlabs, (H + 127) / 128);
+    if (Z <= 8) vae_thin_kernel<8><<<grid, 128, 0, s>>>(a);
+    else if (Z <= 16) vae_thin_kernel<16><<<grid, 128, 0, s>>>(a);
+    else if (Z <= 24) vae_thin_kernel<24><<<grid, 128, 0, s>>>(a);
+    else vae_thin_kernel<32><<<grid, 128, 0, s>>>(a);
+    if ((rc = check_launch()) != D3P_OK) return rc;
+    const uint32_t T2 = 3 * Z * H + H + 2 * Z + 2;
+    vae_thin_reduce_kernel<<<(T2 + 255) / 256, 256, 0, s>>>(a);
+    if ((rc = check_launch()) != D3P_OK) return rc;
+  }
+  return D3P_OK;
+}

@@ -41,19 +41,8 @@ class _Handle:
         return f"<{type(self.family).__name__}.{self.role}>"
 
 
-class MeanFieldFamily:
-    """Mean-field Normal guide over the latents of an elementwise likelihood."""
-    family_id = None
-
-    def __init__(self, d, guide="hand", init_scale=0.1):
-        if guide not in ("hand", "auto"):
-            raise ValueError("guide must be 'hand' (examples' exp-link guide) or 'auto' (AutoDiagonalNormal)")
-        self.d, self.guide_kind, self.init_scale = int(d), guide, float(init_scale)
-        self.model, self.guide = _Handle(self, "model"), _Handle(self, "guide")
-
-    # -- parameter layout ------------------------------------------------------------------------
-    def param_shapes(self):
-        raise NotImplementedError
+class Family:
+    """What ``DPSVI`` needs from a fused model/guide family."""
 
     def layout(self):
         """[(name, offset, shape)] in pytree (sorted-name) order."""
@@ -72,6 +61,37 @@ class MeanFieldFamily:
 
     def offsets(self):
         return {name: off for name, off, _ in self.layout()}
+
+    def constrain(self, name, value):
+        return value
+
+    def observation_scale(self, num_obs_total):
+        """``get_observations_scale`` (d3p/svi.py:43-65) on a one-element batch: the plate scale N / 1."""
+        return float(num_obs_total)
+
+    def param_shapes(self):
+        raise NotImplementedError
+
+    def init_params(self):
+        raise NotImplementedError
+
+    def check_args(self, args):
+        raise NotImplementedError
+
+    def run_step(self, svi, state, tf_key, args, mask, B, pos_begin, pos_end, px_norms, px_grads, px_loss):
+        """-> (partials tensor [n_partials, P + 2], n_partials, B, P)"""
+        raise NotImplementedError
+
+
+class MeanFieldFamily(Family):
+    """Mean-field Normal guide over the latents of an elementwise likelihood."""
+    family_id = None
+
+    def __init__(self, d, guide="hand", init_scale=0.1):
+        if guide not in ("hand", "auto"):
+            raise ValueError("guide must be 'hand' (examples' exp-link guide) or 'auto' (AutoDiagonalNormal)")
+        self.d, self.guide_kind, self.init_scale = int(d), guide, float(init_scale)
+        self.model, self.guide = _Handle(self, "model"), _Handle(self, "guide")
 
     def init_params(self):
         """Unconstrained initial values (zeros for the hand guides; loc 0 / scale ``init_scale``
@@ -93,8 +113,25 @@ class MeanFieldFamily:
     def desc(self, num_obs_total):
         raise NotImplementedError
 
-    def check_args(self, args):
-        raise NotImplementedError
+    def run_step(self, svi, state, tf_key, args, mask, B, pos_begin, pos_end, px_norms, px_grads, px_loss):
+        import ctypes as C
+        Xsrc, stride, ysrc, idx, B = svi._resolve_args(args)
+        desc = self.desc(svi._num_obs_total())
+        n_part = C.c_uint32(0)
+        need = _n.lib().d3p_meanfield_workspace_bytes(C.byref(desc), C.byref(n_part))
+        ws = svi._workspace(need)
+        mask_t, _ = svi._mask_arg(mask, B)
+        flat = state.optim_state.flat
+        if svi.event_hook is not None:
+            svi.event_hook("step_begin")
+        _n.check(_n.lib().d3p_dpsvi_step_meanfield(
+            C.byref(desc), _n.ptr(flat), _n.ptr(Xsrc), stride, _n.ptr(ysrc), _n.ptr(idx), _n.ptr(mask_t), None,
+            B, pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
+            float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_grads), _n.ptr(px_loss), _n.ptr(ws), need,
+            _n.stream_ptr()), "dpsvi_step_meanfield")
+        if svi.event_hook is not None:
+            svi.event_hook("step_end")
+        return ws, n_part.value, B, desc.n_params
 
 
 class LogisticRegression(MeanFieldFamily):
@@ -164,3 +201,81 @@ class GaussianMean(MeanFieldFamily):
             raise ValueError("GaussianMean expects (batch_X,)")
         if len(args[0].shape) != 2 or args[0].shape[1] != self.d:
             raise ValueError(f"batch_X must have shape [B, {self.d}]")
+
+
+class VAE(Family):
+    """``examples/vae.py:65-153``: encoder Dense(D->H) softplus -> {Dense(H->Z), exp(Dense(H->Z))},
+    decoder Dense(Z->H) softplus -> Dense(H->D) sigmoid, z ~ N(0, I), x ~ Bernoulli(probs), model and
+    guide wrapped in ``scale(1 / num_obs_total)`` (``vae.py:193-194``); ``update(state, batch)`` with
+    ``batch`` of shape [B, ...] flattened to [B, D].
+
+    Parameters carry the flat names of the stax pytrees under ``decoder$params`` / ``encoder$params``;
+    their sorted order is the jax leaf order W4, b4, W5, b5, W1, b1, W2, b2, W3, b3.  The clipped
+    sums of the two large layers run on tcgen05 tensor cores (3xTF32), see csrc/vae.cu.
+    """
+    NAMES = ("decoder$params.0.W", "decoder$params.0.b", "decoder$params.2.W", "decoder$params.2.b",
+             "encoder$params.0.W", "encoder$params.0.b", "encoder$params.3.0.W", "encoder$params.3.0.b",
+             "encoder$params.3.1.0.W", "encoder$params.3.1.0.b")
+
+    def __init__(self, out_dim, hidden_dim, z_dim, scaled=True, init_seed=0, init_std=1e-2):
+        self.out_dim, self.hidden_dim, self.z_dim = int(out_dim), int(hidden_dim), int(z_dim)
+        self.scaled, self.init_seed, self.init_std = bool(scaled), int(init_seed), float(init_std)
+        self.model, self.guide = _Handle(self, "model"), _Handle(self, "guide")
+
+    def param_shapes(self):
+        D, H, Z = self.out_dim, self.hidden_dim, self.z_dim
+        return dict(zip(self.NAMES, [(Z, H), (H,), (H, D), (D,), (D, H), (H,), (H, Z), (Z,), (H, Z), (Z,)]))
+
+    def init_params(self):
+        """stax.Dense(W_init=randn(1e-2)) shaped values from a fixed numpy seed (initialisation is off
+        the hot path; pass ``params=`` to ``DPSVI.init`` to start from specific values)."""
+        rs = np.random.RandomState(self.init_seed)
+        return {k: (rs.randn(*shp) * self.init_std).astype(np.float32) for k, shp in self.param_shapes().items()}
+
+    def site_scale(self, num_obs_total):
+        if not self.scaled:
+            return float(num_obs_total)
+        return float(np.float32((1.0 / num_obs_total) * num_obs_total))
+
+    def observation_scale(self, num_obs_total):
+        return self.site_scale(num_obs_total)
+
+    def check_args(self, args):
+        if len(args) != 1:
+            raise ValueError("VAE expects (batch,)")
+        shape = tuple(args[0].shape)
+        if len(shape) < 2 or int(np.prod(shape[1:])) != self.out_dim:
+            raise ValueError(f"batch must have shape [B, ...] with {self.out_dim} values per record")
+
+    def desc(self, num_obs_total):
+        o = self.offsets()
+        d = _n.VaeDesc()
+        d.out_dim, d.hidden_dim, d.z_dim, d.n_params = self.out_dim, self.hidden_dim, self.z_dim, self.n_params
+        (d.off_w4, d.off_b4, d.off_w5, d.off_b5, d.off_w1, d.off_b1, d.off_w2, d.off_b2, d.off_w3,
+         d.off_b3) = [o[k] for k in self.NAMES]
+        d.site_scale = self.site_scale(num_obs_total)
+        return d
+
+    def run_step(self, svi, state, tf_key, args, mask, B, pos_begin, pos_end, px_norms, px_grads, px_loss):
+        import ctypes as C
+        if px_grads is not None:
+            raise NotImplementedError("the VAE path never materialises [B, P] per-example gradients")
+        Xsrc, stride, _, idx, B = svi._resolve_args(args)
+        desc = self.desc(svi._num_obs_total())
+        n_part = C.c_uint32(0)
+        need = _n.lib().d3p_vae_workspace_bytes(C.byref(desc), pos_end - pos_begin, C.byref(n_part))
+        ws = svi._workspace(need + 256)
+        base = ws.data_ptr()
+        shift = (-base) % 256                    # the library wants a 256-byte aligned workspace
+        ws_al = ws[shift // 4:]
+        mask_t, _ = svi._mask_arg(mask, B)
+        if svi.event_hook is not None:
+            svi.event_hook("step_begin")
+        _n.check(_n.lib().d3p_dpsvi_step_vae(
+            C.byref(desc), _n.ptr(state.optim_state.flat), _n.ptr(Xsrc), stride, _n.ptr(idx), _n.ptr(mask_t), None, B,
+            pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
+            float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_loss), _n.ptr(ws_al), need,
+            _n.stream_ptr()), "dpsvi_step_vae")
+        if svi.event_hook is not None:
+            svi.event_hook("step_end")
+        return ws_al, n_part.value, B, desc.n_params

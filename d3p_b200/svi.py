@@ -17,7 +17,7 @@ import torch
 from . import _native as _n
 from . import random as strong_rng
 from .minibatch import BatchView
-from .models import MeanFieldFamily
+from .models import Family
 from .optimizers import OptimState, unflatten
 from .util import example_count
 
@@ -148,7 +148,7 @@ class DPSVI:
         self.static_kwargs = static_kwargs
         fam = getattr(model, "family", model)
         gfam = getattr(guide, "family", guide)
-        if fam is not None and not isinstance(fam, MeanFieldFamily):
+        if fam is not None and not isinstance(fam, Family):
             raise TypeError("model must be the .model handle of a d3p_b200.models family (or None)")
         if fam is not None and gfam is not None and gfam is not fam:
             raise ValueError("model and guide must belong to the same family object")
@@ -187,8 +187,9 @@ class DPSVI:
         optim_state = self.optim.init(p, layout=self.family.layout())
         observation_scale = 1.0
         if self._clip_unscaled_observations:
-            # get_observations_scale on a one-element batch: plate scale = num_obs_total / 1
-            observation_scale = self._num_obs_total()
+            # get_observations_scale on a one-element batch: plate scale = num_obs_total / 1 (times the
+            # family's own scale handler, if any)
+            observation_scale = self.family.observation_scale(self._num_obs_total())
         return DPSVIState(optim_state, rng_key, observation_scale)
 
     def get_params(self, state):
@@ -199,14 +200,13 @@ class DPSVI:
         return {k: self.family.constrain(k, v) for k, v in raw.items()}
 
     # ---- fused path ------------------------------------------------------------------------------
-    def _workspace(self, desc):
-        n_part = C.c_uint32(0)
-        need = _n.lib().d3p_meanfield_workspace_bytes(C.byref(desc), C.byref(n_part))
+    def _workspace(self, need):
+        """A cached, 256-byte aligned float32 scratch tensor of at least ``need`` bytes."""
         if need == 0:
             raise _n.D3PNativeError("unsupported model family configuration")
         if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != _dev():
             self._ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=_dev())
-        return self._ws, need, n_part.value
+        return self._ws
 
     def _resolve_args(self, args):
         """-> (x, x_stride, y, idx, B) for the step kernel."""
@@ -232,6 +232,8 @@ class DPSVI:
         if not isinstance(Xsrc, torch.Tensor):
             Xsrc = torch.as_tensor(np.asarray(Xsrc))
         Xsrc = Xsrc.to(device=_dev(), dtype=torch.float32)
+        if Xsrc.dim() > 2:                       # e.g. [N, 28, 28] images: one flat row per record
+            Xsrc = Xsrc.reshape(Xsrc.shape[0], -1)
         if Xsrc.stride(-1) != 1:
             Xsrc = Xsrc.contiguous()
         B = example_count(X)
@@ -258,28 +260,17 @@ class DPSVI:
         return m.contiguous(), False
 
     def _run_step(self, state, step_rng_key, args, mask, px_norms=None, px_grads=None, px_loss=None):
+        """Launches the family's fused per-example-gradient / clip / sum kernels for this rank's batch
+        positions; returns (partials tensor [n_partials, P + 2], n_partials, B, P)."""
         fam = self.family
-        Xsrc, stride, ysrc, idx, B = self._resolve_args(args)
-        desc = fam.desc(self._num_obs_total())
-        ws, need, n_part = self._workspace(desc)
-        mask_t, _ = self._mask_arg(mask, B)
+        B = example_count(args[0])
         tf_key = np.ascontiguousarray(self._rng_suite.convert_to_jax_rng_key(step_rng_key), dtype=np.uint32)
         pos_begin, pos_end = 0, B
         if self.shard is not None:
             rank, world = self.shard[0], self.shard[1]
             per = (B + world - 1) // world
             pos_begin, pos_end = min(B, rank * per), min(B, (rank + 1) * per)
-        flat = state.optim_state.flat
-        if self.event_hook is not None:
-            self.event_hook("step_begin")
-        _n.check(_n.lib().d3p_dpsvi_step_meanfield(
-            C.byref(desc), _n.ptr(flat), _n.ptr(Xsrc), stride, _n.ptr(ysrc), _n.ptr(idx), _n.ptr(mask_t), None,
-            B, pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
-            float(self._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_grads), _n.ptr(px_loss), _n.ptr(ws), need,
-            _n.stream_ptr()), "dpsvi_step_meanfield")
-        if self.event_hook is not None:
-            self.event_hook("step_end")
-        return ws, n_part, B, desc
+        return fam.run_step(self, state, tf_key, args, mask, B, pos_begin, pos_end, px_norms, px_grads, px_loss)
 
     def _leaf_table(self, layout, rng_key):
         """Per-leaf site keys: ``rng_suite.split(rng, n_leaves)`` (svi.py:490-491)."""
@@ -302,8 +293,7 @@ class DPSVI:
             raise ValueError("DPSVI.update needs a model family; drive the stage methods for custom models")
         svi_state, (k_grad, k_noise) = self._split_rng_key(svi_state, 2)
         os_ = svi_state.optim_state
-        ws, n_part, B, desc = self._run_step(svi_state, k_grad, args, mask)
-        P = desc.n_params
+        ws, n_part, B, P = self._run_step(svi_state, k_grad, args, mask)
         partials = ws
         if self.shard is not None:
             partials, n_part = self.shard[2](ws, n_part, P)

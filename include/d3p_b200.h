@@ -228,6 +228,33 @@ int32_t d3p_gemm_tf32x3(const float* a_hi_d, const float* a_lo_d, int32_t a_mn_m
                         uint32_t split_k, int32_t tile_n, float* out_d, size_t ldc, size_t split_stride,
                         int32_t transpose_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused per-example gradient + ghost-norm clip + clipped sum for the VAE of examples/vae.py:65-153
+ * (encoder Dense(D->H) softplus -> {Dense(H->Z), exp(Dense(H->Z))}; decoder Dense(Z->H) softplus ->
+ * Dense(H->D) sigmoid; Bernoulli(probs) likelihood; Normal(0, I) prior) — replaces d3p/svi.py:238-348.
+ * Flat parameter vector = jax pytree order of {'decoder$params', 'encoder$params'}:
+ * W4 [Z,H], b4 [H], W5 [H,D], b5 [D], W1 [D,H], b1 [H], W2 [H,Z], b2 [Z], W3 [H,Z], b3 [Z].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  uint32_t out_dim, hidden_dim, z_dim; /* D, H (multiples of 4), Z <= 32 */
+  uint32_t n_params;
+  uint32_t off_w4, off_b4, off_w5, off_b5, off_w1, off_b1, off_w2, off_b2, off_w3, off_b3;
+  float site_scale; /* plate scale N / 1 times the scale handler's 1 / N (examples/vae.py:193-194) */
+} d3p_vae_desc;
+
+/* Workspace for batch_rows = pos_end - pos_begin examples; *n_partials_out = S, the number of partial
+ * rows [S, P + 2] at the START of the workspace (input of d3p_perturb_finalize_f32). */
+size_t d3p_vae_workspace_bytes(const d3p_vae_desc* desc, uint32_t batch_rows, uint32_t* n_partials_out);
+
+/* Same contract as d3p_dpsvi_step_meanfield: x_d rows are [D] floats (x_row_stride floats apart), read
+ * through idx_d when given; positions [pos_begin, pos_end) of a batch of B; per-example Threefry keys by
+ * position.  ws_d must be 256-byte aligned.  px_norms_d[B] / px_loss_d[B] (may be NULL) receive the
+ * pre-clip gradient norms and obs_scale * loss_p. */
+int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
+                           const int32_t* idx_d, const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                           uint32_t pos_begin, uint32_t pos_end, const uint32_t threefry_key_h[2], float obs_scale,
+                           float C, float* px_norms_d, float* px_loss_d, void* ws_d, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

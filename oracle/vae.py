@@ -28,10 +28,34 @@ NAMES = ["decoder$params.0.W", "decoder$params.0.b", "decoder$params.2.W", "deco
 W4, B4, W5, B5, W1, B1, W2, B2, W3, B3 = NAMES
 
 
+class _JaxClip(torch.autograd.Function):
+    """jnp.clip(x, lo, hi) = minimum(maximum(x, lo), hi) with jax's gradient convention: 1 strictly
+    inside, 1/2 at a bound (ties of maximum / minimum split evenly), 0 outside [3P-unverified]."""
+
+    generate_vmap_rule = True
+
+    @staticmethod
+    def forward(x, lo, hi):
+        return torch.clamp(x, min=lo, max=hi)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        x, lo, hi = inputs
+        ctx.save_for_backward(x)
+        ctx.lo, ctx.hi = lo, hi
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        w_lo = torch.where(x > ctx.lo, 1.0, torch.where(x == ctx.lo, 0.5, 0.0))
+        w_hi = torch.where(x < ctx.hi, 1.0, torch.where(x == ctx.hi, 0.5, 0.0))
+        return g * (w_lo * w_hi).to(g.dtype), None, None
+
+
 def clamp_probs(p):
-    """numpyro.distributions.util.clamp_probs for float32."""
+    """numpyro.distributions.util.clamp_probs for float32: clip(p, finfo.tiny, 1 - finfo.eps)."""
     fi = torch.finfo(torch.float32)
-    return torch.clamp(p, min=fi.tiny, max=1.0 - fi.eps)
+    return _JaxClip.apply(p, fi.tiny, 1.0 - fi.eps)
 
 
 class VAE:
