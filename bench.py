@@ -1,15 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — DPSVI.update examples/sec on the BASELINE.json workload.
+"""bench.py — DPSVI.update examples/sec on the BASELINE.json workloads.
 
-Workload (config.workload = "c2"): synthetic logistic regression, N = 10M records x d = 1024
-float32 (41 GB resident in HBM, >> L2), Poisson sampling q = 0.01 (max_batch_size = the 0.99
-Poisson quantile = 100736), hand-written mean-field guide, Adam(1e-3), C = 1, dp_scale = 1.
+Default workload (config.workload = "c2", BASELINE.json configs[1]): synthetic logistic regression,
+N = 10M records x d = 1024 float32 (41 GB resident in HBM, >> L2), Poisson sampling q = 0.01
+(max_batch_size = the 0.99 Poisson quantile = 100736), hand-written mean-field guide, Adam(1e-3),
+C = 1, dp_scale = 1.  Other workloads: c1 (N=10k d=8), c3 (Gaussian N=50M d=256, subsample
+B=500k), c5 (VAE 784-400-20, B=4096: tcgen05 clipped-sum GEMMs).
 
-A "step" = sample indices (Poisson sampler kernels) + fused gather / per-example gradient / clip /
-sum kernel + (NCCL all-reduce at N > 1) + reduce / ChaCha noise / rescale / Adam kernel, i.e.
-`get_batch(i, state)` followed by `DPSVI.update(state, *batch, mask=mask)`.
+A "step" = `get_batch(i, state)` (sampler kernels) followed by `DPSVI.update(state, *batch,
+mask=mask)` (fused gather / per-example gradient / clip / sum kernel(s) + (NCCL all-reduce at N > 1)
++ reduce / ChaCha noise / rescale / Adam kernel).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2]
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL); the batch is sharded over the ranks
 (strong scaling: the global batch is fixed by the config).  `--impl reference` times the CPU
@@ -17,6 +19,7 @@ oracle port of the same step on the host cores (the reference itself needs jax/n
 jax-chacha-prng, none of which can be installed here — see DESIGN.md).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -29,12 +32,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (N, d, q, family)
-    "c2": dict(N=10_000_000, d=1024, q=0.01, family="logreg", C=1.0),
-    "c3": dict(N=50_000_000, d=256, q=0.01, family="gauss", C=1.0),
-    "c1": dict(N=10_000, d=8, q=0.02, family="logreg", C=1.0),
+    "c1": dict(N=10_000, d=8, q=0.02, family="logreg", C=1.0, sampler="poisson"),
+    "c2": dict(N=10_000_000, d=1024, q=0.01, family="logreg", C=1.0, sampler="poisson"),
+    "c3": dict(N=50_000_000, d=256, q=0.01, family="gauss", C=1.0, sampler="subsample"),
+    "c5": dict(N=60_000, d=784, q=4096 / 60_000, family="vae", C=10.0, sampler="subsample", batch=4096,
+               hidden=400, z=20),
 }
-ALGO_BYTES_PER_EXAMPLE = {"c2": 4 * (1024 + 1), "c3": 4 * 256, "c1": 4 * (8 + 1)}
+# algorithmic HBM bytes per example of the dominant kernel
+ALGO_BYTES_PER_EXAMPLE = {"c1": 4 * (8 + 1), "c2": 4 * (1024 + 1), "c3": 4 * 256}
+# launches of OUR kernels per step: sampler + step kernel(s) + finalize
+LAUNCHES = {"poisson": 3, "subsample": 1, "logreg": 2, "gauss": 2, "vae": 13}   # vae: 2 split + prep + 7 GEMMs + 2 SIMT + loss (12) + finalize
 
 
 def measured_peaks():
@@ -43,6 +50,15 @@ def measured_peaks():
         with open(p) as f:
             return json.load(f), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
 
 
 class ClockSampler:
@@ -98,9 +114,23 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def max_batch_size(N, q):
-    import scipy.stats
-    return int(scipy.stats.poisson(N * q).ppf(.99))
+def batch_size_of(cfg):
+    if cfg["sampler"] == "poisson":
+        import scipy.stats
+        return int(scipy.stats.poisson(cfg["N"] * cfg["q"]).ppf(.99))
+    return cfg.get("batch", int(cfg["N"] * cfg["q"]))
+
+
+def workload_config(name, cfg):
+    b = batch_size_of(cfg)
+    sampler = (f"Poisson q={cfg['q']} max_batch_size={b}" if cfg["sampler"] == "poisson"
+               else f"subsample without replacement batch={b}")
+    model = (f"VAE {cfg['d']}-{cfg['hidden']}-{cfg['z']}" if cfg["family"] == "vae" else f"{cfg['family']} d={cfg['d']}")
+    return {"workload": f"{name}: synthetic {model} N={cfg['N']} {sampler}",
+            "l2_policy": ("inputs larger than L2 (dataset resident in HBM, rows gathered at random)"
+                          if cfg["N"] * cfg["d"] * 4 > 2 ** 28 else
+                          "working set (activations + partial sums, >300 MB per step) larger than L2"),
+            "optimizer": "Adam(1e-3)", "clipping_threshold": cfg["C"], "dp_scale": 1.0}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -115,12 +145,14 @@ def cpu_port_throughput(cfg, steps, warmup, sample_examples, threads):
     B = sample_examples
     if cfg["family"] == "logreg":
         fam = families.LogisticRegression(d, N)
-        X = rs.randn(B, d).astype(np.float32)
-        y = (rs.rand(B) < .5).astype(np.int32)
-        args = (X, y)
-    else:
+        args = (rs.randn(B, d).astype(np.float32), (rs.rand(B) < .5).astype(np.int32))
+    elif cfg["family"] == "gauss":
         fam = families.GaussianMean(d, N)
         args = ((1 + .1 * rs.randn(B, d)).astype(np.float32),)
+    else:
+        from oracle import vae as ovae
+        fam = ovae.VAE(d, cfg["hidden"], cfg["z"], N)
+        args = ((rs.rand(B, 28, 28) < .3).astype(np.float32),)
     s = osvi.DPSVI(fam, None, osvi.Adam(1e-3), None, cfg["C"], 1.0)
     st = s.init(chacha.PRNGKey(0), *args)
     mask = np.ones(B, dtype=bool)
@@ -133,12 +165,16 @@ def cpu_port_throughput(cfg, steps, warmup, sample_examples, threads):
     return B * steps / dt, dt / steps * 1e3
 
 
+def cpu_sample_size(cfg):
+    return 256 if cfg["family"] == "vae" else (4096 if cfg["d"] >= 256 else 8192)
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 4096 if cfg["d"] >= 256 else 8192
+    sample = cpu_sample_size(cfg)
     steps = max(1, min(args.steps, 8))
     warmup = min(args.warmup, 1)
     value, ms = cpu_port_throughput(cfg, steps, warmup, sample, threads)
@@ -148,19 +184,12 @@ def run_reference(args, cfg):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, cfg),
         "cpu_baseline": {"value": value, "unit": "examples/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} steps of {sample} examples (d={cfg['d']}) through the oracle port of "
-                                   "DPSVI.update (numpy Threefry/ChaCha + torch.func vmap(grad) + clip + noise + Adam); "
+                         "sample": f"{steps} steps of {sample} examples through the oracle port of DPSVI.update "
+                                   "(numpy Threefry/ChaCha + torch.func vmap(grad) + clip + noise + Adam); "
                                    "the reference's JAX path cannot be installed here"},
         "e2e": {"value": value, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
-
-def workload_config(name, cfg):
-    return {"workload": f"{name}: synthetic {cfg['family']} N={cfg['N']} d={cfg['d']} Poisson q={cfg['q']} "
-                        f"max_batch_size={max_batch_size(cfg['N'], cfg['q'])}",
-            "l2_policy": "inputs larger than L2 (dataset resident in HBM, rows gathered at random)",
-            "optimizer": "Adam(1e-3)", "clipping_threshold": cfg["C"], "dp_scale": 1.0}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -168,19 +197,49 @@ def workload_config(name, cfg):
 # ------------------------------------------------------------------------------------------------
 def make_dataset(cfg, device):
     """Synthetic data of the named shape, generated on the device with the build's own ChaCha
-    kernels (reproducible without JAX): X ~ N(0, 1); y ~ Bernoulli(sigmoid(X w* + b*))."""
+    kernels (reproducible without JAX)."""
     import torch
     import d3p_b200.random as rng
     N, d = cfg["N"], cfg["d"]
     kx, kw, ky = rng.split(rng.PRNGKey(123), 3)
+    if cfg["family"] == "vae":      # uniform [0,1] "pixels", Bernoulli-binarised (examples/vae.py:156-168)
+        X = (rng.uniform(kx, (N, 28, 28)) < rng.uniform(kw, (N, 28, 28))).to(torch.float32)
+        return (X,)
     X = rng.normal(kx, (N, d))
-    if cfg["family"] == "gauss":
+    if cfg["family"] == "gauss":    # x ~ N(1, 0.1^2)  (simple_gaussian_posterior.py:62-65,105)
         X.mul_(0.1).add_(1.0)
         return (X,)
-    w = rng.normal(kw, (d + 1,))
+    w = rng.normal(kw, (d + 1,))    # y ~ Bernoulli(sigmoid(X w* + b*))  (logistic_regression.py:88-104)
     logits = torch.mv(X, w[:d]) + w[d]
     y = (rng.uniform(ky, (N,)) < torch.sigmoid(logits)).to(torch.int32)
     return (X, y)
+
+
+def make_family(cfg):
+    from d3p_b200 import models
+    if cfg["family"] == "logreg":
+        return models.LogisticRegression(cfg["d"])
+    if cfg["family"] == "gauss":
+        return models.GaussianMean(cfg["d"])
+    return models.VAE(cfg["d"], cfg["hidden"], cfg["z"])
+
+
+class LibEvents:
+    """CUDA events owned by libd3p_b200 (recorded inside the C call around the dominant kernels)."""
+
+    def __init__(self, n):
+        from d3p_b200 import _native as _n
+        self._n = _n
+        self.arr = (C.c_void_p * n)()
+        for i in range(n):
+            e = C.c_void_p()
+            _n.check(_n.lib().d3p_event_create(C.byref(e)))
+            self.arr[i] = e.value
+
+    def elapsed(self, i, j):
+        ms = C.c_float()
+        self._n.check(self._n.lib().d3p_event_elapsed_ms(C.c_void_p(self.arr[i]), C.c_void_p(self.arr[j]), C.byref(ms)))
+        return ms.value
 
 
 def run_b200(args, cfg):
@@ -197,15 +256,19 @@ def run_b200(args, cfg):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    N, d, q = cfg["N"], cfg["d"], cfg["q"]
+    N, q = cfg["N"], cfg["q"]
+    is_vae = cfg["family"] == "vae"
     dataset = make_dataset(cfg, device)
-    fam = models.LogisticRegression(d) if cfg["family"] == "logreg" else models.GaussianMean(d)
+    fam = make_family(cfg)
     svi = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), cfg["C"], 1.0,
                      num_obs_total=N)
     svi.donate_state = True
     if world > 1:
         parallel.shard_dpsvi(svi, rank, world)
-    init, get_batch = mb.poisson_batchify_data(dataset, q, .99)
+    if cfg["sampler"] == "poisson":
+        init, get_batch = mb.poisson_batchify_data(dataset, q, .99)
+    else:
+        init, get_batch = mb.subsample_batchify_data(dataset, batch_size=batch_size_of(cfg), return_mask=True)
     key = rng.PRNGKey(0)
     key, k_init, k_fetch = rng.split(key, 3)
     _, bstate = init(k_fetch)
@@ -223,7 +286,8 @@ def run_b200(args, cfg):
     def one_step(i, state):
         batch, mask = get_batch(i, bstate)
         state, loss = svi.update(state, *batch, mask=mask)
-        return state, loss, batch[0].num_valid
+        nv = batch[0].num_valid
+        return state, loss, (nv if nv is not None else max_b)
 
     def sync_all():
         if world > 1:
@@ -236,6 +300,11 @@ def run_b200(args, cfg):
         state, loss, _ = one_step(i, state)
     sync_all()
     svi.event_hook = hook
+    lib_events = None
+    gemm_ms = []
+    if is_vae:
+        lib_events = LibEvents(2)
+        fam.profile_events = lib_events.arr
     counts = []
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin.record()
@@ -251,19 +320,25 @@ def run_b200(args, cfg):
         t = torch.tensor([elapsed_ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    n_examples = int(torch.stack([c.reshape(()) for c in counts]).sum().item())
+    n_examples = int(sum(int(c) if isinstance(c, int) else int(c.reshape(()).item()) for c in counts))
     value = n_examples / (elapsed_ms * 1e-3)
     kern_ms = [kernel_events[2 * i].elapsed_time(kernel_events[2 * i + 1]) for i in range(len(kernel_events) // 2)]
     kern_ms_avg = float(np.mean(kern_ms))
     if not np.isfinite(float(loss)):
         raise RuntimeError("bench produced a non-finite loss")
+    if is_vae:
+        # time the clipped-sum GEMMs live: a few more steps, reading the library's events after each
+        for i in range(min(args.steps, 20)):
+            state, loss, _ = one_step(args.warmup + args.steps + i, state)
+            gemm_ms.append(lib_events.elapsed(0, 1))
+        fam.profile_events = None
 
     # ---- end to end through the public API with HOST buffers (rank-local shard at N > 1) -----------
     e2e = None
     if args.e2e:
-        Xb = batch[0].tensor()
-        host = [torch.empty(t_.shape, dtype=t_.dtype).pin_memory() for t_ in (Xb,) + tuple(b.tensor() for b in batch[1:])]
-        for h, src in zip(host, (Xb,) + tuple(b.tensor() for b in batch[1:])):
+        dev_batch = [b.tensor() for b in batch]
+        host = [torch.empty(t_.shape, dtype=t_.dtype).pin_memory() for t_ in dev_batch]
+        for h, src in zip(host, dev_batch):
             h.copy_(src)
         host_mask = torch.empty(mask.shape, dtype=torch.bool).pin_memory()
         host_mask.copy_(mask)
@@ -307,34 +382,56 @@ def run_b200(args, cfg):
             e_ms = float(t.item())
         e2e = {"value": n_valid_host * args.steps / (e_ms * 1e-3), "unit": "examples/s",
                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
-               "note": "DPSVI.update(state, X_batch, y_batch, mask) with the batch in pinned HOST memory: "
+               "note": "DPSVI.update(state, *batch, mask) with the batch in pinned HOST memory: "
                        "H2D copy of the padded batch + update + loss read-back every step (double-buffered)"}
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        algo_bytes = ALGO_BYTES_PER_EXAMPLE[args.workload] * (n_examples / args.steps) / world
-        achieved = algo_bytes / (kern_ms_avg * 1e-3) / 1e9
+        step_ms = elapsed_ms / args.steps
+        per_rank_examples = (n_examples / args.steps) / world
+        if is_vae:
+            D, H = cfg["d"], cfg["hidden"]
+            flops = 2.0 * 2.0 * D * H * per_rank_examples          # dW1 + dW5 clipped-sum GEMMs
+            g_ms = float(np.mean(gemm_ms))
+            achieved = flops / (g_ms * 1e-3) / 1e12
+            peak = peaks["bf16_tflops"] / 2.0                        # TF32 dense = half the bf16 rate
+            roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<MN,MN,224,EpiGrad> x2 (dW1, dW5 clipped sums)",
+                        "achieved": achieved, "peak": peak,
+                        "peak_kind": peak_kind + " bf16 GEMM / 2 (no measured TF32 figure)", "unit": "TFLOP/s",
+                        "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "kernel_ms": g_ms,
+                        "kernel_share_of_step": g_ms / step_ms,
+                        "executed_tflops": 3.0 * achieved,
+                        "note": "algorithmic FLOPs = 2*2*784*400 per example; the kernels execute 3x that "
+                                "(3xTF32 split for fp32 parity), see executed_tflops",
+                        "step_kernels_ms": kern_ms_avg}
+        else:
+            algo_bytes = ALGO_BYTES_PER_EXAMPLE[args.workload] * per_rank_examples
+            achieved = algo_bytes / (kern_ms_avg * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "meanfield_step_vec_kernel" if cfg["d"] >= 256 else "meanfield_step_kernel",
+                        "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
+                        "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload),
+                        "kernel_ms": kern_ms_avg, "kernel_share_of_step": kern_ms_avg / step_ms,
+                        "note": "issue-bound, not HBM-bound: one Threefry-2x32-20 normal per data float "
+                                "(~92 instructions per element, DESIGN.md section 5)"}
         line = {
             "metric": "DPSVI.update examples/sec", "value": value, "unit": "examples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args.workload, cfg),
-            "clocks": clocks, "gpu_launches": 5 * args.steps + (1 if world > 1 else 0) * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "meanfield_step_kernel", "achieved": achieved,
-                         "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-                         "kernel_ms": kern_ms_avg, "kernel_share_of_step": kern_ms_avg / (elapsed_ms / args.steps),
-                         "note": "ALU co-bound: one Threefry normal per data float (SURVEY.md 8d)"},
+            "clocks": clocks,
+            "gpu_launches": (LAUNCHES[cfg["sampler"]] + LAUNCHES[cfg["family"]] + (1 if world > 1 else 0)) * args.steps,
+            "roofline": roofline,
             "examples_per_step": n_examples / args.steps, "max_batch_size": max_b,
         }
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and args.cpu_baseline:
             threads = os.cpu_count() or 1
-            sample = 2048
+            sample = cpu_sample_size(cfg) // 2
             v, ms = cpu_port_throughput(cfg, 3, 1, sample, threads)
             line["cpu_baseline"] = {"value": v, "unit": "examples/s", "cores": threads, "kind": "port",
-                                    "sample": f"3 steps of {sample} examples (d={d}) through the oracle port"}
+                                    "sample": f"3 steps of {sample} examples through the oracle port "
+                                              "(numpy RNG + torch.func vmap(grad) + clip + noise + Adam)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -47,6 +47,10 @@ _vp = C.c_void_p
 _SIGNATURES = {
     "d3p_abi_version": (C.c_int32, []),
     "d3p_error_string": (C.c_char_p, [C.c_int32]),
+    "d3p_event_create": (C.c_int32, [C.POINTER(C.c_void_p)]),
+    "d3p_event_record": (C.c_int32, [_vp, _vp]),
+    "d3p_event_elapsed_ms": (C.c_int32, [_vp, _vp, C.POINTER(C.c_float)]),
+    "d3p_event_destroy": (C.c_int32, [_vp]),
     "d3p_chacha_key_from_seed_h": (C.c_int32, [_vp, C.c_size_t, _u32p]),
     "d3p_chacha_fold_in_h": (C.c_int32, [_u32p, C.c_uint32, _u32p]),
     "d3p_chacha_split_h": (C.c_int32, [_u32p, C.c_int32, _u32p]),
@@ -76,7 +80,8 @@ _SIGNATURES = {
     "d3p_reduce_partials_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "d3p_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.c_uint32, _u32p]),
     "d3p_dpsvi_step_vae": (C.c_int32, [C.POINTER(VaeDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
-                                       C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),
+                                       C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, C.c_size_t,
+                                       C.POINTER(C.c_void_p), _vp]),
     "d3p_split_tf32": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_size_t, _vp]),
     "d3p_gemm_tf32x3": (C.c_int32, [_vp, _vp, C.c_int32, C.c_size_t, _vp, _vp, C.c_int32, C.c_size_t, C.c_uint32,
                                     C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, C.c_size_t,

@@ -120,6 +120,110 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
   }
 }
 
+// Large-P variant (VAE: P = 652 824, few partial rows): one WARP per 512 consecutive elements of one
+// leaf = 32 ChaCha blocks, one per lane, so every keystream block is computed once (finalize_kernel
+// recomputes the block for each of its 16 elements: fine at P ~ 2 k, 90 us at P ~ 650 k).  The
+// keystream is transposed through shared memory so that all global accesses stay coalesced.  Same
+// arithmetic; the partial rows are summed in row order 0, 1, 2, ... (deterministic).
+struct ChunkTable { uint32_t n_chunks; uint32_t chunk_start[D3P_MAX_LEAVES + 1]; };
+
+__global__ void __launch_bounds__(kFinThreads) finalize_block_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites,
+                                                                     ChunkTable ct) {
+  __shared__ float red[2][kFinThreads / 32];
+  __shared__ float s_n, s_loss;
+  __shared__ uint32_t s_ks[kFinThreads / 32][32 * 17];
+  const uint32_t stride = a.P + 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float cnt = 0.f, loss = 0.f;
+  for (uint32_t p = threadIdx.x; p < a.n_partials; p += kFinThreads) {
+    loss += a.partials[(size_t)p * stride + a.P];
+    cnt += a.partials[(size_t)p * stride + a.P + 1];
+  }
+  cnt = group_sum<32>(cnt);
+  loss = group_sum<32>(loss);
+  if (lane == 0) { red[0][warp] = cnt; red[1][warp] = loss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float c = 0.f, l = 0.f;
+#pragma unroll
+    for (int w = 0; w < kFinThreads / 32; ++w) { c += red[0][w]; l += red[1][w]; }
+    s_n = c; s_loss = l;
+  }
+  __syncthreads();
+  const float n = a.use_override ? a.n_override : s_n;
+  const float Bf = (float)a.B;
+  const float f = a.use_override ? a.f_override : ((n == 0.f) ? 0.f : __fdiv_rn(Bf, n));
+  const float sigma = __fmul_rn(a.dp_scale, __fdiv_rn(a.C, n));
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
+    a.stats[0] = __fmul_rn(__fdiv_rn(s_loss, Bf), f);
+    a.stats[1] = n;
+    a.stats[2] = f;
+  }
+  const uint32_t chunk = blockIdx.x * (kFinThreads / 32) + warp;
+  if (chunk >= ct.n_chunks) return;                      // warp-uniform
+  uint32_t leaf = 0;
+#pragma unroll 1
+  for (uint32_t l = 1; l < leaves.n_leaves; ++l)
+    if (chunk >= ct.chunk_start[l]) leaf = l;
+  const uint32_t c0 = chunk - ct.chunk_start[leaf];      // chunk index inside the leaf
+  const uint32_t len = leaves.len[leaf], off = leaves.off[leaf];
+  {
+    uint32_t ks[16];
+    chacha20_block(sites.w[leaf], sites.w[leaf][12] + c0 * 32 + lane, ks);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s_ks[warp][lane * 17 + i] = ks[i];
+  }
+  __syncwarp();
+  const float t1 = (float)(a.step + 1);
+  const float bc1 = 1.0f - powf(a.b1, t1), bc2 = 1.0f - powf(a.b2, t1);
+  const float* __restrict__ parts = a.partials;
+  float* __restrict__ prm = a.params;
+  float* __restrict__ pm = a.m;
+  float* __restrict__ pv = a.v;
+  // 4 elements per lane and pass: all their loads are issued before the first dependent use
+#pragma unroll 1
+  for (int i0 = 0; i0 < 16; i0 += 4) {
+    float sum[4], x[4], m0[4], v0[4];
+    uint32_t jj[4];
+    bool ok[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t e = c0 * 512 + (i0 + t) * 32 + lane;   // element inside the leaf
+      ok[t] = e < len;
+      jj[t] = off + (ok[t] ? e : 0u);
+      sum[t] = 0.f;
+      x[t] = (ok[t] && a.opt_kind != D3P_OPT_NONE) ? prm[jj[t]] : 0.f;
+      m0[t] = (ok[t] && a.opt_kind == D3P_OPT_ADAM) ? pm[jj[t]] : 0.f;
+      v0[t] = (ok[t] && a.opt_kind == D3P_OPT_ADAM) ? pv[jj[t]] : 0.f;
+    }
+    for (uint32_t p = 0; p < a.n_partials; ++p) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) sum[t] += ok[t] ? parts[(size_t)p * stride + jj[t]] : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (!ok[t]) continue;
+      const uint32_t j = jj[t];
+      const uint32_t bits = s_ks[warp][(2 * (i0 + t) + (lane >> 4)) * 17 + (lane & 15)];
+      float g = __fdiv_rn(sum[t], Bf);
+      g = __fadd_rn(g, __fmul_rn(bits_to_normal<false>(bits), sigma));
+      g = __fmul_rn(__fmul_rn(g, a.obs_scale), f);
+      if (a.grad_out) a.grad_out[j] = g;
+      if (a.opt_kind == D3P_OPT_SGD) {
+        prm[j] = x[t] - a.step_size * g;
+      } else if (a.opt_kind == D3P_OPT_ADAM) {
+        float m = (1.0f - a.b1) * g + a.b1 * m0[t];
+        float v = (1.0f - a.b2) * (g * g) + a.b2 * v0[t];
+        float mhat = m / bc1;
+        float vhat = v / bc2;
+        prm[j] = x[t] - a.step_size * mhat / (sqrtf(vhat) + a.eps);
+        pm[j] = m;
+        pv[j] = v;
+      }
+    }
+  }
+}
+
 // out[j] = sum_p partials[p][j] for j < row_len, fixed order (warp w adds rows w, w+4, ...).
 __global__ void __launch_bounds__(kFinThreads) reduce_partials_kernel(const float* __restrict__ partials,
                                                                       uint32_t n_partials, uint32_t row_len,
@@ -187,6 +291,25 @@ extern "C" int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_
       lt.len[l] = leaves_h->leaf_len[l];
       if ((uint64_t)lt.off[l] + lt.len[l] > P) return D3P_ERR_INVALID_ARGUMENT;
       for (int i = 0; i < 16; ++i) ss.w[l][i] = leaves_h->site_state[l][i];
+    }
+  }
+  // large parameter vectors with a leaf table that tiles [0, P): one thread per keystream block
+  if (add_noise && leaves_h && P >= 32768 && n_partials <= 64) {
+    ChunkTable ct;
+    memset(&ct, 0, sizeof(ct));
+    uint64_t covered = 0;
+    uint32_t nc = 0;
+    for (uint32_t l = 0; l < lt.n_leaves; ++l) {
+      ct.chunk_start[l] = nc;
+      nc += (lt.len[l] + 511) / 512;
+      covered += lt.len[l];
+    }
+    ct.chunk_start[lt.n_leaves] = nc;
+    ct.n_chunks = nc;
+    if (covered == P && nc > 0) {
+      const unsigned wpb = kFinThreads / 32;
+      finalize_block_kernel<<<(nc + wpb - 1) / wpb, kFinThreads, 0, (cudaStream_t)stream>>>(a, lt, ss, ct);
+      return check_launch();
     }
   }
   unsigned grid = P ? (P + 31) / 32 : 1;

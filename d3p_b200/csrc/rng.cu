@@ -107,7 +107,28 @@ using namespace d3p;
 
 extern "C" {
 
-int32_t d3p_abi_version(void) { return 1; }
+int32_t d3p_abi_version(void) { return 2; }
+
+// CUDA event helpers so that a host language without a CUDA binding can time kernels on the stream
+// they are launched on (bench.py's roofline block).
+int32_t d3p_event_create(void** event_out) {
+  if (!event_out) return D3P_ERR_INVALID_ARGUMENT;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return D3P_ERR_CUDA;
+  *event_out = e;
+  return D3P_OK;
+}
+int32_t d3p_event_record(void* event, void* stream) {
+  return cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream) == cudaSuccess ? D3P_OK : D3P_ERR_CUDA;
+}
+int32_t d3p_event_elapsed_ms(void* begin, void* end, float* ms_out) {
+  if (!ms_out) return D3P_ERR_INVALID_ARGUMENT;
+  if (cudaEventSynchronize((cudaEvent_t)end) != cudaSuccess) return D3P_ERR_CUDA;
+  return cudaEventElapsedTime(ms_out, (cudaEvent_t)begin, (cudaEvent_t)end) == cudaSuccess ? D3P_OK : D3P_ERR_CUDA;
+}
+int32_t d3p_event_destroy(void* event) {
+  return cudaEventDestroy((cudaEvent_t)event) == cudaSuccess ? D3P_OK : D3P_ERR_CUDA;
+}
 
 const char* d3p_error_string(int32_t code) {
   switch (code) {

@@ -5,12 +5,12 @@
 // Each term is one tcgen05.mma.kind::tf32 into the same TMEM accumulator.  An operand whose values
 // are exact in TF32 (e.g. binarised pixels) passes lo = NULL and its correction MMA is skipped.
 //
-// Structure (one CTA per 128 x BN output tile and K split, 192 threads):
+// Structure (one CTA per 128 x BN output tile and K split, 64 + 32 EW threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of 32 fp32 (one 128 B swizzle span) into
 //               a STAGES-deep shared-memory ring, mbarrier complete_tx
 //   warp 1      MMA issuer (one thread): 4 k-steps of UMMA_K = 8 per 32-deep k-block, 1-3 MMAs each;
 //               tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> Epi::tile()
+//   warps 2..   epilogue (EW warps): tcgen05.ld 32 lanes x 32 columns -> registers -> Epi::tile()
 // Operand major-ness (template): K-major = the contraction index is contiguous in memory,
 // MN-major = the M (or N) index is contiguous (needed for A^T * diag(c) * Delta, where the
 // contraction runs over the batch, the slow axis of both activations).
@@ -23,7 +23,7 @@ namespace tc {
 constexpr int kBM = 128;          // UMMA M
 constexpr int kKB = 32;           // fp32 per k-block = one 128-byte swizzle span
 constexpr int kUK = 8;            // UMMA K for tf32
-constexpr int kGemmThreads = 192;
+constexpr int kGemmEpiWarps = 4;   // default number of epilogue warps (store epilogues)
 
 struct GemmMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo; };
 
@@ -47,8 +47,10 @@ struct GemmCfg {
   static_assert(kStages >= 2, "tile too large for a 2-stage pipeline");
 };
 
-template <bool A_MN, bool B_MN, int BN, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// EW = number of epilogue warps (multiple of 4): the EW / 4 warps that share a TMEM lane quarter take the
+// 32-column chunks round-robin; Epi::begin/end see `part` in [0, EW / 4) for their row reductions.
+template <bool A_MN, bool B_MN, int BN, class Epi, int EW = kGemmEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const typename Epi::Args ea) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
@@ -158,19 +160,23 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
       umma_commit(&bar_acc);            // accumulator complete
     }
   } else {
+    static_assert(EW % 4 == 0 && EW >= 4, "EW must be a multiple of 4");
+    constexpr int PARTS = EW / 4;
     const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int part = (warp - 2) >> 2;   // which of the PARTS warps of that quarter
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
     const uint32_t row = m_tile * kBM + q * 32 + lane;
+    const uint32_t slot = n_tile * PARTS + part;     // row-reduction slot of this (tile, warp)
     typename Epi::RowState rs;
-    Epi::begin(ea, g, row, n_tile, split, rs);
+    Epi::begin(ea, g, row, slot, split, rs);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = part; c < BN / 32; c += PARTS) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
       Epi::tile(ea, g, row, n_tile * BN + c * 32, split, v, rs);
     }
-    Epi::end(ea, g, row, n_tile, split, rs);
+    Epi::end(ea, g, row, slot, split, rs);
   }
   tc_fence_before();
   __syncthreads();
@@ -221,7 +227,7 @@ struct GemmOperand {
   size_t ld;           // row stride in floats (multiple of 4)
 };
 
-template <bool A_MN, bool B_MN, int BN, class Epi>
+template <bool A_MN, bool B_MN, int BN, class Epi, int EW = kGemmEpiWarps>
 int32_t launch_tc_gemm(const GemmOperand& A, const GemmOperand& B, uint32_t M, uint32_t N, uint32_t K, uint32_t split_k,
                        const typename Epi::Args& ea, cudaStream_t stream, const int* a_lo_flag = nullptr) {
   using Cfg = GemmCfg<BN>;
@@ -253,11 +259,11 @@ int32_t launch_tc_gemm(const GemmOperand& A, const GemmOperand& B, uint32_t M, u
     ok = ok && make_map_2d(&maps.b_lo, B.lo ? B.lo : B.hi, K, N, B.ld, kKB, true);
   }
   if (!ok) return D3P_ERR_CUDA;
-  auto kern = tc_gemm_kernel<A_MN, B_MN, BN, Epi>;
+  auto kern = tc_gemm_kernel<A_MN, B_MN, BN, Epi, EW>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
     return D3P_ERR_CUDA;
   dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, g.split_k);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(maps, g, ea);
+  kern<<<grid, 64 + 32 * EW, Cfg::kSmemBytes, stream>>>(maps, g, ea);
   return cudaGetLastError() == cudaSuccess ? D3P_OK : D3P_ERR_CUDA;
 }
 

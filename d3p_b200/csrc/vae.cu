@@ -15,7 +15,8 @@
 //       [c*h2 | c] hi/lo
 //   GW1 [X | 1]^T (c delta1)        -> dW1, db1  (split over the batch, partial rows)
 //   GW5 delta5^T [c h2 | c]         -> dW5^T, db5
-//   S4  thin clipped sums dW4, db4, dW2, db2, dW3, db3, loss, count -> thin partials -> partial row 0
+//   GW23 [H1 | 1]^T (c [delta2|delta3]) -> dW2, dW3, db2, db3;  GW4 (c delta4)^T [z | 1] -> dW4^T, db4
+//   loss / count columns of the partial rows
 // The partial rows [S, P + 2] are reduced in a fixed order by d3p_perturb_finalize_f32.
 #include "common.cuh"
 #include "launch.cuh"
@@ -26,7 +27,6 @@ namespace d3p {
 constexpr int kVaeBN = 224;            // N tile of every VAE GEMM
 constexpr int kMidWarps = 8;
 constexpr int kMidE = 4;               // examples per warp iteration in the SIMT "middle" kernels
-constexpr uint32_t kThinSlabs = 64;
 constexpr float kF32Tiny = 1.17549435e-38f;
 constexpr float kF32OneMinusEps = 0.99999988079071044921875f;   // 1 - 2^-23
 
@@ -130,13 +130,15 @@ struct EpiBwd5 {   // delta4 = acc * softplus'(pre4) = acc * (1 - exp(-h2))
   }
 };
 
-struct EpiGrad {   // clipped-sum tile -> partial row `split`: weight block + the bias row / column
+struct EpiGrad {   // clipped-sum tile -> partial row `split`: weight block(s) + the bias row / column
   struct Args {
     float* partials; size_t row_stride;   // P + 2
     uint32_t w_off, b_off;                // offsets of the weight matrix and of the bias in the flat vector
     uint32_t w_ld;                        // row stride of the weight matrix
     uint32_t main;                        // !transpose: rows < main are weights, row == main is the bias
     int transpose;                        //  transpose: cols < main are weights (stored [col, row]), col == main the bias
+    uint32_t split_col;                   // !transpose only: cols >= split_col belong to a second matrix / bias
+    uint32_t w_off2, b_off2;              //   (both matrices have w_ld columns)
   };
   struct RowState {};
   __device__ static void begin(const Args&, const tc::GemmShape&, uint32_t, uint32_t, uint32_t, RowState&) {}
@@ -146,10 +148,17 @@ struct EpiGrad {   // clipped-sum tile -> partial row `split`: weight block + th
     if (row >= g.M) return;
     float* out = a.partials + (size_t)split * a.row_stride;
     if (!a.transpose) {
-      float* p = row < a.main ? out + a.w_off + (size_t)row * a.w_ld : out + a.b_off;
+      const uint32_t sc = a.split_col ? a.split_col : 0xffffffffu;
+      float* p1 = row < a.main ? out + a.w_off + (size_t)row * a.w_ld : out + a.b_off;
+      float* p2 = row < a.main ? out + a.w_off2 + (size_t)row * a.w_ld : out + a.b_off2;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < g.N) p[col0 + j] = __uint_as_float(v[j]);
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t col = col0 + j;
+        if (col < g.N) {
+          if (col < sc) p1[col] = __uint_as_float(v[j]);
+          else p2[col - sc] = __uint_as_float(v[j]);
+        }
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -164,20 +173,19 @@ struct EpiGrad {   // clipped-sum tile -> partial row `split`: weight block + th
 // ---- SIMT kernels ------------------------------------------------------------------------------------
 struct VaeArgs {
   uint32_t D, H, Z, B, Bl, pos_begin;
-  size_t ldx, ldc2;                   // D + 4, H + 4
+  size_t ldx, ldh, ldz, ld23;         // D + 4, H + 4, roundup(Z + 1, 4), roundup(2 Z, 4)
   const float* params;
   uint32_t off_w4, off_b4, off_w5, off_b5, off_w1, off_b1, off_w2, off_b2, off_w3, off_b3, P;
   const float* x; size_t x_stride; const int32_t* idx; const uint8_t* mask; const int32_t* num_valid;
   uint32_t k0, k1;
   float site_scale, inv_S, C;
-  uint32_t nt_h, nt_d;                // N tiles over H and over D
+  uint32_t ns_h, ns_d;                // row-reduction slots over H and over D (N tiles x epilogue parts)
   uint32_t S;                         // partial rows
   // workspace
   float *x_hi, *x_lo; int* x_lo_flag;
-  float *h1_hi, *h1_lo, *h2_hi, *h2_lo, *ch2_hi, *ch2_lo, *d5_hi, *d5_lo, *d4, *cd1_hi, *cd1_lo;
-  float *z, *u, *cd23;
+  float *h1_hi, *h1_lo, *h2_hi, *h2_lo, *ch2_hi, *ch2_lo, *d5_hi, *d5_lo, *d4, *cd4_hi, *cd4_lo, *cd1_hi, *cd1_lo;
+  float *z_hi, *z_lo, *u, *cd23_hi, *cd23_lo;
   float *sq_x, *sq_h1, *sq_h2, *sq_z, *sq_d5, *loss_rec, *sq_d4, *loss_kl, *lossv, *cnt;
-  float* thin;                        // [kThinSlabs, T + 2]
   float* partials;
   float* px_norms; float* px_loss;
 };
@@ -205,17 +213,30 @@ __global__ void vae_prep_x_kernel(VaeArgs a) {
   if (__any_sync(0xffffffffu, any_lo) && lane == 0) atomicOr(a.x_lo_flag, 1);
 }
 
-// S1: encoder heads, guide sample, KL part of the loss, decoder hidden layer.
+// S1: encoder heads, guide sample, KL part of the loss, decoder hidden layer.  The three thin weight
+// matrices are staged in shared memory once per CTA; each warp walks groups of kMidE examples.
 __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t H = a.H, Z = a.Z;
-  float* h1s = smem + (size_t)warp * kMidE * (H + 3 * 64);      // [E][H]
-  float* zs = h1s + kMidE * H;                                  // [E][64]  (z_loc | log z_std)
-  float* es = zs + kMidE * 64;                                  // [E][64]  eps
-  float* zz = es + kMidE * 64;                                  // [E][64]  z
-  const float* W2 = a.params + a.off_w2; const float* W3 = a.params + a.off_w3;
-  const float* W4 = a.params + a.off_w4;
+  const uint32_t H = a.H, Z = a.Z, Z2 = 2 * a.Z;
+  float* w23s = smem;                                   // [H][2Z]: row k = (W2[k, :], W3[k, :])
+  float* w4s = w23s + (size_t)H * Z2;                   // [Z][H]
+  float* b23s = w4s + (size_t)Z * H;                    // [2Z]
+  float* b4s = b23s + 64;                               // [H]
+  float* wsm = b4s + H + (size_t)warp * kMidE * (H + 3 * 64);
+  float* h1s = wsm;                                     // [E][H]
+  float* zs = h1s + kMidE * H;                          // [E][64]  (z_loc | log z_std)
+  float* es = zs + kMidE * 64;                          // [E][64]  eps
+  float* zz = es + kMidE * 64;                          // [E][64]  z
+  for (uint32_t i = threadIdx.x; i < H * Z; i += blockDim.x) {
+    const uint32_t k = i / Z, j = i - k * Z;
+    w23s[k * Z2 + j] = a.params[a.off_w2 + i];
+    w23s[k * Z2 + Z + j] = a.params[a.off_w3 + i];
+    w4s[i] = a.params[a.off_w4 + i];
+  }
+  for (uint32_t i = threadIdx.x; i < Z; i += blockDim.x) { b23s[i] = a.params[a.off_b2 + i]; b23s[Z + i] = a.params[a.off_b3 + i]; }
+  for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) b4s[i] = a.params[a.off_b4 + i];
+  __syncthreads();
   const TfKey K(a.k0, a.k1);
   const uint32_t half = (Z + 1) / 2;
   const uint32_t groups = (a.Bl + kMidE - 1) / kMidE;
@@ -224,8 +245,25 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
 #pragma unroll
     for (int e = 0; e < kMidE; ++e) {
       const uint32_t r = r0 + e;
-      for (uint32_t k = lane; k < H; k += 32)
-        h1s[e * H + k] = r < a.Bl ? a.h1_hi[(size_t)r * H + k] + a.h1_lo[(size_t)r * H + k] : 0.f;
+      {
+        const float* __restrict__ ph = a.h1_hi + (size_t)r * a.ldh;
+        const float* __restrict__ pl = a.h1_lo + (size_t)r * a.ldh;
+        for (uint32_t k0 = 0; k0 < H; k0 += 128) {          // 8 independent loads in flight per lane
+          float vh[4], vl[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t k = k0 + 32 * t + lane;
+            const bool ok = r < a.Bl && k < H;
+            vh[t] = ok ? __ldg(ph + k) : 0.f;
+            vl[t] = ok ? __ldg(pl + k) : 0.f;
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t k = k0 + 32 * t + lane;
+            if (k < H) h1s[e * H + k] = vh[t] + vl[t];
+          }
+        }
+      }
       // guide noise: key_p -> (_, guide_seed) -> (rng, k_plate) -> (_, k_z); eps = normal(k_z, (Z,))
       if (r < a.Bl) {
         TfKey kp = tf_example_key(K, a.B, a.pos_begin + r);
@@ -240,22 +278,24 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
           es[e * 64 + j] = bits_to_normal<false>(y0);
           if (j + half < Z) es[e * 64 + j + half] = bits_to_normal<false>(y1);
         }
+        if (lane < 4) {     // ones column of [H1 | 1] (bias row of the dW2 / dW3 clipped-sum GEMM)
+          a.h1_hi[(size_t)r * a.ldh + H + lane] = lane == 0 ? 1.0f : 0.f;
+          a.h1_lo[(size_t)r * a.ldh + H + lane] = 0.f;
+        }
       }
     }
     __syncwarp();
     // heads: output j < Z is z_loc_j (W2), Z <= j < 2Z is log z_std (W3); lane owns j = lane, lane + 32
     float acc[kMidE][2];
     const uint32_t j0 = lane, j1 = lane + 32;
-    const bool v0 = j0 < 2 * Z, v1 = j1 < 2 * Z;
-    const float* w0p = v0 ? (j0 < Z ? W2 + j0 : W3 + (j0 - Z)) : W2;
-    const float* w1p = v1 ? (j1 < Z ? W2 + j1 : W3 + (j1 - Z)) : W2;
-    const float bias0 = v0 ? (j0 < Z ? a.params[a.off_b2 + j0] : a.params[a.off_b3 + j0 - Z]) : 0.f;
-    const float bias1 = v1 ? (j1 < Z ? a.params[a.off_b2 + j1] : a.params[a.off_b3 + j1 - Z]) : 0.f;
+    const bool v0 = j0 < Z2, v1 = j1 < Z2;
+    const uint32_t jj0 = v0 ? j0 : 0, jj1 = v1 ? j1 : 0;
 #pragma unroll
     for (int e = 0; e < kMidE; ++e) { acc[e][0] = 0.f; acc[e][1] = 0.f; }
+#pragma unroll 4
     for (uint32_t k = 0; k < H; ++k) {
-      const float w0 = v0 ? __ldg(w0p + (size_t)k * Z) : 0.f;
-      const float w1 = v1 ? __ldg(w1p + (size_t)k * Z) : 0.f;
+      const float w0 = w23s[k * Z2 + jj0];
+      const float w1 = w23s[k * Z2 + jj1];
 #pragma unroll
       for (int e = 0; e < kMidE; ++e) {
         const float h = h1s[e * H + k];
@@ -265,8 +305,8 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
     }
 #pragma unroll
     for (int e = 0; e < kMidE; ++e) {
-      if (v0) zs[e * 64 + j0] = acc[e][0] + bias0;
-      if (v1) zs[e * 64 + j1] = acc[e][1] + bias1;
+      if (v0) zs[e * 64 + j0] = acc[e][0] + b23s[j0];
+      if (v1) zs[e * 64 + j1] = acc[e][1] + b23s[j1];
     }
     __syncwarp();
 #pragma unroll
@@ -278,10 +318,20 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
         const float u = expf(sr) * eps;
         const float z = zl + u;
         zz[e * 64 + j] = z;
-        if (r < a.Bl) { a.z[(size_t)r * Z + j] = z; a.u[(size_t)r * Z + j] = u; }
+        if (r < a.Bl) {
+          const float hi = tc::tf32_hi(z);
+          a.z_hi[(size_t)r * a.ldz + j] = hi;
+          a.z_lo[(size_t)r * a.ldz + j] = z - hi;
+          a.u[(size_t)r * Z + j] = u;
+        }
         kl += 0.5f * z * z - 0.5f * eps * eps - sr;       // -log N(z;0,1) + log N(z; z_loc, z_std), constants cancel
         sqz = fmaf(z, z, sqz);
       }
+      if (r < a.Bl)
+        for (uint32_t j = Z + lane; j < a.ldz; j += 32) {   // ones column of [z | 1] (db4 of the dW4 GEMM) + padding
+          a.z_hi[(size_t)r * a.ldz + j] = j == Z ? 1.0f : 0.f;
+          a.z_lo[(size_t)r * a.ldz + j] = 0.f;
+        }
       kl = group_sum<32>(kl);
       sqz = group_sum<32>(sqz);
       if (lane == 0 && r < a.Bl) { a.loss_kl[r] = kl; a.sq_z[r] = sqz; }
@@ -293,11 +343,12 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
     for (int e = 0; e < kMidE; ++e) sq2[e] = 0.f;
     for (uint32_t h = lane; h < H; h += 32) {
       float s[kMidE];
-      const float b = a.params[a.off_b4 + h];
+      const float b = b4s[h];
 #pragma unroll
       for (int e = 0; e < kMidE; ++e) s[e] = b;
+#pragma unroll 4
       for (uint32_t j = 0; j < Z; ++j) {
-        const float w = __ldg(W4 + (size_t)j * H + h);
+        const float w = w4s[j * H + h];
 #pragma unroll
         for (int e = 0; e < kMidE; ++e) s[e] = fmaf(zz[e * 64 + j], w, s[e]);
       }
@@ -323,16 +374,24 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
 }
 
 // S2: back-propagation through the z layer and the encoder heads, ghost norm, clip factor, scaled
-// operands of the clipped-sum GEMMs.
+// operands of the clipped-sum GEMMs.  W4, W2^T, W3^T staged in shared memory.
 __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_bwd_kernel(VaeArgs a) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t H = a.H, Z = a.Z;
-  float* d4s = smem + (size_t)warp * kMidE * (2 * H + 2 * 64);  // [E][H]
-  float* d1s = d4s + kMidE * H;                                 // [E][H]
-  float* d23 = d1s + kMidE * H;                                 // [E][128]: delta2 at [0,64), delta3 at [64,128)
-  const float* W2 = a.params + a.off_w2; const float* W3 = a.params + a.off_w3;
-  const float* W4 = a.params + a.off_w4;
+  float* w4s = smem;                                    // [Z][H]
+  float* w2t = w4s + (size_t)Z * H;                     // [Z][H] = W2^T
+  float* w3t = w2t + (size_t)Z * H;                     // [Z][H] = W3^T
+  float* wsm = w3t + (size_t)Z * H + (size_t)warp * kMidE * (H + 128);
+  float* d4s = wsm;                                     // [E][H]
+  float* d23 = d4s + kMidE * H;                         // [E][128]: delta2 at [0,64), delta3 at [64,128)
+  for (uint32_t i = threadIdx.x; i < H * Z; i += blockDim.x) {
+    const uint32_t h = i / Z, j = i - h * Z;
+    w4s[i] = a.params[a.off_w4 + i];
+    w2t[j * H + h] = a.params[a.off_w2 + i];
+    w3t[j * H + h] = a.params[a.off_w3 + i];
+  }
+  __syncthreads();
   const uint32_t nv = a.num_valid ? (uint32_t)max(*a.num_valid, 0) : 0xffffffffu;
   const float ratio = a.site_scale * a.inv_S;                   // (1 / obs_scale) * site scale
   const uint32_t groups = (a.Bl + kMidE - 1) / kMidE;
@@ -341,39 +400,55 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_bwd_kernel(VaeArgs a) 
 #pragma unroll
     for (int e = 0; e < kMidE; ++e) {
       const uint32_t r = r0 + e;
-      for (uint32_t h = lane; h < H; h += 32) d4s[e * H + h] = r < a.Bl ? a.d4[(size_t)r * H + h] : 0.f;
+      for (uint32_t h0 = 0; h0 < H; h0 += 128) {
+        float v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t h = h0 + 32 * t + lane;
+          v[t] = (r < a.Bl && h < H) ? __ldg(a.d4 + (size_t)r * H + h) : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t h = h0 + 32 * t + lane;
+          if (h < H) d4s[e * H + h] = v[t];
+        }
+      }
     }
     __syncwarp();
-    // delta_z_j = z_j + sum_h delta4_h W4[j, h]
-    float sq23[kMidE];
+    // delta_z_j = z_j + sum_h delta4_h W4[j, h]; lane j keeps z_j and u_j of every example of the group
+    float sq23[kMidE], zreg[kMidE], ureg[kMidE];
 #pragma unroll
-    for (int e = 0; e < kMidE; ++e) sq23[e] = 0.f;
+    for (int e = 0; e < kMidE; ++e) {
+      const uint32_t r = r0 + e;
+      const bool ok = r < a.Bl && (uint32_t)lane < Z;
+      sq23[e] = 0.f;
+      zreg[e] = ok ? a.z_hi[(size_t)r * a.ldz + lane] + a.z_lo[(size_t)r * a.ldz + lane] : 0.f;
+      ureg[e] = ok ? a.u[(size_t)r * Z + lane] : 0.f;
+    }
     for (uint32_t j = 0; j < Z; ++j) {
       float part[kMidE];
 #pragma unroll
       for (int e = 0; e < kMidE; ++e) part[e] = 0.f;
+#pragma unroll 4
       for (uint32_t h = lane; h < H; h += 32) {
-        const float w = __ldg(W4 + (size_t)j * H + h);
+        const float w = w4s[j * H + h];
 #pragma unroll
         for (int e = 0; e < kMidE; ++e) part[e] = fmaf(d4s[e * H + h], w, part[e]);
       }
 #pragma unroll
       for (int e = 0; e < kMidE; ++e) {
         const float s = group_sum<32>(part[e]);
-        const uint32_t r = r0 + e;
-        if (lane == 0) {
-          const float zj = r < a.Bl ? a.z[(size_t)r * Z + j] : 0.f;
-          const float uj = r < a.Bl ? a.u[(size_t)r * Z + j] : 0.f;
-          const float dz = s + zj;
-          const float d3 = fmaf(dz, uj, -1.0f);
+        if ((uint32_t)lane == j) {
+          const float dz = s + zreg[e];
+          const float d3 = fmaf(dz, ureg[e], -1.0f);
           d23[e * 128 + j] = dz;
           d23[e * 128 + 64 + j] = d3;
-          sq23[e] = fmaf(dz, dz, fmaf(d3, d3, sq23[e]));
+          sq23[e] = fmaf(dz, dz, d3 * d3);
         }
       }
     }
     __syncwarp();
-    // delta_h1 = delta2 W2^T + delta3 W3^T ; delta1 = delta_h1 * softplus'(pre1)
+    // delta_h1 = delta2 W2^T + delta3 W3^T ; delta1 = delta_h1 * softplus'(pre1); raw delta1 parked in cd1_hi
     float sq1[kMidE];
 #pragma unroll
     for (int e = 0; e < kMidE; ++e) sq1[e] = 0.f;
@@ -381,18 +456,26 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_bwd_kernel(VaeArgs a) 
       float s[kMidE];
 #pragma unroll
       for (int e = 0; e < kMidE; ++e) s[e] = 0.f;
+#pragma unroll 4
       for (uint32_t j = 0; j < Z; ++j) {
-        const float w2 = __ldg(W2 + (size_t)h * Z + j), w3 = __ldg(W3 + (size_t)h * Z + j);
+        const float w2 = w2t[j * H + h], w3 = w3t[j * H + h];
 #pragma unroll
         for (int e = 0; e < kMidE; ++e) s[e] = fmaf(d23[e * 128 + j], w2, fmaf(d23[e * 128 + 64 + j], w3, s[e]));
+      }
+      float h1v[kMidE];
+#pragma unroll
+      for (int e = 0; e < kMidE; ++e) {
+        const uint32_t r = r0 + e;
+        h1v[e] = r < a.Bl ? __ldg(a.h1_hi + (size_t)r * a.ldh + h) + __ldg(a.h1_lo + (size_t)r * a.ldh + h) : 0.f;
       }
 #pragma unroll
       for (int e = 0; e < kMidE; ++e) {
         const uint32_t r = r0 + e;
-        const float h1 = r < a.Bl ? a.h1_hi[(size_t)r * H + h] + a.h1_lo[(size_t)r * H + h] : 0.f;
-        const float d1 = s[e] * (-expm1f(-h1));
-        d1s[e * H + h] = d1;
-        sq1[e] = fmaf(d1, d1, sq1[e]);
+        if (r < a.Bl) {
+          const float d1 = s[e] * (-expm1f(-h1v[e]));
+          a.cd1_hi[(size_t)r * H + h] = d1;
+          sq1[e] = fmaf(d1, d1, sq1[e]);
+        }
       }
     }
     __syncwarp();
@@ -401,10 +484,13 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_bwd_kernel(VaeArgs a) 
       const uint32_t r = r0 + e;
       if (r >= a.Bl) continue;                     // warp-uniform
       const float s1 = group_sum<32>(sq1[e]);
-      const float s23 = __shfl_sync(0xffffffffu, sq23[e], 0);
+      const float s23 = group_sum<32>(sq23[e]);
+      // row-reduction slots of the GEMM epilogues: lane t reads slot t, fixed shuffle-tree order
       float sq_h1 = 0.f, sq_d4 = 0.f, sq_d5 = 0.f, lrec = 0.f;
-      for (uint32_t t = 0; t < a.nt_h; ++t) { sq_h1 += a.sq_h1[(size_t)t * a.Bl + r]; sq_d4 += a.sq_d4[(size_t)t * a.Bl + r]; }
-      for (uint32_t t = 0; t < a.nt_d; ++t) { sq_d5 += a.sq_d5[(size_t)t * a.Bl + r]; lrec += a.loss_rec[(size_t)t * a.Bl + r]; }
+      for (uint32_t t = lane; t < a.ns_h; t += 32) { sq_h1 += a.sq_h1[(size_t)t * a.Bl + r]; sq_d4 += a.sq_d4[(size_t)t * a.Bl + r]; }
+      for (uint32_t t = lane; t < a.ns_d; t += 32) { sq_d5 += a.sq_d5[(size_t)t * a.Bl + r]; lrec += a.loss_rec[(size_t)t * a.Bl + r]; }
+      sq_h1 = group_sum<32>(sq_h1); sq_d4 = group_sum<32>(sq_d4);
+      sq_d5 = group_sum<32>(sq_d5); lrec = group_sum<32>(lrec);
       const float n2 = (a.sq_h2[r] + 1.0f) * sq_d5 + (a.sq_z[r] + 1.0f) * sq_d4 + (sq_h1 + 1.0f) * s23 +
                        (a.sq_x[r] + 1.0f) * s1;
       const float norm = fabsf(ratio) * sqrtf(n2);
@@ -419,121 +505,81 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_bwd_kernel(VaeArgs a) 
         if (a.px_norms) a.px_norms[p] = valid ? norm : 0.f;
         if (a.px_loss) a.px_loss[p] = loss_s;
       }
-      for (uint32_t h = lane; h < H; h += 32) {
-        const float v1 = cc * d1s[e * H + h];
-        const float hi1 = tc::tf32_hi(v1);
-        a.cd1_hi[(size_t)r * H + h] = hi1;
-        a.cd1_lo[(size_t)r * H + h] = v1 - hi1;
-        a.d4[(size_t)r * H + h] = cc * d4s[e * H + h];
-        const float v2 = cc * (a.h2_hi[(size_t)r * H + h] + a.h2_lo[(size_t)r * H + h]);
-        const float hi2 = tc::tf32_hi(v2);
-        a.ch2_hi[(size_t)r * a.ldc2 + h] = hi2;
-        a.ch2_lo[(size_t)r * a.ldc2 + h] = v2 - hi2;
+      for (uint32_t h0 = 0; h0 < H; h0 += 128) {             // batched loads: 12 in flight per lane
+        float d1v[4], h2h[4], h2l[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t h = h0 + 32 * t + lane;
+          const bool ok = h < H;
+          d1v[t] = ok ? a.cd1_hi[(size_t)r * H + h] : 0.f;
+          h2h[t] = ok ? __ldg(a.h2_hi + (size_t)r * H + h) : 0.f;
+          h2l[t] = ok ? __ldg(a.h2_lo + (size_t)r * H + h) : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t h = h0 + 32 * t + lane;
+          if (h >= H) continue;
+          const float v1 = cc * d1v[t];
+          const float hi1 = tc::tf32_hi(v1);
+          a.cd1_hi[(size_t)r * H + h] = hi1;
+          a.cd1_lo[(size_t)r * H + h] = v1 - hi1;
+          const float v4 = cc * d4s[e * H + h];
+          const float hi4 = tc::tf32_hi(v4);
+          a.cd4_hi[(size_t)r * H + h] = hi4;
+          a.cd4_lo[(size_t)r * H + h] = v4 - hi4;
+          const float v2 = cc * (h2h[t] + h2l[t]);
+          const float hi2 = tc::tf32_hi(v2);
+          a.ch2_hi[(size_t)r * a.ldh + h] = hi2;
+          a.ch2_lo[(size_t)r * a.ldh + h] = v2 - hi2;
+        }
       }
       if (lane < 4) {
         const float v = lane == 0 ? cc : 0.f;
         const float hi = tc::tf32_hi(v);
-        a.ch2_hi[(size_t)r * a.ldc2 + H + lane] = hi;
-        a.ch2_lo[(size_t)r * a.ldc2 + H + lane] = v - hi;
+        a.ch2_hi[(size_t)r * a.ldh + H + lane] = hi;
+        a.ch2_lo[(size_t)r * a.ldh + H + lane] = v - hi;
       }
-      for (uint32_t j = lane; j < 2 * Z; j += 32)
-        a.cd23[(size_t)r * 2 * Z + j] = cc * (j < Z ? d23[e * 128 + j] : d23[e * 128 + 64 + j - Z]);
+      for (uint32_t j = lane; j < a.ld23; j += 32) {
+        const float v = j < 2 * Z ? cc * (j < Z ? d23[e * 128 + j] : d23[e * 128 + 64 + j - Z]) : 0.f;
+        const float hi = tc::tf32_hi(v);
+        a.cd23_hi[(size_t)r * a.ld23 + j] = hi;
+        a.cd23_lo[(size_t)r * a.ld23 + j] = v - hi;
+      }
     }
     __syncwarp();
   }
 }
 
-// S4: thin clipped sums.  Thin vector T = [dW4 (Z,H) | db4 (H) | dW2 (H,Z) | db2 (Z) | dW3 (H,Z) | db3 (Z) | loss | cnt].
-// grid (kThinSlabs, ceil(H / 128)); thread = one hidden unit h; slab = a contiguous range of examples.
-template <int ZP>
-__global__ void __launch_bounds__(128) vae_thin_kernel(VaeArgs a) {
-  constexpr int TI = 16;
-  __shared__ float zt[TI][ZP];
-  __shared__ float c2[TI][ZP];
-  __shared__ float c3[TI][ZP];
-  const uint32_t H = a.H, Z = a.Z;
-  const uint32_t T = 3 * Z * H + H + 2 * Z;
-  const uint32_t slab = blockIdx.x;
-  const uint32_t per = (a.Bl + kThinSlabs - 1) / kThinSlabs;
-  const uint32_t i0 = slab * per, i1 = min(a.Bl, i0 + per);
-  const uint32_t h = blockIdx.y * 128 + threadIdx.x;
-  const bool hv = h < H;
-  float w4[ZP], w2[ZP], w3[ZP], b4 = 0.f;
-#pragma unroll
-  for (int j = 0; j < ZP; ++j) { w4[j] = 0.f; w2[j] = 0.f; w3[j] = 0.f; }
-  float b23 = 0.f, ls = 0.f, cn = 0.f;       // blockIdx.y == 0: thread j < 2Z sums c*delta23[:, j]; thread 127 loss / count
-  for (uint32_t t0 = i0; t0 < i1; t0 += TI) {
-    __syncthreads();
-    for (uint32_t q = threadIdx.x; q < TI * ZP; q += 128) {
-      const uint32_t i = t0 + q / ZP, j = q % ZP;
-      const bool ok = i < i1 && j < Z;
-      zt[q / ZP][j] = ok ? a.z[(size_t)i * Z + j] : 0.f;
-      c2[q / ZP][j] = ok ? a.cd23[(size_t)i * 2 * Z + j] : 0.f;
-      c3[q / ZP][j] = ok ? a.cd23[(size_t)i * 2 * Z + Z + j] : 0.f;
-    }
-    __syncthreads();
-    const uint32_t n = min((uint32_t)TI, i1 - t0);
-    for (uint32_t t = 0; t < n; ++t) {
-      const uint32_t i = t0 + t;
-      const float d4 = hv ? a.d4[(size_t)i * H + h] : 0.f;                                   // already c * delta4
-      const float h1 = hv ? a.h1_hi[(size_t)i * H + h] + a.h1_lo[(size_t)i * H + h] : 0.f;
-      b4 += d4;
-#pragma unroll
-      for (int j = 0; j < ZP; ++j) {
-        w4[j] = fmaf(zt[t][j], d4, w4[j]);
-        w2[j] = fmaf(h1, c2[t][j], w2[j]);
-        w3[j] = fmaf(h1, c3[t][j], w3[j]);
-      }
-      if (blockIdx.y == 0) {
-        if (threadIdx.x < 2 * Z) b23 += a.cd23[(size_t)i * 2 * Z + threadIdx.x];
-        if (threadIdx.x == 127) { ls += a.lossv[i]; cn += a.cnt[i]; }
-      }
-    }
+// loss / count columns of the partial rows: slab s = a contiguous range of examples, summed in a fixed order
+__global__ void __launch_bounds__(256) vae_loss_kernel(VaeArgs a) {
+  __shared__ float red[2][8];
+  const uint32_t per = (a.Bl + a.S - 1) / a.S;
+  const uint32_t i0 = blockIdx.x * per, i1 = min(a.Bl, i0 + per);
+  float ls = 0.f, cn = 0.f;
+  for (uint32_t i = i0 + threadIdx.x; i < i1; i += 256) { ls += a.lossv[i]; cn += a.cnt[i]; }
+  ls = group_sum<32>(ls);
+  cn = group_sum<32>(cn);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ls; red[1][threadIdx.x >> 5] = cn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { l += red[0][w]; c += red[1][w]; }
+    a.partials[(size_t)blockIdx.x * (a.P + 2) + a.P] = l;
+    a.partials[(size_t)blockIdx.x * (a.P + 2) + a.P + 1] = c;
   }
-  float* out = a.thin + (size_t)slab * (T + 2);
-  if (hv) {
-#pragma unroll
-    for (int j = 0; j < ZP; ++j)
-      if ((uint32_t)j < Z) {
-        out[(size_t)j * H + h] = w4[j];
-        out[Z * H + H + (size_t)h * Z + j] = w2[j];
-        out[2 * Z * H + H + Z + (size_t)h * Z + j] = w3[j];
-      }
-    out[Z * H + h] = b4;
-  }
-  if (blockIdx.y == 0) {
-    if (threadIdx.x < Z) out[2 * Z * H + H + threadIdx.x] = b23;
-    else if (threadIdx.x < 2 * Z) out[3 * Z * H + H + Z + (threadIdx.x - Z)] = b23;
-    if (threadIdx.x == 127) { out[T] = ls; out[T + 1] = cn; }
-  }
-}
-
-// thin partials [kThinSlabs, T + 2] -> partial row 0 (fixed order), rows 1..S-1 zero at the thin offsets
-__global__ void vae_thin_reduce_kernel(VaeArgs a) {
-  const uint32_t H = a.H, Z = a.Z;
-  const uint32_t T = 3 * Z * H + H + 2 * Z;
-  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= T + 2) return;
-  float s = 0.f;
-  for (uint32_t k = 0; k < kThinSlabs; ++k) s += a.thin[(size_t)k * (T + 2) + col];
-  uint32_t dst;
-  if (col < Z * H) dst = a.off_w4 + col;
-  else if (col < Z * H + H) dst = a.off_b4 + (col - Z * H);
-  else if (col < 2 * Z * H + H) dst = a.off_w2 + (col - Z * H - H);
-  else if (col < 2 * Z * H + H + Z) dst = a.off_b2 + (col - 2 * Z * H - H);
-  else if (col < 3 * Z * H + H + Z) dst = a.off_w3 + (col - 2 * Z * H - H - Z);
-  else if (col < T) dst = a.off_b3 + (col - 3 * Z * H - H - Z);
-  else dst = a.P + (col - T);
-  a.partials[dst] = s;
-  for (uint32_t r = 1; r < a.S; ++r) a.partials[(size_t)r * (a.P + 2) + dst] = 0.f;
 }
 
 // ---- host --------------------------------------------------------------------------------------------
+constexpr int kHeavyEW = 16;           // epilogue warps of the GEMMs with transcendental epilogues
+constexpr int kThinBN = 64;            // N tile of the two thin clipped-sum GEMMs (N = 2Z and Z + 1)
+
 struct VaeLayout {
   size_t total;
   size_t partials, w1_hi, w1_lo, w5_hi, w5_lo, x_hi, x_lo, flag, h1_hi, h1_lo, h2_hi, h2_lo, ch2_hi, ch2_lo, d5_hi, d5_lo,
-      d4, cd1_hi, cd1_lo, z, u, cd23, sq_x, sq_h1, sq_h2, sq_z, sq_d5, loss_rec, sq_d4, loss_kl, lossv, cnt, thin;
-  uint32_t S, nt_h, nt_d;
+      d4, cd4_hi, cd4_lo, cd1_hi, cd1_lo, z_hi, z_lo, u, cd23_hi, cd23_lo, sq_x, sq_h1, sq_h2, sq_z, sq_d5, loss_rec, sq_d4,
+      loss_kl, lossv, cnt;
+  uint32_t S, ns_h, ns_d;
+  size_t ldx, ldh, ldz, ld23;
 };
 
 static uint32_t vae_splits(uint32_t Bl) {
@@ -545,30 +591,40 @@ static VaeLayout vae_layout(const d3p_vae_desc* d, uint32_t Bl) {
   VaeLayout L;
   const size_t D = d->out_dim, H = d->hidden_dim, Z = d->z_dim, P = d->n_params;
   L.S = vae_splits(Bl);
-  L.nt_h = (uint32_t)((H + kVaeBN - 1) / kVaeBN);
-  L.nt_d = (uint32_t)((D + kVaeBN - 1) / kVaeBN);
+  L.ns_h = (uint32_t)((H + kVaeBN - 1) / kVaeBN) * (kHeavyEW / 4);
+  L.ns_d = (uint32_t)((D + kVaeBN - 1) / kVaeBN) * (kHeavyEW / 4);
+  L.ldx = D + 4; L.ldh = H + 4; L.ldz = (Z + 1 + 3) / 4 * 4; L.ld23 = (2 * Z + 3) / 4 * 4;
   size_t off = 0;
   auto take = [&](size_t floats) { size_t o = off; off += align_up(floats * sizeof(float), 256); return o; };
   L.partials = take((size_t)L.S * (P + 2));
   L.w1_hi = take(D * H); L.w1_lo = take(D * H); L.w5_hi = take(H * D); L.w5_lo = take(H * D);
-  L.x_hi = take((size_t)Bl * (D + 4)); L.x_lo = take((size_t)Bl * (D + 4)); L.flag = take(4);
-  L.h1_hi = take((size_t)Bl * H); L.h1_lo = take((size_t)Bl * H);
+  L.x_hi = take((size_t)Bl * L.ldx); L.x_lo = take((size_t)Bl * L.ldx); L.flag = take(4);
+  L.h1_hi = take((size_t)Bl * L.ldh); L.h1_lo = take((size_t)Bl * L.ldh);
   L.h2_hi = take((size_t)Bl * H); L.h2_lo = take((size_t)Bl * H);
-  L.ch2_hi = take((size_t)Bl * (H + 4)); L.ch2_lo = take((size_t)Bl * (H + 4));
+  L.ch2_hi = take((size_t)Bl * L.ldh); L.ch2_lo = take((size_t)Bl * L.ldh);
   L.d5_hi = take((size_t)Bl * D); L.d5_lo = take((size_t)Bl * D);
-  L.d4 = take((size_t)Bl * H); L.cd1_hi = take((size_t)Bl * H); L.cd1_lo = take((size_t)Bl * H);
-  L.z = take((size_t)Bl * Z); L.u = take((size_t)Bl * Z); L.cd23 = take((size_t)Bl * 2 * Z);
-  L.sq_x = take(Bl); L.sq_h1 = take((size_t)L.nt_h * Bl); L.sq_h2 = take(Bl); L.sq_z = take(Bl);
-  L.sq_d5 = take((size_t)L.nt_d * Bl); L.loss_rec = take((size_t)L.nt_d * Bl); L.sq_d4 = take((size_t)L.nt_h * Bl);
+  L.d4 = take((size_t)Bl * H); L.cd4_hi = take((size_t)Bl * H); L.cd4_lo = take((size_t)Bl * H);
+  L.cd1_hi = take((size_t)Bl * H); L.cd1_lo = take((size_t)Bl * H);
+  L.z_hi = take((size_t)Bl * L.ldz); L.z_lo = take((size_t)Bl * L.ldz); L.u = take((size_t)Bl * Z);
+  L.cd23_hi = take((size_t)Bl * L.ld23); L.cd23_lo = take((size_t)Bl * L.ld23);
+  L.sq_x = take(Bl); L.sq_h1 = take((size_t)L.ns_h * Bl); L.sq_h2 = take(Bl); L.sq_z = take(Bl);
+  L.sq_d5 = take((size_t)L.ns_d * Bl); L.loss_rec = take((size_t)L.ns_d * Bl); L.sq_d4 = take((size_t)L.ns_h * Bl);
   L.loss_kl = take(Bl); L.lossv = take(Bl); L.cnt = take(Bl);
-  L.thin = take((size_t)kThinSlabs * (3 * Z * H + H + 2 * Z + 2));
   L.total = off;
   return L;
 }
 
+static size_t mid_fwd_smem_bytes(uint32_t H, uint32_t Z) {
+  return ((size_t)H * 2 * Z + (size_t)Z * H + 64 + H + (size_t)kMidWarps * kMidE * (H + 3 * 64)) * sizeof(float);
+}
+static size_t mid_bwd_smem_bytes(uint32_t H, uint32_t Z) {
+  return (3 * (size_t)Z * H + (size_t)kMidWarps * kMidE * (H + 128)) * sizeof(float);
+}
+
 static bool vae_supported(const d3p_vae_desc* d) {
   return d && d->out_dim >= 4 && d->hidden_dim >= 4 && d->z_dim >= 1 && d->z_dim <= 32 && (d->out_dim % 4) == 0 &&
-         (d->hidden_dim % 4) == 0;
+         (d->hidden_dim % 4) == 0 && mid_fwd_smem_bytes(d->hidden_dim, d->z_dim) <= 220 * 1024 &&
+         mid_bwd_smem_bytes(d->hidden_dim, d->z_dim) <= 220 * 1024;
 }
 
 }  // namespace d3p
@@ -586,7 +642,8 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
                                       size_t x_row_stride, const int32_t* idx_d, const uint8_t* mask_d,
                                       const int32_t* num_valid_d, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
                                       const uint32_t threefry_key_h[2], float obs_scale, float C, float* px_norms_d,
-                                      float* px_loss_d, void* ws_d, size_t ws_bytes, void* stream) {
+                                      float* px_loss_d, void* ws_d, size_t ws_bytes, void* const* profile_events_h,
+                                      void* stream) {
   if (!desc || !params_d || !x_d || !threefry_key_h || !ws_d) return D3P_ERR_INVALID_ARGUMENT;
   if (!vae_supported(desc)) return D3P_ERR_UNSUPPORTED;
   if (pos_end > B || pos_begin >= pos_end || !(C > 0.f) || !(obs_scale != 0.f)) return D3P_ERR_INVALID_ARGUMENT;
@@ -602,7 +659,7 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   VaeArgs a;
   memset(&a, 0, sizeof(a));
   a.D = D; a.H = H; a.Z = Z; a.B = B; a.Bl = Bl; a.pos_begin = pos_begin;
-  a.ldx = D + 4; a.ldc2 = H + 4;
+  a.ldx = L.ldx; a.ldh = L.ldh; a.ldz = L.ldz; a.ld23 = L.ld23;
   a.params = params_d;
   a.off_w4 = desc->off_w4; a.off_b4 = desc->off_b4; a.off_w5 = desc->off_w5; a.off_b5 = desc->off_b5;
   a.off_w1 = desc->off_w1; a.off_b1 = desc->off_b1; a.off_w2 = desc->off_w2; a.off_b2 = desc->off_b2;
@@ -610,15 +667,15 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   a.x = x_d; a.x_stride = x_row_stride; a.idx = idx_d; a.mask = mask_d; a.num_valid = num_valid_d;
   a.k0 = threefry_key_h[0]; a.k1 = threefry_key_h[1];
   a.site_scale = desc->site_scale; a.inv_S = 1.0f / obs_scale; a.C = C;
-  a.nt_h = L.nt_h; a.nt_d = L.nt_d; a.S = L.S;
+  a.ns_h = L.ns_h; a.ns_d = L.ns_d; a.S = L.S;
   a.x_hi = F(L.x_hi); a.x_lo = F(L.x_lo); a.x_lo_flag = reinterpret_cast<int*>(ws + L.flag);
   a.h1_hi = F(L.h1_hi); a.h1_lo = F(L.h1_lo); a.h2_hi = F(L.h2_hi); a.h2_lo = F(L.h2_lo);
   a.ch2_hi = F(L.ch2_hi); a.ch2_lo = F(L.ch2_lo); a.d5_hi = F(L.d5_hi); a.d5_lo = F(L.d5_lo);
-  a.d4 = F(L.d4); a.cd1_hi = F(L.cd1_hi); a.cd1_lo = F(L.cd1_lo);
-  a.z = F(L.z); a.u = F(L.u); a.cd23 = F(L.cd23);
+  a.d4 = F(L.d4); a.cd4_hi = F(L.cd4_hi); a.cd4_lo = F(L.cd4_lo); a.cd1_hi = F(L.cd1_hi); a.cd1_lo = F(L.cd1_lo);
+  a.z_hi = F(L.z_hi); a.z_lo = F(L.z_lo); a.u = F(L.u); a.cd23_hi = F(L.cd23_hi); a.cd23_lo = F(L.cd23_lo);
   a.sq_x = F(L.sq_x); a.sq_h1 = F(L.sq_h1); a.sq_h2 = F(L.sq_h2); a.sq_z = F(L.sq_z); a.sq_d5 = F(L.sq_d5);
   a.loss_rec = F(L.loss_rec); a.sq_d4 = F(L.sq_d4); a.loss_kl = F(L.loss_kl); a.lossv = F(L.lossv); a.cnt = F(L.cnt);
-  a.thin = F(L.thin); a.partials = F(L.partials);
+  a.partials = F(L.partials);
   a.px_norms = px_norms_d; a.px_loss = px_loss_d;
   float* w1_hi = F(L.w1_hi); float* w1_lo = F(L.w1_lo); float* w5_hi = F(L.w5_hi); float* w5_lo = F(L.w5_lo);
 
@@ -637,12 +694,11 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   // G1: pre1 = X W1  (A = X K-major [Bl, D]; B = W1 stored [K = D, N = H])
   {
     tc::GemmOperand A{a.x_hi, a.x_lo, 0, a.ldx}, Bo{w1_hi, w1_lo, 1, H};
-    EpiFwd1::Args ea{params_d + a.off_b1, a.h1_hi, a.h1_lo, H, a.sq_h1, Bl};
-    if ((rc = tc::launch_tc_gemm<false, true, kVaeBN, EpiFwd1>(A, Bo, Bl, H, D, 1, ea, s, a.x_lo_flag)) != D3P_OK) return rc;
+    EpiFwd1::Args ea{params_d + a.off_b1, a.h1_hi, a.h1_lo, a.ldh, a.sq_h1, Bl};
+    if ((rc = tc::launch_tc_gemm<false, true, kVaeBN, EpiFwd1, kHeavyEW>(A, Bo, Bl, H, D, 1, ea, s, a.x_lo_flag)) != D3P_OK)
+      return rc;
   }
-  const size_t mid_fwd_smem = (size_t)kMidWarps * kMidE * (H + 3 * 64) * sizeof(float);
-  const size_t mid_bwd_smem = (size_t)kMidWarps * kMidE * (2 * H + 2 * 64) * sizeof(float);
-  if (mid_fwd_smem > 200 * 1024 || mid_bwd_smem > 200 * 1024) return D3P_ERR_UNSUPPORTED;
+  const size_t mid_fwd_smem = mid_fwd_smem_bytes(H, Z), mid_bwd_smem = mid_bwd_smem_bytes(H, Z);
   unsigned mid_grid = ((Bl + kMidE - 1) / kMidE + kMidWarps - 1) / kMidWarps;
   if (mid_grid > (unsigned)sms) mid_grid = sms;
   {
@@ -655,13 +711,15 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   {
     tc::GemmOperand A{a.h2_hi, a.h2_lo, 0, H}, Bo{w5_hi, w5_lo, 1, D};
     EpiFwd5::Args ea{params_d + a.off_b5, a.x_hi, a.x_lo, a.ldx, a.d5_hi, a.d5_lo, D, a.sq_d5, a.loss_rec, Bl};
-    if ((rc = tc::launch_tc_gemm<false, true, kVaeBN, EpiFwd5>(A, Bo, Bl, D, H, 1, ea, s, nullptr)) != D3P_OK) return rc;
+    if ((rc = tc::launch_tc_gemm<false, true, kVaeBN, EpiFwd5, kHeavyEW>(A, Bo, Bl, D, H, 1, ea, s, nullptr)) != D3P_OK)
+      return rc;
   }
   // G5b: dh2 = delta5 W5^T  (B[n = h, k = d] = W5[h, d]: K-major)
   {
     tc::GemmOperand A{a.d5_hi, a.d5_lo, 0, D}, Bo{w5_hi, w5_lo, 0, D};
     EpiBwd5::Args ea{a.h2_hi, a.h2_lo, H, a.d4, a.sq_d4, Bl};
-    if ((rc = tc::launch_tc_gemm<false, false, kVaeBN, EpiBwd5>(A, Bo, Bl, H, D, 1, ea, s, nullptr)) != D3P_OK) return rc;
+    if ((rc = tc::launch_tc_gemm<false, false, kVaeBN, EpiBwd5, kHeavyEW>(A, Bo, Bl, H, D, 1, ea, s, nullptr)) != D3P_OK)
+      return rc;
   }
   {
     if (cudaFuncSetAttribute(vae_mid_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_bwd_smem) != cudaSuccess)
@@ -670,28 +728,32 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
     if ((rc = check_launch()) != D3P_OK) return rc;
   }
   // GW1: [X | 1]^T (c delta1) -> dW1 [D, H] and db1; contraction over the batch
+  if (profile_events_h && cudaEventRecord((cudaEvent_t)profile_events_h[0], s) != cudaSuccess) return D3P_ERR_CUDA;
   {
     tc::GemmOperand A{a.x_hi, a.x_lo, 1, a.ldx}, Bo{a.cd1_hi, a.cd1_lo, 1, H};
-    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w1, a.off_b1, H, D, 0};
+    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w1, a.off_b1, H, D, 0, 0, 0, 0};
     if ((rc = tc::launch_tc_gemm<true, true, kVaeBN, EpiGrad>(A, Bo, D + 1, H, Bl, L.S, ea, s, a.x_lo_flag)) != D3P_OK) return rc;
   }
   // GW5: delta5^T [c h2 | c] -> dW5^T (stored [H, D]) and db5
   {
-    tc::GemmOperand A{a.d5_hi, a.d5_lo, 1, D}, Bo{a.ch2_hi, a.ch2_lo, 1, a.ldc2};
-    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w5, a.off_b5, D, H, 1};
+    tc::GemmOperand A{a.d5_hi, a.d5_lo, 1, D}, Bo{a.ch2_hi, a.ch2_lo, 1, a.ldh};
+    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w5, a.off_b5, D, H, 1, 0, 0, 0};
     if ((rc = tc::launch_tc_gemm<true, true, kVaeBN, EpiGrad>(A, Bo, D, H + 1, Bl, L.S, ea, s, nullptr)) != D3P_OK) return rc;
   }
-  // thin clipped sums
+  if (profile_events_h && cudaEventRecord((cudaEvent_t)profile_events_h[1], s) != cudaSuccess) return D3P_ERR_CUDA;
+  // thin clipped sums on the same GEMM kernel:
+  // GW23: [H1 | 1]^T (c [delta2 | delta3]) -> dW2, dW3 [H, Z] and db2, db3
   {
-    dim3 grid(kThinSlabs, (H + 127) / 128);
-    if (Z <= 8) vae_thin_kernel<8><<<grid, 128, 0, s>>>(a);
-    else if (Z <= 16) vae_thin_kernel<16><<<grid, 128, 0, s>>>(a);
-    else if (Z <= 24) vae_thin_kernel<24><<<grid, 128, 0, s>>>(a);
-    else vae_thin_kernel<32><<<grid, 128, 0, s>>>(a);
-    if ((rc = check_launch()) != D3P_OK) return rc;
-    const uint32_t T2 = 3 * Z * H + H + 2 * Z + 2;
-    vae_thin_reduce_kernel<<<(T2 + 255) / 256, 256, 0, s>>>(a);
-    if ((rc = check_launch()) != D3P_OK) return rc;
+    tc::GemmOperand A{a.h1_hi, a.h1_lo, 1, a.ldh}, Bo{a.cd23_hi, a.cd23_lo, 1, a.ld23};
+    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w2, a.off_b2, Z, H, 0, Z, a.off_w3, a.off_b3};
+    if ((rc = tc::launch_tc_gemm<true, true, kThinBN, EpiGrad>(A, Bo, H + 1, 2 * Z, Bl, L.S, ea, s, nullptr)) != D3P_OK) return rc;
   }
-  return D3P_OK;
+  // GW4: (c delta4)^T [z | 1] -> dW4^T (stored [Z, H]) and db4
+  {
+    tc::GemmOperand A{a.cd4_hi, a.cd4_lo, 1, H}, Bo{a.z_hi, a.z_lo, 1, a.ldz};
+    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w4, a.off_b4, H, Z, 1, 0, 0, 0};
+    if ((rc = tc::launch_tc_gemm<true, true, kThinBN, EpiGrad>(A, Bo, H, Z + 1, Bl, L.S, ea, s, nullptr)) != D3P_OK) return rc;
+  }
+  vae_loss_kernel<<<L.S, 256, 0, s>>>(a);
+  return check_launch();
 }

@@ -221,6 +221,7 @@ class VAE(Family):
         self.out_dim, self.hidden_dim, self.z_dim = int(out_dim), int(hidden_dim), int(z_dim)
         self.scaled, self.init_seed, self.init_std = bool(scaled), int(init_seed), float(init_std)
         self.model, self.guide = _Handle(self, "model"), _Handle(self, "guide")
+        self.profile_events = None   # optional (c_void_p * 2): events around the clipped-sum GEMMs (bench.py)
 
     def param_shapes(self):
         D, H, Z = self.out_dim, self.hidden_dim, self.z_dim
@@ -275,7 +276,7 @@ class VAE(Family):
             C.byref(desc), _n.ptr(state.optim_state.flat), _n.ptr(Xsrc), stride, _n.ptr(idx), _n.ptr(mask_t), None, B,
             pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
             float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_loss), _n.ptr(ws_al), need,
-            _n.stream_ptr()), "dpsvi_step_vae")
+            self.profile_events, _n.stream_ptr()), "dpsvi_step_vae")
         if svi.event_hook is not None:
             svi.event_hook("step_end")
         return ws_al, n_part.value, B, desc.n_params

@@ -36,6 +36,12 @@ extern "C" {
 int32_t d3p_abi_version(void);
 const char* d3p_error_string(int32_t code);
 
+/* CUDA events for callers without a CUDA binding (device timing on the launching stream). */
+int32_t d3p_event_create(void** event_out);
+int32_t d3p_event_record(void* event, void* stream);
+int32_t d3p_event_elapsed_ms(void* begin, void* end, float* ms_out); /* synchronises on `end` */
+int32_t d3p_event_destroy(void* event);
+
 /* ------------------------------------------------------------------------------------------
  * ChaCha20 rng suite — replaces jax-chacha-prng behind d3p/random/__init__.py:28-32.
  * ------------------------------------------------------------------------------------------ */
@@ -249,11 +255,13 @@ size_t d3p_vae_workspace_bytes(const d3p_vae_desc* desc, uint32_t batch_rows, ui
 /* Same contract as d3p_dpsvi_step_meanfield: x_d rows are [D] floats (x_row_stride floats apart), read
  * through idx_d when given; positions [pos_begin, pos_end) of a batch of B; per-example Threefry keys by
  * position.  ws_d must be 256-byte aligned.  px_norms_d[B] / px_loss_d[B] (may be NULL) receive the
- * pre-clip gradient norms and obs_scale * loss_p. */
+ * pre-clip gradient norms and obs_scale * loss_p.  profile_events_h (may be NULL) = two events
+ * (d3p_event_create) recorded immediately before and after the two tcgen05 clipped-sum GEMMs. */
 int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
                            const int32_t* idx_d, const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
                            uint32_t pos_begin, uint32_t pos_end, const uint32_t threefry_key_h[2], float obs_scale,
-                           float C, float* px_norms_d, float* px_loss_d, void* ws_d, size_t ws_bytes, void* stream);
+                           float C, float* px_norms_d, float* px_loss_d, void* ws_d, size_t ws_bytes,
+                           void* const* profile_events_h, void* stream);
 
 #ifdef __cplusplus
 }

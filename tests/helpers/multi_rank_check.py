@@ -1,0 +1,71 @@
+"""Run under torchrun with 2+ ranks (one per GPU): a sharded DPSVI step must equal the unsharded one
+(fp32 reassociation) and leave bit-identical replicas.  Used by tests/test_gpu_multi.py."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import d3p_b200.random as rng  # noqa: E402
+from d3p_b200 import minibatch as mb, models, optimizers, parallel, svi as dsvi  # noqa: E402
+
+
+def run(fam, dataset, C, sharded, steps=3):
+    s = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), C, 1.0, num_obs_total=len(dataset[0]))
+    if sharded:
+        parallel.shard_dpsvi(s)
+    init, get = mb.poisson_batchify_data(dataset, 0.05, .99)
+    key = rng.PRNGKey(5)
+    key, k_init, k_fetch = rng.split(key, 3)
+    _, bst = init(k_fetch)
+    batch, mask = get(0, bst)
+    st = s.init(k_init, *batch)
+    losses = []
+    for i in range(steps):
+        batch, mask = get(i, bst)
+        st, loss = s.update(st, *batch, mask=mask)
+        losses.append(float(loss))
+    return st.optim_state.flat.clone(), losses, np.asarray(st.rng_key).copy()
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    g = torch.Generator(device="cuda").manual_seed(0)      # same data on every rank
+    cases = []
+    X = torch.randn((20000, 256), device=dev, generator=g)
+    y = (torch.rand(20000, device=dev, generator=g) < 0.5).to(torch.int32)
+    cases.append(("logreg", models.LogisticRegression(256), (X, y), 1.0))
+    Xg = 1 + 0.1 * torch.randn((20000, 512), device=dev, generator=g)
+    cases.append(("gauss", models.GaussianMean(512), (Xg,), 1.0))
+    Xv = (torch.rand((8000, 8, 8), device=dev, generator=g) < 0.3).float()
+    cases.append(("vae", models.VAE(64, 40, 8, init_std=0.1), (Xv,), 5.0))
+    ok = True
+    for name, fam, data, C in cases:
+        p_sh, l_sh, k_sh = run(fam, data, C, True)
+        p_1, l_1, k_1 = run(fam, data, C, False)
+        err = float((p_sh - p_1).abs().max() / p_1.abs().max())
+        gathered = [torch.empty_like(p_sh) for _ in range(world)]
+        dist.all_gather(gathered, p_sh)
+        same = all(torch.equal(gathered[0], t) for t in gathered)
+        good = err < 1e-5 and same and np.allclose(l_sh, l_1, rtol=2e-5) and np.array_equal(k_sh, k_1)
+        ok = ok and good
+        if rank == 0:
+            print(f"{name}: sharded-vs-single rel err {err:.2e}, replicas identical {same}, losses {l_sh} vs {l_1}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+    if rank == 0:
+        print("MULTI_RANK_OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()
