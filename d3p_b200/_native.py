@@ -31,6 +31,11 @@ class VaeDesc(C.Structure):
                 ("off_w3", C.c_uint32), ("off_b3", C.c_uint32), ("site_scale", C.c_float)]
 
 
+class GmmDesc(C.Structure):
+    _fields_ = [("K", C.c_uint32), ("d", C.c_uint32), ("n_params", C.c_uint32), ("alpha_off", C.c_uint32),
+                ("mus_off", C.c_uint32), ("num_obs_total", C.c_float)]
+
+
 class LeafTable(C.Structure):
     _fields_ = [("n_leaves", C.c_uint32), ("leaf_off", C.c_uint32 * MAX_LEAVES),
                 ("leaf_len", C.c_uint32 * MAX_LEAVES), ("site_state", (C.c_uint32 * 16) * MAX_LEAVES)]
@@ -82,6 +87,9 @@ _SIGNATURES = {
     "d3p_dpsvi_step_vae": (C.c_int32, [C.POINTER(VaeDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
                                        C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, C.c_size_t,
                                        C.POINTER(C.c_void_p), _vp]),
+    "d3p_gmm_workspace_bytes": (C.c_size_t, [C.POINTER(GmmDesc), _u32p]),
+    "d3p_dpsvi_step_gmm": (C.c_int32, [C.POINTER(GmmDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "d3p_split_tf32": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_size_t, _vp]),
     "d3p_gemm_tf32x3": (C.c_int32, [_vp, _vp, C.c_int32, C.c_size_t, _vp, _vp, C.c_int32, C.c_size_t, C.c_uint32,
                                     C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, C.c_size_t,

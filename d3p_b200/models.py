@@ -280,3 +280,54 @@ class VAE(Family):
         if svi.event_hook is not None:
             svi.event_hook("step_end")
         return ws_al, n_part.value, B, desc.n_params
+
+
+class GaussianMixture(Family):
+    """``examples/gaussian_mixture_model.py:51-85`` with the ``d3p.gmm.GaussianMixture`` likelihood
+    (``d3p/gmm.py:71-86``): pis ~ Dir(1), mus ~ N(0, 10), sigs ~ InvGamma(1, 1); guide
+    pis ~ Dir(exp(alpha_log)), mus ~ N(mus_loc, 1), sigs ~ InvGamma(1, 1), every site drawn per
+    example; ``update(state, X)`` with X of shape [B, d] (the example's ``k`` positional argument is
+    the constructor's ``K``)."""
+
+    def __init__(self, K, d):
+        self.K, self.d = int(K), int(d)
+        self.model, self.guide = _Handle(self, "model"), _Handle(self, "guide")
+
+    def param_shapes(self):
+        return {"alpha_log": (self.K,), "mus_loc": (self.K, self.d)}
+
+    def init_params(self):
+        return {k: np.zeros(s, np.float32) for k, s in self.param_shapes().items()}
+
+    def check_args(self, args):
+        if len(args) != 1:
+            raise ValueError("GaussianMixture expects (batch_X,)")
+        if len(args[0].shape) != 2 or args[0].shape[1] != self.d:
+            raise ValueError(f"batch_X must have shape [B, {self.d}]")
+
+    def desc(self, num_obs_total):
+        o = self.offsets()
+        g = _n.GmmDesc()
+        g.K, g.d, g.n_params = self.K, self.d, self.n_params
+        g.alpha_off, g.mus_off = o["alpha_log"], o["mus_loc"]
+        g.num_obs_total = float(num_obs_total)
+        return g
+
+    def run_step(self, svi, state, tf_key, args, mask, B, pos_begin, pos_end, px_norms, px_grads, px_loss):
+        import ctypes as C
+        Xsrc, stride, _, idx, B = svi._resolve_args(args)
+        desc = self.desc(svi._num_obs_total())
+        n_part = C.c_uint32(0)
+        need = _n.lib().d3p_gmm_workspace_bytes(C.byref(desc), C.byref(n_part))
+        ws = svi._workspace(need)
+        mask_t, _ = svi._mask_arg(mask, B)
+        if svi.event_hook is not None:
+            svi.event_hook("step_begin")
+        _n.check(_n.lib().d3p_dpsvi_step_gmm(
+            C.byref(desc), _n.ptr(state.optim_state.flat), _n.ptr(Xsrc), stride, _n.ptr(idx), _n.ptr(mask_t), None, B,
+            pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
+            float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_grads), _n.ptr(px_loss), _n.ptr(ws), need,
+            _n.stream_ptr()), "dpsvi_step_gmm")
+        if svi.event_hook is not None:
+            svi.event_hook("step_end")
+        return ws, n_part.value, B, desc.n_params

@@ -263,6 +263,29 @@ int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* params_d, cons
                            float C, float* px_norms_d, float* px_loss_d, void* ws_d, size_t ws_bytes,
                            void* const* profile_events_h, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused per-example gradient + clip + sum for the Gaussian mixture model of
+ * examples/gaussian_mixture_model.py:51-85 with the d3p.gmm.GaussianMixture likelihood
+ * (d3p/gmm.py:71-86) — replaces d3p/svi.py:238-348.  Guide: pis ~ Dirichlet(exp(alpha_log)),
+ * mus ~ Normal(mus_loc, 1), sigs ~ InverseGamma(1, 1), all drawn per example.
+ * Flat parameter vector (pytree order): alpha_log [K], mus_loc [K, d].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  uint32_t K, d;        /* components, data columns */
+  uint32_t n_params;    /* K + K * d */
+  uint32_t alpha_off, mus_off;
+  float num_obs_total;  /* plate size N */
+} d3p_gmm_desc;
+
+size_t d3p_gmm_workspace_bytes(const d3p_gmm_desc* desc, uint32_t* n_partials_out);
+
+/* Same contract as d3p_dpsvi_step_meanfield (partial rows [n_partials, P + 2] at the start of ws_d). */
+int32_t d3p_dpsvi_step_gmm(const d3p_gmm_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
+                           const int32_t* idx_d, const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                           uint32_t pos_begin, uint32_t pos_end, const uint32_t threefry_key_h[2], float obs_scale,
+                           float C, float* px_norms_d, float* px_grads_d, float* px_loss_d, void* ws_d, size_t ws_bytes,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

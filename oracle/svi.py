@@ -165,7 +165,10 @@ class DPSVI:
         obs_scale = state.observation_scale
         B = np.shape(args[0])[0]
         px_keys = threefry.split(jax_key, B)
-        eps = fam.sample_eps(px_keys)
+        if getattr(fam, "needs_params_for_eps", False):      # e.g. gamma samples drawn at the current alpha
+            eps = fam.sample_eps(px_keys, params)
+        else:
+            eps = fam.sample_eps(px_keys)
 
         if isinstance(mask, bool):
             num_elements = B * mask
