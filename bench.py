@@ -5,7 +5,7 @@ Default workload (config.workload = "c2", BASELINE.json configs[1]): synthetic l
 N = 10M records x d = 1024 float32 (41 GB resident in HBM, >> L2), Poisson sampling q = 0.01
 (max_batch_size = the 0.99 Poisson quantile = 100736), hand-written mean-field guide, Adam(1e-3),
 C = 1, dp_scale = 1.  Other workloads: c1 (N=10k d=8), c3 (Gaussian N=50M d=256, subsample
-B=500k), c5 (VAE 784-400-20, B=4096: tcgen05 clipped-sum GEMMs).
+B=500k), c4 (GMM K=64 d=128 N=20M, Poisson), c5 (VAE 784-400-20, B=4096: tcgen05 clipped-sum GEMMs).
 
 A "step" = `get_batch(i, state)` (sampler kernels) followed by `DPSVI.update(state, *batch,
 mask=mask)` (fused gather / per-example gradient / clip / sum kernel(s) + (NCCL all-reduce at N > 1)
@@ -35,13 +35,14 @@ WORKLOADS = {
     "c1": dict(N=10_000, d=8, q=0.02, family="logreg", C=1.0, sampler="poisson"),
     "c2": dict(N=10_000_000, d=1024, q=0.01, family="logreg", C=1.0, sampler="poisson"),
     "c3": dict(N=50_000_000, d=256, q=0.01, family="gauss", C=1.0, sampler="subsample"),
+    "c4": dict(N=20_000_000, d=128, q=0.01, family="gmm", C=20.0, sampler="poisson", K=64),
     "c5": dict(N=60_000, d=784, q=4096 / 60_000, family="vae", C=10.0, sampler="subsample", batch=4096,
                hidden=400, z=20),
 }
 # algorithmic HBM bytes per example of the dominant kernel
-ALGO_BYTES_PER_EXAMPLE = {"c1": 4 * (8 + 1), "c2": 4 * (1024 + 1), "c3": 4 * 256}
+ALGO_BYTES_PER_EXAMPLE = {"c1": 4 * (8 + 1), "c2": 4 * (1024 + 1), "c3": 4 * 256, "c4": 4 * 128}
 # launches of OUR kernels per step: sampler + step kernel(s) + finalize
-LAUNCHES = {"poisson": 3, "subsample": 1, "logreg": 2, "gauss": 2, "vae": 13}   # vae: 2 split + prep + 7 GEMMs + 2 SIMT + loss (12) + finalize
+LAUNCHES = {"poisson": 3, "subsample": 1, "logreg": 2, "gauss": 2, "gmm": 2, "vae": 13}   # vae: 2 split + prep + 7 GEMMs + 2 SIMT + loss (12) + finalize
 
 
 def measured_peaks():
@@ -125,7 +126,8 @@ def workload_config(name, cfg):
     b = batch_size_of(cfg)
     sampler = (f"Poisson q={cfg['q']} max_batch_size={b}" if cfg["sampler"] == "poisson"
                else f"subsample without replacement batch={b}")
-    model = (f"VAE {cfg['d']}-{cfg['hidden']}-{cfg['z']}" if cfg["family"] == "vae" else f"{cfg['family']} d={cfg['d']}")
+    model = (f"VAE {cfg['d']}-{cfg['hidden']}-{cfg['z']}" if cfg["family"] == "vae" else
+             f"GMM K={cfg['K']} d={cfg['d']}" if cfg["family"] == "gmm" else f"{cfg['family']} d={cfg['d']}")
     return {"workload": f"{name}: synthetic {model} N={cfg['N']} {sampler}",
             "l2_policy": ("inputs larger than L2 (dataset resident in HBM, rows gathered at random)"
                           if cfg["N"] * cfg["d"] * 4 > 2 ** 28 else
@@ -149,6 +151,10 @@ def cpu_port_throughput(cfg, steps, warmup, sample_examples, threads):
     elif cfg["family"] == "gauss":
         fam = families.GaussianMean(d, N)
         args = ((1 + .1 * rs.randn(B, d)).astype(np.float32),)
+    elif cfg["family"] == "gmm":
+        from oracle import gmm as ogmm
+        fam = ogmm.GaussianMixture(cfg["K"], d, N)
+        args = ((3 * rs.randn(B, d)).astype(np.float32),)
     else:
         from oracle import vae as ovae
         fam = ovae.VAE(d, cfg["hidden"], cfg["z"], N)
@@ -166,6 +172,8 @@ def cpu_port_throughput(cfg, steps, warmup, sample_examples, threads):
 
 
 def cpu_sample_size(cfg):
+    if cfg["family"] == "gmm":
+        return 64
     return 256 if cfg["family"] == "vae" else (4096 if cfg["d"] >= 256 else 8192)
 
 
@@ -206,6 +214,12 @@ def make_dataset(cfg, device):
         X = (rng.uniform(kx, (N, 28, 28)) < rng.uniform(kw, (N, 28, 28))).to(torch.float32)
         return (X,)
     X = rng.normal(kx, (N, d))
+    if cfg["family"] == "gmm":      # K-component diagonal mixture: means ~ N(0, 10^2), unit scales
+        centers = rng.normal(kw, (cfg["K"], d)) * 10.0
+        z = rng.randint(ky, (N,), 0, cfg["K"]).to(torch.int64)
+        for lo in range(0, N, 1 << 20):     # in place, chunked: no second copy of the data set
+            X[lo:lo + (1 << 20)] += centers[z[lo:lo + (1 << 20)]]
+        return (X,)
     if cfg["family"] == "gauss":    # x ~ N(1, 0.1^2)  (simple_gaussian_posterior.py:62-65,105)
         X.mul_(0.1).add_(1.0)
         return (X,)
@@ -221,6 +235,8 @@ def make_family(cfg):
         return models.LogisticRegression(cfg["d"])
     if cfg["family"] == "gauss":
         return models.GaussianMean(cfg["d"])
+    if cfg["family"] == "gmm":
+        return models.GaussianMixture(cfg["K"], cfg["d"])
     return models.VAE(cfg["d"], cfg["hidden"], cfg["z"])
 
 
@@ -407,12 +423,17 @@ def run_b200(args, cfg):
         else:
             algo_bytes = ALGO_BYTES_PER_EXAMPLE[args.workload] * per_rank_examples
             achieved = algo_bytes / (kern_ms_avg * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": "meanfield_step_vec_kernel" if cfg["d"] >= 256 else "meanfield_step_kernel",
+            kname = ("gmm_step_kernel" if cfg["family"] == "gmm" else
+                     "meanfield_step_vec_kernel" if cfg["d"] >= 256 else "meanfield_step_kernel")
+            roofline = {"bound": "hbm", "kernel": kname,
                         "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
                         "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(args.workload),
                         "kernel_ms": kern_ms_avg, "kernel_share_of_step": kern_ms_avg / step_ms,
-                        "note": "issue-bound, not HBM-bound: one Threefry-2x32-20 normal per data float "
-                                "(~92 instructions per element, DESIGN.md section 5)"}
+                        "note": ("ALU-bound by the reference's semantics: ~16 k guide variates (8 k gamma rejection "
+                                 "samples at ~10 Threefry calls each) per 512-byte row, DESIGN.md section 6"
+                                 if cfg["family"] == "gmm" else
+                                 "issue-bound, not HBM-bound: one Threefry-2x32-20 normal per data float "
+                                 "(~92 instructions per element, DESIGN.md section 5)")}
         line = {
             "metric": "DPSVI.update examples/sec", "value": value, "unit": "examples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,

@@ -90,6 +90,9 @@ _SIGNATURES = {
     "d3p_gmm_workspace_bytes": (C.c_size_t, [C.POINTER(GmmDesc), _u32p]),
     "d3p_dpsvi_step_gmm": (C.c_int32, [C.POINTER(GmmDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
                                        C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_elbo_evaluate_workspace_bytes": (C.c_size_t, []),
+    "d3p_elbo_evaluate_meanfield": (C.c_int32, [C.POINTER(MeanfieldDesc), _vp, _vp, C.c_size_t, _vp, _vp, C.c_uint32,
+                                                _u32p, _vp, _vp, C.c_size_t, _vp]),
     "d3p_split_tf32": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_size_t, _vp]),
     "d3p_gemm_tf32x3": (C.c_int32, [_vp, _vp, C.c_int32, C.c_size_t, _vp, _vp, C.c_int32, C.c_size_t, C.c_uint32,
                                     C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, C.c_size_t,

@@ -286,6 +286,17 @@ int32_t d3p_dpsvi_step_gmm(const d3p_gmm_desc* desc, const float* params_d, cons
                            float C, float* px_norms_d, float* px_grads_d, float* px_loss_d, void* ws_d, size_t ws_bytes,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * DPSVI.evaluate (d3p/svi.py:436-449 -> numpyro SVI.evaluate) for the mean-field families: the
+ * non-private loss -(log p(theta) + (N / B) sum_i log p(x_i | theta) - log q(theta)) of a whole batch
+ * with one guide sample drawn from threefry_key_h (= jax.random.split(jax_key)[1]).  loss_d[1].
+ * ------------------------------------------------------------------------------------------ */
+size_t d3p_elbo_evaluate_workspace_bytes(void);
+int32_t d3p_elbo_evaluate_meanfield(const d3p_meanfield_desc* desc, const float* params_d, const float* x_d,
+                                    size_t x_row_stride, const int32_t* y_d, const int32_t* idx_d, uint32_t B,
+                                    const uint32_t threefry_key_h[2], float* loss_d, void* ws_d, size_t ws_bytes,
+                                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -298,3 +298,28 @@ def test_perturbation_function_and_apply_gradient(cuda):
             ost = oopt.update(g, ost)
         for k in p:
             assert_close(opt.get_params(st.optim_state)[k], oopt.get_params(ost)[k], what=k)
+
+
+@pytest.mark.parametrize("kind,d,guide", [("logreg", 8, "hand"), ("logreg", 37, "auto"), ("gauss", 256, "hand"),
+                                          ("gauss", 12, "auto")])
+def test_evaluate_matches_oracle(cuda, kind, d, guide):
+    """DPSVI.evaluate (d3p/svi.py:436-449): one guide sample for the whole batch, plate scale N / B."""
+    from d3p_b200 import models, optimizers, svi
+    from oracle import families as ofam_mod
+    N, B = 5000, 77
+    rs = np.random.RandomState(4)
+    X = rs.randn(B, d).astype(np.float32)
+    if kind == "logreg":
+        y = (rs.rand(B) < .5).astype(np.int32)
+        args, fam, ofam = (X, y), models.LogisticRegression(d, guide=guide), ofam_mod.LogisticRegression(d, N, guide=guide)
+    else:
+        args, fam, ofam = (X,), models.GaussianMean(d, guide=guide), ofam_mod.GaussianMean(d, N, guide=guide)
+    p0 = {k: np.asarray(rs.randn(*np.shape(v)) * 0.3, dtype=np.float32) for k, v in ofam.init_params().items()}
+    o = osvi.DPSVI(ofam, None, osvi.Adam(1e-3), None, 1.0, 1.0)
+    s = svi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), 1.0, 1.0, num_obs_total=N)
+    key = chacha.PRNGKey(9)
+    ost = o.init(key, *args, params=p0)
+    st = s.init(key, *[torch.as_tensor(a).cuda() for a in args], params=p0)
+    want = o.evaluate(ost, *args)
+    got = float(s.evaluate(st, *[torch.as_tensor(a).cuda() for a in args]))
+    assert np.isclose(got, want, rtol=2e-5), (got, want)
