@@ -120,22 +120,23 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
   }
 }
 
-// Large-P variant (VAE: P = 652 824, few partial rows): one WARP per 512 consecutive elements of one
-// leaf = 32 ChaCha blocks, one per lane, so every keystream block is computed once (finalize_kernel
-// recomputes the block for each of its 16 elements: fine at P ~ 2 k, 90 us at P ~ 650 k).  The
-// keystream is transposed through shared memory so that all global accesses stay coalesced.  Same
-// arithmetic; the partial rows are summed in row order 0, 1, 2, ... (deterministic).
-struct ChunkTable { uint32_t n_chunks; uint32_t chunk_start[D3P_MAX_LEAVES + 1]; };
+// Large-P variant (VAE: P = 652 824, few partial rows).  finalize_kernel recomputes a whole ChaCha block
+// (~1000 instructions) for each of its 16 elements: fine at P ~ 2 k, 90 us at P ~ 650 k.  Here FOUR lanes
+// cooperate on one block, each holding one column of the 4 x 4 state (column round = local quarter round,
+// diagonal round = rotate rows 1-3 across the 4 lanes with shuffles), and then finalize the 4 elements whose
+// keystream words they hold.  Same arithmetic as finalize_kernel; partial rows are summed in row order.
+struct ChunkTable { uint32_t n_chunks; uint32_t chunk_start[D3P_MAX_LEAVES + 1]; };   // chunk = one 16-element block
 
-__global__ void __launch_bounds__(kFinThreads) finalize_block_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites,
-                                                                     ChunkTable ct) {
-  __shared__ float red[2][kFinThreads / 32];
+D3P_D void quad_qr(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) { D3P_QR(a, b, c, d) }
+
+__global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites,
+                                                            ChunkTable ct) {
+  __shared__ float red[2][8];
   __shared__ float s_n, s_loss;
-  __shared__ uint32_t s_ks[kFinThreads / 32][32 * 17];
   const uint32_t stride = a.P + 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float cnt = 0.f, loss = 0.f;
-  for (uint32_t p = threadIdx.x; p < a.n_partials; p += kFinThreads) {
+  for (uint32_t p = threadIdx.x; p < a.n_partials; p += 256) {
     loss += a.partials[(size_t)p * stride + a.P];
     cnt += a.partials[(size_t)p * stride + a.P + 1];
   }
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_block_kernel(FinalizeArg
   if (threadIdx.x == 0) {
     float c = 0.f, l = 0.f;
 #pragma unroll
-    for (int w = 0; w < kFinThreads / 32; ++w) { c += red[0][w]; l += red[1][w]; }
+    for (int w = 0; w < 8; ++w) { c += red[0][w]; l += red[1][w]; }
     s_n = c; s_loss = l;
   }
   __syncthreads();
@@ -159,67 +160,74 @@ __global__ void __launch_bounds__(kFinThreads) finalize_block_kernel(FinalizeArg
     a.stats[1] = n;
     a.stats[2] = f;
   }
-  const uint32_t chunk = blockIdx.x * (kFinThreads / 32) + warp;
-  if (chunk >= ct.n_chunks) return;                      // warp-uniform
+  const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t chunk = t >> 2, q = t & 3;
+  const bool live = chunk < ct.n_chunks;                  // uniform per 4-lane group; shuffles stay full-warp
   uint32_t leaf = 0;
 #pragma unroll 1
   for (uint32_t l = 1; l < leaves.n_leaves; ++l)
-    if (chunk >= ct.chunk_start[l]) leaf = l;
-  const uint32_t c0 = chunk - ct.chunk_start[leaf];      // chunk index inside the leaf
-  const uint32_t len = leaves.len[leaf], off = leaves.off[leaf];
-  {
-    uint32_t ks[16];
-    chacha20_block(sites.w[leaf], sites.w[leaf][12] + c0 * 32 + lane, ks);
+    if (live && chunk >= ct.chunk_start[l]) leaf = l;
+  const uint32_t b = live ? chunk - ct.chunk_start[leaf] : 0u;
+  // column q of the state: rows 0..3
+  const uint32_t i0 = sites.w[leaf][q], i1 = sites.w[leaf][4 + q], i2 = sites.w[leaf][8 + q];
+  const uint32_t i3 = (q == 0) ? sites.w[leaf][12] + b : sites.w[leaf][12 + q];
+  uint32_t x0 = i0, x1 = i1, x2 = i2, x3 = i3;
+  const int base = lane & ~3;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s_ks[warp][lane * 17 + i] = ks[i];
+  for (int r = 0; r < 10; ++r) {
+    quad_qr(x0, x1, x2, x3);                              // column round
+    x1 = __shfl_sync(0xffffffffu, x1, base + ((q + 1) & 3));
+    x2 = __shfl_sync(0xffffffffu, x2, base + ((q + 2) & 3));
+    x3 = __shfl_sync(0xffffffffu, x3, base + ((q + 3) & 3));
+    quad_qr(x0, x1, x2, x3);                              // diagonal round
+    x1 = __shfl_sync(0xffffffffu, x1, base + ((q + 3) & 3));
+    x2 = __shfl_sync(0xffffffffu, x2, base + ((q + 2) & 3));
+    x3 = __shfl_sync(0xffffffffu, x3, base + ((q + 1) & 3));
   }
-  __syncwarp();
+  const uint32_t ks[4] = {x0 + i0, x1 + i1, x2 + i2, x3 + i3};   // keystream words q, 4 + q, 8 + q, 12 + q
+  if (!live) return;
+  const uint32_t len = leaves.len[leaf], off = leaves.off[leaf];
   const float t1 = (float)(a.step + 1);
   const float bc1 = 1.0f - powf(a.b1, t1), bc2 = 1.0f - powf(a.b2, t1);
   const float* __restrict__ parts = a.partials;
   float* __restrict__ prm = a.params;
   float* __restrict__ pm = a.m;
   float* __restrict__ pv = a.v;
-  // 4 elements per lane and pass: all their loads are issued before the first dependent use
-#pragma unroll 1
-  for (int i0 = 0; i0 < 16; i0 += 4) {
-    float sum[4], x[4], m0[4], v0[4];
-    uint32_t jj[4];
-    bool ok[4];
+  float sum[4], x[4], m0[4], v0[4];
+  uint32_t jj[4];
+  bool ok[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const uint32_t e = c0 * 512 + (i0 + t) * 32 + lane;   // element inside the leaf
-      ok[t] = e < len;
-      jj[t] = off + (ok[t] ? e : 0u);
-      sum[t] = 0.f;
-      x[t] = (ok[t] && a.opt_kind != D3P_OPT_NONE) ? prm[jj[t]] : 0.f;
-      m0[t] = (ok[t] && a.opt_kind == D3P_OPT_ADAM) ? pm[jj[t]] : 0.f;
-      v0[t] = (ok[t] && a.opt_kind == D3P_OPT_ADAM) ? pv[jj[t]] : 0.f;
-    }
-    for (uint32_t p = 0; p < a.n_partials; ++p) {
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t e = b * 16 + 4 * i + q;
+    ok[i] = e < len;
+    jj[i] = off + (ok[i] ? e : 0u);
+    sum[i] = 0.f;
+    x[i] = (ok[i] && a.opt_kind != D3P_OPT_NONE) ? prm[jj[i]] : 0.f;
+    m0[i] = (ok[i] && a.opt_kind == D3P_OPT_ADAM) ? pm[jj[i]] : 0.f;
+    v0[i] = (ok[i] && a.opt_kind == D3P_OPT_ADAM) ? pv[jj[i]] : 0.f;
+  }
+  for (uint32_t p = 0; p < a.n_partials; ++p) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) sum[t] += ok[t] ? parts[(size_t)p * stride + jj[t]] : 0.f;
-    }
+    for (int i = 0; i < 4; ++i) sum[i] += ok[i] ? parts[(size_t)p * stride + jj[i]] : 0.f;
+  }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (!ok[t]) continue;
-      const uint32_t j = jj[t];
-      const uint32_t bits = s_ks[warp][(2 * (i0 + t) + (lane >> 4)) * 17 + (lane & 15)];
-      float g = __fdiv_rn(sum[t], Bf);
-      g = __fadd_rn(g, __fmul_rn(bits_to_normal<false>(bits), sigma));
-      g = __fmul_rn(__fmul_rn(g, a.obs_scale), f);
-      if (a.grad_out) a.grad_out[j] = g;
-      if (a.opt_kind == D3P_OPT_SGD) {
-        prm[j] = x[t] - a.step_size * g;
-      } else if (a.opt_kind == D3P_OPT_ADAM) {
-        float m = (1.0f - a.b1) * g + a.b1 * m0[t];
-        float v = (1.0f - a.b2) * (g * g) + a.b2 * v0[t];
-        float mhat = m / bc1;
-        float vhat = v / bc2;
-        prm[j] = x[t] - a.step_size * mhat / (sqrtf(vhat) + a.eps);
-        pm[j] = m;
-        pv[j] = v;
-      }
+  for (int i = 0; i < 4; ++i) {
+    if (!ok[i]) continue;
+    const uint32_t j = jj[i];
+    float g = __fdiv_rn(sum[i], Bf);
+    g = __fadd_rn(g, __fmul_rn(bits_to_normal<false>(ks[i]), sigma));
+    g = __fmul_rn(__fmul_rn(g, a.obs_scale), f);
+    if (a.grad_out) a.grad_out[j] = g;
+    if (a.opt_kind == D3P_OPT_SGD) {
+      prm[j] = x[i] - a.step_size * g;
+    } else if (a.opt_kind == D3P_OPT_ADAM) {
+      float m = (1.0f - a.b1) * g + a.b1 * m0[i];
+      float v = (1.0f - a.b2) * (g * g) + a.b2 * v0[i];
+      float mhat = m / bc1;
+      float vhat = v / bc2;
+      prm[j] = x[i] - a.step_size * mhat / (sqrtf(vhat) + a.eps);
+      pm[j] = m;
+      pv[j] = v;
     }
   }
 }
@@ -301,14 +309,13 @@ extern "C" int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_
     uint32_t nc = 0;
     for (uint32_t l = 0; l < lt.n_leaves; ++l) {
       ct.chunk_start[l] = nc;
-      nc += (lt.len[l] + 511) / 512;
+      nc += (lt.len[l] + 15) / 16;
       covered += lt.len[l];
     }
     ct.chunk_start[lt.n_leaves] = nc;
     ct.n_chunks = nc;
     if (covered == P && nc > 0) {
-      const unsigned wpb = kFinThreads / 32;
-      finalize_block_kernel<<<(nc + wpb - 1) / wpb, kFinThreads, 0, (cudaStream_t)stream>>>(a, lt, ss, ct);
+      finalize_quad_kernel<<<(nc * 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, lt, ss, ct);
       return check_launch();
     }
   }

@@ -39,12 +39,15 @@ template <int BN>
 struct GemmCfg {
   static constexpr uint32_t kABytes = kBM * 128;
   static constexpr uint32_t kBBytes = BN * 128;
-  static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kStages = (int)((220u * 1024u) / kStageBytes) > 4 ? 4 : (int)((220u * 1024u) / kStageBytes);
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;       // with both lo parts present
+  static constexpr int kMaxStages = 6;
+  // ring capacity: as many stages as fit 216 KB; the kernel re-derives the stage count at run time from the
+  // operands that are really present (an absent / all-zero lo part frees its slots for deeper pipelining)
+  static constexpr uint32_t kRingBytes = 216u * 1024u;
+  static constexpr uint32_t kSmemBytes = kRingBytes + 1024;
   static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32, 256]");
-  static_assert(kStages >= 2, "tile too large for a 2-stage pipeline");
+  static_assert(kRingBytes >= 2 * kStageBytes, "tile too large for a 2-stage pipeline");
 };
 
 // EW = number of epilogue warps (multiple of 4): the EW / 4 warps that share a TMEM lane quarter take the
@@ -53,7 +56,7 @@ template <bool A_MN, bool B_MN, int BN, class Epi, int EW = kGemmEpiWarps>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const typename Epi::Args ea) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::kStages;
+  constexpr int STAGES = Cfg::kMaxStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bar_full[STAGES];
@@ -69,6 +72,8 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
   const uint32_t kb_end = kb_begin + base + (split < rem ? 1u : 0u);
   const bool has_a_lo = g.has_a_lo && (g.a_lo_flag == nullptr || __ldg(g.a_lo_flag) != 0);
   const bool has_b_lo = g.has_b_lo != 0;
+  const uint32_t stage_bytes = Cfg::kABytes * (has_a_lo ? 2u : 1u) + Cfg::kBBytes * (has_b_lo ? 2u : 1u);
+  const uint32_t stages = Cfg::kRingBytes / stage_bytes > (uint32_t)STAGES ? (uint32_t)STAGES : Cfg::kRingBytes / stage_bytes;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a_hi);
@@ -78,7 +83,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+      for (uint32_t s = 0; s < stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
       mbar_init(&bar_acc, 1);
       fence_barrier_init();
     }
@@ -90,10 +95,10 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  auto stage_ptr = [&](int s, int which) -> uint8_t* {   // which: 0 a_hi, 1 a_lo, 2 b_hi, 3 b_lo
-    uint8_t* p = smem + (size_t)s * Cfg::kStageBytes;
+  auto stage_ptr = [&](uint32_t s, int which) -> uint8_t* {   // which: 0 a_hi, 1 a_lo, 2 b_hi, 3 b_lo
+    uint8_t* p = smem + (size_t)s * stage_bytes;
     if (which >= 1) p += Cfg::kABytes;
-    if (which >= 2) p += Cfg::kABytes;
+    if (which >= 2 && has_a_lo) p += Cfg::kABytes;
     if (which >= 3) p += Cfg::kBBytes;
     return p;
   };
@@ -103,8 +108,8 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
       const uint32_t tx = Cfg::kABytes * (1 + (has_a_lo ? 1 : 0)) + Cfg::kBBytes * (1 + (has_b_lo ? 1 : 0));
       uint32_t it = 0;
       for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1u;
+        const uint32_t s = it % stages;
+        const uint32_t ph = (it / stages) & 1u;
         mbar_wait(&bar_empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&bar_full[s], tx);
         const int32_t k0 = (int32_t)(kb * kKB);
@@ -140,8 +145,8 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
       constexpr uint32_t a_lt = A_MN ? kLayoutSw128Base32 : kLayoutSw128, b_lt = B_MN ? kLayoutSw128Base32 : kLayoutSw128;
       uint32_t it = 0, accumulate = 0;
       for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1u;
+        const uint32_t s = it % stages;
+        const uint32_t ph = (it / stages) & 1u;
         mbar_wait(&bar_full[s], ph);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));

@@ -151,6 +151,13 @@ struct EpiGrad {   // clipped-sum tile -> partial row `split`: weight block(s) +
       const uint32_t sc = a.split_col ? a.split_col : 0xffffffffu;
       float* p1 = row < a.main ? out + a.w_off + (size_t)row * a.w_ld : out + a.b_off;
       float* p2 = row < a.main ? out + a.w_off2 + (size_t)row * a.w_ld : out + a.b_off2;
+      if (col0 + 32 <= g.N && col0 + 32 <= sc && ((reinterpret_cast<uintptr_t>(p1 + col0) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)      // 128 contiguous bytes per thread
+          *reinterpret_cast<float4*>(p1 + col0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        return;
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const uint32_t col = col0 + j;
