@@ -68,6 +68,28 @@ def test_threefry_layouts():
     assert np.allclose(threefry.batched_normal(s, 9)[2], threefry.normal(s[2], (9,)))
 
 
+def test_threefry_matches_published_jax_outputs():
+    """Pins the legacy (non-partitionable) jax.random layouts and the bits -> uniform -> erf_inv
+    normal transform against outputs printed in JAX's own public documentation (jax <= 0.4.x
+    defaults, the versions d3p supports, setup.py:28,47): the `jax.random` module docs /
+    "Sharp Bits" PRNG section (`PRNGKey(0)`, its split chain and the normals drawn from it) and
+    the quickstart's `random.normal(PRNGKey(0), (10,))`."""
+    k = threefry.PRNGKey(0)
+    assert k.tolist() == [0, 0]
+    assert threefry.split(k).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    assert np.float32(threefry.normal(k, ())) == np.float32(-0.20584226)
+    assert np.float32(threefry.uniform(k, ())) == np.float32(0.41845703)
+    quick = np.array([-0.3721109, 0.26423115, -0.18252768, -0.7368197, -0.44030377, -0.1521442,
+                      -0.67135346, -0.5908641, 0.73168886, 0.5673026], dtype=np.float32)
+    np.testing.assert_allclose(threefry.normal(k, (10,)), quick, rtol=0, atol=6e-8)
+    # "Sharp Bits": key, subkey = split(key); normal(subkey, (1,)) twice in a row
+    k1, sub1 = threefry.split(k)
+    assert np.float32(threefry.normal(sub1, (1,))[0]) == np.float32(-1.2515389)
+    k2, sub2 = threefry.split(k1)
+    assert (k2.tolist(), sub2.tolist()) == ([2384771982, 3928867769], [1278412471, 2182328957])
+    assert np.float32(threefry.normal(sub2, (1,))[0]) == np.float32(-0.58665055)
+
+
 # ------------------------------------------------ statistical tests of tests/test_random.py ----
 def test_uniform_normal_statistics():
     key = chacha.PRNGKey(98734)
