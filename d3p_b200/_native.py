@@ -14,7 +14,7 @@ MAX_LEAVES = 16
 OK = 0
 FAMILY_LOGREG, FAMILY_GAUSS = 0, 1
 LINK_EXP, LINK_SOFTPLUS = 0, 1
-OPT_NONE, OPT_SGD, OPT_ADAM = 0, 1, 2
+OPT_NONE, OPT_SGD, OPT_ADAM, OPT_ADADP = 0, 1, 2, 3
 
 
 class MeanfieldDesc(C.Structure):
@@ -43,7 +43,8 @@ class LeafTable(C.Structure):
 
 class OptimDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("step_size", C.c_float), ("b1", C.c_float), ("b2", C.c_float),
-                ("eps", C.c_float), ("step", C.c_int32)]
+                ("eps", C.c_float), ("step", C.c_int32), ("tol", C.c_float), ("stability_check", C.c_int32),
+                ("lr_d", C.c_void_p), ("err_ws_d", C.c_void_p)]
 
 
 _u32p = C.POINTER(C.c_uint32)
@@ -82,6 +83,8 @@ _SIGNATURES = {
                                              C.c_float, C.c_float, C.c_float, C.c_int32, _vp,
                                              C.POINTER(OptimDesc), _vp, _vp, _vp, _vp,
                                              C.POINTER(C.c_float), _vp]),
+    "d3p_adadp_workspace_floats": (C.c_size_t, [C.c_uint32]),
+    "d3p_adadp_finish_f32": (C.c_int32, [C.POINTER(OptimDesc), C.c_uint32, _vp, _vp, _vp]),
     "d3p_reduce_partials_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "d3p_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.c_uint32, _u32p]),
     "d3p_dpsvi_step_vae": (C.c_int32, [C.POINTER(VaeDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,

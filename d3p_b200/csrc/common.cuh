@@ -80,9 +80,10 @@ D3P_HD void tf_split2(const TfKey& k, TfKey& child0, TfKey& child1) {
 // word m of jax.random.split(K, B) flattened ([B,2] row-major): counts iota(2B) halves.
 D3P_HD uint32_t tf_split_word(const TfKey& K, uint32_t B, uint32_t m) {
   uint32_t y0, y1;
-  if (m < B) { threefry2x32(K, m, m + B, y0, y1); return y0; }
-  threefry2x32(K, m - B, m, y0, y1);
-  return y1;
+  const bool first = m < B;                  // one call either way: counts (j, j + B), j = m mod B
+  const uint32_t j = first ? m : m - B;
+  threefry2x32(K, j, j + B, y0, y1);
+  return first ? y0 : y1;
 }
 
 D3P_HD TfKey tf_example_key(const TfKey& K, uint32_t B, uint32_t p) {
@@ -159,8 +160,13 @@ D3P_D float unit_to_u(uint32_t bits) {
   return fmaf(bits_to_unit_float(bits), 2.0f, D3P_NORMAL_LO);
 }
 
+// 1 - u*u lies in [2^-23, 1]: never denormal, so the .ftz forms are bit-identical to the plain ones
+// and compile to a single MUFU (the non-ftz __log2f adds a denormal guard: FSETP + 2 predicated ops).
+D3P_D float lg2_ftz(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+D3P_D float sqrt_ftz(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 D3P_D float normal_central(float u, float& w_out) {
-  const float l2 = __log2f(fmaf(-u, u, 1.0f));
+  const float l2 = lg2_ftz(fmaf(-u, u, 1.0f));
   w_out = l2;                                            // w = -ln2 * l2 ; tail iff w >= 5
   const float w = fmaf(l2, -0.693147182f, -2.5f);
   float p = 2.81022636e-08f * D3P_SQRT2;
@@ -179,7 +185,7 @@ D3P_D float normal_central(float u, float& w_out) {
 #define D3P_TAIL_L2 (-7.21347523f)
 
 D3P_D float normal_tail(float u, float l2) {
-  const float w = __fsqrt_rn(l2 * -0.693147182f) - 3.0f;
+  const float w = sqrt_ftz(l2 * -0.693147182f) - 3.0f;   // MUFU.SQRT: <= 2 ulp in w, tail variates only
   float p = -0.000200214257f * D3P_SQRT2;
   p = fmaf(p, w, 0.000100950558f * D3P_SQRT2);
   p = fmaf(p, w, 0.00134934322f * D3P_SQRT2);

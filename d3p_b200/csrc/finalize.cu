@@ -28,7 +28,24 @@ struct FinalizeArgs {
   float* stats;
   int use_override;
   float n_override, f_override;
+  const float* lr;     // ADADP: device step size
+  float* err_ws;       // ADADP odd steps: [0] = number of CTA partials, [1 + cta] = partial error sums
 };
+
+// d3p/optimizers.py:58-70 (even step) and :72-78,108 (odd step, before the accept/reject decision taken by
+// adadp_finish_kernel).  m = x_stepped, v = x_prev.  Returns this element's squared error term (odd steps).
+D3P_D float adadp_element(const FinalizeArgs& a, float lr, uint32_t j, float x, float g) {
+  const float new_x = x - (0.5f * lr) * g;
+  a.params[j] = new_x;
+  if ((a.step & 1) == 0) {
+    a.v[j] = x;
+    a.m[j] = x - lr * g;
+    return 0.f;
+  }
+  const float xs = a.m[j];
+  const float e = __fdiv_rn(xs - new_x, fmaxf(1.0f, xs));
+  return e * e;
+}
 
 constexpr int kFinThreads = 128;
 
@@ -83,7 +100,10 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
   }
   colred[warp][lane] = part;
   __syncthreads();
-  if (warp != 0 || j >= a.P) return;
+  if (warp != 0) return;
+  const bool live = j < a.P;
+  float err2 = 0.f;
+  if (live) {
   float sum = 0.f;
 #pragma unroll
   for (int w = 0; w < kFinThreads / 32; ++w) sum += colred[w][lane];
@@ -117,6 +137,16 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
     a.params[j] = a.params[j] - a.step_size * mhat / (sqrtf(vhat) + a.eps);
     a.m[j] = m;
     a.v[j] = v;
+  } else if (a.opt_kind == D3P_OPT_ADADP) {
+    err2 = adadp_element(a, *a.lr, j, a.params[j], g);
+  }
+  }
+  if (a.opt_kind == D3P_OPT_ADADP && (a.step & 1)) {
+    err2 = group_sum<32>(err2);
+    if (lane == 0) {
+      a.err_ws[1 + blockIdx.x] = err2;
+      if (blockIdx.x == 0) a.err_ws[0] = (float)gridDim.x;
+    }
   }
 }
 
@@ -185,7 +215,9 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
     x3 = __shfl_sync(0xffffffffu, x3, base + ((q + 1) & 3));
   }
   const uint32_t ks[4] = {x0 + i0, x1 + i1, x2 + i2, x3 + i3};   // keystream words q, 4 + q, 8 + q, 12 + q
-  if (!live) return;
+  const bool adadp_odd = a.opt_kind == D3P_OPT_ADADP && (a.step & 1);
+  float err2 = 0.f;
+  if (live) {
   const uint32_t len = leaves.len[leaf], off = leaves.off[leaf];
   const float t1 = (float)(a.step + 1);
   const float bc1 = 1.0f - powf(a.b1, t1), bc2 = 1.0f - powf(a.b2, t1);
@@ -193,6 +225,7 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
   float* __restrict__ prm = a.params;
   float* __restrict__ pm = a.m;
   float* __restrict__ pv = a.v;
+  const float lr_adadp = (a.opt_kind == D3P_OPT_ADADP) ? *a.lr : 0.f;
   float sum[4], x[4], m0[4], v0[4];
   uint32_t jj[4];
   bool ok[4];
@@ -203,6 +236,7 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
     jj[i] = off + (ok[i] ? e : 0u);
     sum[i] = 0.f;
     x[i] = (ok[i] && a.opt_kind != D3P_OPT_NONE) ? prm[jj[i]] : 0.f;
+
     m0[i] = (ok[i] && a.opt_kind == D3P_OPT_ADAM) ? pm[jj[i]] : 0.f;
     v0[i] = (ok[i] && a.opt_kind == D3P_OPT_ADAM) ? pv[jj[i]] : 0.f;
   }
@@ -228,8 +262,50 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
       prm[j] = x[i] - a.step_size * mhat / (sqrtf(vhat) + a.eps);
       pm[j] = m;
       pv[j] = v;
+    } else if (a.opt_kind == D3P_OPT_ADADP) {
+      err2 += adadp_element(a, lr_adadp, j, x[i], g);
     }
   }
+  }
+  if (adadp_odd) {                                              // fixed-order CTA sum of the error terms
+    err2 = group_sum<32>(err2);
+    if (lane == 0) red[0][warp] = err2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float e = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) e += red[0][w];
+      a.err_ws[1 + blockIdx.x] = e;
+      if (blockIdx.x == 0) a.err_ws[0] = (float)gridDim.x;
+    }
+  }
+}
+
+// ADADP odd step, second half (d3p/optimizers.py:80-99): every CTA adds the error partials in the same
+// order, so all of them take the same accept/reject decision; CTA 0 also updates the step size.
+__global__ void __launch_bounds__(256) adadp_finish_kernel(const float* __restrict__ err_ws, float* lr, float tol,
+                                                           int stability_check, float* __restrict__ params,
+                                                           const float* __restrict__ x_prev, uint32_t P) {
+  __shared__ float red[8];
+  __shared__ float s_err;
+  const uint32_t n = (uint32_t)err_ws[0];
+  float part = 0.f;
+  for (uint32_t p = threadIdx.x; p < n; p += 256) part += err_ws[1 + p];
+  part = group_sum<32>(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float e = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) e += red[w];
+    s_err = sqrtf(e);
+  }
+  __syncthreads();
+  const float err = s_err;
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    *lr = *lr * fminf(fmaxf(sqrtf(__fdiv_rn(tol, err)), 0.9f), 1.1f);
+  if (!(stability_check && err > tol)) return;
+  for (uint32_t j = blockIdx.x * 256 + threadIdx.x; j < P; j += gridDim.x * 256) params[j] = x_prev[j];
 }
 
 // out[j] = sum_p partials[p][j] for j < row_len, fixed order (warp w adds rows w, w+4, ...).
@@ -287,7 +363,12 @@ extern "C" int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_
   a.f_override = nf_override_h ? nf_override_h[1] : 0.f;
   if (a.opt_kind != D3P_OPT_NONE && !params_d) return D3P_ERR_INVALID_ARGUMENT;
   if (a.opt_kind == D3P_OPT_ADAM && (!m_d || !v_d)) return D3P_ERR_INVALID_ARGUMENT;
-  if (a.opt_kind != D3P_OPT_NONE && a.opt_kind != D3P_OPT_SGD && a.opt_kind != D3P_OPT_ADAM) return D3P_ERR_UNSUPPORTED;
+  a.lr = nullptr; a.err_ws = nullptr;
+  if (a.opt_kind == D3P_OPT_ADADP) {
+    if (!m_d || !v_d || !optim_h->lr_d || !optim_h->err_ws_d || a.step < 0) return D3P_ERR_INVALID_ARGUMENT;
+    a.lr = optim_h->lr_d; a.err_ws = optim_h->err_ws_d;
+  }
+  if (a.opt_kind < D3P_OPT_NONE || a.opt_kind > D3P_OPT_ADADP) return D3P_ERR_UNSUPPORTED;
   LeafTable lt;
   SiteStates ss;
   memset(&lt, 0, sizeof(lt));
@@ -321,5 +402,19 @@ extern "C" int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_
   }
   unsigned grid = P ? (P + 31) / 32 : 1;
   finalize_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(a, lt, ss);
+  return check_launch();
+}
+
+extern "C" size_t d3p_adadp_workspace_floats(uint32_t P) { return (size_t)(P + 31) / 32 + 2; }
+
+extern "C" int32_t d3p_adadp_finish_f32(const d3p_optim_desc* optim_h, uint32_t P, float* params_d,
+                                        const float* x_prev_d, void* stream) {
+  if (!optim_h || optim_h->kind != D3P_OPT_ADADP || !optim_h->lr_d || !optim_h->err_ws_d || !params_d || !x_prev_d)
+    return D3P_ERR_INVALID_ARGUMENT;
+  unsigned grid = (P + 255) / 256;
+  if (grid == 0) grid = 1;
+  if (grid > 1184) grid = 1184;
+  adadp_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(optim_h->err_ws_d, optim_h->lr_d, optim_h->tol,
+                                                              optim_h->stability_check, params_d, x_prev_d, P);
   return check_launch();
 }

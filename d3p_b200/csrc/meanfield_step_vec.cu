@@ -30,11 +30,15 @@ D3P_D void normals8(const TfKey& km, uint32_t q0, uint32_t half, float4& lo, flo
 #undef D3P_CENTRAL
   const float wmin = fminf(fminf(fminf(wl.x, wl.y), fminf(wl.z, wl.w)), fminf(fminf(wh.x, wh.y), fminf(wh.z, wh.w)));
   if (__any_sync(0xffffffffu, wmin <= D3P_TAIL_L2)) {        // warp-uniform, ~58 % of the groups
-#define D3P_TAIL(c)                                              \
-    if (wl.c <= D3P_TAIL_L2) lo.c = normal_tail(ul.c, wl.c);     \
-    if (wh.c <= D3P_TAIL_L2) hi.c = normal_tail(uh.c, wh.c);
+#define D3P_TAIL1(v, u_, w_)                                                        \
+    if (__any_sync(0xffffffffu, w_ <= D3P_TAIL_L2)) {      /* warp-uniform, ~10 % */  \
+      const float tv = normal_tail(u_, w_);                                          \
+      v = (w_ <= D3P_TAIL_L2) ? tv : v;                                              \
+    }
+#define D3P_TAIL(c) D3P_TAIL1(lo.c, ul.c, wl.c) D3P_TAIL1(hi.c, uh.c, wh.c)
     D3P_F4_FOREACH(D3P_TAIL)
 #undef D3P_TAIL
+#undef D3P_TAIL1
   }
 }
 
@@ -109,21 +113,31 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
     const uint32_t base = a.pos_begin + wt * TILE;
     const uint32_t my_p = base + lane;
     bool my_valid = (lane < TILE) && (my_p < a.pos_end) && (my_p < nv) && (!a.mask || a.mask[my_p]);
-    uint32_t my_k0 = 0, my_k1 = 0, my_row = 0;
+    uint32_t my_k0, my_k1, my_row = 0;
     float my_eb = 0.f, my_y = 0.f;
-    if (my_valid) {
-      TfKey kp = tf_example_key(K, a.B, my_p);
-      TfKey model_seed, guide_seed, rng, k_main;
-      tf_split2(kp, model_seed, guide_seed);
-      tf_split2(guide_seed, rng, k_main);
-      my_k0 = k_main.k0; my_k1 = k_main.k1;
+    {
+      // Key chain of example base + (lane & 7): split(K,B)[p] -> split -> guide_seed -> split ->
+      // (rng, k_main) [-> split(rng) -> k_b -> eps_b].  Every level is two independent Threefry
+      // calls ((0,2) and (1,3)); lanes with bit 3 clear / set take one each and swap by shuffle,
+      // so the chain costs 3 (5 with an intercept) calls per tile instead of 6 (9).
+      const uint32_t t8 = lane & 7u, part = (lane >> 3) & 1u;
+      const uint32_t w = tf_split_word(K, a.B, 2u * (base + t8) + part);
+      TfKey kk(__shfl_sync(0xffffffffu, w, t8), __shfl_sync(0xffffffffu, w, t8 + 8u));
+      uint32_t y0, y1;
+      threefry2x32(kk, part, part + 2u, y0, y1);                 // (model_seed, guide_seed)
+      kk = TfKey(__shfl_sync(0xffffffffu, y1, t8), __shfl_sync(0xffffffffu, y1, t8 + 8u));
+      threefry2x32(kk, part, part + 2u, y0, y1);                 // (rng, k_main)
+      my_k0 = __shfl_sync(0xffffffffu, y1, t8);
+      my_k1 = __shfl_sync(0xffffffffu, y1, t8 + 8u);
       if (a.has_b) {
-        TfKey rng2, k_b;
-        tf_split2(rng, rng2, k_b);
-        uint32_t y0, y1;
-        threefry2x32(k_b, 0u, 0u, y0, y1);
+        kk = TfKey(__shfl_sync(0xffffffffu, y0, t8), __shfl_sync(0xffffffffu, y0, t8 + 8u));
+        threefry2x32(kk, part, part + 2u, y0, y1);               // (rng2, k_b)
+        kk = TfKey(__shfl_sync(0xffffffffu, y1, t8), __shfl_sync(0xffffffffu, y1, t8 + 8u));
+        threefry2x32(kk, 0u, 0u, y0, y1);
         my_eb = bits_to_normal_fast(y0);
       }
+    }
+    if (my_valid) {
       my_row = a.idx ? (uint32_t)a.idx[my_p] : my_p;
       if (FAMILY == D3P_FAMILY_LOGREG) my_y = (float)a.y[my_row];
     }

@@ -107,7 +107,7 @@ using namespace d3p;
 
 extern "C" {
 
-int32_t d3p_abi_version(void) { return 2; }
+int32_t d3p_abi_version(void) { return 3; }
 
 // CUDA event helpers so that a host language without a CUDA binding can time kernels on the stream
 // they are launched on (bench.py's roofline block).

@@ -1,5 +1,6 @@
 """``numpyro.optim`` SGD / Adam as used by ``DPSVI._apply_gradient`` (``d3p/svi.py:379-393``;
-Adam(b1=.9, b2=.999, eps=1e-8) in every example, e.g. ``examples/logistic_regression.py:141``).
+Adam(b1=.9, b2=.999, eps=1e-8) in every example, e.g. ``examples/logistic_regression.py:141``)
+and ``d3p.optimizers.ADADP`` (``d3p/optimizers.py:29-131``).
 
 The optimizer state is ``OptimState(step, flat, m, v, layout)``: one flat float32 CUDA vector of
 unconstrained parameters in pytree order plus Adam's moments.  The update itself runs inside the
@@ -19,6 +20,7 @@ class OptimState(NamedTuple):
     m: Optional[torch.Tensor]
     v: Optional[torch.Tensor]
     layout: Any   # [(name, offset, shape)]
+    lr: Optional[torch.Tensor] = None   # ADADP: adaptive step size (0-dim CUDA tensor); m = x_stepped, v = x_prev
 
 
 def _flatten(params, layout, device):
@@ -55,15 +57,22 @@ class _Optim:
         dev = torch.device("cuda", torch.cuda.current_device())
         layout = layout or layout_of(params)
         flat = _flatten(params, layout, dev)
-        m = torch.zeros_like(flat) if self.kind == _n.OPT_ADAM else None
+        m = torch.zeros_like(flat) if self.kind in (_n.OPT_ADAM, _n.OPT_ADADP) else None
         v = torch.zeros_like(flat) if self.kind == _n.OPT_ADAM else None
-        return OptimState(0, flat, m, v, layout)
+        lr = None
+        if self.kind == _n.OPT_ADADP:          # optimizers.py:54-57: (x0, lr, zeros, x0)
+            v = flat.clone()
+            lr = torch.full((), self.step_size, dtype=torch.float32, device=dev)
+        return OptimState(0, flat, m, v, layout, lr)
 
     def get_params(self, state: OptimState):
         return unflatten(state.flat, state.layout)
 
-    def desc(self, step) -> _n.OptimDesc:
+    def desc(self, step, lr=None, n_params=0) -> _n.OptimDesc:
         raise NotImplementedError
+
+    def finish(self, od, flat, x_prev):
+        """Second launch of a step, if the optimizer needs one (ADADP odd steps)."""
 
     def update(self, grads, state: OptimState) -> OptimState:
         """Functional update (a new state is returned, like numpyro's)."""
@@ -75,13 +84,15 @@ class _Optim:
         flat = state.flat.clone()
         m = state.m.clone() if state.m is not None else None
         v = state.v.clone() if state.v is not None else None
+        lr = state.lr.clone() if state.lr is not None else None
         import ctypes as C
         nf = (C.c_float * 2)(1.0, 1.0)
-        od = self.desc(state.step)
+        od = self.desc(state.step, lr, P)
         _n.check(_n.lib().d3p_perturb_finalize_f32(_n.ptr(part), 1, P, 1, None, 0.0, 1.0, 1.0, 0, None, C.byref(od),
                                                    _n.ptr(flat), _n.ptr(m), _n.ptr(v), None, nf, _n.stream_ptr()),
                  "optimizer update")
-        return OptimState(state.step + 1, flat, m, v, state.layout)
+        self.finish(od, flat, v)
+        return OptimState(state.step + 1, flat, m, v, state.layout, lr)
 
 
 class SGD(_Optim):
@@ -90,7 +101,7 @@ class SGD(_Optim):
     def __init__(self, step_size):
         self.step_size = float(step_size)
 
-    def desc(self, step):
+    def desc(self, step, lr=None, n_params=0):
         return _n.OptimDesc(self.kind, self.step_size, 0.0, 0.0, 0.0, int(step))
 
 
@@ -100,5 +111,38 @@ class Adam(_Optim):
     def __init__(self, step_size, b1=0.9, b2=0.999, eps=1e-8):
         self.step_size, self.b1, self.b2, self.eps = float(step_size), float(b1), float(b2), float(eps)
 
-    def desc(self, step):
+    def desc(self, step, lr=None, n_params=0):
         return _n.OptimDesc(self.kind, self.step_size, self.b1, self.b2, self.eps, int(step))
+
+
+class ADADP(_Optim):
+    """``d3p.optimizers.ADADP`` (``d3p/optimizers.py:119-131``): Koskela & Honkela's step-size
+    adaptation.  Two gradient steps form one ADADP iteration: the even one takes half a step and
+    remembers the full step, the odd one takes the second half step, compares both end points,
+    adapts the step size and (``stability_check``) rejects the iteration if they disagree by more
+    than ``tol``.  ``alpha_min`` / ``alpha_max`` are accepted and ignored, as in the reference
+    (``:88-90`` hard-codes 0.9 / 1.1).  State: ``flat`` = x, ``m`` = x_stepped, ``v`` = x_prev,
+    ``lr`` = step size (device scalar: nothing here synchronises with the host)."""
+    kind = _n.OPT_ADADP
+
+    def __init__(self, step_size=1e-3, tol=1.0, stability_check=True, alpha_min=0.9, alpha_max=1.1):
+        self.step_size, self.tol, self.stability_check = float(step_size), float(tol), bool(stability_check)
+        self._ws = None
+
+    def desc(self, step, lr=None, n_params=0):
+        if lr is None:
+            raise ValueError("ADADP needs the state's step-size tensor")
+        self._ensure_ws(int(n_params), lr.device)
+        return _n.OptimDesc(self.kind, self.step_size, 0.0, 0.0, 0.0, int(step), self.tol,
+                            int(self.stability_check), lr.data_ptr(), self._ws.data_ptr())
+
+    def _ensure_ws(self, P, device):
+        need = int(_n.lib().d3p_adadp_workspace_floats(P))
+        if self._ws is None or self._ws.device != device or self._ws.numel() < need:
+            self._ws = torch.zeros(max(need, 1 << 12), dtype=torch.float32, device=device)
+
+    def finish(self, od, flat, x_prev):
+        if od.step & 1:
+            import ctypes as C
+            _n.check(_n.lib().d3p_adadp_finish_f32(C.byref(od), flat.numel(), _n.ptr(flat), _n.ptr(x_prev),
+                                                   _n.stream_ptr()), "ADADP finish")

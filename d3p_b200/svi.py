@@ -304,14 +304,16 @@ class DPSVI:
             new_flat = os_.flat.clone()
             new_m = os_.m.clone() if os_.m is not None else None
             new_v = os_.v.clone() if os_.v is not None else None
+        new_lr = os_.lr if (self.donate_state or os_.lr is None) else os_.lr.clone()
         stats = torch.empty(3, dtype=torch.float32, device=new_flat.device)
         lt = self._leaf_table(os_.layout, k_noise)
-        od = self.optim.desc(os_.step)
+        od = self.optim.desc(os_.step, new_lr, P)
         _n.check(_n.lib().d3p_perturb_finalize_f32(
             _n.ptr(partials), n_part, P, B, C.byref(lt), float(self._dp_scale), float(self._clipping_threshold),
             float(svi_state.observation_scale), 1, None, C.byref(od), _n.ptr(new_flat), _n.ptr(new_m), _n.ptr(new_v),
             _n.ptr(stats), None, _n.stream_ptr()), "perturb_finalize")
-        new_os = OptimState(os_.step + 1, new_flat, new_m, new_v, os_.layout)
+        self.optim.finish(od, new_flat, new_v)
+        new_os = OptimState(os_.step + 1, new_flat, new_m, new_v, os_.layout, new_lr)
         return DPSVIState(new_os, svi_state.rng_key, svi_state.observation_scale), stats[0]
 
     # ---- stage methods (the de-facto API of tests/test_dpsvi.py) --------------------------------

@@ -170,6 +170,7 @@ int32_t d3p_dpsvi_step_meanfield(const d3p_meanfield_desc* desc, const float* pa
 #define D3P_OPT_NONE 0
 #define D3P_OPT_SGD 1
 #define D3P_OPT_ADAM 2
+#define D3P_OPT_ADADP 3 /* d3p.optimizers.ADADP (d3p/optimizers.py:29-131) */
 
 typedef struct {
   uint32_t n_leaves;
@@ -183,7 +184,23 @@ typedef struct {
   float step_size;
   float b1, b2, eps;  /* Adam                                     */
   int32_t step;       /* numpyro optimizer step counter i (>= 0)  */
+  /* ADADP only (d3p/optimizers.py:29-116).  State mapping: params_d = x, m_d = x_stepped,
+   * v_d = x_prev; the adaptive step size lives on the device so that no step synchronises.   */
+  float tol;               /* error tolerance                                                */
+  int32_t stability_check; /* reject the odd step when err > tol (optimizers.py:92-97)       */
+  float* lr_d;             /* device scalar: current step size, updated by d3p_adadp_finish  */
+  float* err_ws_d;         /* device scratch, >= d3p_adadp_workspace_floats(P) floats        */
 } d3p_optim_desc;
+
+/* ADADP needs the global error norm before an odd step can be accepted, so an odd step is two
+ * launches: d3p_perturb_finalize_f32 (kind = D3P_OPT_ADADP, odd `step`) stores the tentative
+ * x - lr/2 * g in params_d and per-CTA partial sums of ((x_stepped - x_new) / max(1, x_stepped))^2
+ * in err_ws_d; d3p_adadp_finish_f32 then adds them in a fixed order, sets
+ * lr *= min(max(sqrt(tol / err), 0.9), 1.1) and, if stability_check and err > tol, restores
+ * params_d = x_prev_d (d3p/optimizers.py:72-99).  Even steps need only the first launch. */
+size_t d3p_adadp_workspace_floats(uint32_t P);
+int32_t d3p_adadp_finish_f32(const d3p_optim_desc* optim_h, uint32_t P, float* params_d, const float* x_prev_d,
+                             void* stream);
 
 /* partials_d is [n_partials, P + 2] (grad sum | loss sum | count).  With n = total count,
  * f = (n == 0 ? 0 : B / n):

@@ -126,6 +126,42 @@ class Adam:
         return i + 1, (nx, nm, nv)
 
 
+class ADADP:
+    """``d3p/optimizers.py:29-116`` (Koskela & Honkela's adaptive step size), state
+    ``(i, (x, lr, x_stepped, x_prev))``.  Quirks kept: the error norm divides by
+    ``max(1, x_stepped)`` (no absolute value, ``:76``) and the step-size factor is clamped to the
+    literal ``[0.9, 1.1]`` whatever ``alpha_min``/``alpha_max`` say (``:88-90``)."""
+
+    def __init__(self, step_size=1e-3, tol=1.0, stability_check=True, alpha_min=0.9, alpha_max=1.1):
+        self.step_size, self.tol = np.float32(step_size), np.float32(tol)
+        self.stability_check = bool(stability_check)
+
+    def init(self, params):
+        x = {k: np.asarray(v, np.float32).copy() for k, v in params.items()}
+        return 0, (x, self.step_size, {k: np.zeros_like(v) for k, v in x.items()}, x)
+
+    def get_params(self, state):
+        return state[1][0]
+
+    def update(self, g, state):
+        i, (x, lr, x_stepped, x_prev) = state
+        lr = np.float32(lr)
+        half = np.float32(0.5) * lr
+        new_x = {k: (x[k] - half * np.asarray(g[k], np.float32)).astype(np.float32) for k in x}
+        if i % 2 == 0:                                                   # optimizers.py:62-70
+            x_stepped = {k: (x[k] - lr * np.asarray(g[k], np.float32)).astype(np.float32) for k in x}
+            return i + 1, (new_x, lr, x_stepped, x)
+        parts = [np.sum(np.square((x_stepped[k] - new_x[k]) / np.maximum(np.float32(1), x_stepped[k])),
+                        dtype=np.float32) for k in sorted(x)]            # :75-78
+        with np.errstate(divide="ignore"):
+            err = np.sqrt(np.sum(np.asarray(parts, np.float32), dtype=np.float32))
+            fac = np.minimum(np.maximum(np.sqrt(self.tol / err), np.float32(0.9)), np.float32(1.1))
+        new_lr = np.float32(lr * fac)                                    # :88-90
+        if self.stability_check and err > self.tol:                      # :92-97
+            new_x = x_prev
+        return i + 1, (new_x, new_lr, x_stepped, x_prev)
+
+
 class DPSVI:
     """``model`` is an oracle family (oracle/families.py); guide / per_example_loss are
     accepted for signature parity with ``d3p/svi.py:169-180`` and may be None."""

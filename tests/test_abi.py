@@ -31,7 +31,7 @@ def test_header_symbols_are_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/d3p_b200.h but not exported"
     assert set(declared) == set(_native.EXPORTED_SYMBOLS), "ctypes table out of sync with the header"
-    assert lib.d3p_abi_version() == 2
+    assert lib.d3p_abi_version() == 3
     assert lib.d3p_error_string(-4) == b"workspace too small"
 
 
