@@ -349,6 +349,23 @@ def run_b200(args, cfg):
             gemm_ms.append(lib_events.elapsed(0, 1))
         fam.profile_events = None
 
+    # ---- the same K steps through the C-side epoch driver (row f2): no interpreter between launches ----
+    epoch_line = None
+    if world == 1 and cfg["family"] in ("logreg", "gauss"):
+        base = args.warmup + args.steps + 32
+        state, _ = svi.run_epoch(state, get_batch, bstate, max(args.warmup, 3), first_step=base)
+        sync_all()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        state, ep_stats = svi.run_epoch(state, get_batch, bstate, args.steps, first_step=base + 8)
+        p1.record()
+        sync_all()
+        ep_ms = p0.elapsed_time(p1)
+        epoch_line = {"value": float(ep_stats[:, 1].sum().item()) / (ep_ms * 1e-3), "unit": "examples/s",
+                      "ms_per_step": ep_ms / args.steps,
+                      "note": "DPSVI.run_epoch: the fori_loop(get_batch -> update) of the examples driven by "
+                              "d3p_dpsvi_run_epoch_meanfield (same kernels, host work in C)"}
+
     # ---- end to end through the public API with HOST buffers (rank-local shard at N > 1) -----------
     e2e = None
     if args.e2e:
@@ -446,6 +463,8 @@ def run_b200(args, cfg):
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if epoch_line is not None:
+            line["epoch_driver"] = epoch_line
         if world == 1 and args.cpu_baseline:
             threads = os.cpu_count() or 1
             sample = cpu_sample_size(cfg) // 2

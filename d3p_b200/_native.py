@@ -47,6 +47,13 @@ class OptimDesc(C.Structure):
                 ("lr_d", C.c_void_p), ("err_ws_d", C.c_void_p)]
 
 
+class SamplerDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("q", C.c_float), ("n_records", C.c_uint32), ("batch", C.c_uint32),
+                ("suppress", C.c_int32)]
+
+
+SAMPLER_POISSON, SAMPLER_SUBSAMPLE = 0, 1
+
 _u32p = C.POINTER(C.c_uint32)
 _vp = C.c_void_p
 
@@ -85,6 +92,11 @@ _SIGNATURES = {
                                              C.POINTER(C.c_float), _vp]),
     "d3p_adadp_workspace_floats": (C.c_size_t, [C.c_uint32]),
     "d3p_adadp_finish_f32": (C.c_int32, [C.POINTER(OptimDesc), C.c_uint32, _vp, _vp, _vp]),
+    "d3p_dpsvi_epoch_workspace_bytes": (C.c_size_t, [C.POINTER(MeanfieldDesc), C.POINTER(SamplerDesc)]),
+    "d3p_dpsvi_run_epoch_meanfield": (C.c_int32, [C.POINTER(MeanfieldDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
+                                                  _vp, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
+                                                  C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
+                                                  _vp, _vp, _vp, C.c_size_t, _vp]),
     "d3p_reduce_partials_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "d3p_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.c_uint32, _u32p]),
     "d3p_dpsvi_step_vae": (C.c_int32, [C.POINTER(VaeDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,

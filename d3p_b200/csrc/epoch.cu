@@ -1,0 +1,116 @@
+// Row f2 of the scope table: the whole `fori_loop(fetch -> update)` body of the examples
+// (examples/logistic_regression.py:149-160, README.md:119-126) driven from C for the mean-field
+// families.  One call = n_steps x { fold_in + minibatch sampler, 3-way key split, key conversion,
+// fused per-example-gradient/clip/sum, per-leaf noise keys, finalize (+ ADADP finish) }, queued on one
+// stream with no host synchronisation and no interpreter between the launches.  Host work per step is a
+// handful of ChaCha blocks (<10 us); every device piece is the same entry point DPSVI.update uses, so the
+// parameter trajectory is bit-identical to calling get_batch / update step by step.
+#include <string.h>
+
+#include "common.cuh"
+#include "launch.cuh"
+
+using namespace d3p;
+
+namespace {
+
+struct EpochWs {
+  uint8_t* base;
+  size_t poisson_bytes, step_bytes, total;
+  uint8_t* poisson;   // sampler scratch (Poisson only)
+  int32_t* idx;       // [batch]
+  int32_t* counts;    // [2]
+  uint8_t* mask;      // [batch]
+  float* step;        // [n_partials, P + 2]
+};
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+bool layout_ws(const d3p_meanfield_desc* m, const d3p_sampler_desc* s, void* base, EpochWs& w) {
+  uint32_t n_part = 0;
+  w.step_bytes = d3p_meanfield_workspace_bytes(m, &n_part);
+  if (w.step_bytes == 0) return false;
+  w.poisson_bytes = s->kind == D3P_SAMPLER_POISSON ? d3p_poisson_workspace_bytes(s->n_records) : 0;
+  size_t off = 0;
+  w.base = static_cast<uint8_t*>(base);
+  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  const size_t o_poi = take(w.poisson_bytes), o_idx = take((size_t)s->batch * 4), o_cnt = take(8),
+               o_mask = take(s->batch), o_step = take(w.step_bytes);
+  w.total = off;
+  if (base) {
+    w.poisson = w.base + o_poi;
+    w.idx = reinterpret_cast<int32_t*>(w.base + o_idx);
+    w.counts = reinterpret_cast<int32_t*>(w.base + o_cnt);
+    w.mask = w.base + o_mask;
+    w.step = reinterpret_cast<float*>(w.base + o_step);
+  }
+  return true;
+}
+
+bool sampler_ok(const d3p_sampler_desc* s) {
+  if (!s || s->n_records == 0 || s->batch == 0) return false;
+  if (s->kind == D3P_SAMPLER_POISSON) return s->q >= 0.f && s->q <= 1.f;
+  if (s->kind == D3P_SAMPLER_SUBSAMPLE) return s->batch <= s->n_records;
+  return false;
+}
+
+}  // namespace
+
+extern "C" size_t d3p_dpsvi_epoch_workspace_bytes(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler) {
+  EpochWs w;
+  if (!desc || !sampler_ok(sampler) || !layout_ws(desc, sampler, nullptr, w)) return 0;
+  return w.total;
+}
+
+extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler,
+                                                 const float* x_d, size_t x_row_stride, const int32_t* y_d,
+                                                 const uint32_t batch_key_h[16], uint32_t rng_key_io_h[16],
+                                                 uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
+                                                 float dp_scale, const d3p_leaf_table* leaves_h,
+                                                 d3p_optim_desc* optim_io_h, float* params_d, float* m_d, float* v_d,
+                                                 float* stats_out_d, void* ws_d, size_t ws_bytes, void* stream) {
+  if (!desc || !x_d || !batch_key_h || !rng_key_io_h || !leaves_h || !optim_io_h || !params_d || !ws_d)
+    return D3P_ERR_INVALID_ARGUMENT;
+  if (!sampler_ok(sampler) || leaves_h->n_leaves == 0 || leaves_h->n_leaves > D3P_MAX_LEAVES)
+    return D3P_ERR_INVALID_ARGUMENT;
+  EpochWs w;
+  if (!layout_ws(desc, sampler, ws_d, w)) return D3P_ERR_UNSUPPORTED;
+  if (ws_bytes < w.total) return D3P_ERR_WORKSPACE;
+  const uint32_t B = sampler->batch, P = desc->n_params;
+  uint32_t n_part = 0;
+  d3p_meanfield_workspace_bytes(desc, &n_part);
+  d3p_leaf_table lt = *leaves_h;
+  int32_t rc = D3P_OK;
+  for (uint32_t s = 0; s < n_steps && rc == D3P_OK; ++s) {
+    // ---- get_batch(i, batchifier_state): fold_in, then the index sampler (minibatch.py:103-131,217-237) ----
+    uint32_t bkey[16];
+    if ((rc = d3p_chacha_fold_in_h(batch_key_h, first_step + s, bkey)) != D3P_OK) break;
+    const uint8_t* mask = nullptr;
+    if (sampler->kind == D3P_SAMPLER_POISSON) {
+      rc = d3p_poisson_sample(bkey, sampler->q, sampler->n_records, B, sampler->suppress, w.idx, w.counts, w.mask,
+                              w.poisson, w.poisson_bytes, stream);
+      mask = w.mask;
+    } else {
+      uint32_t rcs[30];
+      if ((rc = d3p_feistel_round_constants_h(bkey, rcs)) != D3P_OK) break;
+      rc = d3p_feistel_sample(rcs, sampler->n_records, 0, B, w.idx, stream);
+    }
+    if (rc != D3P_OK) break;
+    // ---- DPSVI.update (svi.py:395-434) ----------------------------------------------------------------------
+    uint32_t keys[3][16], tf[2];
+    if ((rc = d3p_chacha_split_h(rng_key_io_h, 3, &keys[0][0])) != D3P_OK) break;           // carry, k_grad, k_noise
+    if ((rc = d3p_chacha_random_bits_h(keys[1], 0, tf, 2)) != D3P_OK) break;                // convert_to_jax_rng_key
+    rc = d3p_dpsvi_step_meanfield(desc, params_d, x_d, x_row_stride, y_d, w.idx, mask, nullptr, B, 0, B, tf, obs_scale,
+                                  C, nullptr, nullptr, nullptr, w.step, w.step_bytes, stream);
+    if (rc != D3P_OK) break;
+    if ((rc = d3p_chacha_split_h(keys[2], (int32_t)lt.n_leaves, &lt.site_state[0][0])) != D3P_OK) break;
+    rc = d3p_perturb_finalize_f32(w.step, n_part, P, B, &lt, dp_scale, C, obs_scale, 1, nullptr, optim_io_h, params_d,
+                                  m_d, v_d, stats_out_d ? stats_out_d + 3 * (size_t)s : nullptr, nullptr, stream);
+    if (rc != D3P_OK) break;
+    if (optim_io_h->kind == D3P_OPT_ADADP && (optim_io_h->step & 1))
+      if ((rc = d3p_adadp_finish_f32(optim_io_h, P, params_d, v_d, stream)) != D3P_OK) break;
+    optim_io_h->step += 1;
+    memcpy(rng_key_io_h, keys[0], sizeof(keys[0]));
+  }
+  return rc;
+}

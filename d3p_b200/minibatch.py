@@ -168,6 +168,9 @@ def poisson_batchify_data(dataset, q, max_batch_size, handle_oversized_batch="tr
         num_valid = counts[1:2]
         return tuple(BatchView(a, idxs, num_valid) for a in dataset), mask
 
+    # what DPSVI.run_epoch needs to drive this batchifier from C (d3p_dpsvi_run_epoch_meanfield)
+    get_batch.spec = dict(kind=_n.SAMPLER_POISSON, q=float(np.float32(q)), n_records=num_records,
+                          batch=int(max_batch_size), suppress=suppress, dataset=dataset, rng_suite=rng_suite)
     return init, get_batch
 
 
@@ -197,6 +200,9 @@ def subsample_batchify_data(dataset, batch_size=None, q=None, with_replacement=F
             return batch, torch.ones(batch_size, dtype=torch.bool, device=ret_idx.device)
         return batch
 
+    if not with_replacement:
+        get_batch.spec = dict(kind=_n.SAMPLER_SUBSAMPLE, q=0.0, n_records=num_records, batch=int(batch_size),
+                              suppress=False, dataset=dataset, rng_suite=rng_suite)
     return init, get_batch
 
 

@@ -316,6 +316,64 @@ class DPSVI:
         new_os = OptimState(os_.step + 1, new_flat, new_m, new_v, os_.layout, new_lr)
         return DPSVIState(new_os, svi_state.rng_key, svi_state.observation_scale), stats[0]
 
+    def run_epoch(self, svi_state, get_batch, batchifier_state, num_steps, first_step=0):
+        """The examples' ``lax.fori_loop(first_step, first_step + num_steps, body, state)`` with
+        ``body = lambda i, s: update(s, *get_batch(i, batchifier_state))``
+        (``examples/logistic_regression.py:149-160``): returns ``(new_state, stats)`` where
+        ``stats[num_steps, 3]`` holds ``(loss, n, f)`` per step on the device.
+
+        For the mean-field families fed by ``poisson_batchify_data`` / ``subsample_batchify_data``
+        the whole loop runs inside ``d3p_dpsvi_run_epoch_meanfield`` (no interpreter between
+        launches); the result is bit-identical to the step-by-step calls, which remain the path
+        for everything else (sharded runs, VAE, GMM, custom batchifiers)."""
+        from .models import MeanFieldFamily
+        spec = getattr(get_batch, "spec", None)
+        fused = (spec is not None and isinstance(self.family, MeanFieldFamily) and self.shard is None
+                 and self._rng_suite is strong_rng and spec["rng_suite"] is strong_rng and self.event_hook is None
+                 and num_steps > 0)
+        if not fused:
+            stats = torch.zeros(max(num_steps, 0), 3, dtype=torch.float32, device=_dev())
+            for s in range(num_steps):
+                out = get_batch(first_step + s, batchifier_state)
+                batch, mask = out if (isinstance(out, tuple) and len(out) == 2 and isinstance(out[0], tuple)) else (out, True)
+                svi_state, loss = self.update(svi_state, *batch, mask=mask)
+                stats[s, 0] = loss
+            return svi_state, stats
+        fam = self.family
+        Xsrc, stride, ysrc, _, _ = self._resolve_args(spec["dataset"])
+        desc = fam.desc(self._num_obs_total())
+        sd = _n.SamplerDesc(spec["kind"], spec["q"], spec["n_records"], spec["batch"], 1 if spec["suppress"] else 0)
+        need = _n.lib().d3p_dpsvi_epoch_workspace_bytes(C.byref(desc), C.byref(sd))
+        if need == 0:
+            raise _n.D3PNativeError("unsupported family / sampler configuration for run_epoch")
+        if getattr(self, "_epoch_ws", None) is None or self._epoch_ws.numel() < need or self._epoch_ws.device != _dev():
+            self._epoch_ws = torch.empty(need, dtype=torch.uint8, device=_dev())
+        os_ = svi_state.optim_state
+        if self.donate_state:
+            flat, m, v, lr = os_.flat, os_.m, os_.v, os_.lr
+        else:
+            flat = os_.flat.clone()
+            m = os_.m.clone() if os_.m is not None else None
+            v = os_.v.clone() if os_.v is not None else None
+            lr = os_.lr.clone() if os_.lr is not None else None
+        lt = _n.LeafTable()
+        lt.n_leaves = len(os_.layout)
+        for l, (name, off, shape) in enumerate(os_.layout):
+            lt.leaf_off[l] = off
+            lt.leaf_len[l] = int(np.prod(shape)) if len(shape) else 1
+        od = self.optim.desc(os_.step, lr, desc.n_params)
+        stats = torch.empty(num_steps, 3, dtype=torch.float32, device=_dev())
+        bkey = np.ascontiguousarray(np.asarray(batchifier_state, dtype=np.uint32).reshape(16))
+        rkey = np.array(np.asarray(svi_state.rng_key, dtype=np.uint32).reshape(16), copy=True)
+        u32p = C.POINTER(C.c_uint32)
+        _n.check(_n.lib().d3p_dpsvi_run_epoch_meanfield(
+            C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, _n.ptr(ysrc), bkey.ctypes.data_as(u32p),
+            rkey.ctypes.data_as(u32p), int(first_step), int(num_steps), float(svi_state.observation_scale),
+            float(self._clipping_threshold), float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m),
+            _n.ptr(v), _n.ptr(stats), _n.ptr(self._epoch_ws), need, _n.stream_ptr()), "run_epoch")
+        new_os = OptimState(os_.step + num_steps, flat, m, v, os_.layout, lr)
+        return DPSVIState(new_os, rkey.reshape(np.asarray(svi_state.rng_key).shape), svi_state.observation_scale), stats
+
     # ---- stage methods (the de-facto API of tests/test_dpsvi.py) --------------------------------
     def _compute_per_example_gradients(self, dp_svi_state, step_rng_key, *args, mask=True, **kwargs):
         """``d3p/svi.py:238-308``: materialises the per-example gradients ``[B, *shape]`` per site."""

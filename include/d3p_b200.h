@@ -202,6 +202,39 @@ size_t d3p_adadp_workspace_floats(uint32_t P);
 int32_t d3p_adadp_finish_f32(const d3p_optim_desc* optim_h, uint32_t P, float* params_d, const float* x_prev_d,
                              void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Whole-epoch driver — the `lax.fori_loop(0, num_batches, body)` of
+ * examples/logistic_regression.py:149-160 with body = get_batch(i, batchifier_state) followed by
+ * DPSVI.update (d3p/minibatch.py:103-131,217-237 + d3p/svi.py:395-434), for the mean-field
+ * families.  Queues n_steps steps on `stream` without synchronising; the interpreter is not
+ * involved between launches.  Same kernels and key derivations as the step-by-step calls, so the
+ * trajectory is bit-identical to them.
+ * ------------------------------------------------------------------------------------------ */
+#define D3P_SAMPLER_POISSON 0   /* poisson_batchify_data: q, batch = max_batch_size, suppress */
+#define D3P_SAMPLER_SUBSAMPLE 1 /* subsample_batchify_data(with_replacement=False): batch     */
+
+typedef struct {
+  int32_t kind;       /* D3P_SAMPLER_*                                            */
+  float q;            /* Poisson selection probability                            */
+  uint32_t n_records; /* N                                                        */
+  uint32_t batch;     /* structural batch size B (Poisson: max_batch_size)        */
+  int32_t suppress;   /* Poisson: handle_oversized_batch == 'suppress'            */
+} d3p_sampler_desc;
+
+size_t d3p_dpsvi_epoch_workspace_bytes(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler);
+/* batch_key_h: the batchifier state (the key `init` returned); step i uses fold_in(batch_key, i),
+ * i = first_step .. first_step + n_steps - 1.  rng_key_io_h: DPSVIState.rng_key, advanced in place.
+ * leaves_h: leaf offsets / lengths (site states are derived per step).  optim_io_h->step is advanced.
+ * params_d / m_d / v_d (and optim->lr_d for ADADP) are updated in place.
+ * stats_out_d (may be NULL): [n_steps, 3] = { loss, n, f } of every step. */
+int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler,
+                                      const float* x_d, size_t x_row_stride, const int32_t* y_d,
+                                      const uint32_t batch_key_h[16], uint32_t rng_key_io_h[16],
+                                      uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
+                                      float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h,
+                                      float* params_d, float* m_d, float* v_d, float* stats_out_d, void* ws_d,
+                                      size_t ws_bytes, void* stream);
+
 /* partials_d is [n_partials, P + 2] (grad sum | loss sum | count).  With n = total count,
  * f = (n == 0 ? 0 : B / n):
  *   grad = ((sum / B) + dp_scale * (C / n) * xi) * obs_scale * f     (d3p/svi.py:342-375)

@@ -1,0 +1,123 @@
+"""Row f2: ``DPSVI.run_epoch`` (the C-side ``fori_loop(get_batch -> update)`` driver,
+``d3p_dpsvi_run_epoch_meanfield``) must reproduce the step-by-step calls bit for bit and the
+oracle's trajectory within the fp32 tolerance (examples/logistic_regression.py:149-160)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import chacha, families as ofam, minibatch as omb, svi as osvi
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(kind, sampler, optim, d=12, N=3000):
+    from d3p_b200 import minibatch as mb, models, optimizers, svi
+    rs = np.random.RandomState(7)
+    if kind == "logreg":
+        data = (rs.randn(N, d).astype(np.float32), (rs.rand(N) < .5).astype(np.int32))
+        fam, ofm = models.LogisticRegression(d), ofam.LogisticRegression(d, N)
+    else:
+        data = ((1 + .1 * rs.randn(N, d)).astype(np.float32),)
+        fam, ofm = models.GaussianMean(d), ofam.GaussianMean(d, N)
+    opt = {"adam": lambda: optimizers.Adam(1e-2), "adadp": lambda: optimizers.ADADP(1e-2, tol=.5),
+           "sgd": lambda: optimizers.SGD(1e-3)}[optim]()
+    oopt = {"adam": lambda: osvi.Adam(1e-2), "adadp": lambda: osvi.ADADP(1e-2, tol=.5),
+            "sgd": lambda: osvi.SGD(1e-3)}[optim]()
+    C = 1. if kind == "logreg" else 30.
+    s = svi.DPSVI(fam.model, fam.guide, opt, models.Trace_ELBO(), C, .7, num_obs_total=N)
+    o = osvi.DPSVI(ofm, None, oopt, None, C, .7)
+    if sampler == "poisson":
+        bat, obat = mb.poisson_batchify_data(data, .02, .99), omb.poisson_batchify_data(data, .02, .99)
+    elif sampler == "suppress":
+        bat = mb.poisson_batchify_data(data, .02, 55, handle_oversized_batch="suppress")
+        obat = omb.poisson_batchify_data(data, .02, 55, handle_oversized_batch="suppress")
+    else:
+        bat, obat = mb.subsample_batchify_data(data, batch_size=64), omb.subsample_batchify_data(data, batch_size=64)
+    return s, o, bat, obat
+
+
+@pytest.mark.parametrize("kind,sampler,optim", [("logreg", "poisson", "adam"), ("logreg", "subsample", "adadp"),
+                                                ("gauss", "poisson", "adadp"), ("gauss", "subsample", "sgd"),
+                                                ("logreg", "suppress", "adam")])
+def test_run_epoch_equals_stepwise_and_oracle(cuda, kind, sampler, optim):
+    s, o, (init, get), (oinit, oget) = _setup(kind, sampler, optim)
+    key = chacha.PRNGKey(21)
+    k_init, k_fetch = chacha.split(key, 3)[1:]
+    _, bst = init(k_fetch)
+    _, obst = oinit(k_fetch)
+    first = get(0, bst)
+    batch0 = first[0] if sampler != "subsample" else first
+    st0 = s.init(k_init, *batch0)
+    obatch0 = oget(0, obst)
+    ost = o.init(k_init, *(obatch0[0] if sampler != "subsample" else obatch0))
+    n_steps, first_step = 7, 2
+
+    # step by step through the public API
+    st = st0
+    losses = []
+    for i in range(first_step, first_step + n_steps):
+        out = get(i, bst)
+        batch, mask = out if sampler != "subsample" else (out, True)
+        st, loss = s.update(st, *batch, mask=mask)
+        losses.append(float(loss))
+    # the same range in one call
+    st_e, stats = s.run_epoch(st0, get, bst, n_steps, first_step=first_step)
+    assert stats.shape == (n_steps, 3)
+    assert np.array_equal(np.asarray(st_e.rng_key), np.asarray(st.rng_key))
+    assert st_e.optim_state.step == st.optim_state.step == n_steps
+    assert np.array_equal(st_e.optim_state.flat.cpu().numpy(), st.optim_state.flat.cpu().numpy(), equal_nan=True), \
+        "run_epoch must be bit-identical to stepwise"
+    if st.optim_state.lr is not None:
+        assert torch.equal(st_e.optim_state.lr, st.optim_state.lr)
+    got_losses = stats[:, 0].cpu().numpy()
+    assert np.array_equal(np.isnan(got_losses), np.isnan(np.asarray(losses, np.float32)))
+    ok = ~np.isnan(got_losses)
+    assert np.array_equal(got_losses[ok], np.asarray(losses, np.float32)[ok])
+    # the input state is untouched (functional API)
+    assert st0.optim_state.step == 0
+
+    # oracle trajectory
+    for i in range(first_step, first_step + n_steps):
+        out = oget(i, obst)
+        batch, mask = out if sampler != "subsample" else (out, True)
+        ost, oloss = o.update(ost, *batch, mask=mask)
+    got, ref = s.get_params(st_e), o.get_params(ost)
+    for k in ref:
+        g, r = got[k].cpu().numpy().astype(np.float64), np.asarray(ref[k], np.float64)
+        if np.all(np.isnan(r)):                      # suppressed batch -> NaN parameters
+            assert np.all(np.isnan(g))
+            continue
+        assert np.max(np.abs(g - r)) / max(np.max(np.abs(r)), 1e-30) < 1e-5, k
+
+
+def test_run_epoch_donation_and_continuation(cuda):
+    """Two half-epochs chained == one epoch; donate_state reuses the buffers."""
+    s, _, (init, get), _ = _setup("logreg", "poisson", "adam")
+    key = chacha.PRNGKey(4)
+    _, bst = init(key)
+    st0 = s.init(key, *get(0, bst)[0])
+    full, _ = s.run_epoch(st0, get, bst, 6)
+    half, _ = s.run_epoch(st0, get, bst, 3)
+    s.donate_state = True
+    ptr = half.optim_state.flat.data_ptr()
+    rest, _ = s.run_epoch(half, get, bst, 3, first_step=3)
+    assert rest.optim_state.flat.data_ptr() == ptr
+    assert torch.equal(rest.optim_state.flat, full.optim_state.flat)
+    assert np.array_equal(np.asarray(rest.rng_key), np.asarray(full.rng_key))
+
+
+def test_run_epoch_generic_path(cuda):
+    """Batchifiers without a C-side spec (split_batchify_data) go through the Python loop."""
+    from d3p_b200 import minibatch as mb
+    s, _, _, _ = _setup("gauss", "subsample", "adam")
+    data = ((1 + .1 * np.random.RandomState(0).randn(640, 12)).astype(np.float32),)
+    init, get = mb.split_batchify_data(data, batch_size=64)
+    key = chacha.PRNGKey(9)
+    n, bst = init(key)
+    st0 = s.init(key, *get(0, bst))
+    st, stats = s.run_epoch(st0, get, bst, n)
+    ref = st0
+    for i in range(n):
+        ref, loss = s.update(ref, *get(i, bst))
+    assert torch.equal(st.optim_state.flat, ref.optim_state.flat)
+    assert float(stats[-1, 0]) == float(loss)
