@@ -96,7 +96,15 @@ _SIGNATURES = {
     "d3p_dpsvi_run_epoch_meanfield": (C.c_int32, [C.POINTER(MeanfieldDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
                                                   _vp, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                                   C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
-                                                  _vp, _vp, _vp, C.c_size_t, _vp]),
+                                                  _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_comm_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint8)]),
+    "d3p_comm_connect": (C.c_int32, [_vp, C.POINTER(C.c_uint8)]),
+    "d3p_comm_timeouts": (C.c_int32, [_vp, _u32p]),
+    "d3p_comm_destroy": (C.c_int32, [_vp]),
+    "d3p_perturb_finalize_p2p_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(LeafTable),
+                                                 C.c_float, C.c_float, C.c_float, C.c_int32, _vp,
+                                                 C.POINTER(OptimDesc), _vp, _vp, _vp, _vp,
+                                                 C.POINTER(C.c_float), _vp, _vp]),
     "d3p_reduce_partials_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "d3p_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.c_uint32, _u32p]),
     "d3p_dpsvi_step_vae": (C.c_int32, [C.POINTER(VaeDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,

@@ -1,0 +1,87 @@
+// Host side of the NVLink peer-memory window (see comm.cuh): allocation, CUDA-IPC exchange, teardown.
+#include <new>
+#include <string.h>
+
+#include "comm.cuh"
+#include "launch.cuh"
+
+namespace d3p {
+
+bool comm_next(d3p_comm* c, uint32_t n_params, uint32_t n_ctas, CommDev* out) {
+  if (!c || !c->connected || n_params + 2 > c->max_params + 2 || n_ctas == 0 || n_ctas > D3P_COMM_MAX_CTAS) return false;
+  c->epoch += 1;
+  out->world = c->world;
+  out->rank = c->rank;
+  out->epoch = c->epoch;
+  out->extra_off = c->max_params;
+  out->flags_local = reinterpret_cast<uint32_t*>(c->local);
+  out->err = reinterpret_cast<uint32_t*>(c->local + c->err_off);
+  for (int r = 0; r < D3P_COMM_MAX_RANKS; ++r) {
+    uint8_t* base = r < c->world ? c->peer[r] : c->local;
+    out->flags_peer[r] = reinterpret_cast<uint32_t*>(base);
+    out->data_peer[r] = reinterpret_cast<float*>(base + c->data_off) + (size_t)(c->epoch & 1u) * c->stride_floats;
+  }
+  return true;
+}
+
+}  // namespace d3p
+
+extern "C" int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_params, d3p_comm** comm_out,
+                                   uint8_t handle_out_h[64]) {
+  if (!comm_out || !handle_out_h || world < 1 || world > D3P_COMM_MAX_RANKS || rank < 0 || rank >= world)
+    return D3P_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  d3p_comm* c = new (std::nothrow) d3p_comm();
+  if (!c) return D3P_ERR_CUDA;
+  memset(c, 0, sizeof(*c));
+  c->rank = rank; c->world = world; c->max_params = max_params;
+  c->flags_bytes = (size_t)D3P_COMM_MAX_RANKS * D3P_COMM_MAX_CTAS * sizeof(uint32_t);
+  c->err_off = c->flags_bytes;
+  c->data_off = c->err_off + 256;
+  c->stride_floats = d3p::align_up((size_t)max_params + 2 * (size_t)D3P_COMM_MAX_CTAS, 64);
+  c->total = c->data_off + 2 * c->stride_floats * sizeof(float);
+  void* p = nullptr;
+  if (cudaMalloc(&p, c->total) != cudaSuccess) { delete c; return D3P_ERR_CUDA; }
+  c->local = static_cast<uint8_t*>(p);
+  if (cudaMemset(p, 0, c->total) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    cudaFree(p); delete c; return D3P_ERR_CUDA;
+  }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); delete c; return D3P_ERR_CUDA; }
+  memcpy(handle_out_h, &h, 64);
+  c->peer[rank] = c->local;
+  c->connected = world == 1;
+  *comm_out = c;
+  return D3P_OK;
+}
+
+extern "C" int32_t d3p_comm_connect(d3p_comm* c, const uint8_t* handles_h) {
+  if (!c || !handles_h) return D3P_ERR_INVALID_ARGUMENT;
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles_h + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return D3P_ERR_CUDA;
+    c->peer[r] = static_cast<uint8_t*>(p);
+  }
+  c->connected = true;
+  return D3P_OK;
+}
+
+extern "C" int32_t d3p_comm_timeouts(d3p_comm* c, uint32_t* count_out_h) {
+  if (!c || !count_out_h) return D3P_ERR_INVALID_ARGUMENT;
+  if (cudaMemcpy(count_out_h, c->local + c->err_off, sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return D3P_ERR_CUDA;
+  return D3P_OK;
+}
+
+extern "C" int32_t d3p_comm_destroy(d3p_comm* c) {
+  if (!c) return D3P_ERR_INVALID_ARGUMENT;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->world; ++r)
+    if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+  if (c->local) cudaFree(c->local);
+  delete c;
+  return D3P_OK;
+}

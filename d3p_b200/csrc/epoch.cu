@@ -7,6 +7,7 @@
 // parameter trajectory is bit-identical to calling get_batch / update step by step.
 #include <string.h>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "launch.cuh"
 
@@ -68,7 +69,8 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
                                                  uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
                                                  float dp_scale, const d3p_leaf_table* leaves_h,
                                                  d3p_optim_desc* optim_io_h, float* params_d, float* m_d, float* v_d,
-                                                 float* stats_out_d, void* ws_d, size_t ws_bytes, void* stream) {
+                                                 float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes,
+                                                 void* stream) {
   if (!desc || !x_d || !batch_key_h || !rng_key_io_h || !leaves_h || !optim_io_h || !params_d || !ws_d)
     return D3P_ERR_INVALID_ARGUMENT;
   if (!sampler_ok(sampler) || leaves_h->n_leaves == 0 || leaves_h->n_leaves > D3P_MAX_LEAVES)
@@ -80,6 +82,14 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
   uint32_t n_part = 0;
   d3p_meanfield_workspace_bytes(desc, &n_part);
   d3p_leaf_table lt = *leaves_h;
+  // sharded batch: this rank handles a contiguous range of batch positions; the sampler and
+  // all key derivations are replicated, the clipped sums meet inside the finalize kernel (comm.cuh)
+  uint32_t pos_begin = 0, pos_end = B;
+  if (comm && comm->world > 1) {
+    const uint32_t per = (B + comm->world - 1) / comm->world;
+    pos_begin = per * comm->rank < B ? per * comm->rank : B;
+    pos_end = pos_begin + per < B ? pos_begin + per : B;
+  }
   int32_t rc = D3P_OK;
   for (uint32_t s = 0; s < n_steps && rc == D3P_OK; ++s) {
     // ---- get_batch(i, batchifier_state): fold_in, then the index sampler (minibatch.py:103-131,217-237) ----
@@ -100,12 +110,14 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
     uint32_t keys[3][16], tf[2];
     if ((rc = d3p_chacha_split_h(rng_key_io_h, 3, &keys[0][0])) != D3P_OK) break;           // carry, k_grad, k_noise
     if ((rc = d3p_chacha_random_bits_h(keys[1], 0, tf, 2)) != D3P_OK) break;                // convert_to_jax_rng_key
-    rc = d3p_dpsvi_step_meanfield(desc, params_d, x_d, x_row_stride, y_d, w.idx, mask, nullptr, B, 0, B, tf, obs_scale,
+    rc = d3p_dpsvi_step_meanfield(desc, params_d, x_d, x_row_stride, y_d, w.idx, mask, nullptr, B, pos_begin, pos_end, tf,
+                                  obs_scale,
                                   C, nullptr, nullptr, nullptr, w.step, w.step_bytes, stream);
     if (rc != D3P_OK) break;
     if ((rc = d3p_chacha_split_h(keys[2], (int32_t)lt.n_leaves, &lt.site_state[0][0])) != D3P_OK) break;
-    rc = d3p_perturb_finalize_f32(w.step, n_part, P, B, &lt, dp_scale, C, obs_scale, 1, nullptr, optim_io_h, params_d,
-                                  m_d, v_d, stats_out_d ? stats_out_d + 3 * (size_t)s : nullptr, nullptr, stream);
+    rc = d3p_perturb_finalize_p2p_f32(w.step, n_part, P, B, &lt, dp_scale, C, obs_scale, 1, nullptr, optim_io_h,
+                                      params_d, m_d, v_d, stats_out_d ? stats_out_d + 3 * (size_t)s : nullptr, nullptr,
+                                      comm, stream);
     if (rc != D3P_OK) break;
     if (optim_io_h->kind == D3P_OPT_ADADP && (optim_io_h->step & 1))
       if ((rc = d3p_adadp_finish_f32(optim_io_h, P, params_d, v_d, stream)) != D3P_OK) break;

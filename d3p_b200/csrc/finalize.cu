@@ -2,6 +2,7 @@
 // + rescale + optimizer step, in one launch.  Replaces DPSVI._combine_gradients
 // (d3p/svi.py:327-348), _perturb_and_reassemble_gradients (:350-377), perturbation_function
 // (:470-498) and _apply_gradient (:379-393) with numpyro.optim.SGD / Adam.
+#include "comm.cuh"
 #include "common.cuh"
 #include "launch.cuh"
 
@@ -52,7 +53,8 @@ constexpr int kFinThreads = 128;
 // site states live in constant-bank kernel parameters next to the leaf table
 struct SiteStates { uint32_t w[D3P_MAX_LEAVES][16]; };
 
-__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites) {
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites,
+                                                               CommDev comm) {
   __shared__ float red[2][kFinThreads / 32];
   __shared__ float s_n, s_loss;
   const uint32_t stride = a.P + 2;
@@ -71,16 +73,6 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
 #pragma unroll
     for (int w = 0; w < kFinThreads / 32; ++w) { c += red[0][w]; l += red[1][w]; }
     s_n = c; s_loss = l;
-  }
-  __syncthreads();
-  const float n = a.use_override ? a.n_override : s_n;
-  const float Bf = (float)a.B;
-  const float f = a.use_override ? a.f_override : ((n == 0.f) ? 0.f : __fdiv_rn(Bf, n));   // svi.py:305
-  const float sigma = __fmul_rn(a.dp_scale, __fdiv_rn(a.C, n));        // svi.py:365-366 (inf when n == 0)
-  if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
-    a.stats[0] = __fmul_rn(__fdiv_rn(s_loss, Bf), f);                  // svi.py:306,342
-    a.stats[1] = n;
-    a.stats[2] = f;
   }
   // 32 columns per CTA; warp w adds partials w, w+4, ... and warp 0 combines them in fixed order
   __shared__ float colred[kFinThreads / 32][32];
@@ -102,44 +94,70 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
   __syncthreads();
   if (warp != 0) return;
   const bool live = j < a.P;
-  float err2 = 0.f;
-  if (live) {
   float sum = 0.f;
 #pragma unroll
   for (int w = 0; w < kFinThreads / 32; ++w) sum += colred[w][lane];
-  float g = __fdiv_rn(sum, Bf);                                        // mean over the padded batch size
-  if (a.add_noise) {
-    int leaf = -1;
-#pragma unroll 1
-    for (uint32_t l = 0; l < leaves.n_leaves; ++l)
-      if (j >= leaves.off[l] && j < leaves.off[l] + leaves.len[l]) leaf = (int)l;
-    if (leaf >= 0) {
-      uint32_t e = j - leaves.off[leaf];
-      uint32_t ks[16];
-      chacha20_block(sites.w[leaf], sites.w[leaf][12] + (e >> 4), ks);
-      uint32_t bits = ks[0];
-#pragma unroll
-      for (int i = 1; i < 16; ++i) bits = ((e & 15u) == (uint32_t)i) ? ks[i] : bits;
-      float xi = bits_to_normal<false>(bits);
-      g = __fadd_rn(g, __fmul_rn(xi, sigma));                          // svi.py:485-486
+  float n_all = s_n, loss_all = s_loss;
+  if (comm.world > 1) {
+    // one-shot all-reduce over NVLink peer memory (comm.cuh): publish, signal, wait, add in rank order
+    float* mine = comm.data_peer[comm.rank];
+    if (live) mine[j] = sum;
+    if (lane == 0) { mine[comm.extra_off + 2 * blockIdx.x] = s_n; mine[comm.extra_off + 2 * blockIdx.x + 1] = s_loss; }
+    __threadfence_system();
+    __syncwarp();
+    comm_signal_and_wait(comm, blockIdx.x, lane);
+    sum = 0.f; n_all = 0.f; loss_all = 0.f;
+    for (int r = 0; r < comm.world; ++r) {
+      const float* theirs = comm.data_peer[r];
+      if (live) sum += ld_peer(theirs + j);
+      n_all += ld_peer(theirs + comm.extra_off + 2 * blockIdx.x);
+      loss_all += ld_peer(theirs + comm.extra_off + 2 * blockIdx.x + 1);
     }
   }
-  g = __fmul_rn(__fmul_rn(g, a.obs_scale), f);                         // svi.py:374-375
-  if (a.grad_out) a.grad_out[j] = g;
-  if (a.opt_kind == D3P_OPT_SGD) {
-    a.params[j] = a.params[j] - a.step_size * g;
-  } else if (a.opt_kind == D3P_OPT_ADAM) {
-    float m = (1.0f - a.b1) * g + a.b1 * a.m[j];
-    float v = (1.0f - a.b2) * (g * g) + a.b2 * a.v[j];
-    float t = (float)(a.step + 1);
-    float mhat = m / (1.0f - powf(a.b1, t));
-    float vhat = v / (1.0f - powf(a.b2, t));
-    a.params[j] = a.params[j] - a.step_size * mhat / (sqrtf(vhat) + a.eps);
-    a.m[j] = m;
-    a.v[j] = v;
-  } else if (a.opt_kind == D3P_OPT_ADADP) {
-    err2 = adadp_element(a, *a.lr, j, a.params[j], g);
+  const float n = a.use_override ? a.n_override : n_all;
+  const float Bf = (float)a.B;
+  const float f = a.use_override ? a.f_override : ((n == 0.f) ? 0.f : __fdiv_rn(Bf, n));   // svi.py:305
+  const float sigma = __fmul_rn(a.dp_scale, __fdiv_rn(a.C, n));        // svi.py:365-366 (inf when n == 0)
+  if (blockIdx.x == 0 && lane == 0 && a.stats) {
+    a.stats[0] = __fmul_rn(__fdiv_rn(loss_all, Bf), f);                // svi.py:306,342
+    a.stats[1] = n;
+    a.stats[2] = f;
   }
+  float err2 = 0.f;
+  if (live) {
+    float g = __fdiv_rn(sum, Bf);                                      // mean over the padded batch size
+    if (a.add_noise) {
+      int leaf = -1;
+#pragma unroll 1
+      for (uint32_t l = 0; l < leaves.n_leaves; ++l)
+        if (j >= leaves.off[l] && j < leaves.off[l] + leaves.len[l]) leaf = (int)l;
+      if (leaf >= 0) {
+        uint32_t e = j - leaves.off[leaf];
+        uint32_t ks[16];
+        chacha20_block(sites.w[leaf], sites.w[leaf][12] + (e >> 4), ks);
+        uint32_t bits = ks[0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) bits = ((e & 15u) == (uint32_t)i) ? ks[i] : bits;
+        float xi = bits_to_normal<false>(bits);
+        g = __fadd_rn(g, __fmul_rn(xi, sigma));                        // svi.py:485-486
+      }
+    }
+    g = __fmul_rn(__fmul_rn(g, a.obs_scale), f);                       // svi.py:374-375
+    if (a.grad_out) a.grad_out[j] = g;
+    if (a.opt_kind == D3P_OPT_SGD) {
+      a.params[j] = a.params[j] - a.step_size * g;
+    } else if (a.opt_kind == D3P_OPT_ADAM) {
+      float m = (1.0f - a.b1) * g + a.b1 * a.m[j];
+      float v = (1.0f - a.b2) * (g * g) + a.b2 * a.v[j];
+      float t = (float)(a.step + 1);
+      float mhat = m / (1.0f - powf(a.b1, t));
+      float vhat = v / (1.0f - powf(a.b2, t));
+      a.params[j] = a.params[j] - a.step_size * mhat / (sqrtf(vhat) + a.eps);
+      a.m[j] = m;
+      a.v[j] = v;
+    } else if (a.opt_kind == D3P_OPT_ADADP) {
+      err2 = adadp_element(a, *a.lr, j, a.params[j], g);
+    }
   }
   if (a.opt_kind == D3P_OPT_ADADP && (a.step & 1)) {
     err2 = group_sum<32>(err2);
@@ -160,7 +178,7 @@ struct ChunkTable { uint32_t n_chunks; uint32_t chunk_start[D3P_MAX_LEAVES + 1];
 D3P_D void quad_qr(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) { D3P_QR(a, b, c, d) }
 
 __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites,
-                                                            ChunkTable ct) {
+                                                            ChunkTable ct, CommDev comm) {
   __shared__ float red[2][8];
   __shared__ float s_n, s_loss;
   const uint32_t stride = a.P + 2;
@@ -181,15 +199,6 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
     s_n = c; s_loss = l;
   }
   __syncthreads();
-  const float n = a.use_override ? a.n_override : s_n;
-  const float Bf = (float)a.B;
-  const float f = a.use_override ? a.f_override : ((n == 0.f) ? 0.f : __fdiv_rn(Bf, n));
-  const float sigma = __fmul_rn(a.dp_scale, __fdiv_rn(a.C, n));
-  if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
-    a.stats[0] = __fmul_rn(__fdiv_rn(s_loss, Bf), f);
-    a.stats[1] = n;
-    a.stats[2] = f;
-  }
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
   const uint32_t chunk = t >> 2, q = t & 3;
   const bool live = chunk < ct.n_chunks;                  // uniform per 4-lane group; shuffles stay full-warp
@@ -216,11 +225,7 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
   }
   const uint32_t ks[4] = {x0 + i0, x1 + i1, x2 + i2, x3 + i3};   // keystream words q, 4 + q, 8 + q, 12 + q
   const bool adadp_odd = a.opt_kind == D3P_OPT_ADADP && (a.step & 1);
-  float err2 = 0.f;
-  if (live) {
   const uint32_t len = leaves.len[leaf], off = leaves.off[leaf];
-  const float t1 = (float)(a.step + 1);
-  const float bc1 = 1.0f - powf(a.b1, t1), bc2 = 1.0f - powf(a.b2, t1);
   const float* __restrict__ parts = a.partials;
   float* __restrict__ prm = a.params;
   float* __restrict__ pm = a.m;
@@ -232,11 +237,10 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t e = b * 16 + 4 * i + q;
-    ok[i] = e < len;
+    ok[i] = live && e < len;
     jj[i] = off + (ok[i] ? e : 0u);
     sum[i] = 0.f;
     x[i] = (ok[i] && a.opt_kind != D3P_OPT_NONE) ? prm[jj[i]] : 0.f;
-
     m0[i] = (ok[i] && a.opt_kind == D3P_OPT_ADAM) ? pm[jj[i]] : 0.f;
     v0[i] = (ok[i] && a.opt_kind == D3P_OPT_ADAM) ? pv[jj[i]] : 0.f;
   }
@@ -244,6 +248,39 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
 #pragma unroll
     for (int i = 0; i < 4; ++i) sum[i] += ok[i] ? parts[(size_t)p * stride + jj[i]] : 0.f;
   }
+  float n_all = s_n, loss_all = s_loss;
+  if (comm.world > 1) {                                    // one-shot all-reduce over peer memory (comm.cuh)
+    float* mine = comm.data_peer[comm.rank];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (ok[i]) mine[jj[i]] = sum[i];
+    if (threadIdx.x == 0) { mine[comm.extra_off + 2 * blockIdx.x] = s_n; mine[comm.extra_off + 2 * blockIdx.x + 1] = s_loss; }
+    __threadfence_system();
+    __syncthreads();
+    if (warp == 0) comm_signal_and_wait(comm, blockIdx.x, lane);
+    __syncthreads();
+    n_all = 0.f; loss_all = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sum[i] = 0.f;
+    for (int r = 0; r < comm.world; ++r) {
+      const float* theirs = comm.data_peer[r];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (ok[i]) sum[i] += ld_peer(theirs + jj[i]);
+      n_all += ld_peer(theirs + comm.extra_off + 2 * blockIdx.x);
+      loss_all += ld_peer(theirs + comm.extra_off + 2 * blockIdx.x + 1);
+    }
+  }
+  const float n = a.use_override ? a.n_override : n_all;
+  const float Bf = (float)a.B;
+  const float f = a.use_override ? a.f_override : ((n == 0.f) ? 0.f : __fdiv_rn(Bf, n));
+  const float sigma = __fmul_rn(a.dp_scale, __fdiv_rn(a.C, n));
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
+    a.stats[0] = __fmul_rn(__fdiv_rn(loss_all, Bf), f);
+    a.stats[1] = n;
+    a.stats[2] = f;
+  }
+  const float t1 = (float)(a.step + 1);
+  const float bc1 = 1.0f - powf(a.b1, t1), bc2 = 1.0f - powf(a.b2, t1);
+  float err2 = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (!ok[i]) continue;
@@ -265,7 +302,6 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
     } else if (a.opt_kind == D3P_OPT_ADADP) {
       err2 += adadp_element(a, lr_adadp, j, x[i], g);
     }
-  }
   }
   if (adadp_odd) {                                              // fixed-order CTA sum of the error terms
     err2 = group_sum<32>(err2);
@@ -346,6 +382,16 @@ extern "C" int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_
                                             int32_t add_noise, float* grad_out_d, const d3p_optim_desc* optim_h,
                                             float* params_d, float* m_d, float* v_d, float* stats_d,
                                             const float* nf_override_h, void* stream) {
+  return d3p_perturb_finalize_p2p_f32(partials_d, n_partials, P, B, leaves_h, dp_scale, C, obs_scale, add_noise,
+                                      grad_out_d, optim_h, params_d, m_d, v_d, stats_d, nf_override_h, nullptr, stream);
+}
+
+extern "C" int32_t d3p_perturb_finalize_p2p_f32(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
+                                                const d3p_leaf_table* leaves_h, float dp_scale, float C,
+                                                float obs_scale, int32_t add_noise, float* grad_out_d,
+                                                const d3p_optim_desc* optim_h, float* params_d, float* m_d,
+                                                float* v_d, float* stats_d, const float* nf_override_h,
+                                                d3p_comm* comm, void* stream) {
   if (!partials_d || n_partials == 0 || B == 0) return D3P_ERR_INVALID_ARGUMENT;
   if (add_noise && !leaves_h) return D3P_ERR_INVALID_ARGUMENT;
   if (leaves_h && leaves_h->n_leaves > D3P_MAX_LEAVES) return D3P_ERR_UNSUPPORTED;
@@ -371,6 +417,9 @@ extern "C" int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_
   if (a.opt_kind < D3P_OPT_NONE || a.opt_kind > D3P_OPT_ADADP) return D3P_ERR_UNSUPPORTED;
   LeafTable lt;
   SiteStates ss;
+  CommDev cd;
+  memset(&cd, 0, sizeof(cd));
+  cd.world = 1;
   memset(&lt, 0, sizeof(lt));
   memset(&ss, 0, sizeof(ss));
   if (leaves_h) {
@@ -396,12 +445,15 @@ extern "C" int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_
     ct.chunk_start[lt.n_leaves] = nc;
     ct.n_chunks = nc;
     if (covered == P && nc > 0) {
-      finalize_quad_kernel<<<(nc * 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, lt, ss, ct);
+      const unsigned qgrid = (nc * 4 + 255) / 256;
+      if (comm && !comm_next(comm, P, qgrid, &cd)) return D3P_ERR_INVALID_ARGUMENT;
+      finalize_quad_kernel<<<qgrid, 256, 0, (cudaStream_t)stream>>>(a, lt, ss, ct, cd);
       return check_launch();
     }
   }
   unsigned grid = P ? (P + 31) / 32 : 1;
-  finalize_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(a, lt, ss);
+  if (comm && !comm_next(comm, P, grid, &cd)) return D3P_ERR_INVALID_ARGUMENT;
+  finalize_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(a, lt, ss, cd);
   return check_launch();
 }
 

@@ -16,10 +16,59 @@ import torch.distributed as dist
 from . import _native as _n
 
 
-def shard_dpsvi(svi, rank=None, world_size=None, group=None):
-    """Make ``svi.update`` process only this rank's slice of every batch and all-reduce the sums."""
+class PeerWindow:
+    """This rank's NVLink peer-memory window (``d3p_comm_*``): the finalize kernel publishes the
+    ``P + 2`` clipped sums there and reads the peers' copies, so a sharded step needs neither a
+    reduce kernel nor an NCCL launch.  ``torch.distributed`` is used once, to swap the IPC handles."""
+
+    def __init__(self, rank, world_size, max_params, group=None):
+        import ctypes as C
+        self.rank, self.world_size = rank, world_size
+        handle = (C.c_uint8 * 64)()
+        self._comm = C.c_void_p()
+        _n.check(_n.lib().d3p_comm_create(rank, world_size, int(max_params), C.byref(self._comm), handle),
+                 "comm_create")
+        if world_size > 1:
+            handles = [None] * world_size
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            blob = (C.c_uint8 * (64 * world_size)).from_buffer_copy(b"".join(handles))
+            _n.check(_n.lib().d3p_comm_connect(self._comm, blob), "comm_connect")
+            dist.barrier(group=group)
+        self.max_params = int(max_params)
+
+    @property
+    def ptr(self):
+        return self._comm
+
+    def timeouts(self):
+        import ctypes as C
+        out = C.c_uint32(0)
+        _n.check(_n.lib().d3p_comm_timeouts(self._comm, C.byref(out)), "comm_timeouts")
+        return out.value
+
+    def close(self):
+        if self._comm:
+            _n.lib().d3p_comm_destroy(self._comm)
+            self._comm = None
+
+
+def shard_dpsvi(svi, rank=None, world_size=None, group=None, backend="p2p", max_params=None):
+    """Make ``svi.update`` / ``svi.run_epoch`` process only this rank's slice of every batch.
+
+    ``backend="p2p"`` (default): the clipped sums meet inside the finalize kernel over NVLink peer
+    memory (``PeerWindow``); ``backend="nccl"``: reduce kernel + ``ncclAllReduce`` of ``P + 2`` floats."""
     rank = dist.get_rank(group) if rank is None else rank
     world_size = dist.get_world_size(group) if world_size is None else world_size
+    if backend not in ("p2p", "nccl"):
+        raise ValueError("backend must be 'p2p' or 'nccl'")
+    if backend == "p2p":
+        if max_params is None:
+            if svi.family is None:
+                raise ValueError("max_params is required when DPSVI has no model family")
+            max_params = svi.family.n_params
+        svi.shard = (rank, world_size, None)
+        svi.peer_window = PeerWindow(rank, world_size, max_params, group)
+        return svi
     buf = {}
 
     def reduce_fn(ws, n_partials, P):

@@ -155,7 +155,8 @@ class DPSVI:
         self.family = fam
         self.donate_state = False
         self._ws = None
-        self.shard = None   # (rank, world_size, reduce_fn) set by d3p_b200.parallel.shard_dpsvi
+        self.shard = None   # (rank, world_size, reduce_fn | None) set by d3p_b200.parallel.shard_dpsvi
+        self.peer_window = None   # parallel.PeerWindow when the sums meet over NVLink peer memory
         self.event_hook = None   # optional callable(tag) around the step kernel launch (bench instrumentation)
 
     # ---- state plumbing (svi.py:192-211) -----------------------------------------------------------
@@ -295,8 +296,12 @@ class DPSVI:
         os_ = svi_state.optim_state
         ws, n_part, B, P = self._run_step(svi_state, k_grad, args, mask)
         partials = ws
+        comm = None
         if self.shard is not None:
-            partials, n_part = self.shard[2](ws, n_part, P)
+            if self.shard[2] is not None:                       # NCCL backend: reduce kernel + all-reduce
+                partials, n_part = self.shard[2](ws, n_part, P)
+            else:                                               # sums meet inside the finalize kernel
+                comm = self.peer_window.ptr
         if self.donate_state:
             buf = os_.flat
             new_flat, new_m, new_v = os_.flat, os_.m, os_.v
@@ -308,10 +313,10 @@ class DPSVI:
         stats = torch.empty(3, dtype=torch.float32, device=new_flat.device)
         lt = self._leaf_table(os_.layout, k_noise)
         od = self.optim.desc(os_.step, new_lr, P)
-        _n.check(_n.lib().d3p_perturb_finalize_f32(
+        _n.check(_n.lib().d3p_perturb_finalize_p2p_f32(
             _n.ptr(partials), n_part, P, B, C.byref(lt), float(self._dp_scale), float(self._clipping_threshold),
             float(svi_state.observation_scale), 1, None, C.byref(od), _n.ptr(new_flat), _n.ptr(new_m), _n.ptr(new_v),
-            _n.ptr(stats), None, _n.stream_ptr()), "perturb_finalize")
+            _n.ptr(stats), None, comm, _n.stream_ptr()), "perturb_finalize")
         self.optim.finish(od, new_flat, new_v)
         new_os = OptimState(os_.step + 1, new_flat, new_m, new_v, os_.layout, new_lr)
         return DPSVIState(new_os, svi_state.rng_key, svi_state.observation_scale), stats[0]
@@ -325,11 +330,11 @@ class DPSVI:
         For the mean-field families fed by ``poisson_batchify_data`` / ``subsample_batchify_data``
         the whole loop runs inside ``d3p_dpsvi_run_epoch_meanfield`` (no interpreter between
         launches); the result is bit-identical to the step-by-step calls, which remain the path
-        for everything else (sharded runs, VAE, GMM, custom batchifiers)."""
+        for everything else (NCCL-backend sharded runs, VAE, GMM, custom batchifiers)."""
         from .models import MeanFieldFamily
         spec = getattr(get_batch, "spec", None)
-        fused = (spec is not None and isinstance(self.family, MeanFieldFamily) and self.shard is None
-                 and self._rng_suite is strong_rng and spec["rng_suite"] is strong_rng and self.event_hook is None
+        fused = (spec is not None and isinstance(self.family, MeanFieldFamily)
+                 and (self.shard is None or self.shard[2] is None) and self._rng_suite is strong_rng and spec["rng_suite"] is strong_rng and self.event_hook is None
                  and num_steps > 0)
         if not fused:
             stats = torch.zeros(max(num_steps, 0), 3, dtype=torch.float32, device=_dev())
@@ -370,7 +375,8 @@ class DPSVI:
             C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, _n.ptr(ysrc), bkey.ctypes.data_as(u32p),
             rkey.ctypes.data_as(u32p), int(first_step), int(num_steps), float(svi_state.observation_scale),
             float(self._clipping_threshold), float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m),
-            _n.ptr(v), _n.ptr(stats), _n.ptr(self._epoch_ws), need, _n.stream_ptr()), "run_epoch")
+            _n.ptr(v), _n.ptr(stats), self.peer_window.ptr if self.shard is not None else None,
+            _n.ptr(self._epoch_ws), need, _n.stream_ptr()), "run_epoch")
         new_os = OptimState(os_.step + num_steps, flat, m, v, os_.layout, lr)
         return DPSVIState(new_os, rkey.reshape(np.asarray(svi_state.rng_key).shape), svi_state.observation_scale), stats
 

@@ -33,6 +33,8 @@ extern "C" {
 #define D3P_MAX_LEAVES 16
 
 /* Library / build identification. */
+typedef struct d3p_comm d3p_comm; /* peer-memory window of a sharded run, see d3p_comm_create */
+
 int32_t d3p_abi_version(void);
 const char* d3p_error_string(int32_t code);
 
@@ -225,15 +227,17 @@ size_t d3p_dpsvi_epoch_workspace_bytes(const d3p_meanfield_desc* desc, const d3p
 /* batch_key_h: the batchifier state (the key `init` returned); step i uses fold_in(batch_key, i),
  * i = first_step .. first_step + n_steps - 1.  rng_key_io_h: DPSVIState.rng_key, advanced in place.
  * leaves_h: leaf offsets / lengths (site states are derived per step).  optim_io_h->step is advanced.
- * params_d / m_d / v_d (and optim->lr_d for ADADP) are updated in place.
+ * params_d / m_d / v_d (and optim->lr_d for ADADP) are updated in place.  With `comm` (below) the
+ * batch positions are split contiguously over the ranks and the sums meet over NVLink peer memory.
  * stats_out_d (may be NULL): [n_steps, 3] = { loss, n, f } of every step. */
 int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler,
                                       const float* x_d, size_t x_row_stride, const int32_t* y_d,
                                       const uint32_t batch_key_h[16], uint32_t rng_key_io_h[16],
                                       uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
                                       float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h,
-                                      float* params_d, float* m_d, float* v_d, float* stats_out_d, void* ws_d,
-                                      size_t ws_bytes, void* stream);
+                                      float* params_d, float* m_d, float* v_d, float* stats_out_d,
+                                      d3p_comm* comm /* NULL = single GPU */, void* ws_d, size_t ws_bytes,
+                                      void* stream);
 
 /* partials_d is [n_partials, P + 2] (grad sum | loss sum | count).  With n = total count,
  * f = (n == 0 ? 0 : B / n):
@@ -252,6 +256,30 @@ int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_partials, u
                                  int32_t add_noise, float* grad_out_d, const d3p_optim_desc* optim_h,
                                  float* params_d, float* m_d, float* v_d, float* stats_d,
                                  const float* nf_override_h, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sharded minibatch over the GPUs of one box without NCCL in the step:
+ * every rank owns a peer-mapped window (CUDA IPC over NVLink / NVSwitch) and the finalize kernel
+ * itself exchanges the P + 2 clipped sums (publish -> flag -> wait -> read peers, added in rank
+ * order, so every replica computes bit-identical sums, noise and parameters).
+ *   create  : allocate this rank's window, return its 64-byte IPC handle
+ *   connect : map the windows of all ranks (handles_h = world x 64 bytes, gathered by the caller,
+ *             e.g. torch.distributed.all_gather_object)
+ * All ranks must issue the same sequence of d3p_perturb_finalize_p2p_f32 calls (same P).  A peer
+ * that never shows up makes the kernel give up after ~3 s and count a time-out instead of
+ * hanging the GPU; d3p_comm_timeouts reads the counter (synchronises).
+ * ------------------------------------------------------------------------------------------ */
+int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_params, d3p_comm** comm_out,
+                        uint8_t handle_out_h[64]);
+int32_t d3p_comm_connect(d3p_comm* comm, const uint8_t* handles_h);
+int32_t d3p_comm_timeouts(d3p_comm* comm, uint32_t* count_out_h);
+int32_t d3p_comm_destroy(d3p_comm* comm);
+/* d3p_perturb_finalize_f32 on this rank's partial rows + the peers' (comm may be NULL = local only). */
+int32_t d3p_perturb_finalize_p2p_f32(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
+                                     const d3p_leaf_table* leaves_h, float dp_scale, float C, float obs_scale,
+                                     int32_t add_noise, float* grad_out_d, const d3p_optim_desc* optim_h,
+                                     float* params_d, float* m_d, float* v_d, float* stats_d,
+                                     const float* nf_override_h, d3p_comm* comm, void* stream);
 
 /* Multi-GPU (new; the reference is single-device): out_d[P + 2] = sum over the n_partials rows of
  * a step workspace, in a fixed order.  The caller all-reduces out_d over the ranks that share a
