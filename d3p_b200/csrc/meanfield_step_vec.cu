@@ -109,10 +109,15 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   const uint32_t total_warps = gridDim.x * kStepWarps;
   const float Linv = a.L * a.inv_var;
 
-  for (uint32_t wt = blockIdx.x * kStepWarps + warp; (uint64_t)wt * TILE < npos; wt += total_warps) {
-    const uint32_t base = a.pos_begin + wt * TILE;
+  // Each warp owns one contiguous run of ceil(npos / total_warps) positions and walks it in tiles of 8:
+  // per-warp loads differ by at most one example (measured: same kernel time as dealing whole tiles
+  // round-robin, an SM's 16 warps share its issue slots, so only the per-SM totals matter).
+  const uint32_t per_warp = (npos + total_warps - 1) / total_warps;
+  const uint32_t w_begin = min(npos, (blockIdx.x * kStepWarps + warp) * per_warp);
+  const uint32_t w_end = a.pos_begin + min(npos, w_begin + per_warp);
+  for (uint32_t base = a.pos_begin + w_begin; base < w_end; base += TILE) {
     const uint32_t my_p = base + lane;
-    bool my_valid = (lane < TILE) && (my_p < a.pos_end) && (my_p < nv) && (!a.mask || a.mask[my_p]);
+    bool my_valid = (lane < TILE) && (my_p < w_end) && (my_p < nv) && (!a.mask || a.mask[my_p]);
     uint32_t my_k0, my_k1, my_row = 0;
     float my_eb = 0.f, my_y = 0.f;
     {
