@@ -374,13 +374,20 @@ def run_b200(args, cfg):
     # ---- end to end through the public API with HOST buffers (rank-local shard at N > 1) -----------
     e2e = None
     if args.e2e:
-        dev_batch = [b.tensor() for b in batch]
+        # N > 1 (mean-field families): every rank keeps and uploads only the rows of its own position
+        # range (minibatch.LocalRows), so the H2D traffic is split over the GPUs' PCIe links
+        local = world > 1 and cfg["family"] in ("logreg", "gauss")
+        pb, pe = parallel.position_range(max_b, rank, world) if local else (0, max_b)
+        dev_batch = [b.tensor()[pb:pe] for b in batch]
         host = [torch.empty(t_.shape, dtype=t_.dtype).pin_memory() for t_ in dev_batch]
         for h, src in zip(host, dev_batch):
             h.copy_(src)
-        host_mask = torch.empty(mask.shape, dtype=torch.bool).pin_memory()
-        host_mask.copy_(mask)
+        host_mask = torch.empty(mask[pb:pe].shape, dtype=torch.bool).pin_memory()
+        host_mask.copy_(mask[pb:pe])
         n_valid_host = int(mask.sum().item())
+
+        def wrap(t_):
+            return mb.LocalRows(t_, pb, max_b) if local else t_
         dev_bufs = [[torch.empty_like(h, device=device) for h in host] + [torch.empty_like(host_mask, device=device)]
                     for _ in range(2)]
         loss_host = torch.empty(args.steps + args.warmup, dtype=torch.float32).pin_memory()
@@ -399,7 +406,7 @@ def run_b200(args, cfg):
                         dst.copy_(src, non_blocking=True)
                     ready[slot].record(copy_stream)
                 main.wait_event(ready[slot])
-                state, loss = svi.update(state, *dev_bufs[slot][:-1], mask=dev_bufs[slot][-1])
+                state, loss = svi.update(state, *[wrap(t_) for t_ in dev_bufs[slot][:-1]], mask=wrap(dev_bufs[slot][-1]))
                 consumed[slot].record(main)
                 loss_host[base + i:base + i + 1].copy_(loss.reshape(1), non_blocking=True)
             return state
@@ -418,10 +425,16 @@ def run_b200(args, cfg):
             t = torch.tensor([e_ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
+        if world > 1:
+            t = torch.tensor([float(h2d_bytes)], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            h2d_bytes = int(t.item())
         e2e = {"value": n_valid_host * args.steps / (e_ms * 1e-3), "unit": "examples/s",
-               "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
+               "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4 * world,
                "note": "DPSVI.update(state, *batch, mask) with the batch in pinned HOST memory: "
-                       "H2D copy of the padded batch + update + loss read-back every step (double-buffered)"}
+                       "H2D copy of the padded batch + update + loss read-back every step (double-buffered)"
+                       + ("; each rank uploads the rows of its own position range, bytes are summed over ranks"
+                          if local else "")}
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()

@@ -92,6 +92,26 @@ class BatchView:
         return self.tensor().cpu().numpy()
 
 
+class LocalRows:
+    """Rows ``[first, first + len(tensor))`` of a batch of ``batch_size`` examples whose other rows
+    are handled by other ranks.  A sharded ``DPSVI.update`` (``parallel.shard_dpsvi``) accepts these
+    in place of full batch arrays (and of the mask), so that with host-resident batches every rank
+    uploads only the slice it processes; ``first`` must be the start of this rank's position range
+    (``parallel.position_range``).  Keys stay addressed by the global batch position."""
+
+    def __init__(self, tensor, first, batch_size):
+        self.tensor, self.first, self.batch_size = tensor, int(first), int(batch_size)
+        if self.first < 0 or self.first + tensor.shape[0] > self.batch_size:
+            raise ValueError("LocalRows: the slice does not fit the batch")
+
+    @property
+    def shape(self):
+        return (self.batch_size,) + tuple(self.tensor.shape[1:])
+
+    def __len__(self):
+        return self.batch_size
+
+
 def _to_device(a):
     if isinstance(a, torch.Tensor):
         return a.to(_device()).contiguous()

@@ -122,10 +122,24 @@ class MeanFieldFamily(Family):
         ws = svi._workspace(need)
         mask_t, _ = svi._mask_arg(mask, B)
         flat = state.optim_state.flat
+        x_p, y_p, m_p = _n.ptr(Xsrc), _n.ptr(ysrc), _n.ptr(mask_t)
+        if getattr(svi, "_local_rows", None) is not None:
+            # minibatch.LocalRows: the tensors hold only rows [first, first + n) of the batch; shift the base
+            # pointers so that the kernel's global position p addresses local row p - first
+            first, n_local = svi._local_rows
+            if (first, first + n_local) != (pos_begin, pos_end):
+                raise ValueError(f"LocalRows [{first}, {first + n_local}) is not this rank's position range "
+                                 f"[{pos_begin}, {pos_end})")
+            x_p = C.c_void_p(Xsrc.data_ptr() - first * stride * 4)
+            y_p = C.c_void_p(ysrc.data_ptr() - first * 4) if ysrc is not None else None
+            if mask_t is not None:
+                if mask_t.numel() != n_local:
+                    raise ValueError("with LocalRows the mask must be the matching LocalRows slice")
+                m_p = C.c_void_p(mask_t.data_ptr() - first)
         if svi.event_hook is not None:
             svi.event_hook("step_begin")
         _n.check(_n.lib().d3p_dpsvi_step_meanfield(
-            C.byref(desc), _n.ptr(flat), _n.ptr(Xsrc), stride, _n.ptr(ysrc), _n.ptr(idx), _n.ptr(mask_t), None,
+            C.byref(desc), _n.ptr(flat), x_p, stride, y_p, _n.ptr(idx), m_p, None,
             B, pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
             float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_grads), _n.ptr(px_loss), _n.ptr(ws), need,
             _n.stream_ptr()), "dpsvi_step_meanfield")
@@ -262,6 +276,8 @@ class VAE(Family):
         if px_grads is not None:
             raise NotImplementedError("the VAE path never materialises [B, P] per-example gradients")
         Xsrc, stride, _, idx, B = svi._resolve_args(args)
+        if getattr(svi, "_local_rows", None) is not None:
+            raise NotImplementedError("LocalRows batches are supported by the mean-field families only")
         desc = self.desc(svi._num_obs_total())
         n_part = C.c_uint32(0)
         need = _n.lib().d3p_vae_workspace_bytes(C.byref(desc), pos_end - pos_begin, C.byref(n_part))
@@ -316,6 +332,8 @@ class GaussianMixture(Family):
     def run_step(self, svi, state, tf_key, args, mask, B, pos_begin, pos_end, px_norms, px_grads, px_loss):
         import ctypes as C
         Xsrc, stride, _, idx, B = svi._resolve_args(args)
+        if getattr(svi, "_local_rows", None) is not None:
+            raise NotImplementedError("LocalRows batches are supported by the mean-field families only")
         desc = self.desc(svi._num_obs_total())
         n_part = C.c_uint32(0)
         need = _n.lib().d3p_gmm_workspace_bytes(C.byref(desc), C.byref(n_part))

@@ -16,7 +16,7 @@ import torch
 
 from . import _native as _n
 from . import random as strong_rng
-from .minibatch import BatchView
+from .minibatch import BatchView, LocalRows
 from .models import Family
 from .optimizers import OptimState, unflatten
 from .util import example_count
@@ -215,6 +215,21 @@ class DPSVI:
         fam.check_args(args)
         X = args[0]
         idx = None
+        self._local_rows = None
+        if isinstance(X, LocalRows):
+            # rank-local slice of the batch: (first, n_local); the step kernel addresses rows by global
+            # position, so the family shifts the base pointers back by `first` rows
+            if any(not isinstance(a, LocalRows) or a.first != X.first or a.tensor.shape[0] != X.tensor.shape[0]
+                   for a in args):
+                raise ValueError("all batch arrays must be LocalRows of the same slice")
+            self._local_rows = (X.first, int(X.tensor.shape[0]))
+            B = X.batch_size
+            Xsrc = X.tensor.to(device=_dev(), dtype=torch.float32)
+            if Xsrc.dim() > 2:
+                Xsrc = Xsrc.reshape(Xsrc.shape[0], -1)
+            Xsrc = Xsrc.contiguous()
+            ysrc = args[1].tensor.to(device=_dev(), dtype=torch.int32).contiguous() if len(args) > 1 else None
+            return Xsrc, int(Xsrc.stride(0)), ysrc, None, B
         if isinstance(X, BatchView):
             idx, Xsrc = X.idx, X.source
             ysrc = None
@@ -252,6 +267,8 @@ class DPSVI:
         """-> (mask_uint8_tensor_or_None, all_masked)."""
         if isinstance(mask, (bool, np.bool_)):
             return (None, False) if mask else (torch.zeros(B, dtype=torch.uint8, device=_dev()), True)
+        if isinstance(mask, LocalRows):
+            mask = mask.tensor
         m = mask if isinstance(mask, torch.Tensor) else torch.as_tensor(np.asarray(mask))
         m = m.to(_dev())
         if m.dtype == torch.bool:

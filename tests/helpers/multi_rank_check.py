@@ -42,6 +42,37 @@ def run(fam, dataset, C, sharded, steps=3, epoch=False):
     return st.optim_state.flat.clone(), losses, np.asarray(st.rng_key).copy()
 
 
+def check_local_rows(dev, rank, world):
+    """minibatch.LocalRows: feeding only this rank's rows must equal feeding the whole batch (bit for bit)."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B, d = 1001, 256
+    X = torch.randn((B, d), device=dev, generator=g)
+    y = (torch.rand(B, device=dev, generator=g) < 0.5).to(torch.int32)
+    mask = torch.rand(B, device=dev, generator=g) < 0.9
+    out = []
+    for local in (False, True):
+        fam = models.LogisticRegression(d)
+        s = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), 1.0, 1.0, num_obs_total=50000)
+        parallel.shard_dpsvi(s, backend="p2p")
+        st = s.init(rng.PRNGKey(3), X, y)
+        pb, pe = parallel.position_range(B, rank, world)
+        for _ in range(3):
+            if local:
+                st, loss = s.update(st, mb.LocalRows(X[pb:pe].clone(), pb, B), mb.LocalRows(y[pb:pe].clone(), pb, B),
+                                    mask=mb.LocalRows(mask[pb:pe].clone(), pb, B))
+            else:
+                st, loss = s.update(st, X, y, mask=mask)
+        torch.cuda.synchronize()
+        assert s.peer_window.timeouts() == 0
+        dist.barrier()
+        s.peer_window.close()
+        out.append((st.optim_state.flat.clone(), float(loss)))
+    same = torch.equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+    if rank == 0:
+        print(f"LocalRows == full batch: {same}", flush=True)
+    return same
+
+
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -72,6 +103,7 @@ def main():
             if rank == 0:
                 print(f"{name} [{backend}{' epoch' if epoch else ''}]: sharded-vs-single rel err {err:.2e}, "
                       f"replicas identical {same}, losses {l_sh} vs {l_1}", flush=True)
+    ok = check_local_rows(dev, rank, world) and ok
     dist.barrier()
     dist.destroy_process_group()
     if not ok:
