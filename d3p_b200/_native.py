@@ -97,7 +97,10 @@ _SIGNATURES = {
                                                   _vp, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                                   C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
                                                   _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
-    "d3p_comm_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint8)]),
+    "d3p_comm_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_uint8)]),
+    "d3p_poisson_sample_sharded": (C.c_int32, [_vp, _u32p, C.c_float, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32,
+                                               C.c_uint32, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "d3p_comm_connect": (C.c_int32, [_vp, C.POINTER(C.c_uint8)]),
     "d3p_comm_timeouts": (C.c_int32, [_vp, _u32p]),
     "d3p_comm_destroy": (C.c_int32, [_vp]),

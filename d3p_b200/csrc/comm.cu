@@ -24,10 +24,35 @@ bool comm_next(d3p_comm* c, uint32_t n_params, uint32_t n_ctas, CommDev* out) {
   return true;
 }
 
+bool samp_next(d3p_comm* c, uint32_t n_records, uint32_t n_tiles, SampDev* out) {
+  if (!c || !c->connected || c->max_records == 0 || n_records > c->max_records) return false;
+  c->samp_epoch += 1;
+  const size_t n_blocks_max = ((size_t)c->max_records + 15) / 16;
+  const size_t counts_off = align_up(n_blocks_max * sizeof(uint16_t), 256);
+  out->world = c->world; out->rank = c->rank; out->epoch = c->samp_epoch;
+  out->n_tiles = n_tiles;
+  out->tiles_per_rank = (n_tiles + c->world - 1) / c->world;
+  uint32_t* err = reinterpret_cast<uint32_t*>(c->local + c->err_off);
+  out->err = err;
+  out->flags_local = err + 8;
+  out->done_counter = err + 32;
+  for (int r = 0; r < D3P_COMM_MAX_RANKS; ++r) {
+    uint8_t* base = r < c->world ? c->peer[r] : c->local;
+    uint8_t* buf = base + c->samp_off + (size_t)(c->samp_epoch & 1u) * c->samp_stride;
+    out->flags_peer[r] = reinterpret_cast<uint32_t*>(base + c->err_off) + 8;
+    out->masks_peer[r] = reinterpret_cast<const uint16_t*>(buf);
+    out->counts_peer[r] = reinterpret_cast<int32_t*>(buf + counts_off);
+  }
+  uint8_t* mine = c->local + c->samp_off + (size_t)(c->samp_epoch & 1u) * c->samp_stride;
+  out->masks_local = reinterpret_cast<uint16_t*>(mine);
+  out->counts_local = reinterpret_cast<int32_t*>(mine + counts_off);
+  return true;
+}
+
 }  // namespace d3p
 
-extern "C" int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_params, d3p_comm** comm_out,
-                                   uint8_t handle_out_h[64]) {
+extern "C" int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_params, uint32_t max_records,
+                                   d3p_comm** comm_out, uint8_t handle_out_h[64]) {
   if (!comm_out || !handle_out_h || world < 1 || world > D3P_COMM_MAX_RANKS || rank < 0 || rank >= world)
     return D3P_ERR_INVALID_ARGUMENT;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -39,7 +64,13 @@ extern "C" int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_par
   c->err_off = c->flags_bytes;
   c->data_off = c->err_off + 256;
   c->stride_floats = d3p::align_up((size_t)max_params + 2 * (size_t)D3P_COMM_MAX_CTAS, 64);
-  c->total = c->data_off + 2 * c->stride_floats * sizeof(float);
+  c->samp_off = d3p::align_up(c->data_off + 2 * c->stride_floats * sizeof(float), 256);
+  c->max_records = max_records;
+  if (max_records) {
+    const size_t n_blocks = ((size_t)max_records + 15) / 16, n_tiles = (n_blocks + 255) / 256;
+    c->samp_stride = d3p::align_up(n_blocks * sizeof(uint16_t), 256) + d3p::align_up(n_tiles * sizeof(int32_t), 256);
+  }
+  c->total = c->samp_off + 2 * c->samp_stride;
   void* p = nullptr;
   if (cudaMalloc(&p, c->total) != cudaSuccess) { delete c; return D3P_ERR_CUDA; }
   c->local = static_cast<uint8_t*>(p);

@@ -13,7 +13,9 @@
 struct d3p_comm {
   int rank, world;
   uint32_t max_params, epoch;
+  uint32_t max_records, samp_epoch;             // sharded Poisson sampler (0 = not provisioned)
   size_t flags_bytes, err_off, data_off, stride_floats, total;
+  size_t samp_off, samp_stride;                 // 2 x [masks u16[n_blocks] | tile_counts i32[n_tiles]] by epoch parity
   uint8_t* local;                               // this rank's window
   uint8_t* peer[D3P_COMM_MAX_RANKS];            // mapped windows (peer[rank] == local)
   bool connected;
@@ -51,7 +53,8 @@ D3P_D float ld_peer(const float* p) {
 }
 
 // Called by the first warp of a CTA after every thread of the CTA has stored its values into the local
-// window, executed __threadfence_system() and the CTA (or warp, if only this warp wrote) has synchronised.
+// window and the CTA (or warp, if only this warp wrote) has synchronised: the barrier orders those stores
+// before the signalling lanes, whose st.release.sys is cumulative, so no per-thread system fence is needed.
 // On return the peers' values of this CTA's slots are readable (after the caller's next barrier).
 D3P_D void comm_signal_and_wait(const CommDev& c, uint32_t cta, int lane) {
   if (lane < c.world && lane != c.rank) st_release_sys(c.flags_peer[lane] + (size_t)c.rank * D3P_COMM_MAX_CTAS + cta, c.epoch);
@@ -68,6 +71,25 @@ D3P_D void comm_signal_and_wait(const CommDev& c, uint32_t cta, int lane) {
   __syncwarp();
 }
 
+
+// Sharded Poisson sampler (samplers.cu): rank r draws the selectors of its slice of the records and
+// publishes the 16-bit selection masks and per-tile counts in its window; every rank scans all counts
+// (read from the owners over NVLink) and compacts only the batch positions it owns.
+//   err[8 + r]  "select done" flag written by rank r (sampler epoch);  err[32] = local CTA-done counter
+struct SampDev {
+  int world, rank;
+  uint32_t epoch;
+  uint32_t tiles_per_rank, n_tiles;
+  uint32_t* flags_local;                      // [MAX_RANKS]
+  uint32_t* done_counter;                     // local
+  uint32_t* err;
+  uint32_t* flags_peer[D3P_COMM_MAX_RANKS];
+  const uint16_t* masks_peer[D3P_COMM_MAX_RANKS];     // this epoch's buffer in every window
+  int32_t* counts_peer[D3P_COMM_MAX_RANKS];           // owners PUSH their tile counts into every window
+  uint16_t* masks_local;
+  int32_t* counts_local;
+};
+bool samp_next(d3p_comm* comm, uint32_t n_records, uint32_t n_tiles, SampDev* out);
 
 // Fills the device view for the next exchange (advances the epoch); false if the shapes do not fit.
 bool comm_next(d3p_comm* comm, uint32_t n_params, uint32_t n_ctas, CommDev* out);

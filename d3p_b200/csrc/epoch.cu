@@ -5,7 +5,11 @@
 // stream with no host synchronisation and no interpreter between the launches.  Host work per step is a
 // handful of ChaCha blocks (<10 us); every device piece is the same entry point DPSVI.update uses, so the
 // parameter trajectory is bit-identical to calling get_batch / update step by step.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "comm.cuh"
 #include "common.cuh"
@@ -90,15 +94,31 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
     pos_begin = per * comm->rank < B ? per * comm->rank : B;
     pos_end = pos_begin + per < B ? pos_begin + per : B;
   }
+  // D3P_EPOCH_PROFILE=1: per-phase CUDA-event timings of this call on stderr (synchronises at the end)
+  const bool prof = getenv("D3P_EPOCH_PROFILE") != nullptr;
+  std::vector<cudaEvent_t> ev;
+  auto mark = [&]() {
+    if (!prof) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, (cudaStream_t)stream);
+    ev.push_back(e);
+  };
   int32_t rc = D3P_OK;
   for (uint32_t s = 0; s < n_steps && rc == D3P_OK; ++s) {
+    mark();
     // ---- get_batch(i, batchifier_state): fold_in, then the index sampler (minibatch.py:103-131,217-237) ----
     uint32_t bkey[16];
     if ((rc = d3p_chacha_fold_in_h(batch_key_h, first_step + s, bkey)) != D3P_OK) break;
     const uint8_t* mask = nullptr;
     if (sampler->kind == D3P_SAMPLER_POISSON) {
-      rc = d3p_poisson_sample(bkey, sampler->q, sampler->n_records, B, sampler->suppress, w.idx, w.counts, w.mask,
-                              w.poisson, w.poisson_bytes, stream);
+      rc = D3P_ERR_UNSUPPORTED;
+      if (comm && comm->world > 1)             // selector draw split over the ranks (samplers.cu)
+        rc = d3p_poisson_sample_sharded(comm, bkey, sampler->q, sampler->n_records, B, sampler->suppress, pos_begin,
+                                        pos_end, w.idx, w.counts, w.mask, w.poisson, w.poisson_bytes, stream);
+      if (rc == D3P_ERR_UNSUPPORTED)           // same decision on every rank (window size, tiles >= ranks)
+        rc = d3p_poisson_sample(bkey, sampler->q, sampler->n_records, B, sampler->suppress, w.idx, w.counts, w.mask,
+                                w.poisson, w.poisson_bytes, stream);
       mask = w.mask;
     } else {
       uint32_t rcs[30];
@@ -106,6 +126,7 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
       rc = d3p_feistel_sample(rcs, sampler->n_records, 0, B, w.idx, stream);
     }
     if (rc != D3P_OK) break;
+    mark();
     // ---- DPSVI.update (svi.py:395-434) ----------------------------------------------------------------------
     uint32_t keys[3][16], tf[2];
     if ((rc = d3p_chacha_split_h(rng_key_io_h, 3, &keys[0][0])) != D3P_OK) break;           // carry, k_grad, k_noise
@@ -114,6 +135,7 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
                                   obs_scale,
                                   C, nullptr, nullptr, nullptr, w.step, w.step_bytes, stream);
     if (rc != D3P_OK) break;
+    mark();
     if ((rc = d3p_chacha_split_h(keys[2], (int32_t)lt.n_leaves, &lt.site_state[0][0])) != D3P_OK) break;
     rc = d3p_perturb_finalize_p2p_f32(w.step, n_part, P, B, &lt, dp_scale, C, obs_scale, 1, nullptr, optim_io_h,
                                       params_d, m_d, v_d, stats_out_d ? stats_out_d + 3 * (size_t)s : nullptr, nullptr,
@@ -123,6 +145,20 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
       if ((rc = d3p_adadp_finish_f32(optim_io_h, P, params_d, v_d, stream)) != D3P_OK) break;
     optim_io_h->step += 1;
     memcpy(rng_key_io_h, keys[0], sizeof(keys[0]));
+    mark();
   }
+  if (prof && rc == D3P_OK && ev.size() == 4 * (size_t)n_steps) {
+    cudaStreamSynchronize((cudaStream_t)stream);
+    double t[3] = {0, 0, 0};
+    for (uint32_t s = 0; s < n_steps; ++s)
+      for (int k = 0; k < 3; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[4 * s + k], ev[4 * s + k + 1]);
+        t[k] += ms;
+      }
+    fprintf(stderr, "[d3p epoch profile] rank %d: %u steps, mean ms: sampler %.4f  step kernel %.4f  finalize %.4f\n",
+            comm ? comm->rank : 0, n_steps, t[0] / n_steps, t[1] / n_steps, t[2] / n_steps);
+  }
+  for (cudaEvent_t e : ev) cudaEventDestroy(e);
   return rc;
 }

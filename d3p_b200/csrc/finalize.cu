@@ -48,7 +48,7 @@ D3P_D float adadp_element(const FinalizeArgs& a, float lr, uint32_t j, float x, 
   return e * e;
 }
 
-constexpr int kFinThreads = 128;
+constexpr int kFinThreads = 512;   // 16 warps share the partial rows of a 32-column strip: the row loop is latency-bound
 
 // site states live in constant-bank kernel parameters next to the leaf table
 struct SiteStates { uint32_t w[D3P_MAX_LEAVES][16]; };
@@ -103,8 +103,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
     float* mine = comm.data_peer[comm.rank];
     if (live) mine[j] = sum;
     if (lane == 0) { mine[comm.extra_off + 2 * blockIdx.x] = s_n; mine[comm.extra_off + 2 * blockIdx.x + 1] = s_loss; }
-    __threadfence_system();
-    __syncwarp();
+    __syncwarp();                                          // st.release.sys in the signal is cumulative
     comm_signal_and_wait(comm, blockIdx.x, lane);
     sum = 0.f; n_all = 0.f; loss_all = 0.f;
     for (int r = 0; r < comm.world; ++r) {
@@ -254,8 +253,7 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
 #pragma unroll
     for (int i = 0; i < 4; ++i) if (ok[i]) mine[jj[i]] = sum[i];
     if (threadIdx.x == 0) { mine[comm.extra_off + 2 * blockIdx.x] = s_n; mine[comm.extra_off + 2 * blockIdx.x + 1] = s_loss; }
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                                       // st.release.sys in the signal is cumulative
     if (warp == 0) comm_signal_and_wait(comm, blockIdx.x, lane);
     __syncthreads();
     n_all = 0.f; loss_all = 0.f;

@@ -109,12 +109,13 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   const uint32_t total_warps = gridDim.x * kStepWarps;
   const float Linv = a.L * a.inv_var;
 
-  // Each warp owns one contiguous run of ceil(npos / total_warps) positions and walks it in tiles of 8:
-  // per-warp loads differ by at most one example (measured: same kernel time as dealing whole tiles
-  // round-robin, an SM's 16 warps share its issue slots, so only the per-SM totals matter).
-  const uint32_t per_warp = (npos + total_warps - 1) / total_warps;
-  const uint32_t w_begin = min(npos, (blockIdx.x * kStepWarps + warp) * per_warp);
-  const uint32_t w_end = a.pos_begin + min(npos, w_begin + per_warp);
+  // Each warp owns one contiguous run of floor(npos / total_warps) (+1 for the first npos % total_warps
+  // warps) positions and walks it in tiles of 8: per-warp loads differ by at most one example, which
+  // matters when a rank holds only a few examples per warp (sharded batches: 5.3 at N = 8 on C2).
+  const uint32_t gw = blockIdx.x * kStepWarps + warp;
+  const uint32_t per_q = npos / total_warps, per_r = npos % total_warps;
+  const uint32_t w_begin = gw * per_q + min(gw, per_r);
+  const uint32_t w_end = a.pos_begin + w_begin + per_q + (gw < per_r ? 1u : 0u);
   for (uint32_t base = a.pos_begin + w_begin; base < w_end; base += TILE) {
     const uint32_t my_p = base + lane;
     bool my_valid = (lane < TILE) && (my_p < w_end) && (my_p < nv) && (!a.mask || a.mask[my_p]);

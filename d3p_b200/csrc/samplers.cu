@@ -1,5 +1,10 @@
 // K2 Feistel sampler, K3 Poisson select + ordered compaction, K4 masked row gather.
 // Replace d3p/util.py:216-301 and d3p/minibatch.py:29-39,103-131,210,233,306.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "comm.cuh"
 #include "common.cuh"
 #include "launch.cuh"
 
@@ -44,6 +49,33 @@ __global__ void __launch_bounds__(256) feistel_kernel(FeistelParams p, uint32_t 
 constexpr int kPoisThreads = 256;
 constexpr uint32_t kTileRecords = kPoisThreads * 16;
 
+// 16 selectors of ChaCha block `blk`: rng_suite.uniform(key, (N,), float32) <= q  (d3p/minibatch.py:34)
+D3P_D uint32_t poisson_block_mask(const ChaChaState& st, float q, uint32_t n_records, uint32_t blk) {
+  uint32_t ks[16];
+  chacha20_block(st.w, st.w[12] + blk, ks);
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float u = fmaxf(0.0f, bits_to_unit_float(ks[i]));
+    bool sel = (u <= q) && (blk * 16u + i < n_records);
+    m |= (sel ? 1u : 0u) << i;
+  }
+  return m;
+}
+
+D3P_D int tile_count(uint32_t m, int* warp_c) {      // CTA total of popc(m); valid in thread 0
+  int c = __popc(m);
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) warp_c[threadIdx.x >> 5] = c;
+  __syncthreads();
+  int t = 0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < kPoisThreads / 32; ++w) t += warp_c[w];
+  }
+  return t;
+}
+
 __global__ void __launch_bounds__(kPoisThreads) poisson_select_kernel(ChaChaState st, float q, uint32_t n_records,
                                                                       uint16_t* __restrict__ masks,
                                                                       int32_t* __restrict__ tile_counts) {
@@ -51,117 +83,166 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_select_kernel(ChaChaStat
   uint32_t n_blocks = (n_records + 15) / 16;
   uint32_t m = 0;
   if (blk < n_blocks) {
-    uint32_t ks[16];
-    chacha20_block(st.w, st.w[12] + blk, ks);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      // rng_suite.uniform(key, (N,), float32) <= q   (d3p/minibatch.py:34)
-      float u = fmaxf(0.0f, bits_to_unit_float(ks[i]));
-      bool sel = (u <= q) && (blk * 16u + i < n_records);
-      m |= (sel ? 1u : 0u) << i;
-    }
+    m = poisson_block_mask(st, q, n_records, blk);
     masks[blk] = (uint16_t)m;
   }
-  int c = __popc(m);
-  c = __reduce_add_sync(0xffffffffu, c);
   __shared__ int warp_c[kPoisThreads / 32];
-  if ((threadIdx.x & 31) == 0) warp_c[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-#pragma unroll
-    for (int w = 0; w < kPoisThreads / 32; ++w) t += warp_c[w];
-    tile_counts[blockIdx.x] = t;
-  }
+  const int t = tile_count(m, warp_c);
+  if (threadIdx.x == 0) tile_counts[blockIdx.x] = t;
 }
 
-// tile_off[t] = number of selected records in tiles > t ; counts[0] = total, counts[1] = effective.
-__global__ void __launch_bounds__(1024) poisson_scan_kernel(const int32_t* __restrict__ tile_counts,
-                                                            int32_t* __restrict__ tile_off, uint32_t n_tiles,
-                                                            uint32_t max_b, int suppress, int32_t* __restrict__ counts,
-                                                            uint8_t* __restrict__ mask) {
-  __shared__ int warp_tot[32];
-  __shared__ int carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
+// ---- sharded variant (comm.cuh): tiles [tile_begin, tile_begin + gridDim.x) of this rank ------------------
+__global__ void __launch_bounds__(kPoisThreads) poisson_select_sharded_kernel(ChaChaState st, float q,
+                                                                              uint32_t n_records, uint32_t tile_begin,
+                                                                              SampDev sd) {
+  const uint32_t tile = tile_begin + blockIdx.x;
+  const uint32_t blk = tile * kPoisThreads + threadIdx.x;
+  const uint32_t n_blocks = (n_records + 15) / 16;
+  uint32_t m = 0;
+  if (blk < n_blocks) {
+    m = poisson_block_mask(st, q, n_records, blk);
+    sd.masks_local[blk] = (uint16_t)m;
+  }
+  __shared__ int warp_c[kPoisThreads / 32];
+  const int t = tile_count(m, warp_c);
+  if (threadIdx.x == 0) sd.counts_local[tile] = t;
+}
+
+// Runs after the select kernel of this rank's slice (the kernel boundary makes the slice's masks and counts
+// visible device-wide): pushes the slice's tile counts into every peer's window with coalesced posted stores,
+// then one system-scope fence and one release store per peer.  Keeping fences and atomics out of the
+// 1000+ select CTAs matters: a fence.sys per CTA cost ~20 us per launch.
+__global__ void __launch_bounds__(kPoisThreads) poisson_publish_kernel(uint32_t tile_begin, uint32_t n_local, SampDev sd) {
+  for (uint32_t i = threadIdx.x; i < n_local; i += kPoisThreads) {
+    const int32_t v = sd.counts_local[tile_begin + i];
+    for (int r = 0; r < sd.world; ++r)
+      if (r != sd.rank) sd.counts_peer[r][tile_begin + i] = v;
+  }
+  __threadfence_system();
   __syncthreads();
+  if ((int)threadIdx.x < sd.world && (int)threadIdx.x != sd.rank)
+    st_release_sys(sd.flags_peer[threadIdx.x] + sd.rank, sd.epoch);
+}
+
+D3P_D int tile_owner(const SampDev& sd, uint32_t tile) { return (int)((sd.n_tiles - 1u - tile) / sd.tiles_per_rank); }
+
+// Pass B + C fused: every CTA (one per tile) first adds up the tile counts above it — n_tiles is a few
+// thousand, i.e. ~10 loads per thread — which replaces the former single-CTA scan launch, then compacts its
+// tile in DESCENDING record order: idx[s] for the selected records (s = number of selected records with a
+// larger index), and the unselected ones behind them for the padding slots (d3p/minibatch.py:37).
+// counts[0] = number selected, counts[1] = after truncate / suppress (:119-122), mask = arange(max_b) < counts[1].
+// kSharded (comm.cuh): counts were pushed into the local window by the tile owners, masks are read from the
+// owner's window, only positions [pos_begin, pos_end) are written and padding slots are left alone.
+template <bool kSharded>
+__global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uint16_t* __restrict__ masks,
+                                                                       const int32_t* __restrict__ tile_counts,
+                                                                       uint32_t n_records, uint32_t n_tiles,
+                                                                       uint32_t max_b, int suppress, uint32_t pos_begin,
+                                                                       uint32_t pos_end, int32_t* __restrict__ idx,
+                                                                       int32_t* __restrict__ counts,
+                                                                       uint8_t* __restrict__ mask, SampDev sd) {
+  const uint32_t tile = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < n_tiles; base += 1024) {
-    uint32_t r = base + threadIdx.x;            // r-th tile counted from the high end
-    int v = (r < n_tiles) ? tile_counts[n_tiles - 1 - r] : 0;
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+  __shared__ int red[2][kPoisThreads / 32];
+  __shared__ int warp_tot[kPoisThreads / 32];
+  if (kSharded) {                              // wait until every peer has published its slice
+    if ((int)threadIdx.x < sd.world && (int)threadIdx.x != sd.rank) {
+      const uint32_t* f = sd.flags_local + threadIdx.x;
+      const long long t0 = clock64();
+      while ((int32_t)(ld_acquire_sys(f) - sd.epoch) < 0)
+        if (clock64() - t0 > (3LL << 31)) { atomicAdd(sd.err, 1u); break; }
     }
-    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-      int w = warp_tot[lane];
-      int wi = w;
+  }
+  int above = 0, all = 0;
+  for (uint32_t t = threadIdx.x; t < n_tiles; t += kPoisThreads) {
+    int v;
+    if (kSharded) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(sd.counts_local + t) : "memory");
+    else v = tile_counts[t];
+    all += v;
+    above += t > tile ? v : 0;
+  }
+  above = __reduce_add_sync(0xffffffffu, above);
+  all = __reduce_add_sync(0xffffffffu, all);
+  if (lane == 0) { red[0][warp] = above; red[1][warp] = all; }
+  __syncthreads();
+  above = 0; all = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += t;
+  for (int w = 0; w < kPoisThreads / 32; ++w) { above += red[0][w]; all += red[1][w]; }
+  const uint32_t total = (uint32_t)all;
+  const uint32_t eff = suppress ? (total <= max_b ? total : 0u) : (total < max_b ? total : max_b);
+  if (tile == 0 && threadIdx.x == 0) { counts[0] = (int32_t)total; counts[1] = (int32_t)eff; }
+  if (mask) {                                  // this CTA's slice of the mask, 4 bytes per store when aligned
+    const uint32_t words = (max_b + 3) / 4, per = (words + n_tiles - 1) / n_tiles;
+    const bool aligned = (reinterpret_cast<uintptr_t>(mask) & 3) == 0;
+    for (uint32_t wd = tile * per + threadIdx.x; wd < min(words, (tile + 1) * per); wd += kPoisThreads) {
+      const uint32_t i = wd * 4;
+      if (aligned && i + 4 <= max_b) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v |= ((i + k < eff) ? 1u : 0u) << (8 * k);
+        *reinterpret_cast<uint32_t*>(mask + i) = v;
+      } else {
+        for (uint32_t j = i; j < min(i + 4, max_b); ++j) mask[j] = j < eff ? 1 : 0;
       }
-      warp_tot[lane] = wi - w;   // exclusive
     }
-    __syncthreads();
-    int carry = carry_s;
-    int excl = carry + warp_tot[warp] + incl - v;
-    if (r < n_tiles) tile_off[n_tiles - 1 - r] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = excl + v;
-    __syncthreads();
   }
-  int total = carry_s;
-  int eff = suppress ? ((uint32_t)total <= max_b ? total : 0) : ((uint32_t)total < max_b ? total : (int)max_b);
-  if (threadIdx.x == 0) { counts[0] = total; counts[1] = eff; }
-  if (mask)
-    for (uint32_t i = threadIdx.x; i < max_b; i += 1024) mask[i] = (i < (uint32_t)eff) ? 1 : 0;
-}
-
-__global__ void __launch_bounds__(kPoisThreads) poisson_scatter_kernel(const uint16_t* __restrict__ masks,
-                                                                       const int32_t* __restrict__ tile_off,
-                                                                       const int32_t* __restrict__ counts,
-                                                                       uint32_t n_records, uint32_t max_b,
-                                                                       int32_t* __restrict__ idx) {
-  uint32_t blk = blockIdx.x * kPoisThreads + threadIdx.x;
-  uint32_t n_blocks = (n_records + 15) / 16;
-  uint32_t m = (blk < n_blocks) ? masks[blk] : 0u;
-  int c = __popc(m);
-  // exclusive scan over threads in DESCENDING thread order
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int incl = c;
+  const uint32_t lim = kSharded ? min(min(pos_end, max_b), eff) : max_b;
+  const uint32_t blk = tile * kPoisThreads + threadIdx.x;
+  const uint32_t n_blocks = (n_records + 15) / 16;
+  uint32_t m = 0;
+  if (kSharded) {
+    // CTA-uniform early out: this tile's positions [above, above + count) miss [pos_begin, lim)
+    int cnt;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(cnt) : "l"(sd.counts_local + tile) : "memory");
+    if ((uint32_t)(above + cnt) <= pos_begin || (uint32_t)above >= lim) return;
+    if (blk < n_blocks) {
+      uint16_t mv;
+      asm volatile("ld.relaxed.sys.global.u16 %0, [%1];" : "=h"(mv) : "l"(sd.masks_peer[tile_owner(sd, tile)] + blk) : "memory");
+      m = mv;
+    }
+  } else {
+    m = (blk < n_blocks) ? masks[blk] : 0u;
+  }
+  const int c = __popc(m);
+  int incl = c;                                // exclusive scan over threads in DESCENDING thread order
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     int t = __shfl_down_sync(0xffffffffu, incl, o);
     if (lane + o < 32) incl += t;
   }
-  __shared__ int warp_tot[kPoisThreads / 32];
   if (lane == 0) warp_tot[warp] = incl;
   __syncthreads();
-  int above = 0;
+  int higher = 0;
 #pragma unroll
   for (int w = 0; w < kPoisThreads / 32; ++w)
-    if (w > warp) above += warp_tot[w];
-  uint32_t s = (uint32_t)(tile_off[blockIdx.x] + above + incl - c);   // selected records with a larger index
+    if (w > warp) higher += warp_tot[w];
+  uint32_t s = (uint32_t)(above + higher + incl - c);   // selected records with a larger index
   if (blk >= n_blocks) return;
-  const uint32_t total = (uint32_t)counts[0];
+  if (kSharded) {
+#pragma unroll
+    for (int i = 15; i >= 0; --i) {
+      if ((m >> i) & 1u) {
+        if (s >= pos_begin && s < lim) idx[s] = (int32_t)(blk * 16u + i);
+        ++s;
+      }
+    }
+    return;
+  }
   const uint32_t rec_hi = blk * 16u + 15u;
   // quick reject: nothing from this chacha block can land in [0, max_b)
-  bool any_sel = (m != 0) && (s < max_b);
-  bool any_unsel = total < max_b && ((n_records - 1u - min(rec_hi, n_records - 1u)) - s + total < max_b + 16u);
+  const bool any_sel = (m != 0) && (s < max_b);
+  const bool any_unsel = total < max_b && ((n_records - 1u - min(rec_hi, n_records - 1u)) - s + total < max_b + 16u);
   if (!any_sel && !any_unsel) return;
 #pragma unroll
   for (int i = 15; i >= 0; --i) {
-    uint32_t rec = blk * 16u + i;
+    const uint32_t rec = blk * 16u + i;
     if (rec >= n_records) continue;
     if ((m >> i) & 1u) {
       if (s < max_b) idx[s] = (int32_t)rec;
       ++s;
     } else {
-      uint32_t pos = total + (n_records - 1u - rec) - s;
+      const uint32_t pos = total + (n_records - 1u - rec) - s;
       if (pos < max_b) idx[pos] = (int32_t)rec;
     }
   }
@@ -267,9 +348,57 @@ int32_t d3p_poisson_sample(const uint32_t state_h[16], float q, uint32_t n_recor
   uint32_t n_tiles = (n_blocks + kPoisThreads - 1) / kPoisThreads;
   cudaStream_t s = (cudaStream_t)stream;
   poisson_select_kernel<<<n_tiles, kPoisThreads, 0, s>>>(load_state(state_h), q, n_records, w.masks, w.tile_counts);
-  poisson_scan_kernel<<<1, 1024, 0, s>>>(w.tile_counts, w.tile_off, n_tiles, max_b, suppress, counts_d, mask_d);
-  if (max_b)
-    poisson_scatter_kernel<<<n_tiles, kPoisThreads, 0, s>>>(w.masks, w.tile_off, counts_d, n_records, max_b, idx_d);
+  SampDev none;
+  memset(&none, 0, sizeof(none));
+  poisson_compact_kernel<false><<<n_tiles, kPoisThreads, 0, s>>>(w.masks, w.tile_counts, n_records, n_tiles, max_b,
+                                                                 suppress, 0, max_b, idx_d, counts_d, mask_d, none);
+  return check_launch();
+}
+
+int32_t d3p_poisson_sample_sharded(d3p_comm* comm, const uint32_t state_h[16], float q, uint32_t n_records,
+                                   uint32_t max_b, int32_t suppress, uint32_t pos_begin, uint32_t pos_end,
+                                   int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d, size_t ws_bytes,
+                                   void* stream) {
+  if (!comm || !state_h || !counts_d || !ws_d || (!idx_d && max_b) || n_records == 0 || max_b > n_records ||
+      pos_begin > pos_end || pos_end > max_b)
+    return D3P_ERR_INVALID_ARGUMENT;
+  PoissonWs w = carve_poisson_ws(ws_d, n_records);
+  if (ws_bytes < w.bytes) return D3P_ERR_WORKSPACE;
+  const uint32_t n_blocks = (n_records + 15) / 16;
+  const uint32_t n_tiles = (n_blocks + kPoisThreads - 1) / kPoisThreads;
+  // every rank must own at least one tile (the decision is the same on all ranks: nothing is signalled yet)
+  const uint32_t tpr = (n_tiles + comm->world - 1) / comm->world;
+  if (comm->world < 2 || (uint64_t)(comm->world - 1) * tpr >= n_tiles || comm->max_records < n_records)
+    return D3P_ERR_UNSUPPORTED;
+  SampDev sd;
+  memset(&sd, 0, sizeof(sd));
+  if (!samp_next(comm, n_records, n_tiles, &sd)) return D3P_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  // slices in DESCENDING record order: rank 0 draws the top tiles, whose records fill the first positions
+  const uint32_t hi = n_tiles > (uint32_t)sd.rank * sd.tiles_per_rank ? n_tiles - (uint32_t)sd.rank * sd.tiles_per_rank : 0;
+  const uint32_t lo = hi > sd.tiles_per_rank ? hi - sd.tiles_per_rank : 0;
+  // D3P_SAMPLER_PROFILE=1: per-kernel timings of calls 100..199 on stderr (development aid; synchronises once)
+  static const bool prof = getenv("D3P_SAMPLER_PROFILE") != nullptr;
+  static int calls = 0;
+  static cudaEvent_t pe[100][4];
+  const bool rec = prof && calls >= 100 && calls < 200;
+  auto mark = [&](int k) { if (rec) { cudaEventCreate(&pe[calls - 100][k]); cudaEventRecord(pe[calls - 100][k], s); } };
+  mark(0);
+  poisson_select_sharded_kernel<<<hi - lo, kPoisThreads, 0, s>>>(load_state(state_h), q, n_records, lo, sd);
+  mark(1);
+  poisson_publish_kernel<<<1, kPoisThreads, 0, s>>>(lo, hi - lo, sd);
+  mark(2);
+  poisson_compact_kernel<true><<<n_tiles, kPoisThreads, 0, s>>>(nullptr, nullptr, n_records, n_tiles, max_b, suppress,
+                                                                pos_begin, pos_end, idx_d, counts_d, mask_d, sd);
+  mark(3);
+  if (prof && ++calls == 200) {
+    cudaStreamSynchronize(s);
+    double t[3] = {0, 0, 0};
+    for (int c = 0; c < 100; ++c)
+      for (int k = 0; k < 3; ++k) { float ms; cudaEventElapsedTime(&ms, pe[c][k], pe[c][k + 1]); t[k] += ms; }
+    fprintf(stderr, "[d3p sampler profile] rank %d: select %.4f  scan %.4f  scatter %.4f ms\n", sd.rank, t[0] / 100,
+            t[1] / 100, t[2] / 100);
+  }
   return check_launch();
 }
 

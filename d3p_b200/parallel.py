@@ -21,13 +21,14 @@ class PeerWindow:
     ``P + 2`` clipped sums there and reads the peers' copies, so a sharded step needs neither a
     reduce kernel nor an NCCL launch.  ``torch.distributed`` is used once, to swap the IPC handles."""
 
-    def __init__(self, rank, world_size, max_params, group=None):
+    def __init__(self, rank, world_size, max_params, group=None, max_records=0):
         import ctypes as C
-        self.rank, self.world_size = rank, world_size
+        self.rank, self.world_size, self.group = rank, world_size, group
+        self.max_records = int(max_records)
         handle = (C.c_uint8 * 64)()
         self._comm = C.c_void_p()
-        _n.check(_n.lib().d3p_comm_create(rank, world_size, int(max_params), C.byref(self._comm), handle),
-                 "comm_create")
+        _n.check(_n.lib().d3p_comm_create(rank, world_size, int(max_params), self.max_records, C.byref(self._comm),
+                                          handle), "comm_create")
         if world_size > 1:
             handles = [None] * world_size
             dist.all_gather_object(handles, bytes(handle), group=group)
@@ -39,6 +40,17 @@ class PeerWindow:
     @property
     def ptr(self):
         return self._comm
+
+    def with_records(self, n_records):
+        """A window that can also carry the sharded Poisson sampler for ``n_records`` records (collective:
+        every rank must call it at the same point; the old window is closed)."""
+        if n_records <= self.max_records:
+            return self
+        torch.cuda.synchronize()
+        if self.world_size > 1:
+            dist.barrier(group=self.group)
+        self.close()
+        return PeerWindow(self.rank, self.world_size, self.max_params, self.group, max_records=n_records)
 
     def timeouts(self):
         import ctypes as C

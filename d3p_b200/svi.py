@@ -370,6 +370,8 @@ class DPSVI:
             raise _n.D3PNativeError("unsupported family / sampler configuration for run_epoch")
         if getattr(self, "_epoch_ws", None) is None or self._epoch_ws.numel() < need or self._epoch_ws.device != _dev():
             self._epoch_ws = torch.empty(need, dtype=torch.uint8, device=_dev())
+        if self.peer_window is not None and spec["kind"] == _n.SAMPLER_POISSON:
+            self.peer_window = self.peer_window.with_records(spec["n_records"])   # sharded selector draw
         os_ = svi_state.optim_state
         if self.donate_state:
             flat, m, v, lr = os_.flat, os_.m, os_.v, os_.lr

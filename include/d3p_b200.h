@@ -269,11 +269,20 @@ int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_partials, u
  * that never shows up makes the kernel give up after ~3 s and count a time-out instead of
  * hanging the GPU; d3p_comm_timeouts reads the counter (synchronises).
  * ------------------------------------------------------------------------------------------ */
-int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_params, d3p_comm** comm_out,
-                        uint8_t handle_out_h[64]);
+int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_params, uint32_t max_records /* 0: no sharded
+                        sampler */, d3p_comm** comm_out, uint8_t handle_out_h[64]);
 int32_t d3p_comm_connect(d3p_comm* comm, const uint8_t* handles_h);
 int32_t d3p_comm_timeouts(d3p_comm* comm, uint32_t* count_out_h);
 int32_t d3p_comm_destroy(d3p_comm* comm);
+/* d3p_poisson_sample with the selector draw (the expensive part: N / 16 ChaCha blocks) split over the
+ * ranks: rank r draws its slice of the records, publishes 16-bit selection masks and per-tile counts in
+ * its window, every rank scans all counts and compacts only the positions [pos_begin, pos_end) it owns.
+ * counts_d / mask_d are complete on every rank; idx_d[p] is written for pos_begin <= p < min(pos_end,
+ * counts_d[1]) only.  Bit-identical to d3p_poisson_sample on those positions. */
+int32_t d3p_poisson_sample_sharded(d3p_comm* comm, const uint32_t state_h[16], float q, uint32_t n_records,
+                                   uint32_t max_b, int32_t suppress, uint32_t pos_begin, uint32_t pos_end,
+                                   int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d,
+                                   size_t ws_bytes, void* stream);
 /* d3p_perturb_finalize_f32 on this rank's partial rows + the peers' (comm may be NULL = local only). */
 int32_t d3p_perturb_finalize_p2p_f32(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
                                      const d3p_leaf_table* leaves_h, float dp_scale, float C, float obs_scale,

@@ -73,6 +73,42 @@ def check_local_rows(dev, rank, world):
     return same
 
 
+def check_sharded_sampler(dev, rank, world):
+    """d3p_poisson_sample_sharded == d3p_poisson_sample on this rank's positions, counts and mask (bit-exact)."""
+    import ctypes as C
+    from d3p_b200 import _native as _n
+    N = 300_000
+    win = parallel.PeerWindow(rank, world, 16, max_records=N)
+    need = _n.lib().d3p_poisson_workspace_bytes(N)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    ok = True
+    for it, (q, max_b, suppress) in enumerate([(0.01, 3200, 0), (0.01, 2900, 0), (0.01, 2900, 1), (0.02, 6500, 0),
+                                               (0.0, 10, 0), (0.01, 3200, 0)]):
+        key = rng.fold_in(rng.PRNGKey(11), it)
+        ref_idx, ref_counts, ref_mask = mb.poisson_sample_idxs(key, q, N, cutoff_size=max_b, suppress=bool(suppress))
+        pb, pe = parallel.position_range(max_b, rank, world)
+        idx = torch.full((max_b,), -1, dtype=torch.int32, device=dev)
+        counts = torch.empty(2, dtype=torch.int32, device=dev)
+        mask = torch.empty(max_b, dtype=torch.uint8, device=dev)
+        a = np.ascontiguousarray(np.asarray(key, dtype=np.uint32).reshape(16))
+        _n.check(_n.lib().d3p_poisson_sample_sharded(win.ptr, a.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                     float(np.float32(q)), N, max_b, suppress, pb, pe, _n.ptr(idx),
+                                                     _n.ptr(counts), _n.ptr(mask), _n.ptr(ws), need, _n.stream_ptr()),
+                 "poisson_sample_sharded")
+        torch.cuda.synchronize()
+        eff = int(ref_counts[1])
+        hi = min(pe, eff)
+        good = (torch.equal(counts, ref_counts) and torch.equal(mask.view(torch.bool), ref_mask)
+                and (hi <= pb or torch.equal(idx[pb:hi], ref_idx[pb:hi])))
+        ok = ok and good
+        if rank == 0:
+            print(f"sharded sampler case {it}: counts {counts.tolist()} ok={good}", flush=True)
+    ok = ok and win.timeouts() == 0
+    dist.barrier()
+    win.close()
+    return ok
+
+
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -104,6 +140,7 @@ def main():
                 print(f"{name} [{backend}{' epoch' if epoch else ''}]: sharded-vs-single rel err {err:.2e}, "
                       f"replicas identical {same}, losses {l_sh} vs {l_1}", flush=True)
     ok = check_local_rows(dev, rank, world) and ok
+    ok = check_sharded_sampler(dev, rank, world) and ok
     dist.barrier()
     dist.destroy_process_group()
     if not ok:
