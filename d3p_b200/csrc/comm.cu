@@ -8,18 +8,19 @@
 namespace d3p {
 
 bool comm_next(d3p_comm* c, uint32_t n_params, uint32_t n_ctas, CommDev* out) {
-  if (!c || !c->connected || n_params + 2 > c->max_params + 2 || n_ctas == 0 || n_ctas > D3P_COMM_MAX_CTAS) return false;
+  if (!c || !c->connected || n_params > c->max_params || n_ctas == 0 || n_ctas > D3P_COMM_MAX_CTAS) return false;
   c->epoch += 1;
   out->world = c->world;
   out->rank = c->rank;
   out->epoch = c->epoch;
   out->extra_off = c->max_params;
-  out->flags_local = reinterpret_cast<uint32_t*>(c->local);
   out->err = reinterpret_cast<uint32_t*>(c->local + c->err_off);
+  out->ll_stride = c->ll_stride;
+  const size_t block = (size_t)(c->epoch & 1u) * c->world * c->ll_stride;      // u64 elements
+  out->ll_local = reinterpret_cast<unsigned long long*>(c->local + c->ll_off) + block;
   for (int r = 0; r < D3P_COMM_MAX_RANKS; ++r) {
     uint8_t* base = r < c->world ? c->peer[r] : c->local;
-    out->flags_peer[r] = reinterpret_cast<uint32_t*>(base);
-    out->data_peer[r] = reinterpret_cast<float*>(base + c->data_off) + (size_t)(c->epoch & 1u) * c->stride_floats;
+    out->ll_peer[r] = reinterpret_cast<unsigned long long*>(base + c->ll_off) + block + (size_t)c->rank * c->ll_stride;
   }
   return true;
 }
@@ -32,20 +33,16 @@ bool samp_next(d3p_comm* c, uint32_t n_records, uint32_t n_tiles, SampDev* out) 
   out->world = c->world; out->rank = c->rank; out->epoch = c->samp_epoch;
   out->n_tiles = n_tiles;
   out->tiles_per_rank = (n_tiles + c->world - 1) / c->world;
-  uint32_t* err = reinterpret_cast<uint32_t*>(c->local + c->err_off);
-  out->err = err;
-  out->flags_local = err + 8;
-  out->done_counter = err + 32;
+  out->err = reinterpret_cast<uint32_t*>(c->local + c->err_off);
   for (int r = 0; r < D3P_COMM_MAX_RANKS; ++r) {
     uint8_t* base = r < c->world ? c->peer[r] : c->local;
     uint8_t* buf = base + c->samp_off + (size_t)(c->samp_epoch & 1u) * c->samp_stride;
-    out->flags_peer[r] = reinterpret_cast<uint32_t*>(base + c->err_off) + 8;
     out->masks_peer[r] = reinterpret_cast<const uint16_t*>(buf);
-    out->counts_peer[r] = reinterpret_cast<int32_t*>(buf + counts_off);
+    out->counts_peer[r] = reinterpret_cast<uint32_t*>(buf + counts_off);
   }
   uint8_t* mine = c->local + c->samp_off + (size_t)(c->samp_epoch & 1u) * c->samp_stride;
   out->masks_local = reinterpret_cast<uint16_t*>(mine);
-  out->counts_local = reinterpret_cast<int32_t*>(mine + counts_off);
+  out->counts_local = reinterpret_cast<const uint32_t*>(mine + counts_off);
   return true;
 }
 
@@ -60,15 +57,14 @@ extern "C" int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_par
   if (!c) return D3P_ERR_CUDA;
   memset(c, 0, sizeof(*c));
   c->rank = rank; c->world = world; c->max_params = max_params;
-  c->flags_bytes = (size_t)D3P_COMM_MAX_RANKS * D3P_COMM_MAX_CTAS * sizeof(uint32_t);
-  c->err_off = c->flags_bytes;
-  c->data_off = c->err_off + 256;
-  c->stride_floats = d3p::align_up((size_t)max_params + 2 * (size_t)D3P_COMM_MAX_CTAS, 64);
-  c->samp_off = d3p::align_up(c->data_off + 2 * c->stride_floats * sizeof(float), 256);
+  c->err_off = 0;
+  c->ll_off = 256;
+  c->ll_stride = d3p::align_up((size_t)max_params + 2 * (size_t)D3P_COMM_MAX_CTAS, 32);
+  c->samp_off = d3p::align_up(c->ll_off + 2 * (size_t)world * c->ll_stride * sizeof(unsigned long long), 256);
   c->max_records = max_records;
   if (max_records) {
     const size_t n_blocks = ((size_t)max_records + 15) / 16, n_tiles = (n_blocks + 255) / 256;
-    c->samp_stride = d3p::align_up(n_blocks * sizeof(uint16_t), 256) + d3p::align_up(n_tiles * sizeof(int32_t), 256);
+    c->samp_stride = d3p::align_up(n_blocks * sizeof(uint16_t), 256) + d3p::align_up(n_tiles * sizeof(uint32_t), 256);
   }
   c->total = c->samp_off + 2 * c->samp_stride;
   void* p = nullptr;

@@ -1,9 +1,16 @@
-// NVLink peer-memory exchange used by the finalize kernels when a minibatch is sharded over the GPUs of
-// one box.  Every rank owns one cudaMalloc'ed "window" that all peers map through
-// CUDA IPC; a step's clipped sums are exchanged INSIDE the finalize kernel (one-shot all-reduce: publish
-// my P + 2 partial sums, raise a flag in every peer's window, wait for the peers' flags, read their sums
-// over NVLink and add them in rank order), so the multi-GPU step has no separate reduce kernel and no
-// NCCL launch.  All ranks add in the same order => bit-identical replicas.
+// NVLink peer-memory exchange used when a minibatch is sharded over the GPUs of one box (SURVEY.md
+// section 8e).  Every rank owns one cudaMalloc'ed "window" that all peers map through CUDA IPC.
+//
+// Protocol: tagged words pushed into the READER's window (the scheme NCCL calls LL).  A value travels as
+// one aligned 8-byte store {payload, epoch}; 8-byte stores are single-copy atomic, so the reader simply
+// polls its own memory until the tag equals the current epoch — no flag, no fence, no remote read: the
+// cost of an exchange is ONE NVLink traversal.  (Measured on this pool: a fence.sys with remote stores
+// outstanding costs ~10 us, which is what a publish -> fence -> flag -> pull scheme pays twice per step.)
+//   * finalize kernels: every rank pushes its P + 2 partial sums to all peers and adds the G copies in
+//     rank order => one-shot all-reduce inside the kernel, bit-identical on all ranks;
+//   * sharded Poisson sampler: tile owners push {count, epoch} words of their slice to all peers.
+// Buffers alternate with the epoch parity: a writer can be at most one exchange ahead of a reader, since
+// it cannot finish exchange e + 1 before the reader has pushed its own e + 1 data, i.e. finished reading e.
 #pragma once
 #include "common.cuh"
 
@@ -14,8 +21,8 @@ struct d3p_comm {
   int rank, world;
   uint32_t max_params, epoch;
   uint32_t max_records, samp_epoch;             // sharded Poisson sampler (0 = not provisioned)
-  size_t flags_bytes, err_off, data_off, stride_floats, total;
-  size_t samp_off, samp_stride;                 // 2 x [masks u16[n_blocks] | tile_counts i32[n_tiles]] by epoch parity
+  size_t err_off, ll_off, ll_stride, total;     // ll: u64 [2][world][ll_stride]
+  size_t samp_off, samp_stride;                 // 2 x [masks u16[n_blocks] | tagged tile counts u32[n_tiles]]
   uint8_t* local;                               // this rank's window
   uint8_t* peer[D3P_COMM_MAX_RANKS];            // mapped windows (peer[rank] == local)
   bool connected;
@@ -24,18 +31,18 @@ struct d3p_comm {
 namespace d3p {
 
 // Window layout (identical on every rank):
-//   flags  u32 [MAX_RANKS][MAX_CTAS]   slot [r][cta] is written by rank r, read by the owner
-//   err    u32 [64]                    [0] = number of spin time-outs seen by this rank's kernels
-//   data   f32 [2][stride]             double-buffered by epoch parity: [0, max_params) column sums,
-//                                      [max_params + 2 * cta, +2) = (count, loss) as seen by CTA `cta`
+//   err   u32 [64]                      [0] = number of spin time-outs seen by this rank's kernels
+//   ll    u64 [2][world][ll_stride]     slot [parity][src][j]: written by rank src, read by the owner;
+//                                       j < max_params: column sums, max_params + 2 cta (+1): (count, loss)
+//   samp  2 x { masks, tagged counts }  see SampDev
 struct CommDev {
   int world, rank;
   uint32_t epoch;                 // 1, 2, 3, ... one per exchange; identical on all ranks
   uint32_t extra_off;             // = max_params
-  uint32_t* flags_local;
   uint32_t* err;
-  uint32_t* flags_peer[D3P_COMM_MAX_RANKS];
-  float* data_peer[D3P_COMM_MAX_RANKS];   // already offset to this epoch's buffer
+  unsigned long long* ll_local;                        // this epoch's [world][ll_stride] block of my window
+  unsigned long long* ll_peer[D3P_COMM_MAX_RANKS];     // row `rank` of this epoch's block in every peer's window
+  size_t ll_stride;
 };
 
 D3P_D void st_release_sys(uint32_t* p, uint32_t v) {
@@ -46,50 +53,62 @@ D3P_D uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-D3P_D float ld_peer(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+D3P_D uint32_t ld_relaxed_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
-// Called by the first warp of a CTA after every thread of the CTA has stored its values into the local
-// window and the CTA (or warp, if only this warp wrote) has synchronised: the barrier orders those stores
-// before the signalling lanes, whose st.release.sys is cumulative, so no per-thread system fence is needed.
-// On return the peers' values of this CTA's slots are readable (after the caller's next barrier).
-D3P_D void comm_signal_and_wait(const CommDev& c, uint32_t cta, int lane) {
-  if (lane < c.world && lane != c.rank) st_release_sys(c.flags_peer[lane] + (size_t)c.rank * D3P_COMM_MAX_CTAS + cta, c.epoch);
-  if (lane < c.world && lane != c.rank) {
-    const uint32_t* f = c.flags_local + (size_t)lane * D3P_COMM_MAX_CTAS + cta;
-    const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(f) - c.epoch) < 0) {
-      if (clock64() - t0 > (3LL << 31)) {          // ~3 s: a peer died or diverged; do not hang the GPU
-        atomicAdd(c.err, 1u);
-        break;
-      }
+// push one tagged float to slot j of my row in every peer's window
+D3P_D void ll_push(const CommDev& c, size_t j, float v) {
+  const unsigned long long w = ((unsigned long long)c.epoch << 32) | (unsigned long long)__float_as_uint(v);
+  for (int r = 0; r < c.world; ++r)
+    if (r != c.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(c.ll_peer[r] + j), "l"(w) : "memory");
+}
+// wait for rank src's slot j of this epoch (spins on LOCAL memory)
+D3P_D float ll_wait(const CommDev& c, int src, size_t j) {
+  const unsigned long long* p = c.ll_local + (size_t)src * c.ll_stride + j;
+  unsigned long long w;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    if ((uint32_t)(w >> 32) == c.epoch) break;
+    if (clock64() - t0 > (3LL << 31)) {            // ~3 s: a peer died or diverged; do not hang the GPU
+      atomicAdd(c.err, 1u);
+      break;
     }
   }
-  __syncwarp();
+  return __uint_as_float((uint32_t)w);
 }
 
-
-// Sharded Poisson sampler (samplers.cu): rank r draws the selectors of its slice of the records and
-// publishes the 16-bit selection masks and per-tile counts in its window; every rank scans all counts
-// (read from the owners over NVLink) and compacts only the batch positions it owns.
-//   err[8 + r]  "select done" flag written by rank r (sampler epoch);  err[32] = local CTA-done counter
+// Sharded Poisson sampler (samplers.cu): rank r draws the selectors of its slice of the records, keeps the
+// 16-bit selection masks in its window and pushes one tagged word {count (low 16 bits), epoch} per tile to
+// every rank (itself included); every rank then adds up all counts and compacts only the batch positions
+// it owns, pulling the masks of a tile from its owner (the tagged word is stored with release semantics
+// after the tile's masks, the reader fences before the pull).
 struct SampDev {
   int world, rank;
-  uint32_t epoch;
+  uint32_t epoch;                             // 16-bit tag = epoch & 0xffff
   uint32_t tiles_per_rank, n_tiles;
-  uint32_t* flags_local;                      // [MAX_RANKS]
-  uint32_t* done_counter;                     // local
   uint32_t* err;
-  uint32_t* flags_peer[D3P_COMM_MAX_RANKS];
   const uint16_t* masks_peer[D3P_COMM_MAX_RANKS];     // this epoch's buffer in every window
-  int32_t* counts_peer[D3P_COMM_MAX_RANKS];           // owners PUSH their tile counts into every window
+  uint32_t* counts_peer[D3P_COMM_MAX_RANKS];          // tagged counts: owners push into every window
   uint16_t* masks_local;
-  int32_t* counts_local;
+  const uint32_t* counts_local;
 };
 bool samp_next(d3p_comm* comm, uint32_t n_records, uint32_t n_tiles, SampDev* out);
+
+D3P_D uint32_t samp_wait_count(const SampDev& sd, uint32_t tile) {
+  const uint32_t tag = sd.epoch & 0xffffu;
+  uint32_t w;
+  const long long t0 = clock64();
+  for (;;) {
+    w = ld_relaxed_sys_u32(sd.counts_local + tile);
+    if ((w >> 16) == tag) break;
+    if (clock64() - t0 > (3LL << 31)) { atomicAdd(sd.err, 1u); break; }
+  }
+  return w & 0xffffu;
+}
 
 // Fills the device view for the next exchange (advances the epoch); false if the shapes do not fit.
 bool comm_next(d3p_comm* comm, uint32_t n_params, uint32_t n_ctas, CommDev* out);

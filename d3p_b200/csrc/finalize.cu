@@ -99,18 +99,18 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
   for (int w = 0; w < kFinThreads / 32; ++w) sum += colred[w][lane];
   float n_all = s_n, loss_all = s_loss;
   if (comm.world > 1) {
-    // one-shot all-reduce over NVLink peer memory (comm.cuh): publish, signal, wait, add in rank order
-    float* mine = comm.data_peer[comm.rank];
-    if (live) mine[j] = sum;
-    if (lane == 0) { mine[comm.extra_off + 2 * blockIdx.x] = s_n; mine[comm.extra_off + 2 * blockIdx.x + 1] = s_loss; }
-    __syncwarp();                                          // st.release.sys in the signal is cumulative
-    comm_signal_and_wait(comm, blockIdx.x, lane);
+    // one-shot all-reduce over NVLink peer memory (comm.cuh): push tagged words to every peer, poll my own
+    // window for theirs, add the G copies in rank order (identical on every rank)
+    const float mine = sum, my_n = s_n, my_loss = s_loss;
+    const size_t jn = comm.extra_off + 2 * (size_t)blockIdx.x;
+    if (live) ll_push(comm, j, mine);
+    if (lane == 0) { ll_push(comm, jn, my_n); ll_push(comm, jn + 1, my_loss); }
     sum = 0.f; n_all = 0.f; loss_all = 0.f;
     for (int r = 0; r < comm.world; ++r) {
-      const float* theirs = comm.data_peer[r];
-      if (live) sum += ld_peer(theirs + j);
-      n_all += ld_peer(theirs + comm.extra_off + 2 * blockIdx.x);
-      loss_all += ld_peer(theirs + comm.extra_off + 2 * blockIdx.x + 1);
+      const bool me = r == comm.rank;
+      if (live) sum += me ? mine : ll_wait(comm, r, j);
+      n_all += me ? my_n : ll_wait(comm, r, jn);
+      loss_all += me ? my_loss : ll_wait(comm, r, jn + 1);
     }
   }
   const float n = a.use_override ? a.n_override : n_all;
@@ -249,22 +249,19 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
   }
   float n_all = s_n, loss_all = s_loss;
   if (comm.world > 1) {                                    // one-shot all-reduce over peer memory (comm.cuh)
-    float* mine = comm.data_peer[comm.rank];
+    const float my_n = s_n, my_loss = s_loss;
+    const size_t jn = comm.extra_off + 2 * (size_t)blockIdx.x;
+    float mine[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) if (ok[i]) mine[jj[i]] = sum[i];
-    if (threadIdx.x == 0) { mine[comm.extra_off + 2 * blockIdx.x] = s_n; mine[comm.extra_off + 2 * blockIdx.x + 1] = s_loss; }
-    __syncthreads();                                       // st.release.sys in the signal is cumulative
-    if (warp == 0) comm_signal_and_wait(comm, blockIdx.x, lane);
-    __syncthreads();
+    for (int i = 0; i < 4; ++i) { mine[i] = sum[i]; if (ok[i]) ll_push(comm, jj[i], mine[i]); sum[i] = 0.f; }
+    if (threadIdx.x == 0) { ll_push(comm, jn, my_n); ll_push(comm, jn + 1, my_loss); }
     n_all = 0.f; loss_all = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sum[i] = 0.f;
     for (int r = 0; r < comm.world; ++r) {
-      const float* theirs = comm.data_peer[r];
+      const bool me = r == comm.rank;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) if (ok[i]) sum[i] += ld_peer(theirs + jj[i]);
-      n_all += ld_peer(theirs + comm.extra_off + 2 * blockIdx.x);
-      loss_all += ld_peer(theirs + comm.extra_off + 2 * blockIdx.x + 1);
+      for (int i = 0; i < 4; ++i) if (ok[i]) sum[i] += me ? mine[i] : ll_wait(comm, r, jj[i]);
+      n_all += me ? my_n : ll_wait(comm, r, jn);
+      loss_all += me ? my_loss : ll_wait(comm, r, jn + 1);
     }
   }
   const float n = a.use_override ? a.n_override : n_all;

@@ -91,48 +91,42 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_select_kernel(ChaChaStat
   if (threadIdx.x == 0) tile_counts[blockIdx.x] = t;
 }
 
-// ---- sharded variant (comm.cuh): tiles [tile_begin, tile_begin + gridDim.x) of this rank ------------------
+// ---- sharded variant (comm.cuh) -----------------------------------------------------------------------------
+// This rank draws tiles [cov_lo, cov_lo + gridDim.x): the slice it owns, [own_lo, own_hi), plus a margin on
+// both sides, so that the tiles its batch positions fall into are (with overwhelming probability) local and
+// no selection mask ever crosses NVLink.  Only the owner pushes a tile's tagged count {count, epoch & 0xffff}
+// into every window (posted stores: no fence and no flag, the tag validates the word).
 __global__ void __launch_bounds__(kPoisThreads) poisson_select_sharded_kernel(ChaChaState st, float q,
-                                                                              uint32_t n_records, uint32_t tile_begin,
-                                                                              SampDev sd) {
-  const uint32_t tile = tile_begin + blockIdx.x;
+                                                                              uint32_t n_records, uint32_t cov_lo,
+                                                                              uint32_t own_lo, uint32_t own_hi,
+                                                                              uint16_t* __restrict__ masks, SampDev sd) {
+  const uint32_t tile = cov_lo + blockIdx.x;
   const uint32_t blk = tile * kPoisThreads + threadIdx.x;
   const uint32_t n_blocks = (n_records + 15) / 16;
   uint32_t m = 0;
   if (blk < n_blocks) {
     m = poisson_block_mask(st, q, n_records, blk);
-    sd.masks_local[blk] = (uint16_t)m;
+    masks[blk] = (uint16_t)m;
   }
   __shared__ int warp_c[kPoisThreads / 32];
   const int t = tile_count(m, warp_c);
-  if (threadIdx.x == 0) sd.counts_local[tile] = t;
-}
-
-// Runs after the select kernel of this rank's slice (the kernel boundary makes the slice's masks and counts
-// visible device-wide): pushes the slice's tile counts into every peer's window with coalesced posted stores,
-// then one system-scope fence and one release store per peer.  Keeping fences and atomics out of the
-// 1000+ select CTAs matters: a fence.sys per CTA cost ~20 us per launch.
-__global__ void __launch_bounds__(kPoisThreads) poisson_publish_kernel(uint32_t tile_begin, uint32_t n_local, SampDev sd) {
-  for (uint32_t i = threadIdx.x; i < n_local; i += kPoisThreads) {
-    const int32_t v = sd.counts_local[tile_begin + i];
+  if (threadIdx.x == 0 && tile >= own_lo && tile < own_hi) {
+    const uint32_t w = ((sd.epoch & 0xffffu) << 16) | (uint32_t)t;
     for (int r = 0; r < sd.world; ++r)
-      if (r != sd.rank) sd.counts_peer[r][tile_begin + i] = v;
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(sd.counts_peer[r] + tile), "r"(w) : "memory");
   }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < sd.world && (int)threadIdx.x != sd.rank)
-    st_release_sys(sd.flags_peer[threadIdx.x] + sd.rank, sd.epoch);
 }
 
-D3P_D int tile_owner(const SampDev& sd, uint32_t tile) { return (int)((sd.n_tiles - 1u - tile) / sd.tiles_per_rank); }
 
 // Pass B + C fused: every CTA (one per tile) first adds up the tile counts above it — n_tiles is a few
 // thousand, i.e. ~10 loads per thread — which replaces the former single-CTA scan launch, then compacts its
 // tile in DESCENDING record order: idx[s] for the selected records (s = number of selected records with a
 // larger index), and the unselected ones behind them for the padding slots (d3p/minibatch.py:37).
 // counts[0] = number selected, counts[1] = after truncate / suppress (:119-122), mask = arange(max_b) < counts[1].
-// kSharded (comm.cuh): counts were pushed into the local window by the tile owners, masks are read from the
-// owner's window, only positions [pos_begin, pos_end) are written and padding slots are left alone.
+// kSharded (comm.cuh): counts were pushed into the local window by the tile owners, masks are local (or
+// re-drawn), only positions [pos_begin, pos_end) are written and padding slots are left alone.
+constexpr int kCompactTiles = 1;               // tiles per CTA (8 measured slower: the per-tile barriers serialise)
+
 template <bool kSharded>
 __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uint16_t* __restrict__ masks,
                                                                        const int32_t* __restrict__ tile_counts,
@@ -140,27 +134,21 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uin
                                                                        uint32_t max_b, int suppress, uint32_t pos_begin,
                                                                        uint32_t pos_end, int32_t* __restrict__ idx,
                                                                        int32_t* __restrict__ counts,
-                                                                       uint8_t* __restrict__ mask, SampDev sd) {
-  const uint32_t tile = blockIdx.x;
+                                                                       uint8_t* __restrict__ mask, SampDev sd,
+                                                                       ChaChaState st, float q, uint32_t cov_lo,
+                                                                       uint32_t cov_hi) {
+  const uint32_t t_first = blockIdx.x * kCompactTiles;                       // this CTA's tiles [t_first, t_end)
+  const uint32_t t_end = min(n_tiles, t_first + kCompactTiles);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ int red[2][kPoisThreads / 32];
   __shared__ int warp_tot[kPoisThreads / 32];
-  if (kSharded) {                              // wait until every peer has published its slice
-    if ((int)threadIdx.x < sd.world && (int)threadIdx.x != sd.rank) {
-      const uint32_t* f = sd.flags_local + threadIdx.x;
-      const long long t0 = clock64();
-      while ((int32_t)(ld_acquire_sys(f) - sd.epoch) < 0)
-        if (clock64() - t0 > (3LL << 31)) { atomicAdd(sd.err, 1u); break; }
-    }
-    __syncthreads();
-  }
-  int above = 0, all = 0;
+  __shared__ int own_counts[kCompactTiles];
+  int above = 0, all = 0;                      // above: selected records in tiles >= t_end
   for (uint32_t t = threadIdx.x; t < n_tiles; t += kPoisThreads) {
-    int v;
-    if (kSharded) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(sd.counts_local + t) : "memory");
-    else v = tile_counts[t];
+    const int v = kSharded ? (int)samp_wait_count(sd, t) : tile_counts[t];   // sharded: polls the tagged word
     all += v;
-    above += t > tile ? v : 0;
+    above += t >= t_end ? v : 0;
+    if (t >= t_first && t < t_end) own_counts[t - t_first] = v;
   }
   above = __reduce_add_sync(0xffffffffu, above);
   all = __reduce_add_sync(0xffffffffu, all);
@@ -171,11 +159,11 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uin
   for (int w = 0; w < kPoisThreads / 32; ++w) { above += red[0][w]; all += red[1][w]; }
   const uint32_t total = (uint32_t)all;
   const uint32_t eff = suppress ? (total <= max_b ? total : 0u) : (total < max_b ? total : max_b);
-  if (tile == 0 && threadIdx.x == 0) { counts[0] = (int32_t)total; counts[1] = (int32_t)eff; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { counts[0] = (int32_t)total; counts[1] = (int32_t)eff; }
   if (mask) {                                  // this CTA's slice of the mask, 4 bytes per store when aligned
-    const uint32_t words = (max_b + 3) / 4, per = (words + n_tiles - 1) / n_tiles;
+    const uint32_t words = (max_b + 3) / 4, per = (words + gridDim.x - 1) / gridDim.x;
     const bool aligned = (reinterpret_cast<uintptr_t>(mask) & 3) == 0;
-    for (uint32_t wd = tile * per + threadIdx.x; wd < min(words, (tile + 1) * per); wd += kPoisThreads) {
+    for (uint32_t wd = blockIdx.x * per + threadIdx.x; wd < min(words, (blockIdx.x + 1) * per); wd += kPoisThreads) {
       const uint32_t i = wd * 4;
       if (aligned && i + 4 <= max_b) {
         uint32_t v = 0;
@@ -188,62 +176,64 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uin
     }
   }
   const uint32_t lim = kSharded ? min(min(pos_end, max_b), eff) : max_b;
-  const uint32_t blk = tile * kPoisThreads + threadIdx.x;
   const uint32_t n_blocks = (n_records + 15) / 16;
-  uint32_t m = 0;
-  if (kSharded) {
-    // CTA-uniform early out: this tile's positions [above, above + count) miss [pos_begin, lim)
-    int cnt;
-    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(cnt) : "l"(sd.counts_local + tile) : "memory");
-    if ((uint32_t)(above + cnt) <= pos_begin || (uint32_t)above >= lim) return;
+  uint32_t tile_above = (uint32_t)above;       // selected records in tiles above the current one
+  for (uint32_t tile = t_end; tile-- > t_first;) {                           // descending: running offset
+    const uint32_t cnt = (uint32_t)own_counts[tile - t_first];
+    const uint32_t base = tile_above;
+    tile_above += cnt;
+    // CTA-uniform early outs: nothing of this tile lands in the wanted positions
+    if (kSharded && (base + cnt <= pos_begin || base >= lim)) continue;
+    if (!kSharded && base >= max_b && total >= max_b) continue;
+    const uint32_t blk = tile * kPoisThreads + threadIdx.x;
+    uint32_t m = 0;
     if (blk < n_blocks) {
-      uint16_t mv;
-      asm volatile("ld.relaxed.sys.global.u16 %0, [%1];" : "=h"(mv) : "l"(sd.masks_peer[tile_owner(sd, tile)] + blk) : "memory");
-      m = mv;
+      // sharded: inside the locally drawn range the masks are in this rank's scratch; a tile outside it (a
+      // position boundary further off than the margin: many standard deviations) is simply drawn again
+      m = (!kSharded || (tile >= cov_lo && tile < cov_hi)) ? masks[blk] : poisson_block_mask(st, q, n_records, blk);
     }
-  } else {
-    m = (blk < n_blocks) ? masks[blk] : 0u;
-  }
-  const int c = __popc(m);
-  int incl = c;                                // exclusive scan over threads in DESCENDING thread order
+    const int c = __popc(m);
+    int incl = c;                              // exclusive scan over threads in DESCENDING thread order
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_down_sync(0xffffffffu, incl, o);
-    if (lane + o < 32) incl += t;
-  }
-  if (lane == 0) warp_tot[warp] = incl;
-  __syncthreads();
-  int higher = 0;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += t;
+    }
+    __syncthreads();                           // warp_tot of the previous tile has been consumed
+    if (lane == 0) warp_tot[warp] = incl;
+    __syncthreads();
+    int higher = 0;
 #pragma unroll
-  for (int w = 0; w < kPoisThreads / 32; ++w)
-    if (w > warp) higher += warp_tot[w];
-  uint32_t s = (uint32_t)(above + higher + incl - c);   // selected records with a larger index
-  if (blk >= n_blocks) return;
-  if (kSharded) {
+    for (int w = 0; w < kPoisThreads / 32; ++w)
+      if (w > warp) higher += warp_tot[w];
+    uint32_t s = base + (uint32_t)(higher + incl - c);   // selected records with a larger index
+    if (blk >= n_blocks) continue;
+    if (kSharded) {
+#pragma unroll
+      for (int i = 15; i >= 0; --i) {
+        if ((m >> i) & 1u) {
+          if (s >= pos_begin && s < lim) idx[s] = (int32_t)(blk * 16u + i);
+          ++s;
+        }
+      }
+      continue;
+    }
+    const uint32_t rec_hi = blk * 16u + 15u;
+    // quick reject: nothing from this chacha block can land in [0, max_b)
+    const bool any_sel = (m != 0) && (s < max_b);
+    const bool any_unsel = total < max_b && ((n_records - 1u - min(rec_hi, n_records - 1u)) - s + total < max_b + 16u);
+    if (!any_sel && !any_unsel) continue;
 #pragma unroll
     for (int i = 15; i >= 0; --i) {
+      const uint32_t rec = blk * 16u + i;
+      if (rec >= n_records) continue;
       if ((m >> i) & 1u) {
-        if (s >= pos_begin && s < lim) idx[s] = (int32_t)(blk * 16u + i);
+        if (s < max_b) idx[s] = (int32_t)rec;
         ++s;
+      } else {
+        const uint32_t pos = total + (n_records - 1u - rec) - s;
+        if (pos < max_b) idx[pos] = (int32_t)rec;
       }
-    }
-    return;
-  }
-  const uint32_t rec_hi = blk * 16u + 15u;
-  // quick reject: nothing from this chacha block can land in [0, max_b)
-  const bool any_sel = (m != 0) && (s < max_b);
-  const bool any_unsel = total < max_b && ((n_records - 1u - min(rec_hi, n_records - 1u)) - s + total < max_b + 16u);
-  if (!any_sel && !any_unsel) return;
-#pragma unroll
-  for (int i = 15; i >= 0; --i) {
-    const uint32_t rec = blk * 16u + i;
-    if (rec >= n_records) continue;
-    if ((m >> i) & 1u) {
-      if (s < max_b) idx[s] = (int32_t)rec;
-      ++s;
-    } else {
-      const uint32_t pos = total + (n_records - 1u - rec) - s;
-      if (pos < max_b) idx[pos] = (int32_t)rec;
     }
   }
 }
@@ -350,8 +340,9 @@ int32_t d3p_poisson_sample(const uint32_t state_h[16], float q, uint32_t n_recor
   poisson_select_kernel<<<n_tiles, kPoisThreads, 0, s>>>(load_state(state_h), q, n_records, w.masks, w.tile_counts);
   SampDev none;
   memset(&none, 0, sizeof(none));
-  poisson_compact_kernel<false><<<n_tiles, kPoisThreads, 0, s>>>(w.masks, w.tile_counts, n_records, n_tiles, max_b,
-                                                                 suppress, 0, max_b, idx_d, counts_d, mask_d, none);
+  poisson_compact_kernel<false><<<(n_tiles + kCompactTiles - 1) / kCompactTiles, kPoisThreads, 0, s>>>(w.masks, w.tile_counts, n_records, n_tiles, max_b,
+                                                                 suppress, 0, max_b, idx_d, counts_d, mask_d, none,
+                                                                 load_state(state_h), q, 0, n_tiles);
   return check_launch();
 }
 
@@ -384,12 +375,18 @@ int32_t d3p_poisson_sample_sharded(d3p_comm* comm, const uint32_t state_h[16], f
   const bool rec = prof && calls >= 100 && calls < 200;
   auto mark = [&](int k) { if (rec) { cudaEventCreate(&pe[calls - 100][k]); cudaEventRecord(pe[calls - 100][k], s); } };
   mark(0);
-  poisson_select_sharded_kernel<<<hi - lo, kPoisThreads, 0, s>>>(load_state(state_h), q, n_records, lo, sd);
+  // tiles (4096 records each) drawn redundantly on each side; D3P_SAMPLER_MARGIN overrides it (tests use 0 to
+  // force the re-draw path of the compaction kernel)
+  static const char* margin_env = getenv("D3P_SAMPLER_MARGIN");
+  const uint32_t margin = margin_env ? (uint32_t)atoi(margin_env) : 16u;
+  const uint32_t cov_lo = lo > margin ? lo - margin : 0, cov_hi = hi + margin < n_tiles ? hi + margin : n_tiles;
+  poisson_select_sharded_kernel<<<cov_hi - cov_lo, kPoisThreads, 0, s>>>(load_state(state_h), q, n_records, cov_lo, lo,
+                                                                         hi, w.masks, sd);
   mark(1);
-  poisson_publish_kernel<<<1, kPoisThreads, 0, s>>>(lo, hi - lo, sd);
   mark(2);
-  poisson_compact_kernel<true><<<n_tiles, kPoisThreads, 0, s>>>(nullptr, nullptr, n_records, n_tiles, max_b, suppress,
-                                                                pos_begin, pos_end, idx_d, counts_d, mask_d, sd);
+  poisson_compact_kernel<true><<<(n_tiles + kCompactTiles - 1) / kCompactTiles, kPoisThreads, 0, s>>>(w.masks, nullptr, n_records, n_tiles, max_b, suppress,
+                                                                pos_begin, pos_end, idx_d, counts_d, mask_d, sd,
+                                                                load_state(state_h), q, cov_lo, cov_hi);
   mark(3);
   if (prof && ++calls == 200) {
     cudaStreamSynchronize(s);
