@@ -24,9 +24,12 @@
 
 namespace d3p {
 
-constexpr int kVaeBN = 224;            // N tile of every VAE GEMM
-constexpr int kMidWarps = 8;
-constexpr int kMidE = 4;               // examples per warp iteration in the SIMT "middle" kernels
+constexpr int kVaeBN = 224;            // N tile of the GEMMs with N = D (784 -> 4 tiles x 32 M tiles = 128 CTAs)
+constexpr int kVaeBNH = 128;           // N tile of the forward/backward GEMMs with N = H: 400 -> 4 tiles = 128 CTAs
+                                       // (224 gave 2 tiles = 64 CTAs on 148 SMs: measured 36 / 58 us for G1 / G5b)
+constexpr int kMidWarps = 16;
+constexpr int kMidE = 2;               // examples per warp iteration in the SIMT "middle" kernels (the kernels are
+                                       // latency-bound: 16 warps x 2 examples hide more than 8 x 4 did)
 constexpr float kF32Tiny = 1.17549435e-38f;
 constexpr float kF32OneMinusEps = 0.99999988079071044921875f;   // 1 - 2^-23
 
@@ -80,12 +83,13 @@ struct EpiFwd5 {   // p = sigmoid(acc + b5); Bernoulli(probs) log-lik (numpyro c
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float logit = __uint_as_float(v[j + t]) + __ldg(a.bias + col0 + j + t);
-        const float p = 1.0f / (1.0f + expf(-logit));
+        const float p = __fdividef(1.0f, 1.0f + __expf(-logit));     // MUFU.EX2 / MUFU.RCP: <= 1e-6 relative
         // jnp.clip = minimum(maximum(p, tiny), 1 - eps): gradient 1 inside, 1/2 at a bound, 0 outside
         const float wclip = (p > kF32Tiny ? 1.0f : (p == kF32Tiny ? 0.5f : 0.f)) *
                             (p < kF32OneMinusEps ? 1.0f : (p == kF32OneMinusEps ? 0.5f : 0.f));
         const float pc = fminf(fmaxf(p, kF32Tiny), kF32OneMinusEps);
-        rs.loss -= xs[t] * logf(pc) + (1.0f - xs[t]) * log1pf(-pc);
+        // log1p(-pc) = log(1 - pc): 1 - pc is exact for pc >= 1/2 (Sterbenz) and within 6e-8 below; MUFU.LG2 logs
+        rs.loss -= xs[t] * __logf(pc) + (1.0f - xs[t]) * __logf(1.0f - pc);
         const float d = wclip * (p - xs[t]);
         hi[t] = tc::tf32_hi(d);
         lo[t] = d - hi[t];
@@ -235,11 +239,25 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
   float* zs = h1s + kMidE * H;                          // [E][64]  (z_loc | log z_std)
   float* es = zs + kMidE * 64;                          // [E][64]  eps
   float* zz = es + kMidE * 64;                          // [E][64]  z
-  for (uint32_t i = threadIdx.x; i < H * Z; i += blockDim.x) {
-    const uint32_t k = i / Z, j = i - k * Z;
-    w23s[k * Z2 + j] = a.params[a.off_w2 + i];
-    w23s[k * Z2 + Z + j] = a.params[a.off_w3 + i];
-    w4s[i] = a.params[a.off_w4 + i];
+  for (uint32_t i0 = threadIdx.x; i0 < H * Z; i0 += 4 * blockDim.x) {     // 12 independent loads in flight
+    float v2[4], v3[4], v4[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t i = i0 + t * blockDim.x;
+      const bool ok = i < H * Z;
+      v2[t] = ok ? __ldg(a.params + a.off_w2 + i) : 0.f;
+      v3[t] = ok ? __ldg(a.params + a.off_w3 + i) : 0.f;
+      v4[t] = ok ? __ldg(a.params + a.off_w4 + i) : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t i = i0 + t * blockDim.x;
+      if (i >= H * Z) break;
+      const uint32_t k = i / Z, j = i - k * Z;
+      w23s[k * Z2 + j] = v2[t];
+      w23s[k * Z2 + Z + j] = v3[t];
+      w4s[i] = v4[t];
+    }
   }
   for (uint32_t i = threadIdx.x; i < Z; i += blockDim.x) { b23s[i] = a.params[a.off_b2 + i]; b23s[Z + i] = a.params[a.off_b3 + i]; }
   for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) b4s[i] = a.params[a.off_b4 + i];
@@ -392,11 +410,25 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_bwd_kernel(VaeArgs a) 
   float* wsm = w3t + (size_t)Z * H + (size_t)warp * kMidE * (H + 128);
   float* d4s = wsm;                                     // [E][H]
   float* d23 = d4s + kMidE * H;                         // [E][128]: delta2 at [0,64), delta3 at [64,128)
-  for (uint32_t i = threadIdx.x; i < H * Z; i += blockDim.x) {
-    const uint32_t h = i / Z, j = i - h * Z;
-    w4s[i] = a.params[a.off_w4 + i];
-    w2t[j * H + h] = a.params[a.off_w2 + i];
-    w3t[j * H + h] = a.params[a.off_w3 + i];
+  for (uint32_t i0 = threadIdx.x; i0 < H * Z; i0 += 4 * blockDim.x) {     // 12 independent loads in flight
+    float v2[4], v3[4], v4[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t i = i0 + t * blockDim.x;
+      const bool ok = i < H * Z;
+      v2[t] = ok ? __ldg(a.params + a.off_w2 + i) : 0.f;
+      v3[t] = ok ? __ldg(a.params + a.off_w3 + i) : 0.f;
+      v4[t] = ok ? __ldg(a.params + a.off_w4 + i) : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t i = i0 + t * blockDim.x;
+      if (i >= H * Z) break;
+      const uint32_t h = i / Z, j = i - h * Z;
+      w4s[i] = v4[t];
+      w2t[j * H + h] = v2[t];
+      w3t[j * H + h] = v3[t];
+    }
   }
   __syncthreads();
   const uint32_t nv = a.num_valid ? (uint32_t)max(*a.num_valid, 0) : 0xffffffffu;
@@ -598,7 +630,7 @@ static VaeLayout vae_layout(const d3p_vae_desc* d, uint32_t Bl) {
   VaeLayout L;
   const size_t D = d->out_dim, H = d->hidden_dim, Z = d->z_dim, P = d->n_params;
   L.S = vae_splits(Bl);
-  L.ns_h = (uint32_t)((H + kVaeBN - 1) / kVaeBN) * (kHeavyEW / 4);
+  L.ns_h = (uint32_t)((H + kVaeBNH - 1) / kVaeBNH) * (kHeavyEW / 4);
   L.ns_d = (uint32_t)((D + kVaeBN - 1) / kVaeBN) * (kHeavyEW / 4);
   L.ldx = D + 4; L.ldh = H + 4; L.ldz = (Z + 1 + 3) / 4 * 4; L.ld23 = (2 * Z + 3) / 4 * 4;
   size_t off = 0;
@@ -702,7 +734,7 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   {
     tc::GemmOperand A{a.x_hi, a.x_lo, 0, a.ldx}, Bo{w1_hi, w1_lo, 1, H};
     EpiFwd1::Args ea{params_d + a.off_b1, a.h1_hi, a.h1_lo, a.ldh, a.sq_h1, Bl};
-    if ((rc = tc::launch_tc_gemm<false, true, kVaeBN, EpiFwd1, kHeavyEW>(A, Bo, Bl, H, D, 1, ea, s, a.x_lo_flag)) != D3P_OK)
+    if ((rc = tc::launch_tc_gemm<false, true, kVaeBNH, EpiFwd1, kHeavyEW>(A, Bo, Bl, H, D, 1, ea, s, a.x_lo_flag)) != D3P_OK)
       return rc;
   }
   const size_t mid_fwd_smem = mid_fwd_smem_bytes(H, Z), mid_bwd_smem = mid_bwd_smem_bytes(H, Z);
@@ -725,7 +757,7 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   {
     tc::GemmOperand A{a.d5_hi, a.d5_lo, 0, D}, Bo{w5_hi, w5_lo, 0, D};
     EpiBwd5::Args ea{a.h2_hi, a.h2_lo, H, a.d4, a.sq_d4, Bl};
-    if ((rc = tc::launch_tc_gemm<false, false, kVaeBN, EpiBwd5, kHeavyEW>(A, Bo, Bl, H, D, 1, ea, s, nullptr)) != D3P_OK)
+    if ((rc = tc::launch_tc_gemm<false, false, kVaeBNH, EpiBwd5, kHeavyEW>(A, Bo, Bl, H, D, 1, ea, s, nullptr)) != D3P_OK)
       return rc;
   }
   {
