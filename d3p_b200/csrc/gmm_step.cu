@@ -153,6 +153,19 @@ D3P_D float block_sum(float v, float* red, int lane, int warp) {   // fixed orde
   return s;
 }
 
+template <int NW>
+D3P_D float block_max(float v, float* red, int lane, int warp) {   // all threads get the maximum
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) s = fmaxf(s, red[w]);
+  return s;
+}
+
 __global__ void __launch_bounds__(kGmmThreads, 2) gmm_step_kernel(GmmArgs a) {
   extern __shared__ float smem[];
   constexpr int NW = kGmmThreads / 32;
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(kGmmThreads, 2) gmm_step_kernel(GmmArgs a) {
       for (int h = 0; h < 2; ++h) {
         const uint32_t m = h ? m1 : c;
         if (m >= n) break;
-        const float eps = bits_to_normal<false>(h ? y1 : y0);
+        const float eps = bits_to_normal_fast(h ? y1 : y0);       // value-only use: MUFU.LG2 form (<= 2e-7 relative)
         const uint32_t j = m % d;
         const float mu = a.params[a.mus_off + m] + eps;
         const float sg = S[m];
@@ -270,11 +283,11 @@ __global__ void __launch_bounds__(kGmmThreads, 2) gmm_step_kernel(GmmArgs a) {
     }
     const float sum_mu2 = block_sum<NW>(s_mu2, red, lane, warp);
     const float sum_e2 = block_sum<NW>(s_e2, red, lane, warp);
-    // softmax over log g (thread-serial over K <= 256 on every thread: identical order everywhere)
-    float mx = -3.4e38f;
-    for (uint32_t k = 0; k < K; ++k) mx = fmaxf(mx, comp[k]);
-    float den = 0.f;
-    for (uint32_t k = 0; k < K; ++k) den += expf(comp[k] - mx);
+    // softmax over log g: K <= 256 = one component per thread, fixed-order block reductions (the former
+    // thread-serial loops over K on all 256 threads were 11 % of the kernel's instructions)
+    const float lg_own = tid < K ? comp[tid] : -3.4e38f;
+    const float mx = block_max<NW>(lg_own, red, lane, warp);
+    const float den = block_sum<NW>(tid < K ? expf(lg_own - mx) : 0.f, red, lane, warp);
     __syncthreads();
     for (uint32_t k = tid; k < K; k += kGmmThreads) {
       const float pi = expf(comp[k] - mx) / den;
@@ -294,20 +307,21 @@ __global__ void __launch_bounds__(kGmmThreads, 2) gmm_step_kernel(GmmArgs a) {
       if (lane == 0) comp[k] = s + lpi[k];
     }
     __syncthreads();
-    float cmx = -3.4e38f;
-    for (uint32_t k = 0; k < K; ++k) cmx = fmaxf(cmx, comp[k]);
-    float cden = 0.f;
-    for (uint32_t k = 0; k < K; ++k) cden += expf(comp[k] - cmx);
+    const float c_own = tid < K ? comp[tid] : -3.4e38f;
+    const float cmx = block_max<NW>(c_own, red, lane, warp);
+    const float e_own = tid < K ? expf(c_own - cmx) : 0.f;
+    const float cden = block_sum<NW>(e_own, red, lane, warp);
     const float loglik = cmx + logf(cden);
     // D_m = (alpha_m - 1) - N r_m ; sumDw = sum_m D_m w'_m ; log q(pis) = sum (alpha - 1) log pi + norm
-    float sumDw = 0.f, lq_pis = 0.f;
-    for (uint32_t k = 0; k < K; ++k) {
-      const float r = expf(comp[k] - cmx) / cden;
-      const float D = (alpha_s[k] - 1.0f) - a.N * r;
-      sumDw = fmaf(D, wv[k], sumDw);
-      lq_pis = fmaf(alpha_s[k] - 1.0f, lpi[k], lq_pis);
+    float dw_own = 0.f, lq_own = 0.f;
+    if (tid < K) {
+      const float r = e_own / cden;
+      const float D = (alpha_s[tid] - 1.0f) - a.N * r;
+      dw_own = D * wv[tid];
+      lq_own = (alpha_s[tid] - 1.0f) * lpi[tid];
     }
-    lq_pis += log_norm_q_pis;
+    const float sumDw = block_sum<NW>(dw_own, red, lane, warp);
+    const float lq_pis = block_sum<NW>(lq_own, red, lane, warp) + log_norm_q_pis;
     __syncthreads();
     float nrm_part = 0.f;
     for (uint32_t k = tid; k < K; k += kGmmThreads) {

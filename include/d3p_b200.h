@@ -260,14 +260,17 @@ int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_partials, u
 /* ------------------------------------------------------------------------------------------
  * Sharded minibatch over the GPUs of one box without NCCL in the step:
  * every rank owns a peer-mapped window (CUDA IPC over NVLink / NVSwitch) and the finalize kernel
- * itself exchanges the P + 2 clipped sums (publish -> flag -> wait -> read peers, added in rank
- * order, so every replica computes bit-identical sums, noise and parameters).
- *   create  : allocate this rank's window, return its 64-byte IPC handle
+ * itself exchanges the P + 2 clipped sums: each value is pushed into every peer's window as one
+ * 8-byte word {value, epoch}; the reader polls its own memory for the current epoch's tag and adds
+ * the G copies in rank order, so every replica computes bit-identical sums, noise and parameters.
+ *   create  : allocate this rank's window (max_records > 0 also provisions the sharded Poisson
+ *             sampler for data sets of up to that many records), return its 64-byte IPC handle
  *   connect : map the windows of all ranks (handles_h = world x 64 bytes, gathered by the caller,
  *             e.g. torch.distributed.all_gather_object)
- * All ranks must issue the same sequence of d3p_perturb_finalize_p2p_f32 calls (same P).  A peer
- * that never shows up makes the kernel give up after ~3 s and count a time-out instead of
- * hanging the GPU; d3p_comm_timeouts reads the counter (synchronises).
+ * All ranks must issue the same sequence of d3p_perturb_finalize_p2p_f32 /
+ * d3p_poisson_sample_sharded calls.  A peer that never shows up makes the kernel give up after
+ * ~3 s and count a time-out instead of hanging the GPU; d3p_comm_timeouts reads the counter
+ * (synchronises).
  * ------------------------------------------------------------------------------------------ */
 int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_params, uint32_t max_records /* 0: no sharded
                         sampler */, d3p_comm** comm_out, uint8_t handle_out_h[64]);
