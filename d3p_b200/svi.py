@@ -509,10 +509,10 @@ class DPSVI:
 
     def get_epsilon(self, target_delta, q, num_epochs=None, num_iter=None):
         num_iter = self._validate_epochs_and_iter(num_epochs, num_iter, q)
-        from fourier_accountant.compute_eps import get_epsilon_R   # optional dependency, as in the reference
+        from .accountant import get_epsilon_R       # restatement of fourier_accountant (svi.py:31,461)
         return get_epsilon_R(target_delta, self._dp_scale, q, ncomp=num_iter)
 
     def get_delta(self, target_epsilon, q, num_epochs=None, num_iter=None):
         num_iter = self._validate_epochs_and_iter(num_epochs, num_iter, q)
-        from fourier_accountant.compute_delta import get_delta_R
+        from .accountant import get_delta_R         # svi.py:32,467
         return get_delta_R(target_epsilon, self._dp_scale, q, ncomp=num_iter)
