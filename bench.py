@@ -281,6 +281,7 @@ def run_b200(args, cfg):
     svi.donate_state = True
     if world > 1:
         parallel.shard_dpsvi(svi, rank, world, backend=args.collective)
+        args.collective = "p2p" if svi.peer_window is not None else "nccl"     # what "auto" resolved to
     if cfg["sampler"] == "poisson":
         init, get_batch = mb.poisson_batchify_data(dataset, q, .99)
     else:
@@ -512,7 +513,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N > 1: exchange the clipped sums inside the finalize kernel over NVLink peer memory (p2p) "
                          "or with a reduce kernel + ncclAllReduce (nccl)")
     ap.add_argument("--rows", type=int, default=None, help="override N (development only)")

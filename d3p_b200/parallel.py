@@ -33,8 +33,14 @@ class PeerWindow:
             handles = [None] * world_size
             dist.all_gather_object(handles, bytes(handle), group=group)
             blob = (C.c_uint8 * (64 * world_size)).from_buffer_copy(b"".join(handles))
-            _n.check(_n.lib().d3p_comm_connect(self._comm, blob), "comm_connect")
-            dist.barrier(group=group)
+            rc = _n.lib().d3p_comm_connect(self._comm, blob)
+            # every rank learns whether every mapping succeeded, so that a failure raises everywhere
+            # (a rank raising alone would leave the others waiting in the next collective)
+            rcs = [None] * world_size
+            dist.all_gather_object(rcs, int(rc), group=group)
+            if any(r != _n.OK for r in rcs):
+                self.close()
+                _n.check(next(r for r in rcs if r != _n.OK), "comm_connect (on some rank)")
         self.max_params = int(max_params)
 
     @property
@@ -71,16 +77,34 @@ def shard_dpsvi(svi, rank=None, world_size=None, group=None, backend="p2p", max_
     memory (``PeerWindow``); ``backend="nccl"``: reduce kernel + ``ncclAllReduce`` of ``P + 2`` floats."""
     rank = dist.get_rank(group) if rank is None else rank
     world_size = dist.get_world_size(group) if world_size is None else world_size
-    if backend not in ("p2p", "nccl"):
-        raise ValueError("backend must be 'p2p' or 'nccl'")
-    if backend == "p2p":
+    if backend not in ("p2p", "nccl", "auto"):
+        raise ValueError("backend must be 'p2p', 'nccl' or 'auto'")
+    if backend in ("p2p", "auto"):
         if max_params is None:
             if svi.family is None:
                 raise ValueError("max_params is required when DPSVI has no model family")
             max_params = svi.family.n_params
-        svi.shard = (rank, world_size, None)
-        svi.peer_window = PeerWindow(rank, world_size, max_params, group)
-        return svi
+        window, err = None, None
+        try:
+            window = PeerWindow(rank, world_size, max_params, group)
+        except Exception as e:      # e.g. no peer access between the GPUs of this box
+            if backend == "p2p":
+                raise
+            err = e
+        if backend == "auto" and world_size > 1:
+            # all ranks must take the same path: agree on whether every window came up
+            ok = torch.tensor([1 if window is not None else 0], device=torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                if window is not None:
+                    window.close()
+                window = None
+        if window is not None:
+            svi.shard = (rank, world_size, None)
+            svi.peer_window = window
+            return svi
+        import warnings
+        warnings.warn(f"peer-memory window unavailable ({err}); falling back to the NCCL all-reduce")
     buf = {}
 
     def reduce_fn(ws, n_partials, P):
