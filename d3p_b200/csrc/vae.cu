@@ -73,24 +73,40 @@ struct EpiFwd5 {   // p = sigmoid(acc + b5); Bernoulli(probs) log-lik (numpyro c
   __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t,
                               const uint32_t (&v)[32], RowState& rs) {
     if (row >= g.M) return;
+    // all 16 row loads of this 32-column chunk are issued before the first use: the epilogue was bound by
+    // the latency of one dependent load pair per 4 columns (ncu: long-scoreboard stalls 12.8 per issue)
+    float xs[32];
+    {
+      float4 xh[8], xl[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = col0 + 4 * j < g.N;          // N is a multiple of 4
+        xh[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x_hi + (size_t)row * a.ldx + col0 + 4 * j)) : make_float4(0, 0, 0, 0);
+        xl[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x_lo + (size_t)row * a.ldx + col0 + 4 * j)) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xs[4 * j] = xh[j].x + xl[j].x; xs[4 * j + 1] = xh[j].y + xl[j].y;
+        xs[4 * j + 2] = xh[j].z + xl[j].z; xs[4 * j + 3] = xh[j].w + xl[j].w;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       if (col0 + j >= g.N) break;
-      const float4 xh = *reinterpret_cast<const float4*>(a.x_hi + (size_t)row * a.ldx + col0 + j);
-      const float4 xl = *reinterpret_cast<const float4*>(a.x_lo + (size_t)row * a.ldx + col0 + j);
-      const float xs[4] = {xh.x + xl.x, xh.y + xl.y, xh.z + xl.z, xh.w + xl.w};
+      const float bs[4] = {__ldg(a.bias + col0 + j), __ldg(a.bias + col0 + j + 1), __ldg(a.bias + col0 + j + 2),
+                           __ldg(a.bias + col0 + j + 3)};         // the bias offset need not be 16-byte aligned
       float hi[4], lo[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float logit = __uint_as_float(v[j + t]) + __ldg(a.bias + col0 + j + t);
+        const float logit = __uint_as_float(v[j + t]) + bs[t];
         const float p = __fdividef(1.0f, 1.0f + __expf(-logit));     // MUFU.EX2 / MUFU.RCP: <= 1e-6 relative
         // jnp.clip = minimum(maximum(p, tiny), 1 - eps): gradient 1 inside, 1/2 at a bound, 0 outside
         const float wclip = (p > kF32Tiny ? 1.0f : (p == kF32Tiny ? 0.5f : 0.f)) *
                             (p < kF32OneMinusEps ? 1.0f : (p == kF32OneMinusEps ? 0.5f : 0.f));
         const float pc = fminf(fmaxf(p, kF32Tiny), kF32OneMinusEps);
         // log1p(-pc) = log(1 - pc): 1 - pc is exact for pc >= 1/2 (Sterbenz) and within 6e-8 below; MUFU.LG2 logs
-        rs.loss -= xs[t] * __logf(pc) + (1.0f - xs[t]) * __logf(1.0f - pc);
-        const float d = wclip * (p - xs[t]);
+        rs.loss -= xs[j + t] * __logf(pc) + (1.0f - xs[j + t]) * __logf(1.0f - pc);
+        const float d = wclip * (p - xs[j + t]);
         hi[t] = tc::tf32_hi(d);
         lo[t] = d - hi[t];
         rs.sq = fmaf(d, d, rs.sq);
