@@ -52,12 +52,20 @@ D3P_D void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 // noise u.  Every lane only touches its own 16-byte slots, so no intra-warp synchronisation is
 // needed; the loops over chunks stay rolled, which keeps the hot loop inside the instruction cache
 // (the fully unrolled variant was fetch-bound: ncu `no_instruction` stalls, profiles/r1_*).
-template <int FAMILY, int LINK, int NQ>
+//
+// LPE = lanes per example.  d = 2 * LPE * NQ: with LPE = 32 a warp works on one example at a time; with
+// LPE = 8 / 16 it works on 4 / 2 examples at once (one per group of LPE lanes), every lane still owning
+// NQ elements per half.  Short rows (d = 256) then amortise the per-example work that does not scale
+// with d (key shuffles, reductions, loop control, the link scalars) over 4 examples: d = 256 ran 17 % more
+// cycles per element than d = 1024 with one example per warp.
+template <int FAMILY, int LINK, int NQ, int LPE>
 __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(StepArgs a) {
   static_assert(NQ % 4 == 0, "NQ must be a multiple of 4");
+  static_assert(LPE == 8 || LPE == 16 || LPE == 32, "LPE must be 8, 16 or 32");
   constexpr int NCH = NQ / 4;          // float4 chunks per half per lane
-  constexpr int HALF = 32 * NQ;        // d / 2
+  constexpr int HALF = LPE * NQ;       // d / 2
   constexpr int D = 2 * HALF;
+  constexpr int G = 32 / LPE;          // examples in flight per warp
   constexpr int TILE = 8;
   constexpr bool kExp = LINK == D3P_LINK_EXP;
   extern __shared__ __align__(16) float smem[];
@@ -66,13 +74,14 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   float* s_a = s_scl + D;                       // softplus only
   float* s_sa = s_a + (kExp ? 0 : D);
   float* s_bt = s_sa + (kExp ? 0 : D);
-  float* s_stage = s_bt + (kExp ? 0 : D);       // [kStepWarps][2 * D]
-  float* s_acc = s_stage + kStepWarps * 2 * D;  // [P + 2]
+  float* s_stage = s_bt + (kExp ? 0 : D);       // [kStepWarps][G][2 * D]
+  float* s_acc = s_stage + kStepWarps * G * 2 * D;  // [P + 2]
   __shared__ float s_red[kStepWarps];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* xs = s_stage + warp * 2 * D;           // x, then gl
-  float* us = xs + D;                           // u = eps * s'
+  const int sl = lane & (LPE - 1), sub = lane / LPE;       // lane within its example group, group index
+  float* xs = s_stage + (warp * G + sub) * 2 * D;          // x, then gl
+  float* us = xs + D;                                      // u = eps * s'
 
   float log_s_part = 0.f;
   for (int e = threadIdx.x; e < D; e += kStepThreads) {
@@ -148,11 +157,17 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
       if (FAMILY == D3P_FAMILY_LOGREG) my_y = (float)a.y[my_row];
     }
     const unsigned valid_bits = __ballot_sync(0xffffffffu, my_valid);
+    const uint32_t any_row = __shfl_sync(0xffffffffu, my_row, __ffs(valid_bits | 0x100u) - 1);   // a readable row
 #pragma unroll 1
-    for (int t = 0; t < TILE; ++t) {
-      if (!((valid_bits >> t) & 1u)) continue;           // warp-uniform
+    for (int t0 = 0; t0 < TILE; t0 += G) {
+      if (!((valid_bits >> t0) & ((1u << G) - 1u))) continue;   // warp-uniform: none of the G examples is valid
+      const int t = t0 + sub;                                    // this lane group's example
+      // a group whose example is masked out runs along on a readable row with weight 0 (it must take part
+      // in the warp-wide votes of the tail fix-up); with LPE = 32 this never happens
+      const bool act = (valid_bits >> t) & 1u;
       const TfKey km(__shfl_sync(0xffffffffu, my_k0, t), __shfl_sync(0xffffffffu, my_k1, t));
-      const uint32_t row = __shfl_sync(0xffffffffu, my_row, t);
+      const uint32_t row_t = __shfl_sync(0xffffffffu, my_row, t);
+      const uint32_t row = act ? row_t : any_row;
       const float eb = __shfl_sync(0xffffffffu, my_eb, t);
       const float yv = __shfl_sync(0xffffffffu, my_y, t);
       const float* __restrict__ xr = a.x + (size_t)row * a.x_stride;
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
       // the row goes straight to this lane's staging slots (no register staging)
 #pragma unroll
       for (int i = 0; i < 2 * NCH; ++i) {
-        const int e0 = (i & 1) * HALF + 4 * (lane + 32 * (i >> 1));
+        const int e0 = (i & 1) * HALF + 4 * (sl + LPE * (i >> 1));
         cp_async16(xs + e0, xr + e0);
       }
       asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -169,7 +184,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
       float zdot = 0.f, s_th2 = 0.f, s_e2 = 0.f, s_res2 = 0.f;
 #pragma unroll 1
       for (int kk = 0; kk < NCH; ++kk) {
-        const int q0 = 4 * (lane + 32 * kk);
+        const int q0 = 4 * (sl + LPE * kk);
         float4 ev[2];
         normals8(km, (uint32_t)q0, HALF, ev[0], ev[1]);
         if (kk == 0) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -195,10 +210,10 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
           st4(us + e0, u);
         }
       }
-      if (FAMILY == D3P_FAMILY_LOGREG) zdot = gsum<32>(zdot, 0xffffffffu);
-      else s_res2 = gsum<32>(s_res2, 0xffffffffu);
-      s_th2 = gsum<32>(s_th2, 0xffffffffu);
-      s_e2 = gsum<32>(s_e2, 0xffffffffu);
+      if (FAMILY == D3P_FAMILY_LOGREG) zdot = gsum<LPE>(zdot, 0xffffffffu);
+      else s_res2 = gsum<LPE>(s_res2, 0xffffffffu);
+      s_th2 = gsum<LPE>(s_th2, 0xffffffffu);
+      s_e2 = gsum<LPE>(s_e2, 0xffffffffu);
 
       float th_b = 0.f, Lr = 0.f, loglik;
       if (a.has_b) { th_b = fmaf(eb, b_s, b_loc); s_th2 = fmaf(th_b, th_b, s_th2); s_e2 = fmaf(eb, eb, s_e2); }
@@ -216,7 +231,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
       float nrm = 0.f;
 #pragma unroll 1
       for (int i = 0; i < 2 * NCH; ++i) {
-        const int e0 = (i & 1) * HALF + 4 * (lane + 32 * (i >> 1));
+        const int e0 = (i & 1) * HALF + 4 * (sl + LPE * (i >> 1));
         const float4 loc = ld4(s_loc + e0), xv = ld4(xs + e0), u = ld4(us + e0);
         float4 sa = loc, bt = loc, gl;
         if (!kExp) { sa = ld4(s_sa + e0); bt = ld4(s_bt + e0); }
@@ -231,7 +246,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
         D3P_F4_FOREACH(D3P_P2)
 #undef D3P_P2
         st4(xs + e0, gl);
-        if (a.px_grads) {
+        if (a.px_grads && act) {
           float* pg = a.px_grads + (size_t)(base + t) * a.P;
 #define D3P_PG(c, k)                                                                         \
           pg[a.loc_off + e0 + k] = gl.c;                                                     \
@@ -240,7 +255,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
 #undef D3P_PG
         }
       }
-      nrm = gsum<32>(nrm, 0xffffffffu);
+      nrm = gsum<LPE>(nrm, 0xffffffffu);
       float glb = 0.f, gsb = 0.f;
       if (a.has_b) {
         glb = fmaf(th_b, a.inv_S, Lr);
@@ -248,12 +263,12 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
         nrm = fmaf(glb, glb, fmaf(gsb, gsb, nrm));
       }
       const float norm = sqrtf(nrm);
-      const float c = 1.0f / fmaxf(1.0f, norm / a.C);
+      const float c = act ? 1.0f / fmaxf(1.0f, norm / a.C) : 0.f;
 
       // ---- loop C: clipped accumulation (unrolled: the accumulators live in registers) ---------
 #pragma unroll
       for (int i = 0; i < 2 * NCH; ++i) {
-        const int e0 = (i & 1) * HALF + 4 * (lane + 32 * (i >> 1));
+        const int e0 = (i & 1) * HALF + 4 * (sl + LPE * (i >> 1));
         const float4 gl = ld4(xs + e0), u = ld4(us + e0);
         float4 bt = make_float4(a.inv_S, a.inv_S, a.inv_S, a.inv_S);
         if (!kExp) bt = ld4(s_bt + e0);
@@ -263,7 +278,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
         D3P_F4_FOREACH(D3P_P3)
 #undef D3P_P3
       }
-      if (lane == 0) {
+      if (sl == 0 && act) {
         acc_bloc = fmaf(c, glb, acc_bloc);
         acc_brho = fmaf(c, gsb, acc_brho);
         acc_loss += loss_i;
@@ -279,12 +294,29 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
     }
   }
 
-  // ---- epilogue: warps add into the CTA partial in a fixed order ----------------------------------
-  for (int w = 0; w < kStepWarps; ++w) {
-    if (warp == w) {
+  // ---- epilogue: lane groups fold into group 0 (fixed order), then warps add into the CTA partial -----------
+  if (G > 1) {
+#pragma unroll
+    for (int o = LPE; o < 32; o <<= 1) {
 #pragma unroll
       for (int i = 0; i < 2 * NCH; ++i) {
-        const int e0 = (i & 1) * HALF + 4 * (lane + 32 * (i >> 1));
+#define D3P_FOLD(c_)                                                   \
+        accL[i].c_ += __shfl_xor_sync(0xffffffffu, accL[i].c_, o);     \
+        accR[i].c_ += __shfl_xor_sync(0xffffffffu, accR[i].c_, o);
+        D3P_F4_FOREACH(D3P_FOLD)
+#undef D3P_FOLD
+      }
+      acc_bloc += __shfl_xor_sync(0xffffffffu, acc_bloc, o);
+      acc_brho += __shfl_xor_sync(0xffffffffu, acc_brho, o);
+      acc_loss += __shfl_xor_sync(0xffffffffu, acc_loss, o);
+      acc_cnt += __shfl_xor_sync(0xffffffffu, acc_cnt, o);
+    }
+  }
+  for (int w = 0; w < kStepWarps; ++w) {
+    if (warp == w && sub == 0) {
+#pragma unroll
+      for (int i = 0; i < 2 * NCH; ++i) {
+        const int e0 = (i & 1) * HALF + 4 * (sl + LPE * (i >> 1));
         float* pl = s_acc + a.loc_off + e0;
         float* pr = s_acc + a.rho_off + e0;
         pl[0] += accL[i].x; pl[1] += accL[i].y; pl[2] += accL[i].z; pl[3] += accL[i].w;
@@ -302,11 +334,12 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   for (uint32_t j = threadIdx.x; j < a.P + 2; j += kStepThreads) out[j] = s_acc[j];
 }
 
-template <int FAMILY, int LINK, int NQ>
+template <int FAMILY, int LINK, int NQ, int LPE>
 static int32_t launch_vec_one(const StepArgs& a, unsigned grid, cudaStream_t s) {
-  constexpr int D = 64 * NQ;
-  size_t smem = ((LINK == D3P_LINK_EXP ? 2 : 5) * (size_t)D + (size_t)kStepWarps * 2 * D + a.P + 2) * sizeof(float);
-  auto kern = meanfield_step_vec_kernel<FAMILY, LINK, NQ>;
+  constexpr int D = 2 * LPE * NQ;
+  constexpr int G = 32 / LPE;
+  size_t smem = ((LINK == D3P_LINK_EXP ? 2 : 5) * (size_t)D + (size_t)kStepWarps * G * 2 * D + a.P + 2) * sizeof(float);
+  auto kern = meanfield_step_vec_kernel<FAMILY, LINK, NQ, LPE>;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return D3P_ERR_CUDA;
@@ -317,9 +350,9 @@ static int32_t launch_vec_one(const StepArgs& a, unsigned grid, cudaStream_t s) 
 template <int FAMILY, int LINK>
 static int32_t launch_vec_nq(const StepArgs& a, unsigned grid, cudaStream_t s) {
   switch (a.d) {
-    case 256: return launch_vec_one<FAMILY, LINK, 4>(a, grid, s);
-    case 512: return launch_vec_one<FAMILY, LINK, 8>(a, grid, s);
-    case 1024: return launch_vec_one<FAMILY, LINK, 16>(a, grid, s);
+    case 256: return launch_vec_one<FAMILY, LINK, 16, 8>(a, grid, s);     // 4 examples per warp
+    case 512: return launch_vec_one<FAMILY, LINK, 16, 16>(a, grid, s);    // 2 examples per warp
+    case 1024: return launch_vec_one<FAMILY, LINK, 16, 32>(a, grid, s);
     default: return D3P_ERR_UNSUPPORTED;
   }
 }

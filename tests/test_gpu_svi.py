@@ -380,5 +380,5 @@ def test_c2_full_batch_properties(cuda):
     # relative to the largest norm, like every other gradient comparison here: saturated examples
     # (|logit| ~ 30 at d = 1024) have norms ~1e-5 whose relative error is the fp32 error of the logit itself
     assert_close(norms[sel], ref, what="per-example norms at the full C2 batch shape")
-    well = ref > 1.0
+    well = ref > 20.0            # residual sigmoid(z) - y of order one: the norm is not an amplified logit error
     assert well.sum() > 8 and np.max(np.abs(norms[sel][well] - ref[well]) / ref[well]) < 1e-5
