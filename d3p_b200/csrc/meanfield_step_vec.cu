@@ -48,8 +48,8 @@ D3P_D void cp_async16(float* smem_dst, const float* gsrc) {
 }
 D3P_D void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 
-// Per-warp staging in shared memory: the example's row x (later overwritten by gl) and the scaled
-// noise u.  Every lane only touches its own 16-byte slots, so no intra-warp synchronisation is
+// Per-warp staging in shared memory: the example's row x (later overwritten by g_loc) and the scaled
+// noise u (later overwritten by g_rho).  Every lane only touches its own 16-byte slots, so no intra-warp synchronisation is
 // needed; the loops over chunks stay rolled, which keeps the hot loop inside the instruction cache
 // (the fully unrolled variant was fetch-bound: ncu `no_instruction` stalls, profiles/r1_*).
 //
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   constexpr int HALF = LPE * NQ;       // d / 2
   constexpr int D = 2 * HALF;
   constexpr int G = 32 / LPE;          // examples in flight per warp
-  constexpr int TILE = 8;
+  constexpr int TILE = 16;
   constexpr bool kExp = LINK == D3P_LINK_EXP;
   extern __shared__ __align__(16) float smem[];
   float* s_loc = smem;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   const float Linv = a.L * a.inv_var;
 
   // Each warp owns one contiguous run of floor(npos / total_warps) (+1 for the first npos % total_warps
-  // warps) positions and walks it in tiles of 8: per-warp loads differ by at most one example, which
+  // warps) positions and walks it in tiles of 16: per-warp loads differ by at most one example, which
   // matters when a rank holds only a few examples per warp (sharded batches: 5.3 at N = 8 on C2).
   const uint32_t gw = blockIdx.x * kStepWarps + warp;
   const uint32_t per_q = npos / total_warps, per_r = npos % total_warps;
@@ -131,23 +131,23 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
     uint32_t my_k0, my_k1, my_row = 0;
     float my_eb = 0.f, my_y = 0.f;
     {
-      // Key chain of example base + (lane & 7): split(K,B)[p] -> split -> guide_seed -> split ->
+      // Key chain of example base + (lane & 15): split(K,B)[p] -> split -> guide_seed -> split ->
       // (rng, k_main) [-> split(rng) -> k_b -> eps_b].  Every level is two independent Threefry
-      // calls ((0,2) and (1,3)); lanes with bit 3 clear / set take one each and swap by shuffle,
-      // so the chain costs 3 (5 with an intercept) calls per tile instead of 6 (9).
-      const uint32_t t8 = lane & 7u, part = (lane >> 3) & 1u;
-      const uint32_t w = tf_split_word(K, a.B, 2u * (base + t8) + part);
-      TfKey kk(__shfl_sync(0xffffffffu, w, t8), __shfl_sync(0xffffffffu, w, t8 + 8u));
+      // calls ((0,2) and (1,3)); the lower / upper half-warp take one each and swap by shuffle,
+      // so the chain costs 3 (5 with an intercept) calls per tile of 16 examples instead of 6 (9) per example.
+      const uint32_t tl = lane & 15u, part = lane >> 4;
+      const uint32_t w = tf_split_word(K, a.B, 2u * (base + tl) + part);
+      TfKey kk(__shfl_sync(0xffffffffu, w, tl), __shfl_sync(0xffffffffu, w, tl + 16u));
       uint32_t y0, y1;
       threefry2x32(kk, part, part + 2u, y0, y1);                 // (model_seed, guide_seed)
-      kk = TfKey(__shfl_sync(0xffffffffu, y1, t8), __shfl_sync(0xffffffffu, y1, t8 + 8u));
+      kk = TfKey(__shfl_sync(0xffffffffu, y1, tl), __shfl_sync(0xffffffffu, y1, tl + 16u));
       threefry2x32(kk, part, part + 2u, y0, y1);                 // (rng, k_main)
-      my_k0 = __shfl_sync(0xffffffffu, y1, t8);
-      my_k1 = __shfl_sync(0xffffffffu, y1, t8 + 8u);
+      my_k0 = __shfl_sync(0xffffffffu, y1, tl);
+      my_k1 = __shfl_sync(0xffffffffu, y1, tl + 16u);
       if (a.has_b) {
-        kk = TfKey(__shfl_sync(0xffffffffu, y0, t8), __shfl_sync(0xffffffffu, y0, t8 + 8u));
+        kk = TfKey(__shfl_sync(0xffffffffu, y0, tl), __shfl_sync(0xffffffffu, y0, tl + 16u));
         threefry2x32(kk, part, part + 2u, y0, y1);               // (rng2, k_b)
-        kk = TfKey(__shfl_sync(0xffffffffu, y1, t8), __shfl_sync(0xffffffffu, y1, t8 + 8u));
+        kk = TfKey(__shfl_sync(0xffffffffu, y1, tl), __shfl_sync(0xffffffffu, y1, tl + 16u));
         threefry2x32(kk, 0u, 0u, y0, y1);
         my_eb = bits_to_normal_fast(y0);
       }
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
       if (FAMILY == D3P_FAMILY_LOGREG) my_y = (float)a.y[my_row];
     }
     const unsigned valid_bits = __ballot_sync(0xffffffffu, my_valid);
-    const uint32_t any_row = __shfl_sync(0xffffffffu, my_row, __ffs(valid_bits | 0x100u) - 1);   // a readable row
+    const uint32_t any_row = __shfl_sync(0xffffffffu, my_row, __ffs(valid_bits | 0x10000u) - 1);   // a readable row
 #pragma unroll 1
     for (int t0 = 0; t0 < TILE; t0 += G) {
       if (!((valid_bits >> t0) & ((1u << G) - 1u))) continue;   // warp-uniform: none of the G examples is valid
@@ -227,30 +227,37 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
       }
       const float loss_i = 0.5f * s_th2 - 0.5f * s_e2 - sum_log_s - a.N * loglik;
 
-      // ---- loop B: gradient wrt loc (overwrites x in the staging buffer), norm ----------------
+      // ---- loop B: gradients (g_loc overwrites x, g_rho overwrites u in the staging buffers), norm ----
       float nrm = 0.f;
-#pragma unroll 1
-      for (int i = 0; i < 2 * NCH; ++i) {
-        const int e0 = (i & 1) * HALF + 4 * (sl + LPE * (i >> 1));
-        const float4 loc = ld4(s_loc + e0), xv = ld4(xs + e0), u = ld4(us + e0);
-        float4 sa = loc, bt = loc, gl;
-        if (!kExp) { sa = ld4(s_sa + e0); bt = ld4(s_bt + e0); }
+#pragma unroll 2
+      for (int kk = 0; kk < NCH; ++kk) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e0 = h * HALF + 4 * (sl + LPE * kk);
+          const float4 loc = ld4(s_loc + e0), xv = ld4(xs + e0), u = ld4(us + e0);
+          float4 sa = loc, bt = loc, gl, gs;
+          if (!kExp) { sa = ld4(s_sa + e0); bt = ld4(s_bt + e0); }
 #define D3P_P2(c)                                                                            \
-        {                                                                                    \
-          const float th = kExp ? (loc.c + u.c) : fmaf(u.c, sa.c, loc.c);                    \
-          const float h = (FAMILY == D3P_FAMILY_LOGREG) ? Lr * xv.c : Linv * (th - xv.c);    \
-          gl.c = fmaf(th, a.inv_S, h);                                                       \
-          const float gs = fmaf(gl.c, u.c, -(kExp ? a.inv_S : bt.c));                        \
-          nrm = fmaf(gl.c, gl.c, fmaf(gs, gs, nrm));                                         \
-        }
-        D3P_F4_FOREACH(D3P_P2)
+          {                                                                                  \
+            const float th = kExp ? (loc.c + u.c) : fmaf(u.c, sa.c, loc.c);                  \
+            const float hh = (FAMILY == D3P_FAMILY_LOGREG) ? Lr * xv.c : Linv * (th - xv.c); \
+            gl.c = fmaf(th, a.inv_S, hh);                                                    \
+            gs.c = fmaf(gl.c, u.c, -(kExp ? a.inv_S : bt.c));                                \
+            nrm = fmaf(gl.c, gl.c, fmaf(gs.c, gs.c, nrm));                                   \
+          }
+          D3P_F4_FOREACH(D3P_P2)
 #undef D3P_P2
-        st4(xs + e0, gl);
-        if (a.px_grads && act) {
-          float* pg = a.px_grads + (size_t)(base + t) * a.P;
-#define D3P_PG(c, k)                                                                         \
-          pg[a.loc_off + e0 + k] = gl.c;                                                     \
-          pg[a.rho_off + e0 + k] = fmaf(gl.c, u.c, -(kExp ? a.inv_S : bt.c));
+          st4(xs + e0, gl);
+          st4(us + e0, gs);
+        }
+      }
+      if (a.px_grads && act) {             // stage-method API only (tests): materialise this example's gradient row
+        float* pg = a.px_grads + (size_t)(base + t) * a.P;
+#pragma unroll 1
+        for (int i = 0; i < 2 * NCH; ++i) {
+          const int e0 = (i & 1) * HALF + 4 * (sl + LPE * (i >> 1));
+          const float4 gl = ld4(xs + e0), gs = ld4(us + e0);
+#define D3P_PG(c, k) pg[a.loc_off + e0 + k] = gl.c; pg[a.rho_off + e0 + k] = gs.c;
           D3P_PG(x, 0) D3P_PG(y, 1) D3P_PG(z, 2) D3P_PG(w, 3)
 #undef D3P_PG
         }
@@ -269,12 +276,10 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
 #pragma unroll
       for (int i = 0; i < 2 * NCH; ++i) {
         const int e0 = (i & 1) * HALF + 4 * (sl + LPE * (i >> 1));
-        const float4 gl = ld4(xs + e0), u = ld4(us + e0);
-        float4 bt = make_float4(a.inv_S, a.inv_S, a.inv_S, a.inv_S);
-        if (!kExp) bt = ld4(s_bt + e0);
+        const float4 gl = ld4(xs + e0), gs = ld4(us + e0);
 #define D3P_P3(c_)                                                     \
         accL[i].c_ = fmaf(c, gl.c_, accL[i].c_);                       \
-        accR[i].c_ = fmaf(c, fmaf(gl.c_, u.c_, -bt.c_), accR[i].c_);
+        accR[i].c_ = fmaf(c, gs.c_, accR[i].c_);
         D3P_F4_FOREACH(D3P_P3)
 #undef D3P_P3
       }
