@@ -1,10 +1,15 @@
 // Row f2 of the scope table: the whole `fori_loop(fetch -> update)` body of the examples
 // (examples/logistic_regression.py:149-160, README.md:119-126) driven from C for the mean-field
 // families.  One call = n_steps x { fold_in + minibatch sampler, 3-way key split, key conversion,
-// fused per-example-gradient/clip/sum, per-leaf noise keys, finalize (+ ADADP finish) }, queued on one
-// stream with no host synchronisation and no interpreter between the launches.  Host work per step is a
-// handful of ChaCha blocks (<10 us); every device piece is the same entry point DPSVI.update uses, so the
-// parameter trajectory is bit-identical to calling get_batch / update step by step.
+// fused per-example-gradient/clip/sum, per-leaf noise keys, finalize (+ ADADP finish) }, queued with no host
+// synchronisation and no interpreter between the launches.  Host work per step is a handful of ChaCha blocks
+// (<10 us); every device piece is the same entry point DPSVI.update uses, so the parameter trajectory is
+// bit-identical to calling get_batch / update step by step.
+//
+// get_batch(i, state) depends on the batch key and on i only, never on the parameters, so the index sampler of
+// step i + 1 is queued on a second (forked) stream and runs while step i's gradient kernel drains and its finalize
+// kernel (latency-bound, a few CTAs; at N > 1 it also waits for the peers) holds the main stream.  idx / counts /
+// mask are double-buffered; events order sampler(i) -> step(i) and step(i) -> sampler(i + 2).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -22,10 +27,10 @@ namespace {
 struct EpochWs {
   uint8_t* base;
   size_t poisson_bytes, step_bytes, total;
-  uint8_t* poisson;   // sampler scratch (Poisson only)
-  int32_t* idx;       // [batch]
-  int32_t* counts;    // [2]
-  uint8_t* mask;      // [batch]
+  uint8_t* poisson;   // sampler scratch (Poisson only; used by the sampler stream alone)
+  int32_t* idx[2];    // [batch], double-buffered over the step parity
+  int32_t* counts[2]; // [2]
+  uint8_t* mask[2];   // [batch]
   float* step;        // [n_partials, P + 2]
 };
 
@@ -39,15 +44,18 @@ bool layout_ws(const d3p_meanfield_desc* m, const d3p_sampler_desc* s, void* bas
   size_t off = 0;
   w.base = static_cast<uint8_t*>(base);
   auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
-  const size_t o_poi = take(w.poisson_bytes), o_idx = take((size_t)s->batch * 4), o_cnt = take(8),
-               o_mask = take(s->batch), o_step = take(w.step_bytes);
+  const size_t o_poi = take(w.poisson_bytes), o_step = take(w.step_bytes);
+  size_t o_idx[2], o_cnt[2], o_mask[2];
+  for (int b = 0; b < 2; ++b) { o_idx[b] = take((size_t)s->batch * 4); o_cnt[b] = take(8); o_mask[b] = take(s->batch); }
   w.total = off;
   if (base) {
     w.poisson = w.base + o_poi;
-    w.idx = reinterpret_cast<int32_t*>(w.base + o_idx);
-    w.counts = reinterpret_cast<int32_t*>(w.base + o_cnt);
-    w.mask = w.base + o_mask;
     w.step = reinterpret_cast<float*>(w.base + o_step);
+    for (int b = 0; b < 2; ++b) {
+      w.idx[b] = reinterpret_cast<int32_t*>(w.base + o_idx[b]);
+      w.counts[b] = reinterpret_cast<int32_t*>(w.base + o_cnt[b]);
+      w.mask[b] = w.base + o_mask[b];
+    }
   }
   return true;
 }
@@ -94,58 +102,92 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
     pos_begin = per * comm->rank < B ? per * comm->rank : B;
     pos_end = pos_begin + per < B ? pos_begin + per : B;
   }
-  // D3P_EPOCH_PROFILE=1: per-phase CUDA-event timings of this call on stderr (synchronises at the end)
+  // D3P_EPOCH_PROFILE=1: per-phase CUDA-event timings of this call on stderr (synchronises at the end; the
+  // sampler then stays on the main stream so that the three phases are disjoint in time)
   const bool prof = getenv("D3P_EPOCH_PROFILE") != nullptr;
+  const bool fork = !prof && getenv("D3P_EPOCH_SERIAL") == nullptr && n_steps > 1;
+  cudaStream_t main_s = (cudaStream_t)stream, samp_s = main_s;
+  cudaEvent_t ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_fork = nullptr;
+  if (fork) {
+    bool ok = cudaStreamCreateWithFlags(&samp_s, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int b = 0; b < 2 && ok; ++b)
+      ok = cudaEventCreateWithFlags(&ev_sampled[b], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ev_consumed[b], cudaEventDisableTiming) == cudaSuccess;
+    // the sampler stream starts after everything already queued on the caller's stream
+    ok = ok && cudaEventRecord(ev_fork, main_s) == cudaSuccess && cudaStreamWaitEvent(samp_s, ev_fork, 0) == cudaSuccess;
+    if (!ok) return D3P_ERR_CUDA;
+  }
   std::vector<cudaEvent_t> ev;
   auto mark = [&]() {
     if (!prof) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
-    cudaEventRecord(e, (cudaStream_t)stream);
+    cudaEventRecord(e, main_s);
     ev.push_back(e);
   };
-  int32_t rc = D3P_OK;
-  for (uint32_t s = 0; s < n_steps && rc == D3P_OK; ++s) {
-    mark();
-    // ---- get_batch(i, batchifier_state): fold_in, then the index sampler (minibatch.py:103-131,217-237) ----
+  // get_batch(i, batchifier_state): fold_in, then the index sampler (minibatch.py:103-131,217-237), into buffer i & 1
+  auto queue_sampler = [&](uint32_t s) -> int32_t {
+    const int b = s & 1;
     uint32_t bkey[16];
-    if ((rc = d3p_chacha_fold_in_h(batch_key_h, first_step + s, bkey)) != D3P_OK) break;
-    const uint8_t* mask = nullptr;
+    int32_t r = d3p_chacha_fold_in_h(batch_key_h, first_step + s, bkey);
+    if (r != D3P_OK) return r;
+    if (fork && s >= 2 && cudaStreamWaitEvent(samp_s, ev_consumed[b], 0) != cudaSuccess) return D3P_ERR_CUDA;
     if (sampler->kind == D3P_SAMPLER_POISSON) {
-      rc = D3P_ERR_UNSUPPORTED;
+      r = D3P_ERR_UNSUPPORTED;
       if (comm && comm->world > 1)             // selector draw split over the ranks (samplers.cu)
-        rc = d3p_poisson_sample_sharded(comm, bkey, sampler->q, sampler->n_records, B, sampler->suppress, pos_begin,
-                                        pos_end, w.idx, w.counts, w.mask, w.poisson, w.poisson_bytes, stream);
-      if (rc == D3P_ERR_UNSUPPORTED)           // same decision on every rank (window size, tiles >= ranks)
-        rc = d3p_poisson_sample(bkey, sampler->q, sampler->n_records, B, sampler->suppress, w.idx, w.counts, w.mask,
-                                w.poisson, w.poisson_bytes, stream);
-      mask = w.mask;
+        r = d3p_poisson_sample_sharded(comm, bkey, sampler->q, sampler->n_records, B, sampler->suppress, pos_begin,
+                                       pos_end, w.idx[b], w.counts[b], w.mask[b], w.poisson, w.poisson_bytes, samp_s);
+      if (r == D3P_ERR_UNSUPPORTED)            // same decision on every rank (window size, tiles >= ranks)
+        r = d3p_poisson_sample(bkey, sampler->q, sampler->n_records, B, sampler->suppress, w.idx[b], w.counts[b],
+                               w.mask[b], w.poisson, w.poisson_bytes, samp_s);
     } else {
       uint32_t rcs[30];
-      if ((rc = d3p_feistel_round_constants_h(bkey, rcs)) != D3P_OK) break;
-      rc = d3p_feistel_sample(rcs, sampler->n_records, 0, B, w.idx, stream);
+      if ((r = d3p_feistel_round_constants_h(bkey, rcs)) != D3P_OK) return r;
+      r = d3p_feistel_sample(rcs, sampler->n_records, 0, B, w.idx[b], samp_s);
     }
-    if (rc != D3P_OK) break;
+    if (r == D3P_OK && fork && cudaEventRecord(ev_sampled[b], samp_s) != cudaSuccess) r = D3P_ERR_CUDA;
+    return r;
+  };
+  int32_t rc = D3P_OK;
+  if (fork) rc = queue_sampler(0);
+  for (uint32_t s = 0; s < n_steps && rc == D3P_OK; ++s) {
+    const int b = s & 1;
+    mark();
+    if (fork) {
+      if (s + 1 < n_steps && (rc = queue_sampler(s + 1)) != D3P_OK) break;      // runs ahead on the sampler stream
+      if (cudaStreamWaitEvent(main_s, ev_sampled[b], 0) != cudaSuccess) { rc = D3P_ERR_CUDA; break; }
+    } else if ((rc = queue_sampler(s)) != D3P_OK) {
+      break;
+    }
+    const uint8_t* mask = sampler->kind == D3P_SAMPLER_POISSON ? w.mask[b] : nullptr;
     mark();
     // ---- DPSVI.update (svi.py:395-434) ----------------------------------------------------------------------
     uint32_t keys[3][16], tf[2];
     if ((rc = d3p_chacha_split_h(rng_key_io_h, 3, &keys[0][0])) != D3P_OK) break;           // carry, k_grad, k_noise
     if ((rc = d3p_chacha_random_bits_h(keys[1], 0, tf, 2)) != D3P_OK) break;                // convert_to_jax_rng_key
-    rc = d3p_dpsvi_step_meanfield(desc, params_d, x_d, x_row_stride, y_d, w.idx, mask, nullptr, B, pos_begin, pos_end, tf,
-                                  obs_scale,
-                                  C, nullptr, nullptr, nullptr, w.step, w.step_bytes, stream);
+    rc = d3p_dpsvi_step_meanfield(desc, params_d, x_d, x_row_stride, y_d, w.idx[b], mask, nullptr, B, pos_begin, pos_end,
+                                  tf, obs_scale, C, nullptr, nullptr, nullptr, w.step, w.step_bytes, main_s);
     if (rc != D3P_OK) break;
+    if (fork && cudaEventRecord(ev_consumed[b], main_s) != cudaSuccess) { rc = D3P_ERR_CUDA; break; }
     mark();
     if ((rc = d3p_chacha_split_h(keys[2], (int32_t)lt.n_leaves, &lt.site_state[0][0])) != D3P_OK) break;
     rc = d3p_perturb_finalize_p2p_f32(w.step, n_part, P, B, &lt, dp_scale, C, obs_scale, 1, nullptr, optim_io_h,
                                       params_d, m_d, v_d, stats_out_d ? stats_out_d + 3 * (size_t)s : nullptr, nullptr,
-                                      comm, stream);
+                                      comm, main_s);
     if (rc != D3P_OK) break;
     if (optim_io_h->kind == D3P_OPT_ADADP && (optim_io_h->step & 1))
-      if ((rc = d3p_adadp_finish_f32(optim_io_h, P, params_d, v_d, stream)) != D3P_OK) break;
+      if ((rc = d3p_adadp_finish_f32(optim_io_h, P, params_d, v_d, main_s)) != D3P_OK) break;
     optim_io_h->step += 1;
     memcpy(rng_key_io_h, keys[0], sizeof(keys[0]));
     mark();
+  }
+  if (fork) {
+    // join: whatever is still queued on the sampler stream (only after an error) precedes later work of the caller
+    if (cudaEventRecord(ev_fork, samp_s) == cudaSuccess) cudaStreamWaitEvent(main_s, ev_fork, 0);
+    for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_sampled[b]); cudaEventDestroy(ev_consumed[b]); }
+    cudaEventDestroy(ev_fork);
+    cudaStreamDestroy(samp_s);       // returns at once; the stream is released when its work has drained
   }
   if (prof && rc == D3P_OK && ev.size() == 4 * (size_t)n_steps) {
     cudaStreamSynchronize((cudaStream_t)stream);
