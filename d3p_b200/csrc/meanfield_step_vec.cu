@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   float* s_sa = s_a + (kExp ? 0 : D);
   float* s_bt = s_sa + (kExp ? 0 : D);
   float* s_stage = s_bt + (kExp ? 0 : D);       // [kStepWarps][G][2 * D]
-  float* s_acc = s_stage + kStepWarps * G * 2 * D;  // [P + 2]
   __shared__ float s_red[kStepWarps];
+  __shared__ float s_scal[kStepWarps][4];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sl = lane & (LPE - 1), sub = lane / LPE;       // lane within its example group, group index
@@ -101,7 +101,6 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   }
   log_s_part = gsum<32>(log_s_part, 0xffffffffu);
   if (lane == 0) s_red[warp] = log_s_part;
-  for (uint32_t j = threadIdx.x; j < a.P + 2; j += kStepThreads) s_acc[j] = 0.f;
   __syncthreads();
   float sum_log_s = 0.f;
 #pragma unroll
@@ -317,33 +316,42 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
       acc_cnt += __shfl_xor_sync(0xffffffffu, acc_cnt, o);
     }
   }
-  for (int w = 0; w < kStepWarps; ++w) {
-    if (warp == w && sub == 0) {
+  // every warp parks its sums in its own staging slot (it is done with it), then all threads add the 8 slots of
+  // their columns in warp order (fixed order => run-to-run deterministic) and write the CTA partial
+  float* slot = s_stage + (size_t)warp * G * 2 * D;
+  if (sub == 0) {
 #pragma unroll
-      for (int i = 0; i < 2 * NCH; ++i) {
-        const int e0 = (i & 1) * HALF + 4 * (sl + LPE * (i >> 1));
-        float* pl = s_acc + a.loc_off + e0;
-        float* pr = s_acc + a.rho_off + e0;
-        pl[0] += accL[i].x; pl[1] += accL[i].y; pl[2] += accL[i].z; pl[3] += accL[i].w;
-        pr[0] += accR[i].x; pr[1] += accR[i].y; pr[2] += accR[i].z; pr[3] += accR[i].w;
-      }
-      if (lane == 0) {
-        if (a.has_b) { s_acc[a.b_loc_off] += acc_bloc; s_acc[a.b_rho_off] += acc_brho; }
-        s_acc[a.P] += acc_loss;
-        s_acc[a.P + 1] += acc_cnt;
-      }
+    for (int i = 0; i < 2 * NCH; ++i) {
+      const int e0 = (i & 1) * HALF + 4 * (sl + LPE * (i >> 1));
+      st4(slot + e0, accL[i]);
+      st4(slot + D + e0, accR[i]);
     }
-    __syncthreads();
   }
+  if (lane == 0) {
+    s_scal[warp][0] = acc_bloc; s_scal[warp][1] = acc_brho; s_scal[warp][2] = acc_loss; s_scal[warp][3] = acc_cnt;
+  }
+  __syncthreads();
   float* out = a.partials + (size_t)blockIdx.x * (a.P + 2);
-  for (uint32_t j = threadIdx.x; j < a.P + 2; j += kStepThreads) out[j] = s_acc[j];
+  for (int j = threadIdx.x; j < 2 * D; j += kStepThreads) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kStepWarps; ++w) v += s_stage[(size_t)w * G * 2 * D + j];
+    out[(j < D ? a.loc_off : a.rho_off - D) + j] = v;
+  }
+  if (threadIdx.x < 4) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kStepWarps; ++w) v += s_scal[w][threadIdx.x];
+    if (threadIdx.x >= 2) out[a.P + threadIdx.x - 2] = v;
+    else if (a.has_b) out[threadIdx.x == 0 ? a.b_loc_off : a.b_rho_off] = v;
+  }
 }
 
 template <int FAMILY, int LINK, int NQ, int LPE>
 static int32_t launch_vec_one(const StepArgs& a, unsigned grid, cudaStream_t s) {
   constexpr int D = 2 * LPE * NQ;
   constexpr int G = 32 / LPE;
-  size_t smem = ((LINK == D3P_LINK_EXP ? 2 : 5) * (size_t)D + (size_t)kStepWarps * G * 2 * D + a.P + 2) * sizeof(float);
+  size_t smem = ((LINK == D3P_LINK_EXP ? 2 : 5) * (size_t)D + (size_t)kStepWarps * G * 2 * D) * sizeof(float);
   auto kern = meanfield_step_vec_kernel<FAMILY, LINK, NQ, LPE>;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
