@@ -469,12 +469,12 @@ def run_b200(args, cfg):
                                  "samples at ~10 Threefry calls each) per 512-byte row, DESIGN.md section 6"
                                  if cfg["family"] == "gmm" else
                                  "issue-bound, not HBM-bound: one Threefry-2x32-20 normal per data float "
-                                 "(~87 warp-instructions per element, DESIGN.md section 5)")}
+                                 "(~83 warp-instructions per element, DESIGN.md section 5)")}
             if kname == "meanfield_step_vec_kernel" and cfg["family"] == "logreg" and clocks.get("sm_mhz"):
                 # the bound that does apply: issue slots.  Instruction count per element from the committed ncu
-                # capture (profiles/r1_step_vec_c2_ncu_full_v5.csv: smsp__inst_executed.sum / (examples * 1025 / 32));
+                # capture (profiles/r1_step_vec_c2_ncu_full_v6.csv: smsp__inst_executed.sum / (examples * 1025 / 32));
                 # the slots offered are SMs x 4 schedulers x measured SM clock x kernel time.
-                wi_per_elem = 87.3
+                wi_per_elem = 82.9
                 elems = per_rank_examples * (cfg["d"] + 1)
                 slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * kern_ms_avg * 1e-3
                 roofline["issue_slots"] = {"warp_instr_per_element": wi_per_elem,
