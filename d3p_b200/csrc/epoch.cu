@@ -169,13 +169,14 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
     rc = d3p_dpsvi_step_meanfield(desc, params_d, x_d, x_row_stride, y_d, w.idx[b], mask, nullptr, B, pos_begin, pos_end,
                                   tf, obs_scale, C, nullptr, nullptr, nullptr, w.step, w.step_bytes, main_s);
     if (rc != D3P_OK) break;
-    if (fork && cudaEventRecord(ev_consumed[b], main_s) != cudaSuccess) { rc = D3P_ERR_CUDA; break; }
     mark();
     if ((rc = d3p_chacha_split_h(keys[2], (int32_t)lt.n_leaves, &lt.site_state[0][0])) != D3P_OK) break;
     rc = d3p_perturb_finalize_p2p_f32(w.step, n_part, P, B, &lt, dp_scale, C, obs_scale, 1, nullptr, optim_io_h,
                                       params_d, m_d, v_d, stats_out_d ? stats_out_d + 3 * (size_t)s : nullptr, nullptr,
                                       comm, main_s);
     if (rc != D3P_OK) break;
+    // recorded after the finalize launch so that nothing sits between the step kernel and its programmatic dependent
+    if (fork && cudaEventRecord(ev_consumed[b], main_s) != cudaSuccess) { rc = D3P_ERR_CUDA; break; }
     if (optim_io_h->kind == D3P_OPT_ADADP && (optim_io_h->step & 1))
       if ((rc = d3p_adadp_finish_f32(optim_io_h, P, params_d, v_d, main_s)) != D3P_OK) break;
     optim_io_h->step += 1;

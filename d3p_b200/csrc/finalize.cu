@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
   __shared__ float red[2][kFinThreads / 32];
   __shared__ float s_n, s_loss;
   const uint32_t stride = a.P + 2;
+  asm volatile("griddepcontrol.wait;" ::: "memory");    // no-op unless launched as a programmatic dependent
   // every CTA reduces the (count, loss) columns itself: n_partials is a few hundred at most
   float cnt = 0.f, loss = 0.f;
   for (uint32_t p = threadIdx.x; p < a.n_partials; p += kFinThreads) {
@@ -448,7 +449,18 @@ extern "C" int32_t d3p_perturb_finalize_p2p_f32(const float* partials_d, uint32_
   }
   unsigned grid = P ? (P + 31) / 32 : 1;
   if (comm && !comm_next(comm, P, grid, &cd)) return D3P_ERR_INVALID_ARGUMENT;
-  finalize_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(a, lt, ss, cd);
+  // Programmatic dependent launch: when the preceding kernel on the stream releases its dependents early (the
+  // fused step kernels do, at their first instruction), the CTAs of this latency-bound kernel are placed on SMs as
+  // those drain and wait in griddepcontrol.wait for the producer grid to complete and flush, which takes the
+  // launch latency off the step's critical path.  After any other predecessor this is an ordinary launch.
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kFinThreads); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, finalize_kernel, a, lt, ss, cd) != cudaSuccess) return D3P_ERR_CUDA;
   return check_launch();
 }
 

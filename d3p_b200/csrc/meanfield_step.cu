@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
   float* s_acc = s_bt + (LINK == D3P_LINK_EXP ? 0 : NALLOC);  // [P + 2] CTA partial sums
   __shared__ float s_red[kStepWarps];
 
+  asm volatile("griddepcontrol.launch_dependents;");   // see meanfield_step_vec.cu: the finalize kernel may be placed early
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int glane = lane & (G - 1), sg = lane / G;
   const unsigned gm = group_mask<G>(lane);

@@ -78,6 +78,9 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   __shared__ float s_red[kStepWarps];
   __shared__ float s_scal[kStepWarps][4];
 
+  // let a programmatic dependent (the finalize kernel) be placed on the SMs as this grid drains; it waits for the
+  // whole grid to complete before it reads the partial rows
+  asm volatile("griddepcontrol.launch_dependents;");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sl = lane & (LPE - 1), sub = lane / LPE;       // lane within its example group, group index
   float* xs = s_stage + (warp * G + sub) * 2 * D;          // x, then gl
@@ -117,13 +120,17 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   const uint32_t total_warps = gridDim.x * kStepWarps;
   const float Linv = a.L * a.inv_var;
 
-  // Each warp owns one contiguous run of floor(npos / total_warps) (+1 for the first npos % total_warps
+  // Each warp owns one contiguous run of floor(npos / total_warps) (+1 for npos % total_warps of the
   // warps) positions and walks it in tiles of 16: per-warp loads differ by at most one example, which
   // matters when a rank holds only a few examples per warp (sharded batches: 5.3 at N = 8 on C2).
   const uint32_t gw = blockIdx.x * kStepWarps + warp;
+  // the npos % total_warps longer runs are spread evenly over the grid (Bresenham), so that every SM holds the
+  // same number of examples +-1 whichever CTAs it hosts (the first-come form gave 88 vs 80 per SM at N = 8)
   const uint32_t per_q = npos / total_warps, per_r = npos % total_warps;
-  const uint32_t w_begin = gw * per_q + min(gw, per_r);
-  const uint32_t w_end = a.pos_begin + w_begin + per_q + (gw < per_r ? 1u : 0u);
+  const uint32_t x_lo = (uint32_t)(((unsigned long long)gw * per_r) / total_warps);
+  const uint32_t x_hi = (uint32_t)(((unsigned long long)(gw + 1u) * per_r) / total_warps);
+  const uint32_t w_begin = gw * per_q + x_lo;
+  const uint32_t w_end = a.pos_begin + w_begin + per_q + (x_hi - x_lo);
   for (uint32_t base = a.pos_begin + w_begin; base < w_end; base += TILE) {
     const uint32_t my_p = base + lane;
     bool my_valid = (lane < TILE) && (my_p < w_end) && (my_p < nv) && (!a.mask || a.mask[my_p]);
