@@ -41,8 +41,9 @@ WORKLOADS = {
 }
 # algorithmic HBM bytes per example of the dominant kernel
 ALGO_BYTES_PER_EXAMPLE = {"c1": 4 * (8 + 1), "c2": 4 * (1024 + 1), "c3": 4 * 256, "c4": 4 * 128}
-# launches of OUR kernels per step: sampler + step kernel(s) + finalize
-LAUNCHES = {"poisson": 3, "subsample": 1, "logreg": 2, "gauss": 2, "gmm": 2, "vae": 13}   # vae: 2 split + prep + 7 GEMMs + 2 SIMT + loss (12) + finalize
+# launches of OUR kernels per step: sampler (Poisson: select + compact; Feistel: 1) + step kernel(s) + finalize;
+# matches the ncu launch list profiles/r1_c2_launches_v6.csv (4 per C2 step)
+LAUNCHES = {"poisson": 2, "subsample": 1, "logreg": 2, "gauss": 2, "gmm": 2, "vae": 13}   # vae: 2 split + prep + 7 GEMMs + 2 SIMT + loss (12) + finalize
 
 
 def measured_peaks():
