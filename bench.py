@@ -43,7 +43,7 @@ WORKLOADS = {
 ALGO_BYTES_PER_EXAMPLE = {"c1": 4 * (8 + 1), "c2": 4 * (1024 + 1), "c3": 4 * 256, "c4": 4 * 128}
 # launches of OUR kernels per step: sampler (Poisson: select + compact; Feistel: 1) + step kernel(s) + finalize;
 # matches the ncu launch list profiles/r1_c2_launches_v6.csv (4 per C2 step)
-LAUNCHES = {"poisson": 2, "subsample": 1, "logreg": 2, "gauss": 2, "gmm": 2, "vae": 13}   # vae: 2 split + prep + 7 GEMMs + 2 SIMT + loss (12) + finalize
+LAUNCHES = {"poisson": 2, "subsample": 1, "logreg": 2, "gauss": 2, "gmm": 2, "vae": 14}   # vae: 2 split + prep x + prep mid + 7 GEMMs + 2 thin-layer MMA + loss (13) + finalize
 
 
 def measured_peaks():
@@ -352,7 +352,7 @@ def run_b200(args, cfg):
 
     # ---- the same K steps through the C-side epoch driver (row f2): no interpreter between launches ----
     epoch_line = None
-    if cfg["family"] in ("logreg", "gauss") and (world == 1 or args.collective == "p2p"):
+    if cfg["family"] in ("logreg", "gauss", "vae") and (world == 1 or args.collective == "p2p"):
         base = args.warmup + args.steps + 32
         state, _ = svi.run_epoch(state, get_batch, bstate, max(args.warmup, 3), first_step=base)
         sync_all()
@@ -369,7 +369,8 @@ def run_b200(args, cfg):
         epoch_line = {"value": float(ep_stats[:, 1].sum().item()) / (ep_ms * 1e-3), "unit": "examples/s",
                       "ms_per_step": ep_ms / args.steps,
                       "note": "DPSVI.run_epoch: the fori_loop(get_batch -> update) of the examples driven by "
-                              "d3p_dpsvi_run_epoch_meanfield (same kernels, host work in C)"}
+                              + ("d3p_dpsvi_run_epoch_vae" if is_vae else "d3p_dpsvi_run_epoch_meanfield")
+                              + " (same kernels, host work in C)"}
 
     clocks = sampler.stop()
 
@@ -503,7 +504,8 @@ def run_b200(args, cfg):
             # the interpreter-driven loop above stays as `stepwise` and provides the per-kernel event timings
             line["stepwise"] = {"value": value, "ms_per_step": step_ms}
             line["value"], line["ms_per_step"] = epoch_line["value"], epoch_line["ms_per_step"]
-            line["config"]["driver"] = "DPSVI.run_epoch: get_batch + update for all K steps inside d3p_dpsvi_run_epoch_meanfield"
+            line["config"]["driver"] = ("DPSVI.run_epoch: get_batch + update for all K steps inside "
+                                        + ("d3p_dpsvi_run_epoch_vae" if is_vae else "d3p_dpsvi_run_epoch_meanfield"))
             line["roofline"]["kernel_share_of_step"] = line["roofline"]["kernel_ms"] / epoch_line["ms_per_step"]
         if world == 1 and args.cpu_baseline:
             threads = os.cpu_count() or 1

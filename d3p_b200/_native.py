@@ -97,6 +97,11 @@ _SIGNATURES = {
                                                   _vp, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                                   C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
                                                   _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_dpsvi_epoch_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.POINTER(SamplerDesc), C.c_int32]),
+    "d3p_dpsvi_run_epoch_vae": (C.c_int32, [C.POINTER(VaeDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
+                                            _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
+                                            C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
+                                            _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "d3p_comm_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_uint8)]),
     "d3p_poisson_sample_sharded": (C.c_int32, [_vp, _u32p, C.c_float, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32,

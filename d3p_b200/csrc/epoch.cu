@@ -36,9 +36,8 @@ struct EpochWs {
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-bool layout_ws(const d3p_meanfield_desc* m, const d3p_sampler_desc* s, void* base, EpochWs& w) {
-  uint32_t n_part = 0;
-  w.step_bytes = d3p_meanfield_workspace_bytes(m, &n_part);
+bool layout_ws(size_t step_bytes, const d3p_sampler_desc* s, void* base, EpochWs& w) {
+  w.step_bytes = step_bytes;
   if (w.step_bytes == 0) return false;
   w.poisson_bytes = s->kind == D3P_SAMPLER_POISSON ? d3p_poisson_workspace_bytes(s->n_records) : 0;
   size_t off = 0;
@@ -69,11 +68,62 @@ bool sampler_ok(const d3p_sampler_desc* s) {
 
 }  // namespace
 
+namespace {
+// rows of the batch handled by one rank of `world` (contiguous position ranges, the last one may be shorter)
+uint32_t rows_per_rank(uint32_t B, int world) { return world > 1 ? (B + (uint32_t)world - 1) / (uint32_t)world : B; }
+
+// The family-specific part of a step: launches the fused per-example-gradient / clip / sum kernels of batch positions
+// [pos_begin, pos_end) into the partial rows at `ws`.
+struct StepLauncher {
+  size_t step_bytes;      // workspace of one step (partial rows first)
+  uint32_t n_part, P;
+  virtual int32_t launch(const int32_t* idx, const uint8_t* mask, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
+                         const uint32_t tf[2], float obs_scale, float C, void* ws, cudaStream_t s) const = 0;
+  virtual ~StepLauncher() {}
+};
+
+int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, const uint32_t batch_key_h[16],
+                  uint32_t rng_key_io_h[16], uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
+                  float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d, float* m_d,
+                  float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream);
+
+}  // namespace
+
 extern "C" size_t d3p_dpsvi_epoch_workspace_bytes(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler) {
   EpochWs w;
-  if (!desc || !sampler_ok(sampler) || !layout_ws(desc, sampler, nullptr, w)) return 0;
+  uint32_t n_part = 0;
+  if (!desc || !sampler_ok(sampler) || !layout_ws(d3p_meanfield_workspace_bytes(desc, &n_part), sampler, nullptr, w)) return 0;
   return w.total;
 }
+
+extern "C" size_t d3p_dpsvi_epoch_vae_workspace_bytes(const d3p_vae_desc* desc, const d3p_sampler_desc* sampler,
+                                                      int32_t world) {
+  EpochWs w;
+  if (!desc || !sampler_ok(sampler) || world < 1) return 0;
+  if (!layout_ws(d3p_vae_workspace_bytes(desc, rows_per_rank(sampler->batch, world), nullptr), sampler, nullptr, w)) return 0;
+  return w.total;
+}
+
+namespace {
+struct MeanfieldLauncher : StepLauncher {
+  const d3p_meanfield_desc* desc; const float* x; size_t stride; const int32_t* y;
+  int32_t launch(const int32_t* idx, const uint8_t* mask, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
+                 const uint32_t tf[2], float obs_scale, float C, void* ws, cudaStream_t s) const override {
+    return d3p_dpsvi_step_meanfield(desc, params, x, stride, y, idx, mask, nullptr, B, pos_begin, pos_end, tf, obs_scale, C,
+                                    nullptr, nullptr, nullptr, ws, step_bytes, s);
+  }
+  const float* params;
+};
+struct VaeLauncher : StepLauncher {
+  const d3p_vae_desc* desc; const float* x; size_t stride; const float* params;
+  int32_t launch(const int32_t* idx, const uint8_t* mask, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
+                 const uint32_t tf[2], float obs_scale, float C, void* ws, cudaStream_t s) const override {
+    return d3p_dpsvi_step_vae(desc, params, x, stride, idx, mask, nullptr, B, pos_begin, pos_end, tf, obs_scale, C, nullptr,
+                              nullptr, ws, step_bytes, nullptr, s);
+  }
+};
+}  // namespace
+
 
 extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler,
                                                  const float* x_d, size_t x_row_stride, const int32_t* y_d,
@@ -83,16 +133,47 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
                                                  d3p_optim_desc* optim_io_h, float* params_d, float* m_d, float* v_d,
                                                  float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes,
                                                  void* stream) {
-  if (!desc || !x_d || !batch_key_h || !rng_key_io_h || !leaves_h || !optim_io_h || !params_d || !ws_d)
+  if (!desc || !x_d || !params_d) return D3P_ERR_INVALID_ARGUMENT;
+  MeanfieldLauncher fam;
+  fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.y = y_d; fam.params = params_d;
+  fam.step_bytes = d3p_meanfield_workspace_bytes(desc, &fam.n_part);
+  fam.P = desc->n_params;
+  return run_epoch(fam, sampler, batch_key_h, rng_key_io_h, first_step, n_steps, obs_scale, C, dp_scale, leaves_h,
+                   optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+}
+
+// The same loop for the VAE family (examples/vae.py:216-233 runs fori_loop(get_batch -> update) per epoch).
+extern "C" int32_t d3p_dpsvi_run_epoch_vae(const d3p_vae_desc* desc, const d3p_sampler_desc* sampler, const float* x_d,
+                                           size_t x_row_stride, const uint32_t batch_key_h[16],
+                                           uint32_t rng_key_io_h[16], uint32_t first_step, uint32_t n_steps,
+                                           float obs_scale, float C, float dp_scale, const d3p_leaf_table* leaves_h,
+                                           d3p_optim_desc* optim_io_h, float* params_d, float* m_d, float* v_d,
+                                           float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream) {
+  if (!desc || !x_d || !params_d || !sampler_ok(sampler)) return D3P_ERR_INVALID_ARGUMENT;
+  if (reinterpret_cast<uintptr_t>(ws_d) & 255) return D3P_ERR_INVALID_ARGUMENT;   // the VAE step wants 256-byte alignment
+  VaeLauncher fam;
+  fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.params = params_d;
+  fam.step_bytes = d3p_vae_workspace_bytes(desc, rows_per_rank(sampler->batch, comm ? comm->world : 1), &fam.n_part);
+  fam.P = desc->n_params;
+  return run_epoch(fam, sampler, batch_key_h, rng_key_io_h, first_step, n_steps, obs_scale, C, dp_scale, leaves_h,
+                   optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+}
+
+namespace {
+int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, const uint32_t batch_key_h[16],
+                  uint32_t rng_key_io_h[16], uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
+                  float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d, float* m_d,
+                  float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream) {
+  if (!batch_key_h || !rng_key_io_h || !leaves_h || !optim_io_h || !params_d || !ws_d)
     return D3P_ERR_INVALID_ARGUMENT;
   if (!sampler_ok(sampler) || leaves_h->n_leaves == 0 || leaves_h->n_leaves > D3P_MAX_LEAVES)
     return D3P_ERR_INVALID_ARGUMENT;
   EpochWs w;
-  if (!layout_ws(desc, sampler, ws_d, w)) return D3P_ERR_UNSUPPORTED;
+  if (!layout_ws(fam.step_bytes, sampler, ws_d, w)) return D3P_ERR_UNSUPPORTED;
   if (ws_bytes < w.total) return D3P_ERR_WORKSPACE;
-  const uint32_t B = sampler->batch, P = desc->n_params;
-  uint32_t n_part = 0;
-  d3p_meanfield_workspace_bytes(desc, &n_part);
+  const uint32_t B = sampler->batch, P = fam.P;
+  const uint32_t n_part = fam.n_part;
+
   d3p_leaf_table lt = *leaves_h;
   // sharded batch: this rank handles a contiguous range of batch positions; the sampler and
   // all key derivations are replicated, the clipped sums meet inside the finalize kernel (comm.cuh)
@@ -166,8 +247,7 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
     uint32_t keys[3][16], tf[2];
     if ((rc = d3p_chacha_split_h(rng_key_io_h, 3, &keys[0][0])) != D3P_OK) break;           // carry, k_grad, k_noise
     if ((rc = d3p_chacha_random_bits_h(keys[1], 0, tf, 2)) != D3P_OK) break;                // convert_to_jax_rng_key
-    rc = d3p_dpsvi_step_meanfield(desc, params_d, x_d, x_row_stride, y_d, w.idx[b], mask, nullptr, B, pos_begin, pos_end,
-                                  tf, obs_scale, C, nullptr, nullptr, nullptr, w.step, w.step_bytes, main_s);
+    rc = fam.launch(w.idx[b], mask, B, pos_begin, pos_end, tf, obs_scale, C, w.step, main_s);
     if (rc != D3P_OK) break;
     mark();
     if ((rc = d3p_chacha_split_h(keys[2], (int32_t)lt.n_leaves, &lt.site_state[0][0])) != D3P_OK) break;
@@ -205,3 +285,4 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
   for (cudaEvent_t e : ev) cudaEventDestroy(e);
   return rc;
 }
+}  // namespace

@@ -207,23 +207,6 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
   for (uint32_t l = 1; l < leaves.n_leaves; ++l)
     if (live && chunk >= ct.chunk_start[l]) leaf = l;
   const uint32_t b = live ? chunk - ct.chunk_start[leaf] : 0u;
-  // column q of the state: rows 0..3
-  const uint32_t i0 = sites.w[leaf][q], i1 = sites.w[leaf][4 + q], i2 = sites.w[leaf][8 + q];
-  const uint32_t i3 = (q == 0) ? sites.w[leaf][12] + b : sites.w[leaf][12 + q];
-  uint32_t x0 = i0, x1 = i1, x2 = i2, x3 = i3;
-  const int base = lane & ~3;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    quad_qr(x0, x1, x2, x3);                              // column round
-    x1 = __shfl_sync(0xffffffffu, x1, base + ((q + 1) & 3));
-    x2 = __shfl_sync(0xffffffffu, x2, base + ((q + 2) & 3));
-    x3 = __shfl_sync(0xffffffffu, x3, base + ((q + 3) & 3));
-    quad_qr(x0, x1, x2, x3);                              // diagonal round
-    x1 = __shfl_sync(0xffffffffu, x1, base + ((q + 3) & 3));
-    x2 = __shfl_sync(0xffffffffu, x2, base + ((q + 2) & 3));
-    x3 = __shfl_sync(0xffffffffu, x3, base + ((q + 1) & 3));
-  }
-  const uint32_t ks[4] = {x0 + i0, x1 + i1, x2 + i2, x3 + i3};   // keystream words q, 4 + q, 8 + q, 12 + q
   const bool adadp_odd = a.opt_kind == D3P_OPT_ADADP && (a.step & 1);
   const uint32_t len = leaves.len[leaf], off = leaves.off[leaf];
   const float* __restrict__ parts = a.partials;
@@ -244,10 +227,30 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
     m0[i] = (ok[i] && a.opt_kind == D3P_OPT_ADAM) ? pm[jj[i]] : 0.f;
     v0[i] = (ok[i] && a.opt_kind == D3P_OPT_ADAM) ? pv[jj[i]] : 0.f;
   }
+  // the partial rows are requested before the ChaCha rounds below and 5 rows at a time (20 independent loads per
+  // thread): the row loop was one dependent round trip to L2 / HBM per row
+#pragma unroll 5
   for (uint32_t p = 0; p < a.n_partials; ++p) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sum[i] += ok[i] ? parts[(size_t)p * stride + jj[i]] : 0.f;
+    for (int i = 0; i < 4; ++i) sum[i] += ok[i] ? __ldg(parts + (size_t)p * stride + jj[i]) : 0.f;
   }
+  // column q of the state: rows 0..3
+  const uint32_t i0 = sites.w[leaf][q], i1 = sites.w[leaf][4 + q], i2 = sites.w[leaf][8 + q];
+  const uint32_t i3 = (q == 0) ? sites.w[leaf][12] + b : sites.w[leaf][12 + q];
+  uint32_t x0 = i0, x1 = i1, x2 = i2, x3 = i3;
+  const int base = lane & ~3;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    quad_qr(x0, x1, x2, x3);                              // column round
+    x1 = __shfl_sync(0xffffffffu, x1, base + ((q + 1) & 3));
+    x2 = __shfl_sync(0xffffffffu, x2, base + ((q + 2) & 3));
+    x3 = __shfl_sync(0xffffffffu, x3, base + ((q + 3) & 3));
+    quad_qr(x0, x1, x2, x3);                              // diagonal round
+    x1 = __shfl_sync(0xffffffffu, x1, base + ((q + 3) & 3));
+    x2 = __shfl_sync(0xffffffffu, x2, base + ((q + 2) & 3));
+    x3 = __shfl_sync(0xffffffffu, x3, base + ((q + 1) & 3));
+  }
+  const uint32_t ks[4] = {x0 + i0, x1 + i1, x2 + i2, x3 + i3};   // keystream words q, 4 + q, 8 + q, 12 + q
   float n_all = s_n, loss_all = s_loss;
   if (comm.world > 1) {                                    // one-shot all-reduce over peer memory (comm.cuh)
     const float my_n = s_n, my_loss = s_loss;

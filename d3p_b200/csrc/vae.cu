@@ -18,6 +18,8 @@
 //   GW23 [H1 | 1]^T (c [delta2|delta3]) -> dW2, dW3, db2, db3;  GW4 (c delta4)^T [z | 1] -> dW4^T, db4
 //   loss / count columns of the partial rows
 // The partial rows [S, P + 2] are reduced in a fixed order by d3p_perturb_finalize_f32.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch.cuh"
 #include "tc_gemm_kernel.cuh"
@@ -215,9 +217,13 @@ struct VaeArgs {
   float *sq_x, *sq_h1, *sq_h2, *sq_z, *sq_d5, *loss_rec, *sq_d4, *loss_kl, *lossv, *cnt;
   float* partials;
   float* px_norms; float* px_loss;
+  // fragment-ordered hi/lo copies of the thin weight matrices (vae_prep_mid_kernel) for the warp-MMA mid kernels
+  float4 *wf23, *wf4, *wf4t, *wf23t;
 };
 
-// X rows -> [X | 1 | 0 0 0] hi / lo (row stride D + 4), ||x||^2, "some lo != 0" flag.  One warp per row.
+// X rows -> [X | 1 | 0 0 0] hi / lo (row stride D + 4), ||x||^2, "some lo != 0" flag.  One warp per row, 16-byte
+// accesses when the rows are 16-byte aligned (kVec), several independent loads in flight per lane.
+template <bool kVec>
 __global__ void vae_prep_x_kernel(VaeArgs a) {
   const int lane = threadIdx.x & 31;
   const uint32_t warps = (blockDim.x >> 5) * gridDim.x;
@@ -226,13 +232,30 @@ __global__ void vae_prep_x_kernel(VaeArgs a) {
     const uint32_t p = a.pos_begin + r;
     const size_t src = (size_t)(a.idx ? (uint32_t)a.idx[p] : p) * a.x_stride;
     float sq = 0.f;
-    for (uint32_t j = lane; j < a.D + 4; j += 32) {
-      float v = j < a.D ? a.x[src + j] : (j == a.D ? 1.0f : 0.0f);
-      const float hi = tc::tf32_hi(v), lo = v - hi;
-      a.x_hi[(size_t)r * a.ldx + j] = hi;
-      a.x_lo[(size_t)r * a.ldx + j] = lo;
-      if (j < a.D) sq = fmaf(v, v, sq);
-      any_lo |= (lo != 0.f);
+    if (kVec) {
+      const float4* __restrict__ xs = reinterpret_cast<const float4*>(a.x + src);
+      float4* __restrict__ oh = reinterpret_cast<float4*>(a.x_hi + (size_t)r * a.ldx);
+      float4* __restrict__ ol = reinterpret_cast<float4*>(a.x_lo + (size_t)r * a.ldx);
+      const uint32_t n4 = a.D / 4;
+#pragma unroll 4
+      for (uint32_t j = lane; j <= n4; j += 32) {
+        const float4 v = j < n4 ? __ldg(xs + j) : make_float4(1.0f, 0.f, 0.f, 0.f);
+        const float4 hi = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
+        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        oh[j] = hi;
+        ol[j] = lo;
+        if (j < n4) sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, sq))));
+        any_lo |= (lo.x != 0.f) | (lo.y != 0.f) | (lo.z != 0.f) | (lo.w != 0.f);
+      }
+    } else {
+      for (uint32_t j = lane; j < a.D + 4; j += 32) {
+        float v = j < a.D ? a.x[src + j] : (j == a.D ? 1.0f : 0.0f);
+        const float hi = tc::tf32_hi(v), lo = v - hi;
+        a.x_hi[(size_t)r * a.ldx + j] = hi;
+        a.x_lo[(size_t)r * a.ldx + j] = lo;
+        if (j < a.D) sq = fmaf(v, v, sq);
+        any_lo |= (lo != 0.f);
+      }
     }
     sq = group_sum<32>(sq);
     if (lane == 0) a.sq_x[r] = sq;
@@ -605,6 +628,416 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_bwd_kernel(VaeArgs a) 
   }
 }
 
+
+// ---- thin layers on warp-level tensor-core MMA ------------------------------------------------------------
+// The encoder heads (K = H, N = 2Z), the decoder hidden layer (K = Z, N = H) and their transposes in the backward
+// pass are far too thin for a 128-row tcgen05 tile (N = 40, K = 20) and were SIMT loops that re-read the weights
+// from shared memory per warp (47 + 55 us of the 0.40 ms step).  Here a CTA of 4 warps owns 16 examples = one
+// mma.sync m16n8k8 row block; products are 3xTF32 (a_hi b_hi + a_lo b_hi + a_hi b_lo, fp32 accumulate) like the
+// tcgen05 GEMMs.  B operands come from global memory in fragment order (one LDG.128 per lane per 8x8 block:
+// {hi(b0), hi(b1), lo(b0), lo(b1)}), written once per step by vae_prep_mid_kernel.  The reduction index is
+// permuted so that a lane's two k slots (t, t + 4) are adjacent columns (2t, 2t + 1) in memory: A rows are read
+// as 8-byte pairs.  Shapes: H % 8 == 0, Z % 4 == 0, Z <= 32; other shapes keep the SIMT kernels above.
+constexpr int kMmaRows = 16;
+constexpr int kMmaWarps = 8;              // the kernels are latency-bound (16 rows per CTA): 8 warps split K / N
+constexpr int kMmaThreads = kMmaWarps * 32;
+constexpr int kMmaTpe = kMmaThreads / kMmaRows;   // threads per example in the element-wise phases
+
+template <int W>
+D3P_D float sum_warps(const float (*p)[kMmaRows], int e) {        // fixed order
+  float v = p[0][e];
+#pragma unroll
+  for (int w = 1; w < W; ++w) v += p[w][e];
+  return v;
+}
+
+D3P_D void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// d += a b with a = ah + al, b = (b.x, b.y) + (b.z, b.w); small terms first
+D3P_D void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const float4& b) {
+  mma_tf32(d, al, __float_as_uint(b.x), __float_as_uint(b.y));
+  mma_tf32(d, ah, __float_as_uint(b.z), __float_as_uint(b.w));
+  mma_tf32(d, ah, __float_as_uint(b.x), __float_as_uint(b.y));
+}
+// A fragment of rows (g, g + 8) at permuted columns (k0 + 2t, k0 + 2t + 1) from two row pointers
+D3P_D void load_a_pair(const float* row_g, const float* row_g8, uint32_t k, uint32_t (&a)[4]) {
+  const float2 v0 = *reinterpret_cast<const float2*>(row_g + k), v1 = *reinterpret_cast<const float2*>(row_g8 + k);
+  a[0] = __float_as_uint(v0.x); a[1] = __float_as_uint(v1.x); a[2] = __float_as_uint(v0.y); a[3] = __float_as_uint(v1.y);
+}
+D3P_D void split_a(const float2 v0, const float2 v1, uint32_t (&ah)[4], uint32_t (&al)[4]) {
+  const float h0 = tc::tf32_hi(v0.x), h1 = tc::tf32_hi(v1.x), h2 = tc::tf32_hi(v0.y), h3 = tc::tf32_hi(v1.y);
+  ah[0] = __float_as_uint(h0); ah[1] = __float_as_uint(h1); ah[2] = __float_as_uint(h2); ah[3] = __float_as_uint(h3);
+  al[0] = __float_as_uint(v0.x - h0); al[1] = __float_as_uint(v1.x - h1);
+  al[2] = __float_as_uint(v0.y - h2); al[3] = __float_as_uint(v1.y - h3);
+}
+
+struct MidFragDims {
+  uint32_t ks23, nt23, ks4, nt4, ks4t, nt4t, ks23t, nt23t;
+  __host__ __device__ MidFragDims(uint32_t H, uint32_t Z)
+      : ks23(H / 8), nt23(2 * Z / 8), ks4((Z + 7) / 8), nt4(H / 8), ks4t(H / 8), nt4t((Z + 7) / 8), ks23t(2 * Z / 8),
+        nt23t(H / 8) {}
+  __host__ __device__ size_t n23() const { return (size_t)ks23 * nt23 * 32; }
+  __host__ __device__ size_t n4() const { return (size_t)ks4 * nt4 * 32; }
+  __host__ __device__ size_t n4t() const { return (size_t)ks4t * nt4t * 32; }
+  __host__ __device__ size_t n23t() const { return (size_t)ks23t * nt23t * 32; }
+};
+
+// One thread per float4: entry (ks, nt, lane) of matrix m holds rows k = 8 ks + 2t, k + 1 of column n = 8 nt + g.
+__global__ void vae_prep_mid_kernel(VaeArgs a) {
+  const uint32_t H = a.H, Z = a.Z;
+  const MidFragDims fd(H, Z);
+  const size_t n0 = fd.n23(), n1 = n0 + fd.n4(), n2 = n1 + fd.n4t(), n3 = n2 + fd.n23t();
+  const float* __restrict__ W2 = a.params + a.off_w2;
+  const float* __restrict__ W3 = a.params + a.off_w3;
+  const float* __restrict__ W4 = a.params + a.off_w4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (size_t)gridDim.x * blockDim.x) {
+    int m; size_t loc; uint32_t nt_count;
+    if (i < n0) { m = 0; loc = i; nt_count = fd.nt23; }
+    else if (i < n1) { m = 1; loc = i - n0; nt_count = fd.nt4; }
+    else if (i < n2) { m = 2; loc = i - n1; nt_count = fd.nt4t; }
+    else { m = 3; loc = i - n2; nt_count = fd.nt23t; }
+    const uint32_t lane = (uint32_t)(loc & 31), blk = (uint32_t)(loc >> 5);
+    const uint32_t ks = blk / nt_count, nt = blk - ks * nt_count;
+    const uint32_t k = 8 * ks + 2 * (lane & 3), n = 8 * nt + (lane >> 2);
+    float v[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t kk = k + q;
+      float x;
+      if (m == 0) x = n < Z ? W2[(size_t)kk * Z + n] : W3[(size_t)kk * Z + n - Z];            // [h][j]
+      else if (m == 1) x = kk < Z ? W4[(size_t)kk * H + n] : 0.f;                                // [j][h]
+      else if (m == 2) x = n < Z ? W4[(size_t)n * H + kk] : 0.f;                                 // [h][j] = W4[j][h]
+      else x = kk < Z ? W2[(size_t)n * Z + kk] : W3[(size_t)n * Z + kk - Z];                     // [j'][h]
+      v[q] = x;
+    }
+    const float h0 = tc::tf32_hi(v[0]), h1 = tc::tf32_hi(v[1]);
+    const float4 out = make_float4(h0, h1, v[0] - h0, v[1] - h1);
+    float4* dst = m == 0 ? a.wf23 : m == 1 ? a.wf4 : m == 2 ? a.wf4t : a.wf23t;
+    dst[loc] = out;
+  }
+}
+
+// S1 on MMA: encoder heads, guide sample, KL part of the loss, decoder hidden layer for 16 examples per CTA.
+__global__ void __launch_bounds__(kMmaThreads) vae_mid_fwd_mma_kernel(VaeArgs a) {
+  __shared__ float s_eps[kMmaRows][32];
+  __shared__ float s_red[kMmaWarps][kMmaRows][66];            // per-warp partial head sums (K split over the warps)
+  __shared__ __align__(8) float s_z[2][kMmaRows][32]; // z hi / lo, zero-padded in k
+  __shared__ float s_sq[kMmaWarps][kMmaRows];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const uint32_t H = a.H, Z = a.Z;
+  const MidFragDims fd(H, Z);
+  const uint32_t r0 = blockIdx.x * kMmaRows;
+  const uint32_t e8 = threadIdx.x / kMmaTpe, j8 = threadIdx.x % kMmaTpe;     // phase 0 / 2 mapping: kMmaTpe threads per example
+  // ---- phase 0: guide noise: key_p -> (_, guide_seed) -> (rng, k_plate) -> (_, k_z); eps = normal(k_z, (Z,)) ----
+  for (uint32_t j = j8; j < 32; j += kMmaTpe) { s_z[0][e8][j] = 0.f; s_z[1][e8][j] = 0.f; }
+  if (r0 + e8 < a.Bl) {
+    const TfKey K(a.k0, a.k1);
+    TfKey kp = tf_example_key(K, a.B, a.pos_begin + r0 + e8);
+    TfKey model_seed, guide_seed, rng, k_plate, rng2, k_z;
+    tf_split2(kp, model_seed, guide_seed);
+    tf_split2(guide_seed, rng, k_plate);
+    tf_split2(rng, rng2, k_z);
+    const uint32_t half = (Z + 1) / 2;
+    for (uint32_t j = j8; j < half; j += kMmaTpe) {
+      uint32_t y0, y1;
+      const uint32_t c1 = (j + half < Z) ? j + half : 0u;
+      threefry2x32(k_z, j, c1, y0, y1);
+      s_eps[e8][j] = bits_to_normal<false>(y0);
+      if (j + half < Z) s_eps[e8][j + half] = bits_to_normal<false>(y1);
+    }
+  }
+  // ---- phase 1: heads, [16, H] x [H, 2Z]; warp w takes k-steps w, w + 4, ... -----------------------------------
+  const uint32_t rg = min(r0 + g, a.Bl - 1), rg8 = min(r0 + g + 8, a.Bl - 1);      // clamped rows (results unused)
+  {
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+    const float* ph0 = a.h1_hi + (size_t)rg * a.ldh;
+    const float* ph1 = a.h1_hi + (size_t)rg8 * a.ldh;
+    const float* pl0 = a.h1_lo + (size_t)rg * a.ldh;
+    const float* pl1 = a.h1_lo + (size_t)rg8 * a.ldh;
+#pragma unroll 2
+    for (uint32_t ks = warp; ks < fd.ks23; ks += kMmaWarps) {
+      uint32_t ah[4], al[4];
+      load_a_pair(ph0, ph1, 8 * ks + 2 * t, ah);
+      load_a_pair(pl0, pl1, 8 * ks + 2 * t, al);
+      const float4* bf = a.wf23 + (size_t)ks * fd.nt23 * 32 + lane;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+        if ((uint32_t)nt < fd.nt23) mma3(acc[nt], ah, al, __ldg(bf + nt * 32));
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+      if ((uint32_t)nt < fd.nt23) {
+        s_red[warp][g][8 * nt + 2 * t] = acc[nt][0]; s_red[warp][g][8 * nt + 2 * t + 1] = acc[nt][1];
+        s_red[warp][g + 8][8 * nt + 2 * t] = acc[nt][2]; s_red[warp][g + 8][8 * nt + 2 * t + 1] = acc[nt][3];
+      }
+  }
+  __syncthreads();
+  // ---- phase 2: z = z_loc + exp(log z_std) eps, KL part, operands of the dW4 GEMM ---------------------------
+  {
+    const uint32_t r = r0 + e8;
+    const bool live = r < a.Bl;
+    float kl = 0.f, sqz = 0.f;
+    for (uint32_t j = j8; j < Z; j += kMmaTpe) {
+      float zl = s_red[0][e8][j], sr = s_red[0][e8][Z + j];
+#pragma unroll
+      for (int w = 1; w < kMmaWarps; ++w) { zl += s_red[w][e8][j]; sr += s_red[w][e8][Z + j]; }
+      zl += a.params[a.off_b2 + j];
+      sr += a.params[a.off_b3 + j];
+      const float eps = live ? s_eps[e8][j] : 0.f;
+      const float u = expf(sr) * eps;
+      const float z = zl + u;
+      const float hi = tc::tf32_hi(z);
+      s_z[0][e8][j] = hi; s_z[1][e8][j] = z - hi;
+      if (live) {
+        a.z_hi[(size_t)r * a.ldz + j] = hi;
+        a.z_lo[(size_t)r * a.ldz + j] = z - hi;
+        a.u[(size_t)r * Z + j] = u;
+      }
+      kl += 0.5f * z * z - 0.5f * eps * eps - sr;       // -log N(z;0,1) + log N(z; z_loc, z_std), constants cancel
+      sqz = fmaf(z, z, sqz);
+    }
+    if (live) {
+      for (uint32_t j = Z + j8; j < a.ldz; j += kMmaTpe) {      // ones column of [z | 1] (db4 of the dW4 GEMM) + padding
+        a.z_hi[(size_t)r * a.ldz + j] = j == Z ? 1.0f : 0.f;
+        a.z_lo[(size_t)r * a.ldz + j] = 0.f;
+      }
+      if (j8 < 4) {                                       // ones column of [H1 | 1] (bias row of the dW2 / dW3 GEMM)
+        a.h1_hi[(size_t)r * a.ldh + H + j8] = j8 == 0 ? 1.0f : 0.f;
+        a.h1_lo[(size_t)r * a.ldh + H + j8] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < kMmaTpe; o <<= 1) { kl += __shfl_xor_sync(0xffffffffu, kl, o); sqz += __shfl_xor_sync(0xffffffffu, sqz, o); }
+    if (j8 == 0 && live) { a.loss_kl[r] = kl; a.sq_z[r] = sqz; }
+  }
+  __syncthreads();
+  // ---- phase 3: decoder hidden layer h2 = softplus(z W4 + b4); warp w takes column blocks w, w + 4, ... --------
+  {
+    uint32_t zh[4][4], zl[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      if ((uint32_t)ks < fd.ks4) {
+        load_a_pair(&s_z[0][g][0], &s_z[0][g + 8][0], 8 * ks + 2 * t, zh[ks]);
+        load_a_pair(&s_z[1][g][0], &s_z[1][g + 8][0], 8 * ks + 2 * t, zl[ks]);
+      }
+    float sq0 = 0.f, sq1 = 0.f;
+    const bool live0 = r0 + g < a.Bl, live1 = r0 + g + 8 < a.Bl;
+    for (uint32_t nt = warp; nt < fd.nt4; nt += kMmaWarps) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        if ((uint32_t)ks < fd.ks4) mma3(acc, zh[ks], zl[ks], __ldg(a.wf4 + ((size_t)ks * fd.nt4 + nt) * 32 + lane));
+      const uint32_t n = 8 * nt + 2 * t;
+      const float2 b = make_float2(a.params[a.off_b4 + n], a.params[a.off_b4 + n + 1]);
+      const float v00 = softplus_f(acc[0] + b.x), v01 = softplus_f(acc[1] + b.y);
+      const float v10 = softplus_f(acc[2] + b.x), v11 = softplus_f(acc[3] + b.y);
+      sq0 = fmaf(v00, v00, fmaf(v01, v01, sq0));
+      sq1 = fmaf(v10, v10, fmaf(v11, v11, sq1));
+      const float h00 = tc::tf32_hi(v00), h01 = tc::tf32_hi(v01), h10 = tc::tf32_hi(v10), h11 = tc::tf32_hi(v11);
+      if (live0) {
+        *reinterpret_cast<float2*>(a.h2_hi + (size_t)(r0 + g) * H + n) = make_float2(h00, h01);
+        *reinterpret_cast<float2*>(a.h2_lo + (size_t)(r0 + g) * H + n) = make_float2(v00 - h00, v01 - h01);
+      }
+      if (live1) {
+        *reinterpret_cast<float2*>(a.h2_hi + (size_t)(r0 + g + 8) * H + n) = make_float2(h10, h11);
+        *reinterpret_cast<float2*>(a.h2_lo + (size_t)(r0 + g + 8) * H + n) = make_float2(v10 - h10, v11 - h11);
+      }
+    }
+    sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
+    sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2);
+    if (t == 0) { s_sq[warp][g] = sq0; s_sq[warp][g + 8] = sq1; }
+  }
+  __syncthreads();
+  if (threadIdx.x < kMmaRows && r0 + threadIdx.x < a.Bl)
+    a.sq_h2[r0 + threadIdx.x] = sum_warps<kMmaWarps>(s_sq, threadIdx.x);
+}
+
+// S2 on MMA: back-propagation through the z layer and the encoder heads, ghost norm, clip factor, scaled operands
+// of the clipped-sum GEMMs, 16 examples per CTA.  Dynamic shared memory: raw delta1 [16][H].
+__global__ void __launch_bounds__(kMmaThreads) vae_mid_bwd_mma_kernel(VaeArgs a) {
+  extern __shared__ __align__(16) float s_d1[];        // [16][H]
+  __shared__ float s_red[kMmaWarps][kMmaRows][34];
+  __shared__ __align__(8) float s_dh[2][kMmaRows][64]; // [delta2 | delta3] hi / lo (A operand of the dh1 product)
+  __shared__ float s_d23[kMmaRows][64];                // unsplit [delta2 | delta3]
+  __shared__ float s_sq1[kMmaWarps][kMmaRows];
+  __shared__ float s_sq23[kMmaRows], s_cc[kMmaRows];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const uint32_t H = a.H, Z = a.Z, Z2 = 2 * a.Z;
+  const MidFragDims fd(H, Z);
+  const uint32_t r0 = blockIdx.x * kMmaRows;
+  const uint32_t e8 = threadIdx.x / kMmaTpe, j8 = threadIdx.x % kMmaTpe;
+  const uint32_t rg = min(r0 + g, a.Bl - 1), rg8 = min(r0 + g + 8, a.Bl - 1);
+  const bool live0 = r0 + g < a.Bl, live1 = r0 + g + 8 < a.Bl;
+  // ---- phase 1: delta4 W4^T, [16, H] x [H, Z]; warp w takes k-steps w, w + 4, ... ------------------------------
+  {
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+    const float* p0 = a.d4 + (size_t)rg * H;
+    const float* p1 = a.d4 + (size_t)rg8 * H;
+#pragma unroll 2
+    for (uint32_t ks = warp; ks < fd.ks4t; ks += kMmaWarps) {
+      uint32_t ah[4], al[4];
+      const uint32_t k = 8 * ks + 2 * t;
+      split_a(*reinterpret_cast<const float2*>(p0 + k), *reinterpret_cast<const float2*>(p1 + k), ah, al);
+      const float4* bf = a.wf4t + (size_t)ks * fd.nt4t * 32 + lane;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        if ((uint32_t)nt < fd.nt4t) mma3(acc[nt], ah, al, __ldg(bf + nt * 32));
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if ((uint32_t)nt < fd.nt4t) {
+        s_red[warp][g][8 * nt + 2 * t] = acc[nt][0]; s_red[warp][g][8 * nt + 2 * t + 1] = acc[nt][1];
+        s_red[warp][g + 8][8 * nt + 2 * t] = acc[nt][2]; s_red[warp][g + 8][8 * nt + 2 * t + 1] = acc[nt][3];
+      }
+  }
+  __syncthreads();
+  // ---- phase 2: delta_z = z + delta4 W4^T, delta3 = delta_z u - 1 ----------------------------------------------
+  {
+    const uint32_t r = r0 + e8;
+    const bool live = r < a.Bl;
+    float sq23 = 0.f;
+    for (uint32_t j = j8; j < Z; j += kMmaTpe) {
+      const float zv = live ? a.z_hi[(size_t)r * a.ldz + j] + a.z_lo[(size_t)r * a.ldz + j] : 0.f;
+      const float uv = live ? a.u[(size_t)r * Z + j] : 0.f;
+      float dz = s_red[0][e8][j];
+#pragma unroll
+      for (int w = 1; w < kMmaWarps; ++w) dz += s_red[w][e8][j];
+      dz += zv;
+      const float d3 = fmaf(dz, uv, -1.0f);
+      s_d23[e8][j] = dz; s_d23[e8][Z + j] = d3;
+      const float hz = tc::tf32_hi(dz), h3 = tc::tf32_hi(d3);
+      s_dh[0][e8][j] = hz; s_dh[1][e8][j] = dz - hz;
+      s_dh[0][e8][Z + j] = h3; s_dh[1][e8][Z + j] = d3 - h3;
+      sq23 = fmaf(dz, dz, fmaf(d3, d3, sq23));
+    }
+#pragma unroll
+    for (int o = 1; o < kMmaTpe; o <<= 1) sq23 += __shfl_xor_sync(0xffffffffu, sq23, o);
+    if (j8 == 0) s_sq23[e8] = sq23;
+  }
+  __syncthreads();
+  // ---- phase 3: delta_h1 = delta2 W2^T + delta3 W3^T; delta1 = delta_h1 softplus'(pre1); raw delta1 kept in smem -----
+  {
+    float sq0 = 0.f, sq1 = 0.f;
+    const float* ph0 = a.h1_hi + (size_t)rg * a.ldh;
+    const float* ph1 = a.h1_hi + (size_t)rg8 * a.ldh;
+    const float* pl0 = a.h1_lo + (size_t)rg * a.ldh;
+    const float* pl1 = a.h1_lo + (size_t)rg8 * a.ldh;
+    for (uint32_t nt = warp; nt < fd.nt23t; nt += kMmaWarps) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (uint32_t ks = 0; ks < fd.ks23t; ++ks) {
+        uint32_t ah[4], al[4];
+        load_a_pair(&s_dh[0][g][0], &s_dh[0][g + 8][0], 8 * ks + 2 * t, ah);
+        load_a_pair(&s_dh[1][g][0], &s_dh[1][g + 8][0], 8 * ks + 2 * t, al);
+        mma3(acc, ah, al, __ldg(a.wf23t + ((size_t)ks * fd.nt23t + nt) * 32 + lane));
+      }
+      const uint32_t n = 8 * nt + 2 * t;
+      const float2 hh0 = *reinterpret_cast<const float2*>(ph0 + n), hl0 = *reinterpret_cast<const float2*>(pl0 + n);
+      const float2 hh1 = *reinterpret_cast<const float2*>(ph1 + n), hl1 = *reinterpret_cast<const float2*>(pl1 + n);
+      const float d00 = live0 ? acc[0] * (-expm1f(-(hh0.x + hl0.x))) : 0.f;
+      const float d01 = live0 ? acc[1] * (-expm1f(-(hh0.y + hl0.y))) : 0.f;
+      const float d10 = live1 ? acc[2] * (-expm1f(-(hh1.x + hl1.x))) : 0.f;
+      const float d11 = live1 ? acc[3] * (-expm1f(-(hh1.y + hl1.y))) : 0.f;
+      sq0 = fmaf(d00, d00, fmaf(d01, d01, sq0));
+      sq1 = fmaf(d10, d10, fmaf(d11, d11, sq1));
+      *reinterpret_cast<float2*>(s_d1 + (size_t)g * H + n) = make_float2(d00, d01);
+      *reinterpret_cast<float2*>(s_d1 + (size_t)(g + 8) * H + n) = make_float2(d10, d11);
+    }
+    sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
+    sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2);
+    if (t == 0) { s_sq1[warp][g] = sq0; s_sq1[warp][g + 8] = sq1; }
+  }
+  __syncthreads();
+  // ---- phase 4: ghost norm, clip factor, per-example loss -----------------------------------------------------
+  {
+    const uint32_t r = r0 + e8;
+    const bool live = r < a.Bl;
+    const uint32_t nv = a.num_valid ? (uint32_t)max(*a.num_valid, 0) : 0xffffffffu;
+    const float ratio = a.site_scale * a.inv_S;                   // (1 / obs_scale) * site scale
+    float sq_h1 = 0.f, sq_d4 = 0.f, sq_d5 = 0.f, lrec = 0.f;
+    if (live) {
+      for (uint32_t q = j8; q < a.ns_h; q += kMmaTpe) { sq_h1 += a.sq_h1[(size_t)q * a.Bl + r]; sq_d4 += a.sq_d4[(size_t)q * a.Bl + r]; }
+      for (uint32_t q = j8; q < a.ns_d; q += kMmaTpe) { sq_d5 += a.sq_d5[(size_t)q * a.Bl + r]; lrec += a.loss_rec[(size_t)q * a.Bl + r]; }
+    }
+#pragma unroll
+    for (int o = 1; o < kMmaTpe; o <<= 1) {
+      sq_h1 += __shfl_xor_sync(0xffffffffu, sq_h1, o); sq_d4 += __shfl_xor_sync(0xffffffffu, sq_d4, o);
+      sq_d5 += __shfl_xor_sync(0xffffffffu, sq_d5, o); lrec += __shfl_xor_sync(0xffffffffu, lrec, o);
+    }
+    if (j8 == 0) {
+      float cc = 0.f;
+      if (live) {
+        const float s1 = sum_warps<kMmaWarps>(s_sq1, e8);
+        const float n2 = (a.sq_h2[r] + 1.0f) * sq_d5 + (a.sq_z[r] + 1.0f) * sq_d4 + (sq_h1 + 1.0f) * s_sq23[e8] +
+                         (a.sq_x[r] + 1.0f) * s1;
+        const float norm = fabsf(ratio) * sqrtf(n2);
+        const uint32_t p = a.pos_begin + r;
+        const bool valid = (p < nv) && (!a.mask || a.mask[p]);
+        const float c = valid ? 1.0f / fmaxf(1.0f, norm / a.C) : 0.f;
+        cc = c * ratio;
+        const float loss_s = valid ? a.site_scale * (a.loss_kl[r] + lrec) : 0.f;   // = obs_scale * loss_i
+        a.lossv[r] = loss_s;
+        a.cnt[r] = valid ? 1.0f : 0.f;
+        if (a.px_norms) a.px_norms[p] = valid ? norm : 0.f;
+        if (a.px_loss) a.px_loss[p] = loss_s;
+      }
+      s_cc[e8] = cc;
+    }
+  }
+  __syncthreads();
+  // ---- phase 5: scaled hi / lo operands of the clipped-sum GEMMs (streaming) ---------------------------------------
+  const uint32_t H4 = H / 4;
+#pragma unroll 2
+  for (uint32_t i = threadIdx.x; i < kMmaRows * H4; i += kMmaThreads) {
+    const uint32_t e = i / H4, h = 4 * (i - e * H4), r = r0 + e;
+    if (r >= a.Bl) continue;
+    const float cc = s_cc[e];
+    const float4 d1 = *reinterpret_cast<const float4*>(s_d1 + (size_t)e * H + h);
+    const float4 d4 = *reinterpret_cast<const float4*>(a.d4 + (size_t)r * H + h);
+    const float4 hh = *reinterpret_cast<const float4*>(a.h2_hi + (size_t)r * H + h);
+    const float4 hl = *reinterpret_cast<const float4*>(a.h2_lo + (size_t)r * H + h);
+    float4 o_hi, o_lo;
+#define D3P_SPLIT4(src_x, src_y, src_z, src_w)                                                     \
+    { const float vx = (src_x), vy = (src_y), vz = (src_z), vw = (src_w);                          \
+      o_hi = make_float4(tc::tf32_hi(vx), tc::tf32_hi(vy), tc::tf32_hi(vz), tc::tf32_hi(vw));      \
+      o_lo = make_float4(vx - o_hi.x, vy - o_hi.y, vz - o_hi.z, vw - o_hi.w); }
+    D3P_SPLIT4(cc * d1.x, cc * d1.y, cc * d1.z, cc * d1.w)
+    *reinterpret_cast<float4*>(a.cd1_hi + (size_t)r * H + h) = o_hi;
+    *reinterpret_cast<float4*>(a.cd1_lo + (size_t)r * H + h) = o_lo;
+    D3P_SPLIT4(cc * d4.x, cc * d4.y, cc * d4.z, cc * d4.w)
+    *reinterpret_cast<float4*>(a.cd4_hi + (size_t)r * H + h) = o_hi;
+    *reinterpret_cast<float4*>(a.cd4_lo + (size_t)r * H + h) = o_lo;
+    D3P_SPLIT4(cc * (hh.x + hl.x), cc * (hh.y + hl.y), cc * (hh.z + hl.z), cc * (hh.w + hl.w))
+    *reinterpret_cast<float4*>(a.ch2_hi + (size_t)r * a.ldh + h) = o_hi;
+    *reinterpret_cast<float4*>(a.ch2_lo + (size_t)r * a.ldh + h) = o_lo;
+#undef D3P_SPLIT4
+  }
+  {
+    const uint32_t r = r0 + e8;
+    if (r < a.Bl) {
+      const float cc = s_cc[e8];
+      if (j8 < 4) {
+        const float v = j8 == 0 ? cc : 0.f;
+        const float hi = tc::tf32_hi(v);
+        a.ch2_hi[(size_t)r * a.ldh + H + j8] = hi;
+        a.ch2_lo[(size_t)r * a.ldh + H + j8] = v - hi;
+      }
+      for (uint32_t j = j8; j < a.ld23; j += kMmaTpe) {
+        const float v = j < Z2 ? cc * s_d23[e8][j] : 0.f;
+        const float hi = tc::tf32_hi(v);
+        a.cd23_hi[(size_t)r * a.ld23 + j] = hi;
+        a.cd23_lo[(size_t)r * a.ld23 + j] = v - hi;
+      }
+    }
+  }
+}
+
 // loss / count columns of the partial rows: slab s = a contiguous range of examples, summed in a fixed order
 __global__ void __launch_bounds__(256) vae_loss_kernel(VaeArgs a) {
   __shared__ float red[2][8];
@@ -632,7 +1065,7 @@ struct VaeLayout {
   size_t total;
   size_t partials, w1_hi, w1_lo, w5_hi, w5_lo, x_hi, x_lo, flag, h1_hi, h1_lo, h2_hi, h2_lo, ch2_hi, ch2_lo, d5_hi, d5_lo,
       d4, cd4_hi, cd4_lo, cd1_hi, cd1_lo, z_hi, z_lo, u, cd23_hi, cd23_lo, sq_x, sq_h1, sq_h2, sq_z, sq_d5, loss_rec, sq_d4,
-      loss_kl, lossv, cnt;
+      loss_kl, lossv, cnt, wf23, wf4, wf4t, wf23t;
   uint32_t S, ns_h, ns_d;
   size_t ldx, ldh, ldz, ld23;
 };
@@ -665,6 +1098,10 @@ static VaeLayout vae_layout(const d3p_vae_desc* d, uint32_t Bl) {
   L.sq_x = take(Bl); L.sq_h1 = take((size_t)L.ns_h * Bl); L.sq_h2 = take(Bl); L.sq_z = take(Bl);
   L.sq_d5 = take((size_t)L.ns_d * Bl); L.loss_rec = take((size_t)L.ns_d * Bl); L.sq_d4 = take((size_t)L.ns_h * Bl);
   L.loss_kl = take(Bl); L.lossv = take(Bl); L.cnt = take(Bl);
+  {
+    const MidFragDims fd((uint32_t)H, (uint32_t)Z);          // float4 entries (sized for every shape: a few hundred KB)
+    L.wf23 = take(4 * fd.n23()); L.wf4 = take(4 * fd.n4()); L.wf4t = take(4 * fd.n4t()); L.wf23t = take(4 * fd.n23t());
+  }
   L.total = off;
   return L;
 }
@@ -732,6 +1169,10 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   a.loss_rec = F(L.loss_rec); a.sq_d4 = F(L.sq_d4); a.loss_kl = F(L.loss_kl); a.lossv = F(L.lossv); a.cnt = F(L.cnt);
   a.partials = F(L.partials);
   a.px_norms = px_norms_d; a.px_loss = px_loss_d;
+  a.wf23 = reinterpret_cast<float4*>(ws + L.wf23); a.wf4 = reinterpret_cast<float4*>(ws + L.wf4);
+  a.wf4t = reinterpret_cast<float4*>(ws + L.wf4t); a.wf23t = reinterpret_cast<float4*>(ws + L.wf23t);
+  // thin layers: warp-MMA kernels for the shapes they tile (H % 8 == 0, Z % 4 == 0), SIMT kernels otherwise
+  const bool mid_mma = (H % 8) == 0 && (Z % 4) == 0 && Z <= 32 && getenv("D3P_VAE_MID_SIMT") == nullptr;
   float* w1_hi = F(L.w1_hi); float* w1_lo = F(L.w1_lo); float* w5_hi = F(L.w5_hi); float* w5_lo = F(L.w5_lo);
 
   const int sms = sm_count();
@@ -743,7 +1184,14 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   {
     unsigned grid = (Bl + 7) / 8;
     if (grid > (unsigned)sms * 8) grid = sms * 8;
-    vae_prep_x_kernel<<<grid, 256, 0, s>>>(a);
+    if ((reinterpret_cast<uintptr_t>(x_d) & 15) == 0 && (x_row_stride & 3) == 0) vae_prep_x_kernel<true><<<grid, 256, 0, s>>>(a);
+    else vae_prep_x_kernel<false><<<grid, 256, 0, s>>>(a);
+    if ((rc = check_launch()) != D3P_OK) return rc;
+  }
+  if (mid_mma) {
+    const MidFragDims fd(H, Z);
+    const size_t n = fd.n23() + fd.n4() + fd.n4t() + fd.n23t();
+    vae_prep_mid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
     if ((rc = check_launch()) != D3P_OK) return rc;
   }
   // G1: pre1 = X W1  (A = X K-major [Bl, D]; B = W1 stored [K = D, N = H])
@@ -756,7 +1204,11 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   const size_t mid_fwd_smem = mid_fwd_smem_bytes(H, Z), mid_bwd_smem = mid_bwd_smem_bytes(H, Z);
   unsigned mid_grid = ((Bl + kMidE - 1) / kMidE + kMidWarps - 1) / kMidWarps;
   if (mid_grid > (unsigned)sms) mid_grid = sms;
-  {
+  const unsigned mma_grid = (Bl + kMmaRows - 1) / kMmaRows;
+  if (mid_mma) {
+    vae_mid_fwd_mma_kernel<<<mma_grid, kMmaThreads, 0, s>>>(a);
+    if ((rc = check_launch()) != D3P_OK) return rc;
+  } else {
     if (cudaFuncSetAttribute(vae_mid_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_fwd_smem) != cudaSuccess)
       return D3P_ERR_CUDA;
     vae_mid_fwd_kernel<<<mid_grid, kMidWarps * 32, mid_fwd_smem, s>>>(a);
@@ -776,7 +1228,14 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
     if ((rc = tc::launch_tc_gemm<false, false, kVaeBNH, EpiBwd5, kHeavyEW>(A, Bo, Bl, H, D, 1, ea, s, nullptr)) != D3P_OK)
       return rc;
   }
-  {
+  if (mid_mma) {
+    const size_t smem = (size_t)kMmaRows * H * sizeof(float);
+    if (smem > 24 * 1024 &&
+        cudaFuncSetAttribute(vae_mid_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return D3P_ERR_CUDA;
+    vae_mid_bwd_mma_kernel<<<mma_grid, kMmaThreads, smem, s>>>(a);
+    if ((rc = check_launch()) != D3P_OK) return rc;
+  } else {
     if (cudaFuncSetAttribute(vae_mid_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_bwd_smem) != cudaSuccess)
       return D3P_ERR_CUDA;
     vae_mid_bwd_kernel<<<mid_grid, kMidWarps * 32, mid_bwd_smem, s>>>(a);

@@ -344,13 +344,15 @@ class DPSVI:
         (``examples/logistic_regression.py:149-160``): returns ``(new_state, stats)`` where
         ``stats[num_steps, 3]`` holds ``(loss, n, f)`` per step on the device.
 
-        For the mean-field families fed by ``poisson_batchify_data`` / ``subsample_batchify_data``
-        the whole loop runs inside ``d3p_dpsvi_run_epoch_meanfield`` (no interpreter between
-        launches); the result is bit-identical to the step-by-step calls, which remain the path
-        for everything else (NCCL-backend sharded runs, VAE, GMM, custom batchifiers)."""
-        from .models import MeanFieldFamily
+        For the mean-field families and the VAE fed by ``poisson_batchify_data`` /
+        ``subsample_batchify_data`` the whole loop runs inside ``d3p_dpsvi_run_epoch_meanfield`` /
+        ``d3p_dpsvi_run_epoch_vae`` (no interpreter between launches); the result is bit-identical to
+        the step-by-step calls, which remain the path for everything else (NCCL-backend sharded runs,
+        GMM, custom batchifiers)."""
+        from .models import MeanFieldFamily, VAE
         spec = getattr(get_batch, "spec", None)
-        fused = (spec is not None and isinstance(self.family, MeanFieldFamily)
+        is_vae = isinstance(self.family, VAE)
+        fused = (spec is not None and (isinstance(self.family, MeanFieldFamily) or is_vae)
                  and (self.shard is None or self.shard[2] is None) and self._rng_suite is strong_rng and spec["rng_suite"] is strong_rng and self.event_hook is None
                  and num_steps > 0)
         if not fused:
@@ -365,11 +367,16 @@ class DPSVI:
         Xsrc, stride, ysrc, _, _ = self._resolve_args(spec["dataset"])
         desc = fam.desc(self._num_obs_total())
         sd = _n.SamplerDesc(spec["kind"], spec["q"], spec["n_records"], spec["batch"], 1 if spec["suppress"] else 0)
-        need = _n.lib().d3p_dpsvi_epoch_workspace_bytes(C.byref(desc), C.byref(sd))
+        world = self.shard[1] if self.shard is not None else 1
+        if is_vae:
+            need = _n.lib().d3p_dpsvi_epoch_vae_workspace_bytes(C.byref(desc), C.byref(sd), world)
+        else:
+            need = _n.lib().d3p_dpsvi_epoch_workspace_bytes(C.byref(desc), C.byref(sd))
         if need == 0:
             raise _n.D3PNativeError("unsupported family / sampler configuration for run_epoch")
-        if getattr(self, "_epoch_ws", None) is None or self._epoch_ws.numel() < need or self._epoch_ws.device != _dev():
-            self._epoch_ws = torch.empty(need, dtype=torch.uint8, device=_dev())
+        if getattr(self, "_epoch_ws", None) is None or self._epoch_ws.numel() < need + 256 or self._epoch_ws.device != _dev():
+            self._epoch_ws = torch.empty(need + 256, dtype=torch.uint8, device=_dev())
+        ws_al = self._epoch_ws[(-self._epoch_ws.data_ptr()) % 256:]          # the VAE step wants 256-byte alignment
         if self.peer_window is not None and spec["kind"] == _n.SAMPLER_POISSON:
             self.peer_window = self.peer_window.with_records(spec["n_records"])   # sharded selector draw
         os_ = svi_state.optim_state
@@ -390,12 +397,19 @@ class DPSVI:
         bkey = np.ascontiguousarray(np.asarray(batchifier_state, dtype=np.uint32).reshape(16))
         rkey = np.array(np.asarray(svi_state.rng_key, dtype=np.uint32).reshape(16), copy=True)
         u32p = C.POINTER(C.c_uint32)
-        _n.check(_n.lib().d3p_dpsvi_run_epoch_meanfield(
-            C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, _n.ptr(ysrc), bkey.ctypes.data_as(u32p),
-            rkey.ctypes.data_as(u32p), int(first_step), int(num_steps), float(svi_state.observation_scale),
-            float(self._clipping_threshold), float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m),
-            _n.ptr(v), _n.ptr(stats), self.peer_window.ptr if self.shard is not None else None,
-            _n.ptr(self._epoch_ws), need, _n.stream_ptr()), "run_epoch")
+        comm = self.peer_window.ptr if self.shard is not None else None
+        if is_vae:
+            _n.check(_n.lib().d3p_dpsvi_run_epoch_vae(
+                C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, bkey.ctypes.data_as(u32p),
+                rkey.ctypes.data_as(u32p), int(first_step), int(num_steps), float(svi_state.observation_scale),
+                float(self._clipping_threshold), float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m),
+                _n.ptr(v), _n.ptr(stats), comm, _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch_vae")
+        else:
+            _n.check(_n.lib().d3p_dpsvi_run_epoch_meanfield(
+                C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, _n.ptr(ysrc), bkey.ctypes.data_as(u32p),
+                rkey.ctypes.data_as(u32p), int(first_step), int(num_steps), float(svi_state.observation_scale),
+                float(self._clipping_threshold), float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m),
+                _n.ptr(v), _n.ptr(stats), comm, _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch")
         new_os = OptimState(os_.step + num_steps, flat, m, v, os_.layout, lr)
         return DPSVIState(new_os, rkey.reshape(np.asarray(svi_state.rng_key).shape), svi_state.observation_scale), stats
 

@@ -353,6 +353,18 @@ int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* params_d, cons
                            float C, float* px_norms_d, float* px_loss_d, void* ws_d, size_t ws_bytes,
                            void* const* profile_events_h, void* stream);
 
+/* The same loop for the VAE family (examples/vae.py:216-233: lax.fori_loop over get_batch -> update for one epoch;
+ * d3p/svi.py:395-434 per step).  `world` = number of ranks sharing the batch (1 without `comm`); ws_d must be
+ * 256-byte aligned. */
+size_t d3p_dpsvi_epoch_vae_workspace_bytes(const d3p_vae_desc* desc, const d3p_sampler_desc* sampler, int32_t world);
+int32_t d3p_dpsvi_run_epoch_vae(const d3p_vae_desc* desc, const d3p_sampler_desc* sampler, const float* x_d,
+                                size_t x_row_stride, const uint32_t batch_key_h[16], uint32_t rng_key_io_h[16],
+                                uint32_t first_step, uint32_t n_steps, float obs_scale, float C, float dp_scale,
+                                const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d,
+                                float* m_d, float* v_d, float* stats_out_d, d3p_comm* comm /* NULL = single GPU */,
+                                void* ws_d, size_t ws_bytes, void* stream);
+
+
 /* ------------------------------------------------------------------------------------------
  * Fused per-example gradient + clip + sum for the Gaussian mixture model of
  * examples/gaussian_mixture_model.py:51-85 with the d3p.gmm.GaussianMixture likelihood

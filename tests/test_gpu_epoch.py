@@ -121,3 +121,37 @@ def test_run_epoch_generic_path(cuda):
         ref, loss = s.update(ref, *get(i, bst))
     assert torch.equal(st.optim_state.flat, ref.optim_state.flat)
     assert float(stats[-1, 0]) == float(loss)
+
+
+@pytest.mark.parametrize("sampler", ["subsample", "poisson"])
+def test_run_epoch_vae_equals_stepwise(cuda, sampler):
+    """Row f2 for the VAE family: d3p_dpsvi_run_epoch_vae (sampler on a forked stream, step, finalize queued from C)
+    is bit-identical to get_batch + update per step (examples/vae.py:216-233)."""
+    from d3p_b200 import minibatch as mb, models, optimizers, svi as dsvi
+    D, H, Z, N, B = 64, 40, 8, 600, 48
+    rs = np.random.RandomState(3)
+    X = torch.as_tensor((rs.rand(N, 8, 8) < 0.35).astype(np.float32)).cuda()
+    fam = models.VAE(D, H, Z, init_std=0.1)
+    s = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), 2.0, 1.0, num_obs_total=N)
+    if sampler == "subsample":
+        init, get = mb.subsample_batchify_data((X,), batch_size=B)
+    else:
+        init, get = mb.poisson_batchify_data((X,), B / N, 64)
+    key = chacha.PRNGKey(5)
+    k_init, k_fetch = chacha.split(key, 3)[1:]
+    _, bst = init(k_fetch)
+    first = get(0, bst)
+    st0 = s.init(k_init, *(first if sampler == "subsample" else first[0]))
+    n_steps, first_step = 5, 1
+    st, losses = st0, []
+    for i in range(first_step, first_step + n_steps):
+        out = get(i, bst)
+        batch, mask = (out, True) if sampler == "subsample" else out
+        st, loss = s.update(st, *batch, mask=mask)
+        losses.append(float(loss))
+    st_e, stats = s.run_epoch(st0, get, bst, n_steps, first_step=first_step)
+    assert np.array_equal(np.asarray(st_e.rng_key), np.asarray(st.rng_key))
+    assert st_e.optim_state.step == st.optim_state.step == n_steps
+    assert torch.equal(st_e.optim_state.flat, st.optim_state.flat), "run_epoch must be bit-identical to stepwise"
+    assert np.array_equal(stats[:, 0].cpu().numpy(), np.asarray(losses, np.float32))
+    assert st0.optim_state.step == 0
