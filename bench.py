@@ -444,19 +444,22 @@ def run_b200(args, cfg):
         step_ms = elapsed_ms / args.steps
         per_rank_examples = (n_examples / args.steps) / world
         if is_vae:
-            D, H = cfg["d"], cfg["hidden"]
-            flops = 2.0 * 2.0 * D * H * per_rank_examples          # dW1 + dW5 clipped-sum GEMMs
+            D, H, Zd = cfg["d"], cfg["hidden"], cfg["z"]
+            # the clipped-sum GEMMs dW1, dW5 (+ the thin dW2|dW3, dW4), which run as one concurrent group
+            flops = 2.0 * (2.0 * D * H + 3.0 * H * Zd) * per_rank_examples
             g_ms = float(np.mean(gemm_ms))
             achieved = flops / (g_ms * 1e-3) / 1e12
             peak = peaks["bf16_tflops"] / 2.0                        # TF32 dense = half the bf16 rate
-            roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<MN,MN,224,EpiGrad> x2 (dW1, dW5 clipped sums)",
+            roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<MN,MN,*,EpiGrad> x4 (dW1, dW5, dW2|dW3, dW4 clipped sums, "
+                                                     "concurrent on forked streams: one wave of CTAs)",
                         "achieved": achieved, "peak": peak,
                         "peak_kind": peak_kind + " bf16 GEMM / 2 (no measured TF32 figure)", "unit": "TFLOP/s",
                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "kernel_ms": g_ms,
                         "kernel_share_of_step": g_ms / step_ms,
                         "executed_tflops": 3.0 * achieved,
-                        "note": "algorithmic FLOPs = 2*2*784*400 per example; the kernels execute 3x that "
-                                "(3xTF32 split for fp32 parity), see executed_tflops",
+                        "note": "algorithmic FLOPs = 2*(2*784*400 + 3*400*20) per example; the kernels execute 3x that "
+                                "(3xTF32 split for fp32 parity), see executed_tflops; kernel_ms = CUDA events around "
+                                "the concurrent group",
                         "step_kernels_ms": kern_ms_avg}
         else:
             algo_bytes = ALGO_BYTES_PER_EXAMPLE[args.workload] * per_rank_examples

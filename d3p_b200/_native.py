@@ -125,6 +125,8 @@ _SIGNATURES = {
     "d3p_elbo_evaluate_meanfield": (C.c_int32, [C.POINTER(MeanfieldDesc), _vp, _vp, C.c_size_t, _vp, _vp, C.c_uint32,
                                                 _u32p, _vp, _vp, C.c_size_t, _vp]),
     "d3p_split_tf32": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_gemm_f32x3": (C.c_int32, [_vp, C.c_int32, C.c_size_t, _vp, C.c_int32, C.c_size_t, C.c_uint32, C.c_uint32,
+                                   C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, C.c_size_t, C.c_int32, _vp]),
     "d3p_gemm_tf32x3": (C.c_int32, [_vp, _vp, C.c_int32, C.c_size_t, _vp, _vp, C.c_int32, C.c_size_t, C.c_uint32,
                                     C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, C.c_size_t,
                                     C.c_int32, _vp]),

@@ -21,12 +21,12 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int EW = tc::kGemmEpiWarps>
 static int32_t dispatch_bn(int bn, const tc::GemmOperand& A, const tc::GemmOperand& B, uint32_t M, uint32_t N, uint32_t K,
                            uint32_t split_k, const tc::EpiStore::Args& ea, cudaStream_t s) {
   switch (bn) {
-    case 128: return tc::launch_tc_gemm<A_MN, B_MN, 128, tc::EpiStore>(A, B, M, N, K, split_k, ea, s);
-    case 224: return tc::launch_tc_gemm<A_MN, B_MN, 224, tc::EpiStore>(A, B, M, N, K, split_k, ea, s);
+    case 128: return tc::launch_tc_gemm<A_MN, B_MN, 128, tc::EpiStore, EW>(A, B, M, N, K, split_k, ea, s);
+    case 224: return tc::launch_tc_gemm<A_MN, B_MN, 224, tc::EpiStore, EW>(A, B, M, N, K, split_k, ea, s);
     default: return D3P_ERR_UNSUPPORTED;
   }
 }
@@ -58,4 +58,18 @@ extern "C" int32_t d3p_gemm_tf32x3(const float* a_hi_d, const float* a_lo_d, int
   if (!a_mn_major && b_mn_major) return dispatch_bn<false, true>(tile_n, A, B, M, N, K, split_k, ea, s);
   if (a_mn_major && !b_mn_major) return dispatch_bn<true, false>(tile_n, A, B, M, N, K, split_k, ea, s);
   return dispatch_bn<true, true>(tile_n, A, B, M, N, K, split_k, ea, s);
+}
+
+// Same product from unsplit fp32 operands: the kernel splits every stage in shared memory (tc_gemm_kernel.cuh).
+extern "C" int32_t d3p_gemm_f32x3(const float* a_d, int32_t a_mn_major, size_t lda, const float* b_d, int32_t b_mn_major,
+                                  size_t ldb, uint32_t M, uint32_t N, uint32_t K, uint32_t split_k, int32_t tile_n,
+                                  float* out_d, size_t ldc, size_t split_stride, int32_t transpose_out, void* stream) {
+  if (!out_d) return D3P_ERR_INVALID_ARGUMENT;
+  tc::GemmOperand A{a_d, nullptr, a_mn_major, lda, 1}, B{b_d, nullptr, b_mn_major, ldb, 1};
+  tc::EpiStore::Args ea{out_d, ldc, split_stride, transpose_out};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!a_mn_major && !b_mn_major) return dispatch_bn<false, false, 16>(tile_n, A, B, M, N, K, split_k, ea, s);
+  if (!a_mn_major && b_mn_major) return dispatch_bn<false, true, 16>(tile_n, A, B, M, N, K, split_k, ea, s);
+  if (a_mn_major && !b_mn_major) return dispatch_bn<true, false, 16>(tile_n, A, B, M, N, K, split_k, ea, s);
+  return dispatch_bn<true, true, 16>(tile_n, A, B, M, N, K, split_k, ea, s);
 }

@@ -5,6 +5,15 @@
 // Each term is one tcgen05.mma.kind::tf32 into the same TMEM accumulator.  An operand whose values
 // are exact in TF32 (e.g. binarised pixels) passes lo = NULL and its correction MMA is skipped.
 //
+// In-kernel split (GemmOperand::split): the operand arrives as ONE fp32 array.  kind::tf32 reads the top 19 bits of
+// a 32-bit operand word, i.e. it TRUNCATES (measured: scripts/tf32_operand_rounding.py — raw x as the hi operand
+// with lo = x - trunc(x) gives bit-identical products to a masked hi), so the raw tile IS the hi operand and only
+// lo = x - trunc(x) has to be made: the epilogue warps, idle during the main loop, compute it for every landed stage
+// (an element-wise pass over the stage, so the TMA swizzle is irrelevant) into a separate 2-slot lo ring, then
+// fence.proxy.async and arrive on the slot's barrier the MMA issuer waits on.  A raw stage is half the size of a
+// hi + lo stage, so the TMA ring is 3 deep instead of 2 for a 128 x 224 tile and half the operand bytes cross
+// L2 -> shared memory.
+//
 // Structure (one CTA per 128 x BN output tile and K split, 64 + 32 EW threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of 32 fp32 (one 128 B swizzle span) into
 //               a STAGES-deep shared-memory ring, mbarrier complete_tx
@@ -33,6 +42,7 @@ struct GemmShape {
   uint32_t split_k;               // gridDim.z
   int has_a_lo, has_b_lo;
   const int* a_lo_flag;           // optional device flag: 0 = a_lo is all zeros, skip its MMA (and its loads)
+  int a_split, b_split;           // operand given as one fp32 array: hi / lo are produced in shared memory
 };
 
 template <int BN>
@@ -41,9 +51,9 @@ struct GemmCfg {
   static constexpr uint32_t kBBytes = BN * 128;
   static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;       // with both lo parts present
   static constexpr int kMaxStages = 6;
-  // ring capacity: as many stages as fit 216 KB; the kernel re-derives the stage count at run time from the
+  // ring capacity: as many stages as fit 220 KB; the kernel re-derives the stage count at run time from the
   // operands that are really present (an absent / all-zero lo part frees its slots for deeper pipelining)
-  static constexpr uint32_t kRingBytes = 216u * 1024u;
+  static constexpr uint32_t kRingBytes = 220u * 1024u;
   static constexpr uint32_t kSmemBytes = kRingBytes + 1024;
   static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32, 256]");
@@ -61,6 +71,8 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bar_full[STAGES];
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
+  __shared__ __align__(8) uint64_t bar_lo_full[2];    // in-kernel split: lo slot written by the epilogue warps
+  __shared__ __align__(8) uint64_t bar_lo_empty[2];   // ... and read by the MMAs that were committed
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_base_s;
 
@@ -70,11 +82,16 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
   const uint32_t base = g.num_k_blocks / g.split_k, rem = g.num_k_blocks % g.split_k;
   const uint32_t kb_begin = split * base + (split < rem ? split : rem);
   const uint32_t kb_end = kb_begin + base + (split < rem ? 1u : 0u);
-  const bool has_a_lo = g.has_a_lo && (g.a_lo_flag == nullptr || __ldg(g.a_lo_flag) != 0);
-  const bool has_b_lo = g.has_b_lo != 0;
-  const uint32_t stage_bytes = Cfg::kABytes * (has_a_lo ? 2u : 1u) + Cfg::kBBytes * (has_b_lo ? 2u : 1u);
-  const uint32_t stages = Cfg::kRingBytes / stage_bytes > (uint32_t)STAGES ? (uint32_t)STAGES : Cfg::kRingBytes / stage_bytes;
-
+  const bool has_a_lo = (g.has_a_lo || g.a_split) && (g.a_lo_flag == nullptr || __ldg(g.a_lo_flag) != 0);
+  const bool has_b_lo = g.has_b_lo != 0 || g.b_split != 0;
+  const bool a_conv = g.a_split && has_a_lo, b_conv = g.b_split != 0;      // lo parts made here, not loaded
+  const bool any_conv = a_conv || b_conv;
+  const bool load_a_lo = has_a_lo && !a_conv, load_b_lo = has_b_lo && !b_conv;     // lo parts that arrive by TMA
+  // TMA ring: [A | A lo (loaded)] [B | B lo (loaded)] per stage; in-kernel split: 2 more slots of [A lo | B lo] made here
+  const uint32_t stage_bytes = Cfg::kABytes * (load_a_lo ? 2u : 1u) + Cfg::kBBytes * (load_b_lo ? 2u : 1u);
+  const uint32_t lo_slot_bytes = (a_conv ? Cfg::kABytes : 0u) + (b_conv ? Cfg::kBBytes : 0u);
+  const uint32_t ring_avail = Cfg::kRingBytes - 2u * lo_slot_bytes;
+  const uint32_t stages = ring_avail / stage_bytes > (uint32_t)STAGES ? (uint32_t)STAGES : ring_avail / stage_bytes;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a_hi);
     tma_prefetch_desc(&maps.b_hi);
@@ -84,6 +101,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
   if (warp == 1) {
     if (lane == 0) {
       for (uint32_t s = 0; s < stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+      for (uint32_t l = 0; l < 2; ++l) { mbar_init(&bar_lo_full[l], EW); mbar_init(&bar_lo_empty[l], 1); }
       mbar_init(&bar_acc, 1);
       fence_barrier_init();
     }
@@ -95,17 +113,22 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  auto stage_ptr = [&](uint32_t s, int which) -> uint8_t* {   // which: 0 a_hi, 1 a_lo, 2 b_hi, 3 b_lo
+  auto stage_ptr = [&](uint32_t s, int which) -> uint8_t* {   // which: 0 a (hi), 1 a_lo (loaded), 2 b (hi), 3 b_lo (loaded)
     uint8_t* p = smem + (size_t)s * stage_bytes;
     if (which >= 1) p += Cfg::kABytes;
-    if (which >= 2 && has_a_lo) p += Cfg::kABytes;
+    if (which >= 2 && load_a_lo) p += Cfg::kABytes;
     if (which >= 3) p += Cfg::kBBytes;
+    return p;
+  };
+  auto lo_ptr = [&](uint32_t l, int which) -> uint8_t* {      // in-kernel split: which 0 a_lo, 1 b_lo
+    uint8_t* p = smem + (size_t)stages * stage_bytes + (size_t)l * lo_slot_bytes;
+    if (which >= 1 && a_conv) p += Cfg::kABytes;
     return p;
   };
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx = Cfg::kABytes * (1 + (has_a_lo ? 1 : 0)) + Cfg::kBBytes * (1 + (has_b_lo ? 1 : 0));
+      const uint32_t tx = Cfg::kABytes * (1 + (load_a_lo ? 1 : 0)) + Cfg::kBBytes * (1 + (load_b_lo ? 1 : 0));
       uint32_t it = 0;
       for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++it) {
         const uint32_t s = it % stages;
@@ -116,22 +139,22 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
         const int32_t m0 = (int32_t)(m_tile * kBM), n0 = (int32_t)(n_tile * BN);
         if (!A_MN) {
           tma_load_2d(&maps.a_hi, &bar_full[s], stage_ptr(s, 0), k0, m0);
-          if (has_a_lo) tma_load_2d(&maps.a_lo, &bar_full[s], stage_ptr(s, 1), k0, m0);
+          if (load_a_lo) tma_load_2d(&maps.a_lo, &bar_full[s], stage_ptr(s, 1), k0, m0);
         } else {
 #pragma unroll
           for (int c = 0; c < kBM / 32; ++c) {
             tma_load_2d(&maps.a_hi, &bar_full[s], stage_ptr(s, 0) + c * 4096, m0 + c * 32, k0);
-            if (has_a_lo) tma_load_2d(&maps.a_lo, &bar_full[s], stage_ptr(s, 1) + c * 4096, m0 + c * 32, k0);
+            if (load_a_lo) tma_load_2d(&maps.a_lo, &bar_full[s], stage_ptr(s, 1) + c * 4096, m0 + c * 32, k0);
           }
         }
         if (!B_MN) {
           tma_load_2d(&maps.b_hi, &bar_full[s], stage_ptr(s, 2), k0, n0);
-          if (has_b_lo) tma_load_2d(&maps.b_lo, &bar_full[s], stage_ptr(s, 3), k0, n0);
+          if (load_b_lo) tma_load_2d(&maps.b_lo, &bar_full[s], stage_ptr(s, 3), k0, n0);
         } else {
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c) {
             tma_load_2d(&maps.b_hi, &bar_full[s], stage_ptr(s, 2) + c * 4096, n0 + c * 32, k0);
-            if (has_b_lo) tma_load_2d(&maps.b_lo, &bar_full[s], stage_ptr(s, 3) + c * 4096, n0 + c * 32, k0);
+            if (load_b_lo) tma_load_2d(&maps.b_lo, &bar_full[s], stage_ptr(s, 3) + c * 4096, n0 + c * 32, k0);
           }
         }
       }
@@ -147,10 +170,11 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
       for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++it) {
         const uint32_t s = it % stages;
         const uint32_t ph = (it / stages) & 1u;
-        mbar_wait(&bar_full[s], ph);
+        const uint32_t l = it & 1u, lph = (it >> 1) & 1u;
+        mbar_wait(any_conv ? &bar_lo_full[l] : &bar_full[s], any_conv ? lph : ph);
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
-        const uint32_t b_hi = smem_u32(stage_ptr(s, 2)), b_lo = smem_u32(stage_ptr(s, 3));
+        const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(a_conv ? lo_ptr(l, 0) : stage_ptr(s, 1));
+        const uint32_t b_hi = smem_u32(stage_ptr(s, 2)), b_lo = smem_u32(b_conv ? lo_ptr(l, 1) : stage_ptr(s, 3));
 #pragma unroll
         for (int ks = 0; ks < kKB / kUK; ++ks) {
           const uint64_t da_hi = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
@@ -161,6 +185,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
           if (has_a_lo) umma_tf32(tmem_base, make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt), db_hi, idesc, 1);
         }
         umma_commit(&bar_empty[s]);     // frees the stage once these MMAs have read it
+        if (any_conv) umma_commit(&bar_lo_empty[l]);
       }
       umma_commit(&bar_acc);            // accumulator complete
     }
@@ -169,6 +194,31 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
     constexpr int PARTS = EW / 4;
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;   // which of the PARTS warps of that quarter
+    if (any_conv) {
+      // main-loop duty of the epilogue warps: split the operands of every landed stage (see the file header)
+      const uint32_t ct = (uint32_t)(warp - 2) * 32u + (uint32_t)lane, nct = (uint32_t)EW * 32u;
+      auto convert = [&](const uint8_t* raw_p, uint8_t* lo_p, uint32_t bytes) {
+#pragma unroll 4
+        for (uint32_t off = ct * 16u; off < bytes; off += nct * 16u) {
+          const float4 v = *reinterpret_cast<const float4*>(raw_p + off);
+          *reinterpret_cast<float4*>(lo_p + off) =
+              make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+        }
+      };
+      uint32_t it = 0;
+      for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const uint32_t s = it % stages;
+        const uint32_t ph = (it / stages) & 1u;
+        const uint32_t l = it & 1u, lph = (it >> 1) & 1u;
+        mbar_wait(&bar_lo_empty[l], lph ^ 1u);        // the MMAs that read this lo slot two k-blocks ago are done
+        mbar_wait(&bar_full[s], ph);
+        if (a_conv) convert(stage_ptr(s, 0), lo_ptr(l, 0), Cfg::kABytes);
+        if (b_conv) convert(stage_ptr(s, 2), lo_ptr(l, 1), Cfg::kBBytes);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> tensor-core reads
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bar_lo_full[l])) : "memory");
+      }
+    }
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
     const uint32_t row = m_tile * kBM + q * 32 + lane;
@@ -227,9 +277,10 @@ struct EpiStore {
 // ---- host launcher ------------------------------------------------------------------------------------
 struct GemmOperand {
   const float* hi;
-  const float* lo;     // may be NULL (operand exact in TF32)
+  const float* lo;     // may be NULL (operand exact in TF32, or split == 1)
   int mn_major;        // 0: stored [rows = M or N, K] (K contiguous); 1: stored [K, M or N]
   size_t ld;           // row stride in floats (multiple of 4)
+  int split = 0;       // 1: `hi` holds the full fp32 values, the kernel makes hi / lo in shared memory (lo == NULL)
 };
 
 template <bool A_MN, bool B_MN, int BN, class Epi, int EW = kGemmEpiWarps>
@@ -244,9 +295,12 @@ int32_t launch_tc_gemm(const GemmOperand& A, const GemmOperand& B, uint32_t M, u
   g.M = M; g.N = N; g.K = K;
   g.num_k_blocks = (K + kKB - 1) / kKB;
   g.split_k = split_k > g.num_k_blocks ? g.num_k_blocks : split_k;
+  if ((A.split && A.lo) || (B.split && B.lo)) return D3P_ERR_INVALID_ARGUMENT;
   g.has_a_lo = A.lo ? 1 : 0;
   g.has_b_lo = B.lo ? 1 : 0;
   g.a_lo_flag = a_lo_flag;
+  g.a_split = A.split ? 1 : 0;
+  g.b_split = B.split ? 1 : 0;
   GemmMaps maps;
   bool ok = true;
   if (!A_MN) {

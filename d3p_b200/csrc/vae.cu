@@ -19,6 +19,7 @@
 //   loss / count columns of the partial rows
 // The partial rows [S, P + 2] are reduced in a fixed order by d3p_perturb_finalize_f32.
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 #include "launch.cuh"
@@ -1070,15 +1071,26 @@ struct VaeLayout {
   size_t ldx, ldh, ldz, ld23;
 };
 
-static uint32_t vae_splits(uint32_t Bl) {
-  uint32_t kb = (Bl + tc::kKB - 1) / tc::kKB;
-  return kb < 10 ? (kb ? kb : 1) : 10;
+// Batch splits of the clipped-sum GEMMs = partial rows.  The four GEMMs (dW1, dW5, dW2|dW3, dW4) are independent and
+// run concurrently (forked streams), every CTA owns one SM (the operand ring takes the whole shared memory), so the
+// split count is chosen to put all their CTAs on the GPU in ONE wave with as many k-blocks per CTA as possible
+// (784-400-20: 36 tiles -> 4 splits = 144 CTAs of 32 k-blocks; the old 10 splits ran 140-CTA grids of 13 k-blocks back
+// to back, each paying its prologue, pipeline fill and epilogue).
+static uint32_t vae_splits(const d3p_vae_desc* d, uint32_t Bl) {
+  const uint32_t kb = (Bl + tc::kKB - 1) / tc::kKB;
+  auto tiles = [](uint32_t m, uint32_t n, uint32_t bn) { return ((m + tc::kBM - 1) / tc::kBM) * ((n + bn - 1) / bn); };
+  const uint32_t D = d->out_dim, H = d->hidden_dim, Z = d->z_dim;
+  const uint32_t total = tiles(D + 1, H, kVaeBN) + tiles(D, H + 1, kVaeBN) + tiles(H + 1, 2 * Z, kThinBN) + tiles(H, Z + 1, kThinBN);
+  uint32_t s = (uint32_t)sm_count() / (total ? total : 1);
+  if (s > 10) s = 10;
+  if (s > kb) s = kb;
+  return s ? s : 1;
 }
 
 static VaeLayout vae_layout(const d3p_vae_desc* d, uint32_t Bl) {
   VaeLayout L;
   const size_t D = d->out_dim, H = d->hidden_dim, Z = d->z_dim, P = d->n_params;
-  L.S = vae_splits(Bl);
+  L.S = vae_splits(d, Bl);
   L.ns_h = (uint32_t)((H + kVaeBNH - 1) / kVaeBNH) * (kHeavyEW / 4);
   L.ns_d = (uint32_t)((D + kVaeBN - 1) / kVaeBN) * (kHeavyEW / 4);
   L.ldx = D + 4; L.ldh = H + 4; L.ldz = (Z + 1 + 3) / 4 * 4; L.ld23 = (2 * Z + 3) / 4 * 4;
@@ -1111,6 +1123,32 @@ static size_t mid_fwd_smem_bytes(uint32_t H, uint32_t Z) {
 }
 static size_t mid_bwd_smem_bytes(uint32_t H, uint32_t Z) {
   return (3 * (size_t)Z * H + (size_t)kMidWarps * kMidE * (H + 128)) * sizeof(float);
+}
+
+// Side streams for the four independent clipped-sum GEMMs: one set per device, created on first use and kept (the
+// step path must not create or destroy streams).  `mu` serialises the fork / join bookkeeping of concurrent callers.
+struct VaeSideStreams {
+  std::mutex mu;
+  cudaStream_t s[3];
+  cudaEvent_t fork, join[3];
+  bool ok = false;
+};
+static VaeSideStreams* vae_side_streams() {
+  static std::mutex tab_mu;
+  static VaeSideStreams* tab[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(tab_mu);
+  if (!tab[dev]) {
+    VaeSideStreams* v = new VaeSideStreams();
+    bool ok = cudaEventCreateWithFlags(&v->fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3 && ok; ++i)
+      ok = cudaStreamCreateWithFlags(&v->s[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&v->join[i], cudaEventDisableTiming) == cudaSuccess;
+    v->ok = ok;
+    tab[dev] = v;
+  }
+  return tab[dev]->ok ? tab[dev] : nullptr;
 }
 
 static bool vae_supported(const d3p_vae_desc* d) {
@@ -1241,8 +1279,33 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
     vae_mid_bwd_kernel<<<mid_grid, kMidWarps * 32, mid_bwd_smem, s>>>(a);
     if ((rc = check_launch()) != D3P_OK) return rc;
   }
-  // GW1: [X | 1]^T (c delta1) -> dW1 [D, H] and db1; contraction over the batch
+  // The four clipped-sum GEMMs are independent: GW1 stays on the caller's stream, GW5 / GW23 / GW4 run on side streams
+  // forked from it and joined before the loss kernel (one wave of CTAs, see vae_splits).  The optional profile events
+  // (bench) bracket the whole concurrent group on the caller's stream.
+  VaeSideStreams* ss = vae_side_streams();
   if (profile_events_h && cudaEventRecord((cudaEvent_t)profile_events_h[0], s) != cudaSuccess) return D3P_ERR_CUDA;
+  std::unique_lock<std::mutex> ss_lock;
+  cudaStream_t s5 = s, s23 = s, s4 = s;
+  if (ss) {
+    ss_lock = std::unique_lock<std::mutex>(ss->mu);
+    if (cudaEventRecord(ss->fork, s) != cudaSuccess) return D3P_ERR_CUDA;
+    for (int i = 0; i < 3; ++i)
+      if (cudaStreamWaitEvent(ss->s[i], ss->fork, 0) != cudaSuccess) return D3P_ERR_CUDA;
+    s5 = ss->s[0]; s23 = ss->s[1]; s4 = ss->s[2];
+  }
+  // GW23: [H1 | 1]^T (c [delta2 | delta3]) -> dW2, dW3 [H, Z] and db2, db3   (thin GEMMs first: they are short)
+  {
+    tc::GemmOperand A{a.h1_hi, a.h1_lo, 1, a.ldh}, Bo{a.cd23_hi, a.cd23_lo, 1, a.ld23};
+    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w2, a.off_b2, Z, H, 0, Z, a.off_w3, a.off_b3};
+    if ((rc = tc::launch_tc_gemm<true, true, kThinBN, EpiGrad>(A, Bo, H + 1, 2 * Z, Bl, L.S, ea, s23, nullptr)) != D3P_OK) return rc;
+  }
+  // GW4: (c delta4)^T [z | 1] -> dW4^T (stored [Z, H]) and db4
+  {
+    tc::GemmOperand A{a.cd4_hi, a.cd4_lo, 1, H}, Bo{a.z_hi, a.z_lo, 1, a.ldz};
+    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w4, a.off_b4, H, Z, 1, 0, 0, 0};
+    if ((rc = tc::launch_tc_gemm<true, true, kThinBN, EpiGrad>(A, Bo, H, Z + 1, Bl, L.S, ea, s4, nullptr)) != D3P_OK) return rc;
+  }
+  // GW1: [X | 1]^T (c delta1) -> dW1 [D, H] and db1; contraction over the batch
   {
     tc::GemmOperand A{a.x_hi, a.x_lo, 1, a.ldx}, Bo{a.cd1_hi, a.cd1_lo, 1, H};
     EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w1, a.off_b1, H, D, 0, 0, 0, 0};
@@ -1252,22 +1315,15 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   {
     tc::GemmOperand A{a.d5_hi, a.d5_lo, 1, D}, Bo{a.ch2_hi, a.ch2_lo, 1, a.ldh};
     EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w5, a.off_b5, D, H, 1, 0, 0, 0};
-    if ((rc = tc::launch_tc_gemm<true, true, kVaeBN, EpiGrad>(A, Bo, D, H + 1, Bl, L.S, ea, s, nullptr)) != D3P_OK) return rc;
+    if ((rc = tc::launch_tc_gemm<true, true, kVaeBN, EpiGrad>(A, Bo, D, H + 1, Bl, L.S, ea, s5, nullptr)) != D3P_OK) return rc;
+  }
+  if (ss) {
+    for (int i = 0; i < 3; ++i)
+      if (cudaEventRecord(ss->join[i], ss->s[i]) != cudaSuccess || cudaStreamWaitEvent(s, ss->join[i], 0) != cudaSuccess)
+        return D3P_ERR_CUDA;
+    ss_lock.unlock();
   }
   if (profile_events_h && cudaEventRecord((cudaEvent_t)profile_events_h[1], s) != cudaSuccess) return D3P_ERR_CUDA;
-  // thin clipped sums on the same GEMM kernel:
-  // GW23: [H1 | 1]^T (c [delta2 | delta3]) -> dW2, dW3 [H, Z] and db2, db3
-  {
-    tc::GemmOperand A{a.h1_hi, a.h1_lo, 1, a.ldh}, Bo{a.cd23_hi, a.cd23_lo, 1, a.ld23};
-    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w2, a.off_b2, Z, H, 0, Z, a.off_w3, a.off_b3};
-    if ((rc = tc::launch_tc_gemm<true, true, kThinBN, EpiGrad>(A, Bo, H + 1, 2 * Z, Bl, L.S, ea, s, nullptr)) != D3P_OK) return rc;
-  }
-  // GW4: (c delta4)^T [z | 1] -> dW4^T (stored [Z, H]) and db4
-  {
-    tc::GemmOperand A{a.cd4_hi, a.cd4_lo, 1, H}, Bo{a.z_hi, a.z_lo, 1, a.ldz};
-    EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w4, a.off_b4, H, Z, 1, 0, 0, 0};
-    if ((rc = tc::launch_tc_gemm<true, true, kThinBN, EpiGrad>(A, Bo, H, Z + 1, Bl, L.S, ea, s, nullptr)) != D3P_OK) return rc;
-  }
   vae_loss_kernel<<<L.S, 256, 0, s>>>(a);
   return check_launch();
 }

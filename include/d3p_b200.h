@@ -323,6 +323,12 @@ int32_t d3p_gemm_tf32x3(const float* a_hi_d, const float* a_lo_d, int32_t a_mn_m
                         const float* b_lo_d, int32_t b_mn_major, size_t ldb, uint32_t M, uint32_t N, uint32_t K,
                         uint32_t split_k, int32_t tile_n, float* out_d, size_t ldc, size_t split_stride,
                         int32_t transpose_out, void* stream);
+/* The same product from UNSPLIT fp32 operands: every shared-memory stage is split into hi / lo by the kernel's
+ * epilogue warps while the previous stages are being multiplied, which halves the operand bytes read per tile. */
+int32_t d3p_gemm_f32x3(const float* a_d, int32_t a_mn_major, size_t lda, const float* b_d, int32_t b_mn_major, size_t ldb,
+                       uint32_t M, uint32_t N, uint32_t K, uint32_t split_k, int32_t tile_n, float* out_d, size_t ldc,
+                       size_t split_stride, int32_t transpose_out, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------
  * Fused per-example gradient + ghost-norm clip + clipped sum for the VAE of examples/vae.py:65-153

@@ -77,3 +77,32 @@ def test_split_tf32_is_exact(cuda):
     v = x * s[:, None]
     assert torch.equal(hi + lo, v)
     assert torch.all((hi.view(torch.int32) & 0x1FFF) == 0)
+
+
+def gemm_unsplit(A, B, a_mn, b_mn, split_k=1, tile_n=224, transpose=False):
+    """d3p_gemm_f32x3: operands as plain fp32 arrays, hi / lo made in shared memory by the kernel."""
+    M = A.shape[1] if a_mn else A.shape[0]
+    K = A.shape[0] if a_mn else A.shape[1]
+    N = B.shape[1] if b_mn else B.shape[0]
+    rows, cols = (N, M) if transpose else (M, N)
+    out = torch.full((split_k, rows, cols), float("nan"), dtype=torch.float32, device=A.device)
+    _n.check(_n.lib().d3p_gemm_f32x3(_n.ptr(A), int(a_mn), A.stride(0), _n.ptr(B), int(b_mn), B.stride(0), M, N, K,
+                                     split_k, tile_n, _n.ptr(out), cols, rows * cols, int(transpose), _n.stream_ptr()),
+             "gemm_f32x3")
+    torch.cuda.synchronize()
+    return out.sum(0)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,tile_n,split_k", [(128, 224, 64, 224, 1), (784, 400, 520, 224, 3), (100, 40, 36, 128, 1),
+                                                  (4096, 400, 784, 128, 1), (784, 400, 4096, 224, 10)])
+def test_gemm_in_kernel_split_matches_fp64_and_presplit(cuda, a_mn, b_mn, M, N, K, tile_n, split_k):
+    g = torch.Generator(device="cuda").manual_seed(M * 5 + N * 11 + K)
+    A = torch.randn((K, M) if a_mn else (M, K), device=cuda, generator=g)
+    B = torch.randn((K, N) if b_mn else (N, K), device=cuda, generator=g)
+    got = gemm_unsplit(A, B, a_mn, b_mn, split_k=split_k, tile_n=tile_n)
+    want = ref(A, B, a_mn, b_mn)
+    scale = (A.double().abs().max() * B.double().abs().max() * np.sqrt(K)).item()
+    assert (got.double() - want).abs().max().item() / scale < 2e-6
+    # the same MMAs on the same operand bits as the pre-split path => identical results
+    assert torch.equal(got, gemm(A, B, a_mn, b_mn, split_k=split_k, tile_n=tile_n))
