@@ -110,8 +110,8 @@ struct EpiFwd5 {   // p = sigmoid(acc + b5); Bernoulli(probs) log-lik (numpyro c
         // log1p(-pc) = log(1 - pc): 1 - pc is exact for pc >= 1/2 (Sterbenz) and within 6e-8 below; MUFU.LG2 logs
         rs.loss -= xs[j + t] * __logf(pc) + (1.0f - xs[j + t]) * __logf(1.0f - pc);
         const float d = wclip * (p - xs[j + t]);
-        hi[t] = tc::tf32_hi(d);
-        lo[t] = d - hi[t];
+        hi[t] = d;                        // unmasked: kind::tf32 truncates, and dW5's GEMM splits delta5 itself
+        lo[t] = d - tc::tf32_hi(d);
         rs.sq = fmaf(d, d, rs.sq);
       }
       *reinterpret_cast<float4*>(a.d_hi + (size_t)row * a.ld + col0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
@@ -599,24 +599,21 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_bwd_kernel(VaeArgs a) 
           const uint32_t h = h0 + 32 * t + lane;
           if (h >= H) continue;
           const float v1 = cc * d1v[t];
-          const float hi1 = tc::tf32_hi(v1);
-          a.cd1_hi[(size_t)r * H + h] = hi1;
-          a.cd1_lo[(size_t)r * H + h] = v1 - hi1;
+          a.cd1_hi[(size_t)r * H + h] = v1;          // unmasked: split by the dW1 GEMM itself (tc_gemm_kernel.cuh)
+          a.cd1_lo[(size_t)r * H + h] = v1 - tc::tf32_hi(v1);
           const float v4 = cc * d4s[e * H + h];
           const float hi4 = tc::tf32_hi(v4);
           a.cd4_hi[(size_t)r * H + h] = hi4;
           a.cd4_lo[(size_t)r * H + h] = v4 - hi4;
           const float v2 = cc * (h2h[t] + h2l[t]);
-          const float hi2 = tc::tf32_hi(v2);
-          a.ch2_hi[(size_t)r * a.ldh + h] = hi2;
-          a.ch2_lo[(size_t)r * a.ldh + h] = v2 - hi2;
+          a.ch2_hi[(size_t)r * a.ldh + h] = v2;      // unmasked, as above (dW5 GEMM)
+          a.ch2_lo[(size_t)r * a.ldh + h] = v2 - tc::tf32_hi(v2);
         }
       }
       if (lane < 4) {
         const float v = lane == 0 ? cc : 0.f;
-        const float hi = tc::tf32_hi(v);
-        a.ch2_hi[(size_t)r * a.ldh + H + lane] = hi;
-        a.ch2_lo[(size_t)r * a.ldh + H + lane] = v - hi;
+        a.ch2_hi[(size_t)r * a.ldh + H + lane] = v;
+        a.ch2_lo[(size_t)r * a.ldh + H + lane] = v - tc::tf32_hi(v);
       }
       for (uint32_t j = lane; j < a.ld23; j += 32) {
         const float v = j < 2 * Z ? cc * (j < Z ? d23[e * 128 + j] : d23[e * 128 + 64 + j - Z]) : 0.f;
@@ -1008,15 +1005,13 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_bwd_mma_kernel(VaeArgs a)
     { const float vx = (src_x), vy = (src_y), vz = (src_z), vw = (src_w);                          \
       o_hi = make_float4(tc::tf32_hi(vx), tc::tf32_hi(vy), tc::tf32_hi(vz), tc::tf32_hi(vw));      \
       o_lo = make_float4(vx - o_hi.x, vy - o_hi.y, vz - o_hi.z, vw - o_hi.w); }
-    D3P_SPLIT4(cc * d1.x, cc * d1.y, cc * d1.z, cc * d1.w)
-    *reinterpret_cast<float4*>(a.cd1_hi + (size_t)r * H + h) = o_hi;
-    *reinterpret_cast<float4*>(a.cd1_lo + (size_t)r * H + h) = o_lo;
+    // c delta1 and c h2 go out unsplit: the dW1 / dW5 GEMMs make their lo parts in shared memory (GemmOperand::split)
+    *reinterpret_cast<float4*>(a.cd1_hi + (size_t)r * H + h) = make_float4(cc * d1.x, cc * d1.y, cc * d1.z, cc * d1.w);
     D3P_SPLIT4(cc * d4.x, cc * d4.y, cc * d4.z, cc * d4.w)
     *reinterpret_cast<float4*>(a.cd4_hi + (size_t)r * H + h) = o_hi;
     *reinterpret_cast<float4*>(a.cd4_lo + (size_t)r * H + h) = o_lo;
-    D3P_SPLIT4(cc * (hh.x + hl.x), cc * (hh.y + hl.y), cc * (hh.z + hl.z), cc * (hh.w + hl.w))
-    *reinterpret_cast<float4*>(a.ch2_hi + (size_t)r * a.ldh + h) = o_hi;
-    *reinterpret_cast<float4*>(a.ch2_lo + (size_t)r * a.ldh + h) = o_lo;
+    *reinterpret_cast<float4*>(a.ch2_hi + (size_t)r * a.ldh + h) =
+        make_float4(cc * (hh.x + hl.x), cc * (hh.y + hl.y), cc * (hh.z + hl.z), cc * (hh.w + hl.w));
 #undef D3P_SPLIT4
   }
   {
@@ -1025,9 +1020,8 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_bwd_mma_kernel(VaeArgs a)
       const float cc = s_cc[e8];
       if (j8 < 4) {
         const float v = j8 == 0 ? cc : 0.f;
-        const float hi = tc::tf32_hi(v);
-        a.ch2_hi[(size_t)r * a.ldh + H + j8] = hi;
-        a.ch2_lo[(size_t)r * a.ldh + H + j8] = v - hi;
+        a.ch2_hi[(size_t)r * a.ldh + H + j8] = v;          // unmasked; the dW5 GEMM never reads ch2_lo
+
       }
       for (uint32_t j = j8; j < a.ld23; j += kMmaTpe) {
         const float v = j < Z2 ? cc * s_d23[e8][j] : 0.f;
@@ -1215,22 +1209,37 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
 
   const int sms = sm_count();
   int32_t rc;
-  // parameter splits + X preparation
-  if ((rc = d3p_split_tf32(params_d + a.off_w1, nullptr, 0, w1_hi, w1_lo, (size_t)D * H, stream)) != D3P_OK) return rc;
-  if ((rc = d3p_split_tf32(params_d + a.off_w5, nullptr, 0, w5_hi, w5_lo, (size_t)H * D, stream)) != D3P_OK) return rc;
-  if (cudaMemsetAsync(a.x_lo_flag, 0, sizeof(int), s) != cudaSuccess) return D3P_ERR_CUDA;
+  // parameter splits + X preparation: four independent small kernels; the weight splits and the thin-layer fragments
+  // run on side streams beside the X preparation (the longest of them)
+  VaeSideStreams* ss = vae_side_streams();
   {
+    std::unique_lock<std::mutex> lk;
+    cudaStream_t sw = s, sm = s;
+    if (ss) {
+      lk = std::unique_lock<std::mutex>(ss->mu);
+      if (cudaEventRecord(ss->fork, s) != cudaSuccess) return D3P_ERR_CUDA;
+      for (int i = 0; i < 2; ++i)
+        if (cudaStreamWaitEvent(ss->s[i], ss->fork, 0) != cudaSuccess) return D3P_ERR_CUDA;
+      sw = ss->s[0]; sm = ss->s[1];
+    }
+    if ((rc = d3p_split_tf32(params_d + a.off_w1, nullptr, 0, w1_hi, w1_lo, (size_t)D * H, sw)) != D3P_OK) return rc;
+    if ((rc = d3p_split_tf32(params_d + a.off_w5, nullptr, 0, w5_hi, w5_lo, (size_t)H * D, sw)) != D3P_OK) return rc;
+    if (mid_mma) {
+      const MidFragDims fd(H, Z);
+      const size_t n = fd.n23() + fd.n4() + fd.n4t() + fd.n23t();
+      vae_prep_mid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sm>>>(a);
+      if ((rc = check_launch()) != D3P_OK) return rc;
+    }
+    if (cudaMemsetAsync(a.x_lo_flag, 0, sizeof(int), s) != cudaSuccess) return D3P_ERR_CUDA;
     unsigned grid = (Bl + 7) / 8;
     if (grid > (unsigned)sms * 8) grid = sms * 8;
     if ((reinterpret_cast<uintptr_t>(x_d) & 15) == 0 && (x_row_stride & 3) == 0) vae_prep_x_kernel<true><<<grid, 256, 0, s>>>(a);
     else vae_prep_x_kernel<false><<<grid, 256, 0, s>>>(a);
     if ((rc = check_launch()) != D3P_OK) return rc;
-  }
-  if (mid_mma) {
-    const MidFragDims fd(H, Z);
-    const size_t n = fd.n23() + fd.n4() + fd.n4t() + fd.n23t();
-    vae_prep_mid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
-    if ((rc = check_launch()) != D3P_OK) return rc;
+    if (ss)
+      for (int i = 0; i < 2; ++i)
+        if (cudaEventRecord(ss->join[i], ss->s[i]) != cudaSuccess || cudaStreamWaitEvent(s, ss->join[i], 0) != cudaSuccess)
+          return D3P_ERR_CUDA;
   }
   // G1: pre1 = X W1  (A = X K-major [Bl, D]; B = W1 stored [K = D, N = H])
   {
@@ -1282,7 +1291,6 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   // The four clipped-sum GEMMs are independent: GW1 stays on the caller's stream, GW5 / GW23 / GW4 run on side streams
   // forked from it and joined before the loss kernel (one wave of CTAs, see vae_splits).  The optional profile events
   // (bench) bracket the whole concurrent group on the caller's stream.
-  VaeSideStreams* ss = vae_side_streams();
   if (profile_events_h && cudaEventRecord((cudaEvent_t)profile_events_h[0], s) != cudaSuccess) return D3P_ERR_CUDA;
   std::unique_lock<std::mutex> ss_lock;
   cudaStream_t s5 = s, s23 = s, s4 = s;
@@ -1307,15 +1315,15 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   }
   // GW1: [X | 1]^T (c delta1) -> dW1 [D, H] and db1; contraction over the batch
   {
-    tc::GemmOperand A{a.x_hi, a.x_lo, 1, a.ldx}, Bo{a.cd1_hi, a.cd1_lo, 1, H};
+    tc::GemmOperand A{a.x_hi, a.x_lo, 1, a.ldx}, Bo{a.cd1_hi, nullptr, 1, H, 1};      // c delta1: split in the kernel
     EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w1, a.off_b1, H, D, 0, 0, 0, 0};
-    if ((rc = tc::launch_tc_gemm<true, true, kVaeBN, EpiGrad>(A, Bo, D + 1, H, Bl, L.S, ea, s, a.x_lo_flag)) != D3P_OK) return rc;
+    if ((rc = tc::launch_tc_gemm<true, true, kVaeBN, EpiGrad, kHeavyEW>(A, Bo, D + 1, H, Bl, L.S, ea, s, a.x_lo_flag)) != D3P_OK) return rc;
   }
   // GW5: delta5^T [c h2 | c] -> dW5^T (stored [H, D]) and db5
   {
-    tc::GemmOperand A{a.d5_hi, a.d5_lo, 1, D}, Bo{a.ch2_hi, a.ch2_lo, 1, a.ldh};
+    tc::GemmOperand A{a.d5_hi, nullptr, 1, D, 1}, Bo{a.ch2_hi, nullptr, 1, a.ldh, 1};   // both split in the kernel
     EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w5, a.off_b5, D, H, 1, 0, 0, 0};
-    if ((rc = tc::launch_tc_gemm<true, true, kVaeBN, EpiGrad>(A, Bo, D, H + 1, Bl, L.S, ea, s5, nullptr)) != D3P_OK) return rc;
+    if ((rc = tc::launch_tc_gemm<true, true, kVaeBN, EpiGrad, kHeavyEW>(A, Bo, D, H + 1, Bl, L.S, ea, s5, nullptr)) != D3P_OK) return rc;
   }
   if (ss) {
     for (int i = 0; i < 3; ++i)
