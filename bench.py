@@ -42,7 +42,7 @@ WORKLOADS = {
 # algorithmic HBM bytes per example of the dominant kernel
 ALGO_BYTES_PER_EXAMPLE = {"c1": 4 * (8 + 1), "c2": 4 * (1024 + 1), "c3": 4 * 256, "c4": 4 * 128}
 # launches of OUR kernels per step: sampler (Poisson: select + compact; Feistel: 1) + step kernel(s) + finalize;
-# matches the ncu launch list profiles/r1_c2_launches_v6.csv (4 per C2 step)
+# matches the ncu launch list profiles/r1_c2_launches_v7.csv (4 per C2 step)
 LAUNCHES = {"poisson": 2, "subsample": 1, "logreg": 2, "gauss": 2, "gmm": 2, "vae": 14}   # vae: 2 split + prep x + prep mid + 7 GEMMs + 2 thin-layer MMA + loss (13) + finalize
 
 
@@ -477,7 +477,7 @@ def run_b200(args, cfg):
                                  "(~83 warp-instructions per element, DESIGN.md section 5)")}
             if kname == "meanfield_step_vec_kernel" and cfg["family"] == "logreg" and clocks.get("sm_mhz"):
                 # the bound that does apply: issue slots.  Instruction count per element from the committed ncu
-                # capture (profiles/r1_step_vec_c2_ncu_full_v6.csv: smsp__inst_executed.sum / (examples * 1025 / 32));
+                # capture (profiles/r1_step_vec_c2_ncu_full_v7.csv: smsp__inst_executed.sum / (examples * 1025 / 32));
                 # the slots offered are SMs x 4 schedulers x measured SM clock x kernel time.
                 wi_per_elem = 82.9
                 elems = per_rank_examples * (cfg["d"] + 1)
