@@ -231,7 +231,10 @@ __global__ void vae_prep_x_kernel(VaeArgs a) {
   bool any_lo = false;
   for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < a.Bl; r += warps) {
     const uint32_t p = a.pos_begin + r;
-    const size_t src = (size_t)(a.idx ? (uint32_t)a.idx[p] : p) * a.x_stride;
+    // masked-out positions are never dereferenced (the sharded Poisson sampler leaves their index slots unwritten):
+    // they become all-zero rows, which the clip factor 0 removes from every sum anyway
+    const bool valid = (!a.num_valid || p < (uint32_t)max(*a.num_valid, 0)) && (!a.mask || a.mask[p]);
+    const size_t src = valid ? (size_t)(a.idx ? (uint32_t)a.idx[p] : p) * a.x_stride : 0;
     float sq = 0.f;
     if (kVec) {
       const float4* __restrict__ xs = reinterpret_cast<const float4*>(a.x + src);
@@ -240,7 +243,7 @@ __global__ void vae_prep_x_kernel(VaeArgs a) {
       const uint32_t n4 = a.D / 4;
 #pragma unroll 4
       for (uint32_t j = lane; j <= n4; j += 32) {
-        const float4 v = j < n4 ? __ldg(xs + j) : make_float4(1.0f, 0.f, 0.f, 0.f);
+        const float4 v = j < n4 ? (valid ? __ldg(xs + j) : make_float4(0.f, 0.f, 0.f, 0.f)) : make_float4(1.0f, 0.f, 0.f, 0.f);
         const float4 hi = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
         const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
         oh[j] = hi;
@@ -250,7 +253,7 @@ __global__ void vae_prep_x_kernel(VaeArgs a) {
       }
     } else {
       for (uint32_t j = lane; j < a.D + 4; j += 32) {
-        float v = j < a.D ? a.x[src + j] : (j == a.D ? 1.0f : 0.0f);
+        float v = j < a.D ? (valid ? a.x[src + j] : 0.f) : (j == a.D ? 1.0f : 0.0f);
         const float hi = tc::tf32_hi(v), lo = v - hi;
         a.x_hi[(size_t)r * a.ldx + j] = hi;
         a.x_lo[(size_t)r * a.ldx + j] = lo;

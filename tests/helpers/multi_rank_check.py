@@ -127,7 +127,7 @@ def main():
     ok = True
     for name, fam, data, C in cases:
         p_1, l_1, k_1 = run(fam, data, C, None)
-        modes = [("nccl", False), ("p2p", False)] + ([("p2p", True)] if name != "vae" else [])
+        modes = [("nccl", False), ("p2p", False), ("p2p", True)]      # epoch drivers: mean-field and VAE
         for backend, epoch in modes:
             p_sh, l_sh, k_sh = run(fam, data, C, backend, epoch=epoch)
             err = float((p_sh - p_1).abs().max() / p_1.abs().max())
