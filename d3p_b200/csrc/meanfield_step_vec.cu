@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
       asm volatile("cp.async.commit_group;\n" ::: "memory");
 
       // ---- loop A: noise + pass 1 ----------------------------------------------------------------
-      float zdot = 0.f, s_th2 = 0.f, s_e2 = 0.f, s_res2 = 0.f;
+      float zdot = 0.f, s_th2 = 0.f, s_e2 = 0.f, s_res2 = 0.f, nrm = 0.f;
 #pragma unroll 1
       for (int kk = 0; kk < NCH; ++kk) {
         const int q0 = 4 * (sl + LPE * kk);
@@ -199,21 +199,30 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
           const int e0 = h * HALF + q0;
           const float4 xv = ld4(xs + e0);
           const float4 loc = ld4(s_loc + e0), sc = ld4(s_scl + e0);
-          float4 aa = sc;
-          if (!kExp) aa = ld4(s_a + e0);
-          float4 u;
+          float4 aa = sc, bt = sc;
+          if (!kExp) { aa = ld4(s_a + e0); if (FAMILY == D3P_FAMILY_GAUSS) bt = ld4(s_bt + e0); }
+          float4 u, gl;
+          // Gaussian family: the gradient needs no reduction over the row (h = L (theta - x) / var element-wise), so
+          // loop B is folded in here: g_loc goes over x, g_rho goes where logreg parks u
 #define D3P_P1(c)                                                      \
           {                                                            \
             const float th = fmaf(ev[h].c, sc.c, loc.c);               \
             s_e2 = fmaf(ev[h].c, ev[h].c, s_e2);                       \
             s_th2 = fmaf(th, th, s_th2);                               \
-            if (FAMILY == D3P_FAMILY_LOGREG) zdot = fmaf(xv.c, th, zdot); \
-            else { const float r = xv.c - th; s_res2 = fmaf(r, r, s_res2); } \
             u.c = ev[h].c * aa.c;                                      \
+            if (FAMILY == D3P_FAMILY_LOGREG) zdot = fmaf(xv.c, th, zdot); \
+            else {                                                     \
+              const float r = xv.c - th;                               \
+              s_res2 = fmaf(r, r, s_res2);                             \
+              gl.c = fmaf(th, a.inv_S, -(Linv * r));                   \
+              u.c = fmaf(gl.c, u.c, -(kExp ? a.inv_S : bt.c));         \
+              nrm = fmaf(gl.c, gl.c, fmaf(u.c, u.c, nrm));             \
+            }                                                          \
           }
           D3P_F4_FOREACH(D3P_P1)
 #undef D3P_P1
           st4(us + e0, u);
+          if (FAMILY == D3P_FAMILY_GAUSS) st4(xs + e0, gl);
         }
       }
       if (FAMILY == D3P_FAMILY_LOGREG) zdot = gsum<LPE>(zdot, 0xffffffffu);
@@ -233,10 +242,9 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
       }
       const float loss_i = 0.5f * s_th2 - 0.5f * s_e2 - sum_log_s - a.N * loglik;
 
-      // ---- loop B: gradients (g_loc overwrites x, g_rho overwrites u in the staging buffers), norm ----
-      float nrm = 0.f;
+      // ---- loop B (logreg: needs the logit first): gradients (g_loc overwrites x, g_rho overwrites u), norm ----
 #pragma unroll 2
-      for (int kk = 0; kk < NCH; ++kk) {
+      for (int kk = 0; kk < (FAMILY == D3P_FAMILY_LOGREG ? NCH : 0); ++kk) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int e0 = h * HALF + 4 * (sl + LPE * kk);
