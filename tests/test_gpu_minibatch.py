@@ -107,6 +107,30 @@ def test_poisson_full_size_properties(cuda):
     assert np.array_equal(_np(idx[:len(top_sel)]), top_sel)
 
 
+@pytest.mark.parametrize("N,q,max_b,seed", [(10_000_000, .01, 100_736, 3),      # BASELINE config 2
+                                            (20_000_000, .01, 201_041, 4)])     # BASELINE config 4
+def test_poisson_full_size_bit_exact(cuda, N, q, max_b, seed):
+    """The whole index vector (selected records and the padding slots behind them) and the count at the real
+    problem sizes, bit for bit against the oracle (numpy draws the N uniforms and argsorts them in ~1-2 s)."""
+    from d3p_b200.minibatch import poisson_sample_idxs
+    key = chacha.PRNGKey(seed)
+    idx, counts, mask = poisson_sample_idxs(key, q, N, cutoff_size=max_b)
+    oidx, onum = omb.poisson_sample_idxs(key, q, N, cutoff_size=max_b)
+    assert int(counts[0]) == onum
+    assert np.array_equal(_np(idx), oidx)
+    assert np.array_equal(_np(mask).astype(bool), np.arange(max_b) < min(onum, max_b))
+
+
+def test_feistel_full_size_bit_exact(cuda):
+    """BASELINE config 3: the 500 000 indices of one batch out of N = 50 M, bit for bit against the oracle, for
+    two batch keys (the cycle-walk depth differs per index)."""
+    from d3p_b200.util import sample_indices
+    N, B = 50_000_000, 500_000
+    for seed in (0, 11):
+        key = chacha.PRNGKey(seed)
+        assert np.array_equal(_np(sample_indices(key, N, B)).astype(np.uint32), omb.sample_indices(key, N, B))
+
+
 def test_gather_rows_masked(cuda):
     from d3p_b200.minibatch import gather_rows
     rs = np.random.RandomState(0)

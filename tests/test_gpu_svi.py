@@ -384,3 +384,59 @@ def test_c2_full_batch_properties(cuda):
     assert_close(norms[sel], ref, what="per-example norms at the full C2 batch shape")
     well = ref > 20.0            # residual sigmoid(z) - y of order one: the norm is not an amplified logit error
     assert well.sum() > 8 and np.max(np.abs(norms[sel][well] - ref[well]) / ref[well]) < 1e-5
+
+
+def test_c3_full_batch_properties(cuda):
+    """BASELINE config 3 at its real batch shape (500 000 x d = 256, N = 50 M, Gaussian family — the kernel variant
+    with 4 examples per warp and the gradient pass folded into the noise pass): the clipped sums of two position
+    ranges add up to the whole (sharding identity of SURVEY 8e), the count column is the batch size, and the oracle's
+    per-example norms and losses (float64 autodiff on the same fp32 noise) on a strided subset of positions."""
+    from d3p_b200 import models, optimizers, svi
+    from oracle import threefry
+    B, d, N, C = 500_000, 256, 50_000_000, 1.0
+    g = torch.Generator(device="cuda").manual_seed(9)
+    X = 1.0 + 0.1 * torch.randn((B, d), device=cuda, generator=g)
+    fam, ofm = models.GaussianMean(d), ofam.GaussianMean(d, N)
+    s = svi.DPSVI(fam.model, fam.guide, optimizers.SGD(1.), models.Trace_ELBO(), C, 0., num_obs_total=N)
+    p = _rand_params(fam, seed=4, scale=.05)
+    p["mu_loc"] = (p["mu_loc"] + 1.0).astype(np.float32)          # near the data, like a run in progress
+    st = s.init(chacha.PRNGKey(6), X, params=p)
+    P = st.optim_state.flat.numel()
+
+    def partial_sum(shard):
+        s.shard = shard
+        norms = torch.zeros(B, device=cuda)
+        losses = torch.zeros(B, device=cuda)
+        ws, n_part, _, _ = s._run_step(st, st.rng_key, (X,), True, px_norms=norms, px_loss=losses)
+        s.shard = None
+        return (ws[:n_part * (P + 2)].reshape(n_part, P + 2).double().sum(0).cpu().numpy(), norms.cpu().numpy(),
+                losses.cpu().numpy())
+
+    whole, norms, losses = partial_sum(None)
+    lo, norms_lo, _ = partial_sum((0, 2, None))
+    hi, norms_hi, _ = partial_sum((1, 2, None))
+    assert whole[P + 1] == B and lo[P + 1] + hi[P + 1] == B
+    scale = np.max(np.abs(whole[:P]))
+    assert np.max(np.abs(lo[:P] + hi[:P] - whole[:P])) / scale < 1e-5
+    assert np.isclose(lo[P] + hi[P], whole[P], rtol=1e-5)
+    assert np.linalg.norm(whole[:P]) <= B * C * (1 + 1e-5)
+    half = (B + 1) // 2
+    assert np.array_equal(norms[:half], norms_lo[:half]) and np.array_equal(norms[half:], norms_hi[half:])
+    assert np.all(norms > 0)
+
+    sel = np.arange(0, B, B // 64)[:64]
+    jax_key = chacha.random_bits(st.rng_key, 32, (2,))
+    px_keys = threefry.split(jax_key, B)[sel]
+    eps = ofm.sample_eps(px_keys)
+    tp = {k: torch.tensor(v).double() for k, v in p.items()}
+    te = {k: torch.tensor(v).double() for k, v in eps.items()}
+    Xs = X[sel].cpu().double()
+
+    def loss(prm, e, xi):
+        return (1.0 / N) * ofm.neg_elbo(prm, e, xi.unsqueeze(0))
+
+    vals, grads = torch.func.vmap(torch.func.grad_and_value(loss), in_dims=(None, 0, 0))(tp, te, Xs)[::-1]
+    ref = np.sqrt(sum((v.reshape(len(sel), -1) ** 2).sum(1) for v in grads.values()).numpy())
+    assert np.max(np.abs(norms[sel] - ref) / ref) < 1e-5
+    ref_loss = vals.numpy() * N            # px_loss is reported on the observation scale (svi.py:306)
+    assert np.allclose(losses[sel], ref_loss, rtol=2e-5), (losses[sel][:4], ref_loss[:4])
