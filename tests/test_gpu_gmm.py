@@ -75,3 +75,41 @@ def test_gmm_sampler_statistics(cuda):
     a, _ = s.update(st, X)
     b, _ = s.update(st, X)
     assert torch.equal(a.optim_state.flat, b.optim_state.flat)
+
+
+def test_gmm_full_shape_properties(cuda):
+    """BASELINE config 4 at its real batch shape (max_batch_size 201 041 of N = 20 M, K = 64, d = 128): too slow for
+    the autodiff oracle, so size-independent properties — bitwise repeatability, the clipped sums of two disjoint
+    halves of the batch add up to the whole, the clipped sum is bounded by n C, norms are finite and positive."""
+    import d3p_b200.random as rng
+    K, d, N, B, C = 64, 128, 20_000_000, 201_041, 20.0
+    g = torch.Generator(device="cuda").manual_seed(2)
+    centers = 3.0 * torch.randn((K, d), device=cuda, generator=g)
+    X = centers[torch.randint(0, K, (B,), device=cuda, generator=g)] + torch.randn((B, d), device=cuda, generator=g)
+    fam = models.GaussianMixture(K, d)
+    p0 = {"alpha_log": np.zeros(K, np.float32), "mus_loc": (centers.cpu().numpy() + 0.3).astype(np.float32)}
+
+    def grad(mask):
+        s = dsvi.DPSVI(fam.model, fam.guide, optimizers.SGD(1.0), models.Trace_ELBO(), C, 0.0, num_obs_total=N)
+        st = s.init(rng.PRNGKey(1), X, params=p0)
+        before = st.optim_state.flat.clone()
+        st2, loss = s.update(st, X, mask=mask)
+        n = float(mask.sum())
+        return (before - st2.optim_state.flat) * n, float(loss)      # = obs_scale * sum_i c_i g_i
+
+    full = torch.ones(B, dtype=torch.bool, device=cuda)
+    lo = full.clone(); lo[B // 2:] = False
+    g_full, l_full = grad(full)
+    g_again, _ = grad(full)
+    assert torch.equal(g_full, g_again)
+    g_lo, _ = grad(lo)
+    g_hi, _ = grad(~lo)
+    assert float((g_lo + g_hi - g_full).abs().max() / g_full.abs().max()) < 2e-5
+    assert np.isfinite(l_full)
+    assert float(g_full.norm()) <= N * B * C * (1 + 1e-5)             # obs_scale = N for this model
+    s = dsvi.DPSVI(fam.model, fam.guide, optimizers.SGD(1.0), models.Trace_ELBO(), C, 0.0, num_obs_total=N)
+    st = s.init(rng.PRNGKey(1), X, params=p0)
+    st1, keys = s._split_rng_key(st, 2)
+    norms = torch.zeros(B, device=cuda)
+    s._run_step(st1, keys[0], (X,), True, px_norms=norms)
+    assert float(norms.min()) > 0 and bool(torch.isfinite(norms).all())
