@@ -76,26 +76,22 @@ struct EpiFwd5 {   // p = sigmoid(acc + b5); Bernoulli(probs) log-lik (numpyro c
   __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t,
                               const uint32_t (&v)[32], RowState& rs) {
     if (row >= g.M) return;
-    // all 16 row loads of this 32-column chunk are issued before the first use: the epilogue was bound by
-    // the latency of one dependent load pair per 4 columns (ncu: long-scoreboard stalls 12.8 per issue)
+    // the 8 row loads of this 32-column chunk are issued before the first use (the x_hi array holds x unmasked, so
+    // one array is read; the earlier form read hi and lo, 64 registers of staging that ended up in local memory)
     float xs[32];
     {
-      float4 xh[8], xl[8];
+      float4 xh[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const bool ok = col0 + 4 * j < g.N;          // N is a multiple of 4
         xh[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x_hi + (size_t)row * a.ldx + col0 + 4 * j)) : make_float4(0, 0, 0, 0);
-        xl[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x_lo + (size_t)row * a.ldx + col0 + 4 * j)) : make_float4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xs[4 * j] = xh[j].x + xl[j].x; xs[4 * j + 1] = xh[j].y + xl[j].y;
-        xs[4 * j + 2] = xh[j].z + xl[j].z; xs[4 * j + 3] = xh[j].w + xl[j].w;
-      }
+      for (int j = 0; j < 8; ++j) { xs[4 * j] = xh[j].x; xs[4 * j + 1] = xh[j].y; xs[4 * j + 2] = xh[j].z; xs[4 * j + 3] = xh[j].w; }
     }
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      if (col0 + j >= g.N) break;
+      if (col0 + j < g.N) {                          // a guard, not a break: the loop must unroll to keep v / xs in registers
       const float bs[4] = {__ldg(a.bias + col0 + j), __ldg(a.bias + col0 + j + 1), __ldg(a.bias + col0 + j + 2),
                            __ldg(a.bias + col0 + j + 3)};         // the bias offset need not be 16-byte aligned
       float hi[4], lo[4];
@@ -116,6 +112,7 @@ struct EpiFwd5 {   // p = sigmoid(acc + b5); Bernoulli(probs) log-lik (numpyro c
       }
       *reinterpret_cast<float4*>(a.d_hi + (size_t)row * a.ld + col0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<float4*>(a.d_lo + (size_t)row * a.ld + col0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
     }
   }
   __device__ static void end(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t n_tile, uint32_t, RowState& rs) {
@@ -246,7 +243,7 @@ __global__ void vae_prep_x_kernel(VaeArgs a) {
         const float4 v = j < n4 ? (valid ? __ldg(xs + j) : make_float4(0.f, 0.f, 0.f, 0.f)) : make_float4(1.0f, 0.f, 0.f, 0.f);
         const float4 hi = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
         const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-        oh[j] = hi;
+        oh[j] = v;               // unmasked: kind::tf32 truncates the operand itself, and EpiFwd5 reads x from here
         ol[j] = lo;
         if (j < n4) sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, sq))));
         any_lo |= (lo.x != 0.f) | (lo.y != 0.f) | (lo.z != 0.f) | (lo.w != 0.f);
@@ -255,7 +252,7 @@ __global__ void vae_prep_x_kernel(VaeArgs a) {
       for (uint32_t j = lane; j < a.D + 4; j += 32) {
         float v = j < a.D ? (valid ? a.x[src + j] : 0.f) : (j == a.D ? 1.0f : 0.0f);
         const float hi = tc::tf32_hi(v), lo = v - hi;
-        a.x_hi[(size_t)r * a.ldx + j] = hi;
+        a.x_hi[(size_t)r * a.ldx + j] = v;       // unmasked, see the vector path
         a.x_lo[(size_t)r * a.ldx + j] = lo;
         if (j < a.D) sq = fmaf(v, v, sq);
         any_lo |= (lo != 0.f);
