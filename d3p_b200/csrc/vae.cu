@@ -132,17 +132,17 @@ struct EpiBwd5 {   // delta4 = acc * softplus'(pre4) = acc * (1 - exp(-h2))
     if (row >= g.M) return;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      if (col0 + j >= g.N) break;
-      const float4 hh = *reinterpret_cast<const float4*>(a.h_hi + (size_t)row * a.ld + col0 + j);
-      const float4 hl = *reinterpret_cast<const float4*>(a.h_lo + (size_t)row * a.ld + col0 + j);
-      const float hs[4] = {hh.x + hl.x, hh.y + hl.y, hh.z + hl.z, hh.w + hl.w};
-      float d[4];
+      if (col0 + j < g.N) {
+        const float4 hh = *reinterpret_cast<const float4*>(a.h_hi + (size_t)row * a.ld + col0 + j);   // h2, unmasked
+        const float hs[4] = {hh.x, hh.y, hh.z, hh.w};
+        float d[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        d[t] = __uint_as_float(v[j + t]) * (-expm1f(-hs[t]));
-        rs.sq = fmaf(d[t], d[t], rs.sq);
+        for (int t = 0; t < 4; ++t) {
+          d[t] = __uint_as_float(v[j + t]) * (-expm1f(-hs[t]));
+          rs.sq = fmaf(d[t], d[t], rs.sq);
+        }
+        *reinterpret_cast<float4*>(a.d4 + (size_t)row * a.ld + col0 + j) = make_float4(d[0], d[1], d[2], d[3]);
       }
-      *reinterpret_cast<float4*>(a.d4 + (size_t)row * a.ld + col0 + j) = make_float4(d[0], d[1], d[2], d[3]);
     }
   }
   __device__ static void end(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t n_tile, uint32_t, RowState& rs) {
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
         sq2[e] = fmaf(h2, h2, sq2[e]);
         if (r < a.Bl) {
           const float hi = tc::tf32_hi(h2);
-          a.h2_hi[(size_t)r * H + h] = hi;
+          a.h2_hi[(size_t)r * H + h] = h2;          // unmasked (kind::tf32 truncates; consumers read h2 from here)
           a.h2_lo[(size_t)r * H + h] = h2 - hi;
         }
       }
@@ -591,8 +591,8 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_bwd_kernel(VaeArgs a) 
           const uint32_t h = h0 + 32 * t + lane;
           const bool ok = h < H;
           d1v[t] = ok ? a.cd1_hi[(size_t)r * H + h] : 0.f;
-          h2h[t] = ok ? __ldg(a.h2_hi + (size_t)r * H + h) : 0.f;
-          h2l[t] = ok ? __ldg(a.h2_lo + (size_t)r * H + h) : 0.f;
+          h2h[t] = ok ? __ldg(a.h2_hi + (size_t)r * H + h) : 0.f;      // h2, unmasked
+          h2l[t] = 0.f;
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -838,11 +838,11 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_fwd_mma_kernel(VaeArgs a)
       sq1 = fmaf(v10, v10, fmaf(v11, v11, sq1));
       const float h00 = tc::tf32_hi(v00), h01 = tc::tf32_hi(v01), h10 = tc::tf32_hi(v10), h11 = tc::tf32_hi(v11);
       if (live0) {
-        *reinterpret_cast<float2*>(a.h2_hi + (size_t)(r0 + g) * H + n) = make_float2(h00, h01);
+        *reinterpret_cast<float2*>(a.h2_hi + (size_t)(r0 + g) * H + n) = make_float2(v00, v01);     // unmasked
         *reinterpret_cast<float2*>(a.h2_lo + (size_t)(r0 + g) * H + n) = make_float2(v00 - h00, v01 - h01);
       }
       if (live1) {
-        *reinterpret_cast<float2*>(a.h2_hi + (size_t)(r0 + g + 8) * H + n) = make_float2(h10, h11);
+        *reinterpret_cast<float2*>(a.h2_hi + (size_t)(r0 + g + 8) * H + n) = make_float2(v10, v11);
         *reinterpret_cast<float2*>(a.h2_lo + (size_t)(r0 + g + 8) * H + n) = make_float2(v10 - h10, v11 - h11);
       }
     }
@@ -998,8 +998,7 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_bwd_mma_kernel(VaeArgs a)
     const float cc = s_cc[e];
     const float4 d1 = *reinterpret_cast<const float4*>(s_d1 + (size_t)e * H + h);
     const float4 d4 = *reinterpret_cast<const float4*>(a.d4 + (size_t)r * H + h);
-    const float4 hh = *reinterpret_cast<const float4*>(a.h2_hi + (size_t)r * H + h);
-    const float4 hl = *reinterpret_cast<const float4*>(a.h2_lo + (size_t)r * H + h);
+    const float4 hh = *reinterpret_cast<const float4*>(a.h2_hi + (size_t)r * H + h);      // h2, unmasked
     float4 o_hi, o_lo;
 #define D3P_SPLIT4(src_x, src_y, src_z, src_w)                                                     \
     { const float vx = (src_x), vy = (src_y), vz = (src_z), vw = (src_w);                          \
@@ -1011,7 +1010,7 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_bwd_mma_kernel(VaeArgs a)
     *reinterpret_cast<float4*>(a.cd4_hi + (size_t)r * H + h) = o_hi;
     *reinterpret_cast<float4*>(a.cd4_lo + (size_t)r * H + h) = o_lo;
     *reinterpret_cast<float4*>(a.ch2_hi + (size_t)r * a.ldh + h) =
-        make_float4(cc * (hh.x + hl.x), cc * (hh.y + hl.y), cc * (hh.z + hl.z), cc * (hh.w + hl.w));
+        make_float4(cc * hh.x, cc * hh.y, cc * hh.z, cc * hh.w);
 #undef D3P_SPLIT4
   }
   {
