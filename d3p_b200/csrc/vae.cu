@@ -171,12 +171,26 @@ struct EpiGrad {   // clipped-sum tile -> partial row `split`: weight block(s) +
       const uint32_t sc = a.split_col ? a.split_col : 0xffffffffu;
       float* p1 = row < a.main ? out + a.w_off + (size_t)row * a.w_ld : out + a.b_off;
       float* p2 = row < a.main ? out + a.w_off2 + (size_t)row * a.w_ld : out + a.b_off2;
-      if (col0 + 32 <= g.N && col0 + 32 <= sc && ((reinterpret_cast<uintptr_t>(p1 + col0) & 15) == 0)) {
+      if (col0 + 32 <= g.N && col0 + 32 <= sc) {
+        const uintptr_t mis = reinterpret_cast<uintptr_t>(p1 + col0) & 15;
+        if (mis == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)      // 128 contiguous bytes per thread
-          *reinterpret_cast<float4*>(p1 + col0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        return;
+          for (int j = 0; j < 32; j += 4)      // 128 contiguous bytes per thread
+            *reinterpret_cast<float4*>(p1 + col0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          return;
+        }
+        if (mis == 8) {
+          // the partial rows are P + 2 floats apart, so every other K split starts 8 bytes off a 16-byte boundary: 8 + 7 x 16 + 8
+          // bytes instead of 32 scalar stores (which made the dW1 GEMM the critical path of the clipped-sum wave)
+          *reinterpret_cast<float2*>(p1 + col0) = make_float2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+#pragma unroll
+          for (int j = 2; j < 30; j += 4)
+            *reinterpret_cast<float4*>(p1 + col0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          *reinterpret_cast<float2*>(p1 + col0 + 30) = make_float2(__uint_as_float(v[30]), __uint_as_float(v[31]));
+          return;
+        }
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
