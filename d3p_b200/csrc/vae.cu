@@ -130,10 +130,15 @@ struct EpiBwd5 {   // delta4 = acc * softplus'(pre4) = acc * (1 - exp(-h2))
   __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t,
                               const uint32_t (&v)[32], RowState& rs) {
     if (row >= g.M) return;
+    float4 hq[8];                                   // the 8 row loads of the chunk before the first use (h2, unmasked)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      hq[j] = col0 + 4 * j < g.N ? __ldg(reinterpret_cast<const float4*>(a.h_hi + (size_t)row * a.ld + col0 + 4 * j))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       if (col0 + j < g.N) {
-        const float4 hh = *reinterpret_cast<const float4*>(a.h_hi + (size_t)row * a.ld + col0 + j);   // h2, unmasked
+        const float4 hh = hq[j / 4];
         const float hs[4] = {hh.x, hh.y, hh.z, hh.w};
         float d[4];
 #pragma unroll
