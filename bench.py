@@ -275,6 +275,14 @@ def run_b200(args, cfg):
 
     N, q = cfg["N"], cfg["q"]
     is_vae = cfg["family"] == "vae"
+    # N > 1, outside the timed region: the sharded path (p2p update + run_epoch, logreg and VAE) must reproduce the
+    # unsharded one on small problems before anything is measured (d3p_b200/selfcheck.py); a mismatch is fatal
+    parity = None
+    if world > 1:
+        from d3p_b200 import selfcheck
+        parity = selfcheck.sharded_parity_check(device)
+        if not parity["ok"]:
+            raise RuntimeError(f"sharded-vs-unsharded parity check failed: {json.dumps(parity)}")
     dataset = make_dataset(cfg, device)
     fam = make_family(cfg)
     svi = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), cfg["C"], 1.0,
@@ -311,7 +319,12 @@ def run_b200(args, cfg):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        # fail loudly: a peer-memory exchange that timed out poisons the step (NaN) and is counted; no bench value
+        # may come out of such a run
+        if svi.peer_window is not None:
+            svi.peer_window.check(synchronize=False)
 
+    sync_all()        # ranks finish generating 41 GB of data at different times: align them before the first exchange
     sampler = ClockSampler(local_rank)
     sampler.start()
     for i in range(args.warmup):
@@ -501,6 +514,8 @@ def run_b200(args, cfg):
             line["e2e"] = e2e
         line["config"]["driver"] = "python loop: get_batch(i, state) + DPSVI.update per step"
         if world > 1:
+            line["parity_check"] = parity
+            line["peer_timeouts"] = 0 if svi.peer_window is None else svi.peer_window.timeouts()
             line["config"]["collective"] = ("clipped sums exchanged inside the finalize kernel over NVLink peer memory"
                                             if args.collective == "p2p" else "reduce kernel + ncclAllReduce(P + 2 floats)")
         if epoch_line is not None:

@@ -12,6 +12,7 @@ from . import _build
 MAX_LEAVES = 16
 
 OK = 0
+ERR_PEER_TIMEOUT = -5
 FAMILY_LOGREG, FAMILY_GAUSS = 0, 1
 LINK_EXP, LINK_SOFTPLUS = 0, 1
 OPT_NONE, OPT_SGD, OPT_ADAM, OPT_ADADP = 0, 1, 2, 3
@@ -108,6 +109,9 @@ _SIGNATURES = {
                                                C.c_uint32, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "d3p_comm_connect": (C.c_int32, [_vp, C.POINTER(C.c_uint8)]),
     "d3p_comm_timeouts": (C.c_int32, [_vp, _u32p]),
+    "d3p_comm_window": (C.c_int32, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "d3p_comm_connect_local": (C.c_int32, [_vp, C.POINTER(C.c_void_p)]),
+    "d3p_comm_set_timeout_ms": (C.c_int32, [_vp, C.c_uint32]),
     "d3p_comm_destroy": (C.c_int32, [_vp]),
     "d3p_perturb_finalize_p2p_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(LeafTable),
                                                  C.c_float, C.c_float, C.c_float, C.c_int32, _vp,

@@ -24,8 +24,12 @@ struct d3p_comm {
   size_t err_off, ll_off, ll_stride, total;     // ll: u64 [2][world][ll_stride]
   size_t samp_off, samp_stride;                 // 2 x [masks u16[n_blocks] | tagged tile counts u32[n_tiles]]
   uint8_t* local;                               // this rank's window
+  uint32_t* err_host;                           // pinned, device-mapped mirror of the window's time-out counter
+  uint32_t* err_host_dev;                       // device address of err_host
+  unsigned long long timeout_ns;                // spin time-out of the waiting kernels
   uint8_t* peer[D3P_COMM_MAX_RANKS];            // mapped windows (peer[rank] == local)
   bool connected;
+  bool ipc;                                     // peers were mapped with cudaIpcOpenMemHandle (else: same-process pointers)
 };
 
 namespace d3p {
@@ -39,7 +43,9 @@ struct CommDev {
   int world, rank;
   uint32_t epoch;                 // 1, 2, 3, ... one per exchange; identical on all ranks
   uint32_t extra_off;             // = max_params
-  uint32_t* err;
+  uint32_t* err;                  // window word [0]: number of spin time-outs seen by this rank's kernels (sticky)
+  uint32_t* err_host;             // host-mapped mirror: the host polls it without synchronising the device
+  unsigned long long timeout_ns;
   unsigned long long* ll_local;                        // this epoch's [world][ll_stride] block of my window
   unsigned long long* ll_peer[D3P_COMM_MAX_RANKS];     // row `rank` of this epoch's block in every peer's window
   size_t ll_stride;
@@ -65,21 +71,38 @@ D3P_D void ll_push(const CommDev& c, size_t j, float v) {
   for (int r = 0; r < c.world; ++r)
     if (r != c.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(c.ll_peer[r] + j), "l"(w) : "memory");
 }
-// wait for rank src's slot j of this epoch (spins on LOCAL memory)
+D3P_D unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// A peer did not deliver within the time-out (it died, diverged or stalled): count it in the window (device
+// flag, read by every later finalize kernel) and in the host-mapped mirror (read by the next d3p_* call).
+D3P_D void comm_flag_timeout(uint32_t* err, uint32_t* err_host) {
+  atomicAdd(err, 1u);
+  atomicAdd_system(err_host, 1u);
+}
+// wait for rank src's slot j of this epoch (spins on LOCAL memory).  A slot whose tag never matches is NOT
+// consumed: the result is NaN, which poisons this step's gradient, parameters and loss on this rank and, through
+// the next exchange, on every rank; the error is sticky (comm_next refuses further exchanges).
 D3P_D float ll_wait(const CommDev& c, int src, size_t j) {
   const unsigned long long* p = c.ll_local + (size_t)src * c.ll_stride + j;
   unsigned long long w;
-  const long long t0 = clock64();
-  for (;;) {
+  unsigned long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-    if ((uint32_t)(w >> 32) == c.epoch) break;
-    if (clock64() - t0 > (3LL << 31)) {            // ~3 s: a peer died or diverged; do not hang the GPU
-      atomicAdd(c.err, 1u);
-      break;
+    if ((uint32_t)(w >> 32) == c.epoch) return __uint_as_float((uint32_t)w);
+    if ((spins & 1023u) == 1023u) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > c.timeout_ns || ld_relaxed_sys_u32(c.err) != 0u) break;   // once flagged, nobody waits long
     }
   }
-  return __uint_as_float((uint32_t)w);
+  comm_flag_timeout(c.err, c.err_host);
+  return __uint_as_float(0x7fc00000u);
 }
+// true when an earlier kernel of this rank has seen a time-out (sampler or exchange): the caller poisons its output
+D3P_D bool comm_poisoned(const CommDev& c) { return ld_relaxed_sys_u32(c.err) != 0u; }
 
 // Sharded Poisson sampler (samplers.cu): rank r draws the selectors of its slice of the records, keeps the
 // 16-bit selection masks in its window and pushes one tagged word {count (low 16 bits), epoch} per tile to
@@ -91,26 +114,36 @@ struct SampDev {
   uint32_t epoch;                             // 16-bit tag = epoch & 0xffff
   uint32_t tiles_per_rank, n_tiles;
   uint32_t* err;
+  uint32_t* err_host;
+  unsigned long long timeout_ns;
   const uint16_t* masks_peer[D3P_COMM_MAX_RANKS];     // this epoch's buffer in every window
   uint32_t* counts_peer[D3P_COMM_MAX_RANKS];          // tagged counts: owners push into every window
   uint16_t* masks_local;
   const uint32_t* counts_local;
 };
-bool samp_next(d3p_comm* comm, uint32_t n_records, uint32_t n_tiles, SampDev* out);
+// D3P_OK, D3P_ERR_INVALID_ARGUMENT (shapes do not fit) or D3P_ERR_PEER_TIMEOUT (sticky: an earlier exchange timed out)
+int32_t samp_next(d3p_comm* comm, uint32_t n_records, uint32_t n_tiles, SampDev* out);
 
+// A count that never arrives is flagged (sticky, see ll_wait) and read as 0; the finalize kernel of the step
+// sees the flag and poisons the update.
 D3P_D uint32_t samp_wait_count(const SampDev& sd, uint32_t tile) {
   const uint32_t tag = sd.epoch & 0xffffu;
   uint32_t w;
-  const long long t0 = clock64();
-  for (;;) {
+  unsigned long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
     w = ld_relaxed_sys_u32(sd.counts_local + tile);
-    if ((w >> 16) == tag) break;
-    if (clock64() - t0 > (3LL << 31)) { atomicAdd(sd.err, 1u); break; }
+    if ((w >> 16) == tag) return w & 0xffffu;
+    if ((spins & 1023u) == 1023u) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > sd.timeout_ns || ld_relaxed_sys_u32(sd.err) != 0u) break;
+    }
   }
-  return w & 0xffffu;
+  comm_flag_timeout(sd.err, sd.err_host);
+  return 0u;
 }
 
-// Fills the device view for the next exchange (advances the epoch); false if the shapes do not fit.
-bool comm_next(d3p_comm* comm, uint32_t n_params, uint32_t n_ctas, CommDev* out);
+// Fills the device view for the next exchange (advances the epoch).  Same return codes as samp_next.
+int32_t comm_next(d3p_comm* comm, uint32_t n_params, uint32_t n_ctas, CommDev* out);
 
 }  // namespace d3p

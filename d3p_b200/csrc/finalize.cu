@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
     const size_t jn = comm.extra_off + 2 * (size_t)blockIdx.x;
     if (live) ll_push(comm, j, mine);
     if (lane == 0) { ll_push(comm, jn, my_n); ll_push(comm, jn + 1, my_loss); }
-    sum = 0.f; n_all = 0.f; loss_all = 0.f;
+    // an earlier time-out on this rank (sampler counts, a previous exchange) poisons everything from here on
+    sum = comm_poisoned(comm) ? __uint_as_float(0x7fc00000u) : 0.f;
+    n_all = 0.f; loss_all = sum;
     for (int r = 0; r < comm.world; ++r) {
       const bool me = r == comm.rank;
       if (live) sum += me ? mine : ll_wait(comm, r, j);
@@ -257,9 +259,10 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
     const size_t jn = comm.extra_off + 2 * (size_t)blockIdx.x;
     float mine[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { mine[i] = sum[i]; if (ok[i]) ll_push(comm, jj[i], mine[i]); sum[i] = 0.f; }
+    const float zero = comm_poisoned(comm) ? __uint_as_float(0x7fc00000u) : 0.f;   // see finalize_kernel
+    for (int i = 0; i < 4; ++i) { mine[i] = sum[i]; if (ok[i]) ll_push(comm, jj[i], mine[i]); sum[i] = zero; }
     if (threadIdx.x == 0) { ll_push(comm, jn, my_n); ll_push(comm, jn + 1, my_loss); }
-    n_all = 0.f; loss_all = 0.f;
+    n_all = 0.f; loss_all = zero;
     for (int r = 0; r < comm.world; ++r) {
       const bool me = r == comm.rank;
 #pragma unroll
@@ -445,13 +448,13 @@ extern "C" int32_t d3p_perturb_finalize_p2p_f32(const float* partials_d, uint32_
     ct.n_chunks = nc;
     if (covered == P && nc > 0) {
       const unsigned qgrid = (nc * 4 + 255) / 256;
-      if (comm && !comm_next(comm, P, qgrid, &cd)) return D3P_ERR_INVALID_ARGUMENT;
+      if (comm) { const int32_t rc = comm_next(comm, P, qgrid, &cd); if (rc != D3P_OK) return rc; }
       finalize_quad_kernel<<<qgrid, 256, 0, (cudaStream_t)stream>>>(a, lt, ss, ct, cd);
       return check_launch();
     }
   }
   unsigned grid = P ? (P + 31) / 32 : 1;
-  if (comm && !comm_next(comm, P, grid, &cd)) return D3P_ERR_INVALID_ARGUMENT;
+  if (comm) { const int32_t rc = comm_next(comm, P, grid, &cd); if (rc != D3P_OK) return rc; }
   // Programmatic dependent launch: when the preceding kernel on the stream releases its dependents early (the
   // fused step kernels do, at their first instruction), the CTAs of this latency-bound kernel are placed on SMs as
   // those drain and wait in griddepcontrol.wait for the producer grid to complete and flush, which takes the

@@ -137,6 +137,7 @@ const char* d3p_error_string(int32_t code) {
     case D3P_ERR_CUDA: return "CUDA error (kernel launch failed)";
     case D3P_ERR_UNSUPPORTED: return "unsupported configuration";
     case D3P_ERR_WORKSPACE: return "workspace too small";
+    case D3P_ERR_PEER_TIMEOUT: return "a peer-memory exchange timed out earlier (sticky; the replicas have diverged)";
     default: return "unknown error";
   }
 }

@@ -363,7 +363,7 @@ int32_t d3p_poisson_sample_sharded(d3p_comm* comm, const uint32_t state_h[16], f
     return D3P_ERR_UNSUPPORTED;
   SampDev sd;
   memset(&sd, 0, sizeof(sd));
-  if (!samp_next(comm, n_records, n_tiles, &sd)) return D3P_ERR_INVALID_ARGUMENT;
+  { const int32_t rc = samp_next(comm, n_records, n_tiles, &sd); if (rc != D3P_OK) return rc; }
   cudaStream_t s = (cudaStream_t)stream;
   // slices in DESCENDING record order: rank 0 draws the top tiles, whose records fill the first positions
   const uint32_t hi = n_tiles > (uint32_t)sd.rank * sd.tiles_per_rank ? n_tiles - (uint32_t)sd.rank * sd.tiles_per_rank : 0;

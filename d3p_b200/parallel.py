@@ -21,15 +21,17 @@ class PeerWindow:
     ``P + 2`` clipped sums there and reads the peers' copies, so a sharded step needs neither a
     reduce kernel nor an NCCL launch.  ``torch.distributed`` is used once, to swap the IPC handles."""
 
-    def __init__(self, rank, world_size, max_params, group=None, max_records=0):
+    def __init__(self, rank, world_size, max_params, group=None, max_records=0, _connect=True):
         import ctypes as C
         self.rank, self.world_size, self.group = rank, world_size, group
         self.max_records = int(max_records)
+        self.max_params = int(max_params)
+        self._local_group = None
         handle = (C.c_uint8 * 64)()
         self._comm = C.c_void_p()
         _n.check(_n.lib().d3p_comm_create(rank, world_size, int(max_params), self.max_records, C.byref(self._comm),
                                           handle), "comm_create")
-        if world_size > 1:
+        if world_size > 1 and _connect:
             handles = [None] * world_size
             dist.all_gather_object(handles, bytes(handle), group=group)
             blob = (C.c_uint8 * (64 * world_size)).from_buffer_copy(b"".join(handles))
@@ -41,7 +43,27 @@ class PeerWindow:
             if any(r != _n.OK for r in rcs):
                 self.close()
                 _n.check(next(r for r in rcs if r != _n.OK), "comm_connect (on some rank)")
-        self.max_params = int(max_params)
+
+    @classmethod
+    def local_group(cls, world_size, max_params, max_records=0):
+        """``world_size`` windows owned by THIS process and connected by pointer (``d3p_comm_connect_local``):
+        logical ranks that share one device (each driven on its own stream) or several devices of one
+        process with peer access enabled.  No ``torch.distributed``.  Used by the one-GPU tests of the
+        exchange protocol; the launch order across ranks is the caller's business (a rank's kernel spins
+        until the peers' kernels have been launched)."""
+        import ctypes as C
+        wins = [cls(r, world_size, max_params, None, max_records, _connect=False) for r in range(world_size)]
+        ptrs = (C.c_void_p * world_size)()
+        for r, w in enumerate(wins):
+            p = C.c_void_p()
+            _n.check(_n.lib().d3p_comm_window(w._comm, C.byref(p), None), "comm_window")
+            ptrs[r] = p.value
+        if world_size > 1:
+            for w in wins:
+                _n.check(_n.lib().d3p_comm_connect_local(w._comm, ptrs), "comm_connect_local")
+        for w in wins:
+            w._local_group = wins
+        return wins
 
     @property
     def ptr(self):
@@ -52,17 +74,35 @@ class PeerWindow:
         every rank must call it at the same point; the old window is closed)."""
         if n_records <= self.max_records:
             return self
-        torch.cuda.synchronize()
+        if self._local_group is not None:
+            raise ValueError("a local_group window must be created with max_records large enough for the sampler")
+        self.check()
         if self.world_size > 1:
             dist.barrier(group=self.group)
         self.close()
         return PeerWindow(self.rank, self.world_size, self.max_params, self.group, max_records=n_records)
 
     def timeouts(self):
+        """Exchanges that timed out on this rank so far (host-mapped counter, no device synchronisation: covers
+        the work that has completed).  Non-zero is fatal: the step that saw it was poisoned with NaN and every
+        later call through this window raises ``D3PNativeError`` (``D3P_ERR_PEER_TIMEOUT``)."""
         import ctypes as C
         out = C.c_uint32(0)
         _n.check(_n.lib().d3p_comm_timeouts(self._comm, C.byref(out)), "comm_timeouts")
         return out.value
+
+    def set_timeout_ms(self, ms):
+        """How long a kernel waits for a peer's words before it gives up (default 10 s)."""
+        _n.check(_n.lib().d3p_comm_set_timeout_ms(self._comm, int(ms)), "comm_set_timeout_ms")
+
+    def check(self, synchronize=True):
+        """Raise on every rank's own evidence if an exchange timed out (``synchronize=True`` drains the device first)."""
+        if synchronize:
+            torch.cuda.synchronize()
+        n = self.timeouts()
+        if n:
+            raise _n.D3PNativeError(f"rank {self.rank}: {n} peer-memory exchange time-out(s); this step was poisoned "
+                                    "(NaN) and the replicas can no longer be trusted")
 
     def close(self):
         if self._comm:
@@ -70,11 +110,19 @@ class PeerWindow:
             self._comm = None
 
 
-def shard_dpsvi(svi, rank=None, world_size=None, group=None, backend="p2p", max_params=None):
+def shard_dpsvi(svi, rank=None, world_size=None, group=None, backend="p2p", max_params=None, window=None):
     """Make ``svi.update`` / ``svi.run_epoch`` process only this rank's slice of every batch.
 
     ``backend="p2p"`` (default): the clipped sums meet inside the finalize kernel over NVLink peer
-    memory (``PeerWindow``); ``backend="nccl"``: reduce kernel + ``ncclAllReduce`` of ``P + 2`` floats."""
+    memory (``PeerWindow``); ``backend="nccl"``: reduce kernel + ``ncclAllReduce`` of ``P + 2`` floats.
+
+    A step that waits longer than the window's time-out for a peer is poisoned (NaN loss and parameters) and
+    every later ``update`` / ``run_epoch`` raises ``D3PNativeError``; ``svi.peer_window.check()`` asks
+    explicitly (call it at least once per epoch)."""
+    if window is not None:          # a window built by the caller (e.g. PeerWindow.local_group)
+        svi.shard = (window.rank, window.world_size, None)
+        svi.peer_window = window
+        return svi
     rank = dist.get_rank(group) if rank is None else rank
     world_size = dist.get_world_size(group) if world_size is None else world_size
     if backend not in ("p2p", "nccl", "auto"):

@@ -307,11 +307,22 @@ class DPSVI:
     def update(self, svi_state, *args, mask=True, **kwargs):
         """``d3p/svi.py:395-434``: one DP-SVI step; returns ``(new_state, loss)``.  ``loss`` is a
         0-dim CUDA tensor (asynchronous, like a jax array)."""
+        return self._update_finalize(self._update_launch_step(svi_state, args, mask))
+
+    def _update_launch_step(self, svi_state, args, mask):
+        """First half of ``update``: key split + the fused per-example-gradient / clip / sum kernels of this rank's
+        batch positions.  (Split out so that a test can drive several logical ranks on ONE device: all ranks' step
+        kernels first, then all ranks' finalize kernels, which wait for each other.)"""
         if self.family is None:
             raise ValueError("DPSVI.update needs a model family; drive the stage methods for custom models")
         svi_state, (k_grad, k_noise) = self._split_rng_key(svi_state, 2)
-        os_ = svi_state.optim_state
         ws, n_part, B, P = self._run_step(svi_state, k_grad, args, mask)
+        return svi_state, k_noise, ws, n_part, B, P
+
+    def _update_finalize(self, ctx):
+        """Second half of ``update``: reduce (+ exchange with the peers) + noise + rescale + optimizer."""
+        svi_state, k_noise, ws, n_part, B, P = ctx
+        os_ = svi_state.optim_state
         partials = ws
         comm = None
         if self.shard is not None:
@@ -320,7 +331,6 @@ class DPSVI:
             else:                                               # sums meet inside the finalize kernel
                 comm = self.peer_window.ptr
         if self.donate_state:
-            buf = os_.flat
             new_flat, new_m, new_v = os_.flat, os_.m, os_.v
         else:
             new_flat = os_.flat.clone()

@@ -29,6 +29,7 @@ extern "C" {
 #define D3P_ERR_CUDA (-2)
 #define D3P_ERR_UNSUPPORTED (-3)
 #define D3P_ERR_WORKSPACE (-4)
+#define D3P_ERR_PEER_TIMEOUT (-5) /* sticky: a peer-memory exchange of this window timed out earlier */
 
 #define D3P_MAX_LEAVES 16
 
@@ -268,14 +269,24 @@ int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_partials, u
  *   connect : map the windows of all ranks (handles_h = world x 64 bytes, gathered by the caller,
  *             e.g. torch.distributed.all_gather_object)
  * All ranks must issue the same sequence of d3p_perturb_finalize_p2p_f32 /
- * d3p_poisson_sample_sharded calls.  A peer that never shows up makes the kernel give up after
- * ~3 s and count a time-out instead of hanging the GPU; d3p_comm_timeouts reads the counter
- * (synchronises).
+ * d3p_poisson_sample_sharded calls.  A peer that never shows up makes the waiting kernel give up
+ * after the time-out (default 10 s, d3p_comm_set_timeout_ms) instead of hanging the GPU.  A slot whose
+ * tag never matched is never consumed: the kernel yields NaN for it, which poisons that step's
+ * gradient, parameters and loss (and, through the next exchange, every replica), and the error is
+ * STICKY: the time-out is counted in a host-mapped word, and every later call that takes the window
+ * (d3p_perturb_finalize_p2p_f32, d3p_poisson_sample_sharded, d3p_dpsvi_run_epoch_*) returns
+ * D3P_ERR_PEER_TIMEOUT.  d3p_comm_timeouts reads that word without synchronising the device (it
+ * covers the work that has completed; synchronise the stream first for a definitive answer).
  * ------------------------------------------------------------------------------------------ */
 int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_params, uint32_t max_records /* 0: no sharded
                         sampler */, d3p_comm** comm_out, uint8_t handle_out_h[64]);
 int32_t d3p_comm_connect(d3p_comm* comm, const uint8_t* handles_h);
+/* Same-process peers instead of CUDA IPC (one process driving several GPUs with peer access enabled, or
+ * several logical ranks on one device, each on its own stream): windows_h[r] = d3p_comm_window of rank r. */
+int32_t d3p_comm_window(d3p_comm* comm, void** window_out_h, size_t* bytes_out_h);
+int32_t d3p_comm_connect_local(d3p_comm* comm, void* const* windows_h);
 int32_t d3p_comm_timeouts(d3p_comm* comm, uint32_t* count_out_h);
+int32_t d3p_comm_set_timeout_ms(d3p_comm* comm, uint32_t timeout_ms);
 int32_t d3p_comm_destroy(d3p_comm* comm);
 /* d3p_poisson_sample with the selector draw (the expensive part: N / 16 ChaCha blocks) split over the
  * ranks: rank r draws its slice of the records, publishes 16-bit selection masks and per-tile counts in

@@ -14,34 +14,6 @@ import d3p_b200.random as rng  # noqa: E402
 from d3p_b200 import minibatch as mb, models, optimizers, parallel, svi as dsvi  # noqa: E402
 
 
-def run(fam, dataset, C, sharded, steps=3, epoch=False):
-    """sharded: None (single GPU), "nccl" or "p2p" (sums exchanged inside the finalize kernel)."""
-    s = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), C, 1.0, num_obs_total=len(dataset[0]))
-    if sharded:
-        parallel.shard_dpsvi(s, backend=sharded)
-    init, get = mb.poisson_batchify_data(dataset, 0.05, .99)
-    key = rng.PRNGKey(5)
-    key, k_init, k_fetch = rng.split(key, 3)
-    _, bst = init(k_fetch)
-    batch, mask = get(0, bst)
-    st = s.init(k_init, *batch)
-    losses = []
-    if epoch:
-        st, stats = s.run_epoch(st, get, bst, steps)
-        losses = [float(v) for v in stats[:, 0].cpu()]
-    else:
-        for i in range(steps):
-            batch, mask = get(i, bst)
-            st, loss = s.update(st, *batch, mask=mask)
-            losses.append(float(loss))
-    torch.cuda.synchronize()
-    if s.peer_window is not None:
-        assert s.peer_window.timeouts() == 0, "peer exchange timed out"
-        dist.barrier()
-        s.peer_window.close()
-    return st.optim_state.flat.clone(), losses, np.asarray(st.rng_key).copy()
-
-
 def check_local_rows(dev, rank, world):
     """minibatch.LocalRows: feeding only this rank's rows must equal feeding the whole batch (bit for bit)."""
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -115,30 +87,10 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
-    g = torch.Generator(device="cuda").manual_seed(0)      # same data on every rank
-    cases = []
-    X = torch.randn((20000, 256), device=dev, generator=g)
-    y = (torch.rand(20000, device=dev, generator=g) < 0.5).to(torch.int32)
-    cases.append(("logreg", models.LogisticRegression(256), (X, y), 1.0))
-    Xg = 1 + 0.1 * torch.randn((20000, 512), device=dev, generator=g)
-    cases.append(("gauss", models.GaussianMean(512), (Xg,), 1.0))
-    Xv = (torch.rand((8000, 8, 8), device=dev, generator=g) < 0.3).float()
-    cases.append(("vae", models.VAE(64, 40, 8, init_std=0.1), (Xv,), 5.0))
-    ok = True
-    for name, fam, data, C in cases:
-        p_1, l_1, k_1 = run(fam, data, C, None)
-        modes = [("nccl", False), ("p2p", False), ("p2p", True)]      # epoch drivers: mean-field and VAE
-        for backend, epoch in modes:
-            p_sh, l_sh, k_sh = run(fam, data, C, backend, epoch=epoch)
-            err = float((p_sh - p_1).abs().max() / p_1.abs().max())
-            gathered = [torch.empty_like(p_sh) for _ in range(world)]
-            dist.all_gather(gathered, p_sh)
-            same = all(torch.equal(gathered[0], t) for t in gathered)
-            good = err < 1e-5 and same and np.allclose(l_sh, l_1, rtol=2e-5) and np.array_equal(k_sh, k_1)
-            ok = ok and good
-            if rank == 0:
-                print(f"{name} [{backend}{' epoch' if epoch else ''}]: sharded-vs-single rel err {err:.2e}, "
-                      f"replicas identical {same}, losses {l_sh} vs {l_1}", flush=True)
+    from d3p_b200 import selfcheck
+    res = selfcheck.sharded_parity_check(dev, which=("logreg", "gauss", "vae"),
+                                         modes=(("nccl", False), ("p2p", False), ("p2p", True)), verbose=True)
+    ok = res["ok"]
     ok = check_local_rows(dev, rank, world) and ok
     ok = check_sharded_sampler(dev, rank, world) and ok
     dist.barrier()
