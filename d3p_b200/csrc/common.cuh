@@ -105,8 +105,11 @@ D3P_HD float bits_to_unit_float(uint32_t bits) {
 template <bool kFast>
 D3P_D float erfinv_f32(float x) {
   float w;
-  if (kFast) w = -__logf(fmaf(-x, x, 1.0f));
-  else w = -log1pf(-x * x);
+  // XLA lowers erf_inv's w = -log1p(x * -x) with the PRODUCT ROUNDED to float32 first: in the tails (|x| -> 1) that
+  // rounding moves w by up to 2e-4 and the result by ~1e-5 relative, so it is part of the reference's arithmetic
+  // and is kept (a fused 1 - x*x is more accurate and therefore different)
+  if (kFast) w = -__logf(__fadd_rn(1.0f, __fmul_rn(-x, x)));
+  else w = -log1pf(__fmul_rn(-x, x));
   float p;
   if (w < 5.0f) {
     w = w - 2.5f;
@@ -149,7 +152,8 @@ D3P_D float bits_to_normal(uint32_t bits) {
 // Same function as bits_to_normal, restructured for throughput:
 //   * u = fma(f, 2, lo) already satisfies u >= lo and |u| < 1, so the max() and the |x| == 1 test
 //     of the reference transform are no-ops and are dropped (bit-identical);
-//   * w - 2.5 = fma(lg2(1 - u*u), -ln2, -2.5) through MUFU.LG2 (absolute error ~4e-7 in w);
+//   * w - 2.5 = fma(lg2(1 - rn(u*u)), -ln2, -2.5) through MUFU.LG2 (absolute error ~4e-7 in w); u*u is rounded to
+//     float32 before the subtraction like XLA's log1p(x * -x) (see erfinv_f32);
 //   * sqrt(2) is folded into the polynomial coefficients (<= 1 ulp difference);
 //   * the |u| > 0.9966 tail (0.34 % of the variates) is not evaluated here: the caller checks
 //     `needs_tail` for a whole group of variates with one warp-uniform branch and patches them
@@ -166,7 +170,7 @@ D3P_D float lg2_ftz(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(
 D3P_D float sqrt_ftz(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 D3P_D float normal_central(float u, float& w_out) {
-  const float l2 = lg2_ftz(fmaf(-u, u, 1.0f));
+  const float l2 = lg2_ftz(__fadd_rn(1.0f, __fmul_rn(-u, u)));   // product rounded first, as XLA's log1p(x * -x)
   w_out = l2;                                            // w = -ln2 * l2 ; tail iff w >= 5
   const float w = fmaf(l2, -0.693147182f, -2.5f);
   float p = 2.81022636e-08f * D3P_SQRT2;

@@ -2,8 +2,15 @@
 // accuracy, with A = a_hi + a_lo and B = b_hi + b_lo pre-split by the producing kernel
 // (a_hi = A with the 13 low mantissa bits cleared, exactly representable in TF32):
 //     D = a_hi*b_hi + a_hi*b_lo + a_lo*b_hi        (the a_lo*b_lo term is < 2^-22 relative)
-// Each term is one tcgen05.mma.kind::tf32 into the same TMEM accumulator.  An operand whose values
-// are exact in TF32 (e.g. binarised pixels) passes lo = NULL and its correction MMA is skipped.
+// Each term is one tcgen05.mma.kind::tf32.  An operand whose values are exact in TF32 (e.g. binarised pixels)
+// passes lo = NULL and its correction MMA is skipped.
+//
+// TWO TMEM accumulators.  Measured (scripts/gemm_accuracy.py): the fp32 accumulation of tcgen05.mma TRUNCATES —
+// with operands exact in TF32 (every product exact) a K = 4096 sum of positive terms comes out 3.0e-5 low, i.e.
+// ~2^-24 per UMMA_K = 8 step, and 3 MMAs per step into one accumulator tripled that (8.8e-5).  The small cross
+// terms a_hi*b_lo + a_lo*b_hi (2^-10 of the product) therefore go to a second accumulator (columns [BN, 2 BN)),
+// where their truncation is 2^-10 times smaller, and the epilogue adds the two in fp32 (round to nearest): the
+// main accumulator sees one addition per k-step instead of three.
 //
 // In-kernel split (GemmOperand::split): the operand arrives as ONE fp32 array.  kind::tf32 reads the top 19 bits of
 // a 32-bit operand word, i.e. it TRUNCATES (measured: scripts/tf32_operand_rounding.py — raw x as the hi operand
@@ -55,7 +62,8 @@ struct GemmCfg {
   // operands that are really present (an absent / all-zero lo part frees its slots for deeper pipelining)
   static constexpr uint32_t kRingBytes = 220u * 1024u;
   static constexpr uint32_t kSmemBytes = kRingBytes + 1024;
-  static constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  // hi*hi accumulator in columns [0, BN), cross-term accumulator in [BN, 2 BN); allocations are powers of two
+  static constexpr uint32_t kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32, 256]");
   static_assert(kRingBytes >= 2 * kStageBytes, "tile too large for a 2-stage pipeline");
 };
@@ -166,7 +174,8 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
       constexpr uint32_t a_step = A_MN ? 1024u : 32u, b_step = B_MN ? 1024u : 32u;
       constexpr uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
       constexpr uint32_t a_lt = A_MN ? kLayoutSw128Base32 : kLayoutSw128, b_lt = B_MN ? kLayoutSw128Base32 : kLayoutSw128;
-      uint32_t it = 0, accumulate = 0;
+      uint32_t it = 0, accumulate = 0, accumulate_x = 0;
+      const uint32_t tmem_x = tmem_base + (uint32_t)BN;      // cross-term accumulator
       for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++it) {
         const uint32_t s = it % stages;
         const uint32_t ph = (it / stages) & 1u;
@@ -181,8 +190,14 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
           const uint64_t db_hi = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
           umma_tf32(tmem_base, da_hi, db_hi, idesc, accumulate);
           accumulate = 1;
-          if (has_b_lo) umma_tf32(tmem_base, da_hi, make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt), idesc, 1);
-          if (has_a_lo) umma_tf32(tmem_base, make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt), db_hi, idesc, 1);
+          if (has_b_lo) {
+            umma_tf32(tmem_x, da_hi, make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt), idesc, accumulate_x);
+            accumulate_x = 1;
+          }
+          if (has_a_lo) {
+            umma_tf32(tmem_x, make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt), db_hi, idesc, accumulate_x);
+            accumulate_x = 1;
+          }
         }
         umma_commit(&bar_empty[s]);     // frees the stage once these MMAs have read it
         if (any_conv) umma_commit(&bar_lo_empty[l]);
@@ -229,6 +244,12 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
     for (int c = part; c < BN / 32; c += PARTS) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (has_a_lo || has_b_lo) {                     // + the cross-term accumulator (fp32, round to nearest)
+        uint32_t x[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), x);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(x[j]));
+      }
       Epi::tile(ea, g, row, n_tile * BN + c * 32, split, v, rs);
     }
     Epi::end(ea, g, row, slot, split, rs);

@@ -213,10 +213,15 @@ class DPSVI:
             mask_arr = np.asarray(mask, dtype=bool)
             num_elements = int(mask_arr.sum())
 
-        tparams = {k: torch.tensor(np.asarray(v, np.float32)) for k, v in params.items()}
-        teps = {k: torch.tensor(v) for k, v in eps.items()}
-        targs = tuple(torch.tensor(np.asarray(a)) for a in args)
-        tmask = torch.tensor(mask_arr.astype(np.float32))
+        # grad_dtype (attribute, default float32 = the reference's arithmetic): float64 evaluates the SAME float32
+        # inputs (parameters, guide noise, data) in double precision, which takes the oracle's own rounding out of a
+        # comparison (used where a 1024-term float32 dot product on either side is the larger error)
+        gd = np.dtype(getattr(self, "grad_dtype", np.float32))
+        fl = lambda a: a.astype(gd) if np.issubdtype(np.asarray(a).dtype, np.floating) else a      # noqa: E731
+        tparams = {k: torch.tensor(np.asarray(v, np.float32).astype(gd)) for k, v in params.items()}
+        teps = {k: torch.tensor(fl(np.asarray(v))) for k, v in eps.items()}
+        targs = tuple(torch.tensor(fl(np.asarray(a))) for a in args)
+        tmask = torch.tensor(mask_arr.astype(gd))
 
         def wrapped_px_loss(prms, e, loss_args, m):
             new_args = tuple(a.unsqueeze(0) for a in loss_args)
@@ -227,7 +232,7 @@ class DPSVI:
         px_grads = {k: v.numpy() for k, v in px_grads.items()}
         px_losses = px_losses.numpy()
         f = np.float32(0.) if num_elements == 0 else np.float32(B / num_elements)
-        px_losses = (px_losses * np.float32(obs_scale) * f).astype(np.float32)
+        px_losses = (px_losses * gd.type(obs_scale) * gd.type(f)).astype(gd)
         return state, px_losses, px_grads, num_elements, f
 
     def _clip_gradients(self, state, px_grads):

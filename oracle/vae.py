@@ -101,3 +101,57 @@ class VAE:
 
     def flat_param_order(self):
         return list(NAMES)
+
+
+def explicit_clipped_sum(params, X, eps_z, clip, mask, site_scale=1.0, obs_scale=1.0):
+    """The same per-example gradients WITHOUT autodiff, in float64, at any batch size: forward and delta
+    backward passes as matmuls, per-example norms through the ghost-norm identity
+    ``||a (x) delta||^2 = ||a||^2 ||delta||^2`` and the clipped sum as ``A^T diag(c) Delta`` — the shape the
+    CUDA path computes in.  Pinned against ``vmap(grad(neg_elbo))`` (``tests/test_oracle_families.py``); used
+    where the autodiff oracle is too slow (BASELINE config 5 at its real batch of 4096).
+
+    Follows ``d3p/svi.py:283-290`` (loss_i = neg_elbo_i / obs_scale * mask_i), ``:106-124`` (clip factor
+    ``1 / max(1, norm / C)``) and the model/guide of ``examples/vae.py:65-153`` (see the module docstring).
+    Returns ``(px_loss [B], px_norm [B], clipped_sum {name: array})``: losses and norms of the gradient of
+    ``loss_i`` (masked examples: 0), ``clipped_sum = sum_i c_i grad loss_i``.
+    """
+    f8 = np.float64
+    p = {k: np.asarray(v, f8) for k, v in params.items()}
+    B = X.shape[0]
+    x = np.asarray(X, f8).reshape(B, -1)
+    eps = np.asarray(eps_z, f8).reshape(B, -1)
+    m = np.asarray(mask, f8).reshape(B)
+    s = f8(site_scale)
+    sig = lambda t: 1.0 / (1.0 + np.exp(-t))                                     # noqa: E731
+    softplus = lambda t: np.maximum(t, 0) + np.log1p(np.exp(-np.abs(t)))         # noqa: E731
+    pre1 = x @ p[W1] + p[B1]
+    h1 = softplus(pre1)
+    z_loc = h1 @ p[W2] + p[B2]
+    t3 = h1 @ p[W3] + p[B3]
+    z_std = np.exp(t3)
+    z = z_loc + z_std * eps
+    pre4 = z @ p[W4] + p[B4]
+    h2 = softplus(pre4)
+    logits = h2 @ p[W5] + p[B5]
+    # clamp_probs is the identity for |logit| < 15.9 (float32 eps); the explicit form does not model the clamp
+    assert np.max(np.abs(logits)) < 15.0, "explicit oracle: logits too large for the unclamped Bernoulli form"
+    half_log_2pi = 0.5 * np.log(2 * np.pi)
+    log_q = np.sum(-0.5 * eps ** 2 - t3 - half_log_2pi, axis=1)
+    log_pz = np.sum(-0.5 * z ** 2 - half_log_2pi, axis=1)
+    log_px = np.sum(x * logits - softplus(logits), axis=1)
+    w = m / f8(obs_scale)                                                        # d loss_i / d neg_elbo_i
+    px_loss = -(s * (log_pz + log_px) - s * log_q) * w
+    d5 = (s * (sig(logits) - x)) * w[:, None]
+    d4 = (d5 @ p[W5].T) * sig(pre4)
+    dz = d4 @ p[W4].T + (s * z) * w[:, None]
+    d2 = dz
+    d3 = dz * z_std * eps - s * w[:, None]
+    d1 = (d2 @ p[W2].T + d3 @ p[W3].T) * sig(pre1)
+    sq = lambda a: np.sum(a * a, axis=1)                                         # noqa: E731
+    norm2 = ((sq(x) + 1) * sq(d1) + (sq(h1) + 1) * (sq(d2) + sq(d3)) + (sq(z) + 1) * sq(d4) + (sq(h2) + 1) * sq(d5))
+    px_norm = np.sqrt(norm2)
+    c = 1.0 / np.maximum(1.0, px_norm / f8(clip))
+    cs = {W1: x.T @ (c[:, None] * d1), B1: c @ d1, W2: h1.T @ (c[:, None] * d2), B2: c @ d2,
+          W3: h1.T @ (c[:, None] * d3), B3: c @ d3, W4: z.T @ (c[:, None] * d4), B4: c @ d4,
+          W5: h2.T @ (c[:, None] * d5), B5: c @ d5}
+    return px_loss, px_norm, cs

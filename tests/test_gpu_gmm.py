@@ -5,9 +5,12 @@ import pytest
 import torch
 
 from d3p_b200 import models, optimizers, svi as dsvi
+from helpers.tolerance import rel_err as ew_rel_err
 from oracle import chacha, gmm as ogmm, svi as osvi
 
 pytestmark = pytest.mark.gpu
+
+REL = 1e-5   # BASELINE.json: fp32 within 1e-5 relative; element-wise, floor = rms of the row (helpers/tolerance.py)
 
 
 def make(K, d, N, B, C, dp_scale, optim="adam", seed=0):
@@ -25,7 +28,9 @@ def make(K, d, N, B, C, dp_scale, optim="adam", seed=0):
     return X, o, o.init(key, X, params=p0), s, s.init(key, torch.as_tensor(X).cuda(), params=p0)
 
 
-@pytest.mark.parametrize("K,d,B", [(3, 2, 24), (8, 5, 40), (64, 128, 6)])
+# (64, 128, 96): BASELINE config 4's K and d with 96 examples (the autodiff oracle draws ~16 k gamma / normal variates
+# per example through numpy rejection loops: ~10 s)
+@pytest.mark.parametrize("K,d,B", [(3, 2, 24), (8, 5, 40), (64, 128, 96)])
 def test_gmm_per_example_gradients(cuda, K, d, B):
     X, o, ost, s, st = make(K, d, 2000, B, 20.0, 1.0)
     ost1, okeys = o._split_rng_key(ost, 2)
@@ -33,12 +38,10 @@ def test_gmm_per_example_gradients(cuda, K, d, B):
     st1, keys = s._split_rng_key(st, 2)
     _, px_loss, px_grads, n2, f2 = s._compute_per_example_gradients(st1, keys[0], torch.as_tensor(X).cuda())
     assert n == n2
-    np.testing.assert_allclose(px_loss.cpu().numpy(), opx_loss, rtol=3e-5)
-    for k in opx_grads:
-        got, ref = px_grads[k].cpu().numpy(), opx_grads[k]
-        scale = np.abs(ref).reshape(B, -1).max(axis=1).reshape((B,) + (1,) * (ref.ndim - 1))
-        err = np.max(np.abs(got - ref) / np.maximum(scale, 1e-30))
-        assert err < 3e-5, (k, err)
+    np.testing.assert_allclose(px_loss.cpu().numpy(), opx_loss, rtol=REL)
+    for k in opx_grads:      # every example's gradient row, element-wise against that row's rms
+        err = ew_rel_err(px_grads[k], opx_grads[k], axis=0)
+        assert err < REL, (k, err)
 
 
 @pytest.mark.parametrize("K,d,B,C", [(3, 2, 24, 0.5), (8, 5, 40, 20.0)])
@@ -50,11 +53,11 @@ def test_gmm_clipped_sum_and_trajectory(cuda, K, d, B, C):
     for _ in range(3):
         ost, oloss = o.update(ost, X, mask=mask)
         st, loss = s.update(st, Xd, mask=md)
-        assert np.isclose(float(loss), float(oloss), rtol=3e-5)
+        assert np.isclose(float(loss), float(oloss), rtol=REL)
     oref, got = o.get_params(ost), s.get_params(st)
     for k in oref:
-        err = np.max(np.abs(got[k].cpu().numpy() - oref[k])) / np.max(np.abs(oref[k]))
-        assert err < 1e-5, (k, err)
+        err = ew_rel_err(got[k], oref[k])
+        assert err < REL, (k, err)
 
 
 def test_gmm_sampler_statistics(cuda):

@@ -1,8 +1,9 @@
 """GPU parity: the fused DP-VI step (C ABI via the DPSVI facade) vs the oracle's literal
 vmap(grad) -> clip -> mean -> noise -> optimizer restatement, on identical inputs.
 
-Tolerances (BASELINE.json): clipped-sum gradients and parameters fp32 within 1e-5 relative
-(relative to the vector's max magnitude); minibatch indices / keystream bit-exact (other files).
+Tolerances (BASELINE.json): clipped-sum gradients and parameters fp32 within 1e-5 relative,
+ELEMENT-WISE with the vector's rms as absolute floor (tests/helpers/tolerance.py); minibatch indices /
+keystream bit-exact (other files).
 """
 import numpy as np
 import pytest
@@ -19,11 +20,9 @@ def _np(t):
     return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
 
-def assert_close(got, ref, rtol=RTOL, what=""):
-    got, ref = _np(got).astype(np.float64), np.asarray(ref, dtype=np.float64)
-    scale = max(np.max(np.abs(ref)), 1e-30)
-    err = np.max(np.abs(got - ref)) / scale
-    assert err <= rtol, f"{what}: max rel-to-scale error {err:.3e} > {rtol}"
+def assert_close(got, ref, rtol=RTOL, what="", axis=None):
+    from helpers.tolerance import assert_rel
+    assert_rel(got, ref, rtol=rtol, what=what, axis=axis)
 
 
 def _data(kind, B, d, seed=0):
@@ -71,6 +70,9 @@ def test_per_example_gradients_match_oracle(cuda, kind, d, guide):
     mask = np.arange(B) < B - 5
     _, losses, grads, n, f = s._compute_per_example_gradients(
         st, st.rng_key, *[torch.as_tensor(a).to(cuda) for a in args], mask=torch.as_tensor(mask).to(cuda))
+    # float64 evaluation of the same float32 inputs: at d = 1024 the float32 autodiff side's own rounding (a
+    # 1024-term dot product feeding exp / log) is as large as the kernel's
+    o.grad_dtype = np.float64
     _, olosses, ograds, on, of = o._compute_per_example_gradients(ost, ost.rng_key, *args, mask=mask)
     assert n == on and np.isclose(f, of)
     assert set(grads) == set(ograds)
@@ -78,7 +80,7 @@ def test_per_example_gradients_match_oracle(cuda, kind, d, guide):
         assert grads[k].shape == ograds[k].shape
         assert_close(grads[k], ograds[k], what=f"px_grads[{k}]")
         assert np.all(_np(grads[k])[B - 5:] == 0)
-    assert_close(losses, olosses, rtol=2e-5, what="px_losses")
+    assert_close(losses, olosses, what="px_losses")
 
 
 @pytest.mark.parametrize("kind,d,guide", CASES)
@@ -98,7 +100,7 @@ def test_update_trajectory_matches_oracle(cuda, kind, d, guide):
         st, loss = s.update(st, *targs, mask=tmask)
         ost, oloss = o.update(ost, *args, mask=mask)
         assert np.array_equal(st.rng_key, ost.rng_key)
-        assert np.isclose(float(loss), float(oloss), rtol=2e-5), (step, float(loss), float(oloss))
+        assert np.isclose(float(loss), float(oloss), rtol=RTOL), (step, float(loss), float(oloss))
         got, ref = s.get_params(st), o.get_params(ost)
         for k in ref:
             r = ref[k] if k != "auto_scale" else np.log1p(np.exp(ref[k]))
@@ -155,7 +157,7 @@ def test_update_with_batch_views_equals_materialised(cuda):
     ost, oloss = o.update(ost, obX, obY, mask=omask)
     for k, v in o.get_params(ost).items():
         assert_close(s.get_params(st_a)[k], v, what=k)
-    assert np.isclose(float(loss_a), float(oloss), rtol=2e-5)
+    assert np.isclose(float(loss_a), float(oloss), rtol=RTOL)
 
 
 def test_mask_variants_and_empty_batch(cuda):

@@ -107,3 +107,32 @@ def test_gmm_oracle_golden_and_alpha_gradient(g2):
     np.testing.assert_allclose(losses, g2["gmm_losses"], rtol=1e-6)
     np.testing.assert_allclose(s.get_params(state)["alpha_log"], g2["gmm_alpha_log"], rtol=1e-6)
     np.testing.assert_allclose(s.get_params(state)["mus_loc"], g2["gmm_mus_loc"], rtol=1e-6, atol=1e-8)
+
+
+def test_vae_explicit_oracle_matches_autodiff():
+    """oracle.vae.explicit_clipped_sum (float64 matmuls, ghost norms, A^T diag(c) Delta: what the full-shape GPU test
+    is held against) == the literal vmap(grad) -> clip -> sum restatement of d3p/svi.py:238-325."""
+    import numpy as np
+    from oracle import chacha, svi as osvi, threefry, vae as ovae
+    for (D, H, Z, B, C, std) in [(36, 24, 4, 16, 0.5, 0.1), (64, 40, 8, 33, 3.0, 0.1), (196, 64, 20, 20, 10.0, 0.05)]:
+        rs = np.random.RandomState(D)
+        side = int(np.sqrt(D))
+        X = (rs.rand(B, side, side) < 0.35).astype(np.float32)
+        fam = ovae.VAE(D, H, Z, 1000)
+        p0 = fam.init_params(0, std)
+        o = osvi.DPSVI(fam, None, osvi.SGD(1.0), None, C, 0.0)
+        st = o.init(chacha.PRNGKey(11), X, params=p0)
+        st1, keys = o._split_rng_key(st, 2)
+        mask = np.ones(B, bool)
+        mask[3::4] = False
+        _, pxl, pxg, n, f = o._compute_per_example_gradients(st1, keys[0], X, mask=mask)
+        eps = fam.sample_eps(threefry.split(chacha.convert_to_jax_rng_key(keys[0]), B))["z"]
+        loss, norm, cs = ovae.explicit_clipped_sum(p0, X, eps, C, mask, fam.site_scale, st.observation_scale)
+        onorm = np.sqrt(sum(np.sum(np.square(g.reshape(B, -1).astype(np.float64)), axis=1) for g in pxg.values()))
+        assert np.max(np.abs(norm - onorm)[mask] / onorm[mask]) < 2e-6      # the autodiff side is float32
+        assert np.all(norm[~mask] == 0) and np.all(onorm[~mask] == 0)
+        np.testing.assert_allclose(loss * st.observation_scale * f, pxl, rtol=2e-6, atol=0)
+        _, clipped = o._clip_gradients(st1, pxg)
+        for k in cs:
+            ref = clipped[k].astype(np.float64).sum(0)
+            assert np.max(np.abs(cs[k] - ref)) < 2e-6 * np.sqrt(np.mean(ref ** 2)) + 1e-12, k
