@@ -129,73 +129,111 @@ def workload_config(name, cfg):
                else f"subsample without replacement batch={b}")
     model = (f"VAE {cfg['d']}-{cfg['hidden']}-{cfg['z']}" if cfg["family"] == "vae" else
              f"GMM K={cfg['K']} d={cfg['d']}" if cfg["family"] == "gmm" else f"{cfg['family']} d={cfg['d']}")
-    return {"workload": f"{name}: synthetic {model} N={cfg['N']} {sampler}",
-            "l2_policy": ("inputs larger than L2 (dataset resident in HBM, rows gathered at random)"
-                          if cfg["N"] * cfg["d"] * 4 > 2 ** 28 else
-                          "working set (activations + partial sums, >300 MB per step) larger than L2"),
+    data_mb = cfg["N"] * cfg["d"] * 4 / 1e6
+    if data_mb > 126:
+        l2 = (f"inputs larger than L2: the {data_mb:.0f} MB data set stays in HBM and every step gathers a fresh random "
+              "batch of rows from it")
+    else:
+        l2 = (f"the {data_mb:.2f} MB data set is L2-resident by construction (BASELINE configs[0], the reference's "
+              "CPU-runnable case): a latency / parity configuration, not a roofline one; no L2 flush")
+    return {"workload": f"{name}: synthetic {model} N={cfg['N']} {sampler}", "l2_policy": l2,
             "optimizer": "Adam(1e-3)", "clipping_threshold": cfg["C"], "dp_scale": 1.0}
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU port (oracle) — the cpu_baseline leg and `--impl reference`
+# CPU arm — the cpu_baseline leg and `--impl reference`
 # ------------------------------------------------------------------------------------------------
-def cpu_port_throughput(cfg, steps, warmup, sample_examples, threads):
+# Rows of the data set the CPU arm keeps in host memory (same d, q, sampler, clip, optimizer as the workload;
+# examples/s does not depend on N except through the Poisson selector draw, which is part of the step and scales
+# with it: SURVEY.md section 8d).  The batch follows from q: c2 at 1 M rows = Poisson(1e4) batches, max 10 233.
+CPU_ROWS = {"c1": 10_000, "c2": 1_000_000, "c3": 1_000_000, "c4": 5_000, "c5": 60_000}
+CPU_BATCH = {"c5": 256}        # the autodiff port materialises [B, P] per-example gradients: 4096 x 652 824 x 4 B = 10.7 GB
+
+
+def cpu_port_setup(name, cfg, threads):
+    """-> (step(i, state) -> (state, n_valid), state, description).  A step = get_batch(i) (oracle sampler + masked
+    gather, oracle/minibatch.py) + DPSVI.update (oracle/svi.py: Threefry keys and guide noise in numpy,
+    torch.func vmap(grad), clip, mean, ChaCha noise, Adam) — the same work as one step of the B200 arm."""
     import torch
-    from oracle import chacha, families, svi as osvi
+    from oracle import chacha, families, minibatch as omb, svi as osvi
     torch.set_num_threads(threads)
-    d, N = cfg["d"], cfg["N"]
-    rs = np.random.RandomState(123)
-    B = sample_examples
+    d, q = cfg["d"], cfg["q"]
+    N = min(cfg["N"], CPU_ROWS[name])
+    rs = np.random.default_rng(123)
     if cfg["family"] == "logreg":
         fam = families.LogisticRegression(d, N)
-        args = (rs.randn(B, d).astype(np.float32), (rs.rand(B) < .5).astype(np.int32))
+        data = (rs.standard_normal((N, d), dtype=np.float32), (rs.random(N) < .5).astype(np.int32))
     elif cfg["family"] == "gauss":
         fam = families.GaussianMean(d, N)
-        args = ((1 + .1 * rs.randn(B, d)).astype(np.float32),)
+        data = ((1 + .1 * rs.standard_normal((N, d), dtype=np.float32)),)
     elif cfg["family"] == "gmm":
         from oracle import gmm as ogmm
         fam = ogmm.GaussianMixture(cfg["K"], d, N)
-        args = ((3 * rs.randn(B, d)).astype(np.float32),)
+        data = ((3 * rs.standard_normal((N, d), dtype=np.float32)),)
     else:
         from oracle import vae as ovae
         fam = ovae.VAE(d, cfg["hidden"], cfg["z"], N)
-        args = ((rs.rand(B, 28, 28) < .3).astype(np.float32),)
+        data = ((rs.random((N, 28, 28), dtype=np.float32) < .3).astype(np.float32),)
+    if cfg["sampler"] == "poisson":
+        init, get = omb.poisson_batchify_data(data, q, .99)
+        sampler = f"Poisson q={q}"
+    else:
+        B = CPU_BATCH.get(name, max(1, int(round(N * q))))
+        init, get = omb.subsample_batchify_data(data, batch_size=B, return_mask=True)
+        sampler = f"subsample batch={B}"
+    key, k_init, k_fetch = chacha.split(chacha.PRNGKey(0), 3)
+    _, bstate = init(k_fetch)
+    batch, mask = get(0, bstate)
     s = osvi.DPSVI(fam, None, osvi.Adam(1e-3), None, cfg["C"], 1.0)
-    st = s.init(chacha.PRNGKey(0), *args)
-    mask = np.ones(B, dtype=bool)
-    for _ in range(warmup):
-        st, _ = s.update(st, *args, mask=mask)
+    state = s.init(k_init, *batch)
+
+    def step(i, state):
+        batch, mask = get(i, bstate)
+        state, _ = s.update(state, *batch, mask=mask)
+        return state, int(np.sum(mask))
+
+    desc = (f"oracle port (numpy ChaCha / Threefry / sampler + gather, torch.func vmap(grad), clip, noise, Adam) on "
+            f"{N} rows x d={d}, {sampler}, padded batch {len(mask)}: each step = get_batch + DPSVI.update")
+    return step, state, desc
+
+
+def cpu_run(name, cfg, steps, warmup, threads):
+    step, state, desc = cpu_port_setup(name, cfg, threads)
+    for i in range(warmup):
+        state, _ = step(i, state)
+    n = 0
     t0 = time.perf_counter()
-    for _ in range(steps):
-        st, _ = s.update(st, *args, mask=mask)
+    for i in range(steps):
+        state, nv = step(warmup + i, state)
+        n += nv
     dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps * 1e3
-
-
-def cpu_sample_size(cfg):
-    if cfg["family"] == "gmm":
-        return 64
-    return 256 if cfg["family"] == "vae" else (4096 if cfg["d"] >= 256 else 8192)
+    return n / dt, dt / steps * 1e3, desc
 
 
 def run_reference(args, cfg):
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores.  The real d3p (jax +
+    numpyro + jax-chacha-prng) when importable (baseline/run_reference.py, kind = "reference"), else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = cpu_sample_size(cfg)
-    steps = max(1, min(args.steps, 8))
-    warmup = min(args.warmup, 1)
-    value, ms = cpu_port_throughput(cfg, steps, warmup, sample, threads)
+    from baseline import run_reference as rr
+    ok, why = rr.available()
+    kind = "port"
+    if ok and cfg["family"] == "logreg":
+        r = rr.time_update(cfg, args.steps, args.warmup, min(cfg["N"], CPU_ROWS[args.workload]))
+        value, ms, kind = r["value"], r["ms_per_step"], "reference"
+        desc = (f"the reference itself (d3p from {why}, {r['versions']}): jitted get_batch + DPSVI.update on "
+                f"{min(cfg['N'], CPU_ROWS[args.workload])} rows x d={cfg['d']}, padded batch {r['max_batch_size']}")
+    else:
+        value, ms, desc = cpu_run(args.workload, cfg, args.steps, args.warmup, threads)
+        desc += f"; the reference's JAX path is unavailable here ({why})"
     line = {
         "impl": "reference", "metric": "DPSVI.update examples/sec", "value": value, "unit": "examples/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, cfg),
-        "cpu_baseline": {"value": value, "unit": "examples/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} steps of {sample} examples through the oracle port of DPSVI.update "
-                                   "(numpy Threefry/ChaCha + torch.func vmap(grad) + clip + noise + Adam); "
-                                   "the reference's JAX path cannot be installed here"},
+        "cpu_baseline": {"value": value, "unit": "examples/s", "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -512,27 +550,25 @@ def run_b200(args, cfg):
         }
         if e2e is not None:
             line["e2e"] = e2e
-        line["config"]["driver"] = "python loop: get_batch(i, state) + DPSVI.update per step"
+        line["driver"] = "python loop: get_batch(i, state) + DPSVI.update per step"
         if world > 1:
             line["parity_check"] = parity
             line["peer_timeouts"] = 0 if svi.peer_window is None else svi.peer_window.timeouts()
-            line["config"]["collective"] = ("clipped sums exchanged inside the finalize kernel over NVLink peer memory"
+            line["collective"] = ("clipped sums exchanged inside the finalize kernel over NVLink peer memory"
                                             if args.collective == "p2p" else "reduce kernel + ncclAllReduce(P + 2 floats)")
         if epoch_line is not None:
             # headline = the same K steps through DPSVI.run_epoch (the examples' fori_loop, driven from C);
             # the interpreter-driven loop above stays as `stepwise` and provides the per-kernel event timings
             line["stepwise"] = {"value": value, "ms_per_step": step_ms}
             line["value"], line["ms_per_step"] = epoch_line["value"], epoch_line["ms_per_step"]
-            line["config"]["driver"] = ("DPSVI.run_epoch: get_batch + update for all K steps inside "
+            line["driver"] = ("DPSVI.run_epoch: get_batch + update for all K steps inside "
                                         + ("d3p_dpsvi_run_epoch_vae" if is_vae else "d3p_dpsvi_run_epoch_meanfield"))
             line["roofline"]["kernel_share_of_step"] = line["roofline"]["kernel_ms"] / epoch_line["ms_per_step"]
         if world == 1 and args.cpu_baseline:
             threads = os.cpu_count() or 1
-            sample = cpu_sample_size(cfg) // 2
-            v, ms = cpu_port_throughput(cfg, 3, 1, sample, threads)
+            v, ms, desc = cpu_run(args.workload, cfg, 4, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": "examples/s", "cores": threads, "kind": "port",
-                                    "sample": f"3 steps of {sample} examples through the oracle port "
-                                              "(numpy RNG + torch.func vmap(grad) + clip + noise + Adam)"}
+                                    "sample": "4 steps: " + desc}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

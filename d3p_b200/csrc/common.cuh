@@ -44,6 +44,30 @@ D3P_HD void chacha20_block(const uint32_t (&in)[16], uint32_t counter, uint32_t 
   out[12] = x12 + counter; out[13] = x13 + in[13]; out[14] = x14 + in[14]; out[15] = x15 + in[15];
 }
 
+// ---- ChaCha key derivation: the ONE swappable rule behind rng_suite.split / fold_in ---------------------------
+// (d3p/random/__init__.py:28-30 -> jax-chacha-prng >= 1, < 2, which is not in the reference tree: PARITY UNPINNED.
+// tests/golden/make_reference_golden.py dumps the real package's outputs where it is installed and
+// tests/test_reference_golden.py then holds this rule — and oracle/chacha.py:derive_key, its mirror — to them.)
+//   child key  = words 0..7 of the ChaCha20 block of the parent state with counter := data and nonce word 2 ^= tag
+//   child      = {constants, child key, counter 0, nonce of the parent}
+// split(S, n)[i] = derive(S, i, SPLIT) and fold_in(S, d) = derive(S, d, FOLD_IN) use DIFFERENT tags, so a key that is
+// both split and folded (DPSVI splits its state key 3 ways, the batchifiers fold the step index into theirs) never
+// reuses a stream; neither tag can collide with a keystream block of S itself (those have nonce word 2 unchanged).
+enum : uint32_t { D3P_DERIVE_SPLIT = 0x80000000u, D3P_DERIVE_FOLD_IN = 0x40000000u };
+
+D3P_HD void chacha_derive_key(const uint32_t (&in)[16], uint32_t data, uint32_t domain_tag, uint32_t (&out)[16]) {
+  uint32_t tmp[16], blk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tmp[i] = in[i];
+  tmp[15] ^= domain_tag;
+  chacha20_block(tmp, data, blk);
+  out[0] = 0x61707865u; out[1] = 0x3320646Eu; out[2] = 0x79622D32u; out[3] = 0x6B206574u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[4 + i] = blk[i];
+  out[12] = 0;
+  out[13] = in[13]; out[14] = in[14]; out[15] = in[15];
+}
+
 // Threefry-2x32, 20 rounds (Random123), as used by jax.random (d3p/svi.py:290).
 struct TfKey {
   uint32_t k0, k1, k2;

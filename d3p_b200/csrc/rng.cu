@@ -73,19 +73,6 @@ static ChaChaState load_state(const uint32_t* s) {
   return st;
 }
 
-// The single key-derivation rule of this build (DESIGN.md "ChaCha key derivation"; mirrored by
-// oracle/chacha.py:derive_key).  [parity unpinned: jax-chacha-prng's rule is not in the reference tree]
-static void derive_key(const uint32_t in[16], uint32_t data, uint32_t out[16]) {
-  uint32_t tmp[16], blk[16];
-  for (int i = 0; i < 16; ++i) tmp[i] = in[i];
-  tmp[15] ^= 0x80000000u;
-  chacha20_block(tmp, data, blk);
-  out[0] = 0x61707865u; out[1] = 0x3320646Eu; out[2] = 0x79622D32u; out[3] = 0x6B206574u;
-  for (int i = 0; i < 8; ++i) out[4 + i] = blk[i];
-  out[12] = 0;
-  out[13] = in[13]; out[14] = in[14]; out[15] = in[15];
-}
-
 template <int kMode>
 static int32_t launch_stream(const uint32_t* state_h, uint64_t first_block, void* out_d, size_t n, float lo,
                              float hi, void* stream) {
@@ -157,7 +144,9 @@ int32_t d3p_chacha_key_from_seed_h(const uint8_t* seed_h, size_t len, uint32_t o
 int32_t d3p_chacha_fold_in_h(const uint32_t in_h[16], uint32_t data, uint32_t out_h[16]) {
   if (!in_h || !out_h) return D3P_ERR_INVALID_ARGUMENT;
   uint32_t tmp[16];
-  derive_key(in_h, data, tmp);
+  uint32_t src[16];
+  for (int i = 0; i < 16; ++i) src[i] = in_h[i];
+  chacha_derive_key(src, data, D3P_DERIVE_FOLD_IN, tmp);
   for (int i = 0; i < 16; ++i) out_h[i] = tmp[i];
   return D3P_OK;
 }
@@ -166,7 +155,11 @@ int32_t d3p_chacha_split_h(const uint32_t in_h[16], int32_t num, uint32_t* out_h
   if (!in_h || num < 0 || (!out_h && num)) return D3P_ERR_INVALID_ARGUMENT;
   uint32_t src[16];
   for (int i = 0; i < 16; ++i) src[i] = in_h[i];
-  for (int32_t k = 0; k < num; ++k) derive_key(src, (uint32_t)k, out_h + 16 * (size_t)k);
+  for (int32_t k = 0; k < num; ++k) {
+    uint32_t child[16];
+    chacha_derive_key(src, (uint32_t)k, D3P_DERIVE_SPLIT, child);
+    for (int i = 0; i < 16; ++i) out_h[16 * (size_t)k + i] = child[i];
+  }
   return D3P_OK;
 }
 

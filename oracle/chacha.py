@@ -14,12 +14,16 @@ layer over the un-vendored ``jax-chacha-prng >=1,<2`` (``setup.py:49``):
 * ``convert_to_jax_rng_key`` — first two keystream words (``random/__init__.py:149-155``).
 * ``PRNGKey`` / ``split`` / ``fold_in`` — **parity unpinned** (third-party rule, not in
   /root/reference, no golden vector in the reference tests).  The rule used here:
-      state layout  = RFC 8439: words 0-3 constants, 4-11 key, 12 counter, 13-15 nonce
-      PRNGKey(int)  = 32-byte big-endian integer as key bytes; bytes are zero-padded
-      fold_in(S, d) = state whose key is words 0..7 of block(S with counter := d and
-                      nonce word 2 ^= 0x80000000), counter 0, nonce of S
-      split(S, n)[i]= fold_in(S, i)
-  Everything that depends on it goes through ``derive_key`` only.
+      state layout   = RFC 8439: words 0-3 constants, 4-11 key, 12 counter, 13-15 nonce
+      PRNGKey(int)   = 32-byte big-endian integer as key bytes; bytes are zero-padded
+      derive(S,d,tag)= state whose key is words 0..7 of block(S with counter := d and
+                       nonce word 2 ^= tag), counter 0, nonce of S
+      split(S, n)[i] = derive(S, i, 0x80000000)
+      fold_in(S, d)  = derive(S, d, 0x40000000)     (a different domain: a key that is both split
+                       and folded never reuses a stream)
+  Everything that depends on it goes through ``derive_key`` only; where the real package is
+  installed, ``tests/golden/make_reference_golden.py`` dumps its outputs and
+  ``tests/test_reference_golden.py`` holds this rule to them.
 """
 import secrets
 
@@ -27,7 +31,7 @@ import numpy as np
 
 U32 = np.uint32
 CONSTANTS = np.array([0x61707865, 0x3320646E, 0x79622D32, 0x6B206574], dtype=U32)
-DERIVE_TAG = U32(0x80000000)
+DERIVE_SPLIT, DERIVE_FOLD_IN = U32(0x80000000), U32(0x40000000)
 STATE_SHAPE = (4, 4)
 
 
@@ -87,22 +91,22 @@ def PRNGKey(seed=None):
     return setup_state(words)
 
 
-def derive_key(state, data):
+def derive_key(state, data, domain_tag):
     """The single swappable key-derivation rule (see module docstring)."""
     st = np.asarray(state, dtype=U32).reshape(16)
     tmp = st.copy()
     tmp[12] = U32(int(data) & 0xFFFFFFFF)
-    tmp[15] ^= DERIVE_TAG
+    tmp[15] ^= U32(domain_tag)
     b = block(tmp)
     return setup_state(b[0:8], st[13:16], 0)
 
 
 def fold_in(key, data):
-    return derive_key(key, data)
+    return derive_key(key, data, DERIVE_FOLD_IN)
 
 
 def split(key, num=2):
-    return np.stack([derive_key(key, i) for i in range(num)])
+    return np.stack([derive_key(key, i, DERIVE_SPLIT) for i in range(num)])
 
 
 def keystream_words(key, n_words, first_block=0):

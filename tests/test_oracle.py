@@ -41,8 +41,11 @@ def test_chacha_split_fold_in_properties():
     s = chacha.split(k, 4)
     assert s.shape == (4, 4, 4)
     assert len({bytes(x.tobytes()) for x in s}) == 4
-    assert np.array_equal(chacha.fold_in(k, 2), s[2])
-    assert not np.array_equal(chacha.fold_in(k, 1), chacha.fold_in(k, 2))
+    # split and fold_in are different domains: no index collides (round-1 ADVICE: split(k, n)[i] == fold_in(k, i))
+    folded = [chacha.fold_in(k, i) for i in range(4)]
+    assert len({bytes(np.asarray(x).tobytes()) for x in list(s) + folded}) == 8
+    # the 3-way split inside DPSVI.update and the batchifier's fold_in(key, i) never share a stream
+    assert not np.array_equal(chacha.random_bits(folded[0], 32, (16,)), chacha.random_bits(s[0], 32, (16,)))
     # children do not reproduce the parent's keystream
     assert not np.array_equal(chacha.random_bits(s[0], 32, (16,)), chacha.random_bits(k, 32, (16,)))
 
