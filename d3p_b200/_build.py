@@ -36,12 +36,19 @@ def _deps_mtime():
     return max(os.path.getmtime(h) for h in hdrs)
 
 
+def _defines():
+    """Development builds only (e.g. D3P_NVCC_DEFINES=D3P_GEMM_TRACE python -m d3p_b200._build): extra -D flags; the
+    object cache is invalidated whenever the set changes, so the next plain build is the product library again."""
+    return [d for d in os.environ.get("D3P_NVCC_DEFINES", "").split(",") if d]
+
+
 def _compile(src, verbose):
     obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
     srcp = os.path.join(CSRC, src)
     if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(srcp), _deps_mtime()):
         return obj, ""
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", srcp, "-o", obj]
+    cmd = ([_nvcc()] + NVCC_FLAGS + ["-D" + d for d in _defines()] + (["-Xptxas", "-v"] if verbose else [])
+           + ["-c", srcp, "-o", obj])
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -50,6 +57,13 @@ def _compile(src, verbose):
 
 def build(verbose=False, force=False):
     os.makedirs(LIBDIR, exist_ok=True)
+    flags_file = os.path.join(LIBDIR, ".defines")
+    want = ",".join(_defines())
+    have = open(flags_file).read() if os.path.exists(flags_file) else ""
+    if want != have:
+        force = True
+        with open(flags_file, "w") as f:
+            f.write(want)
     if force:
         for f in os.listdir(LIBDIR):
             if f.endswith((".o", ".so")):

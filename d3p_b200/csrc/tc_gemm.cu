@@ -6,6 +6,19 @@
 #include "launch.cuh"
 #include "tc_gemm_kernel.cuh"
 
+#ifdef D3P_GEMM_TRACE
+namespace d3p { namespace tc {
+unsigned long long* g_trace_buf = nullptr;
+unsigned int g_trace_next = 0, g_trace_cap = 0;
+} }
+// development build only: register a device buffer of `records` x 8 u64; returns the number of records used so far
+extern "C" uint32_t d3p_dev_gemm_trace(unsigned long long* buf_d, uint32_t records) {
+  const uint32_t used = d3p::tc::g_trace_next;
+  d3p::tc::g_trace_buf = buf_d; d3p::tc::g_trace_cap = records; d3p::tc::g_trace_next = 0;
+  return used;
+}
+#endif
+
 namespace d3p {
 
 // hi = x * scale[row] with the low 13 mantissa bits cleared, lo = x * scale[row] - hi (exact in fp32)

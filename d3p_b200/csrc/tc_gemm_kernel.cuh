@@ -21,12 +21,15 @@
 // hi + lo stage, so the TMA ring is 3 deep instead of 2 for a 128 x 224 tile and half the operand bytes cross
 // L2 -> shared memory.
 //
-// Structure (one CTA per 128 x BN output tile and K split, 64 + 32 EW threads):
+// Structure (one CTA per 128 x BN output tile and K split, 32 EW threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of 32 fp32 (one 128 B swizzle span) into
 //               a STAGES-deep shared-memory ring, mbarrier complete_tx
 //   warp 1      MMA issuer (one thread): 4 k-steps of UMMA_K = 8 per 32-deep k-block, 1-3 MMAs each;
 //               tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2..   epilogue (EW warps): tcgen05.ld 32 lanes x 32 columns -> registers -> Epi::tile()
+//   warps 2..   main loop: split landed stages into hi / lo when an operand arrives unsplit
+//   all EW warps (0 and 1 join when their loops are done): epilogue, tcgen05.ld 32 lanes x 32 columns -> registers ->
+//               Epi::tile().  EW = 16 means 16 warps in the CTA, 4 per scheduler, i.e. 128 registers per thread
+//               (the former 2 + 16 warps put 5 warps on two schedulers: a 96-register cap and a spilling epilogue)
 // Operand major-ness (template): K-major = the contraction index is contiguous in memory,
 // MN-major = the M (or N) index is contiguous (needed for A^T * diag(c) * Delta, where the
 // contraction runs over the batch, the slow axis of both activations).
@@ -50,7 +53,28 @@ struct GemmShape {
   int has_a_lo, has_b_lo;
   const int* a_lo_flag;           // optional device flag: 0 = a_lo is all zeros, skip its MMA (and its loads)
   int a_split, b_split;           // operand given as one fp32 array: hi / lo are produced in shared memory
+#ifdef D3P_GEMM_TRACE
+  unsigned long long* trace;      // development build only: 8 x u64 per CTA (see trace_stamp)
+  uint32_t trace_id;
+#endif
 };
+
+#ifdef D3P_GEMM_TRACE
+// Development build (D3P_NVCC_DEFINES=D3P_GEMM_TRACE): %globaltimer stamps of one CTA's life, written to a buffer the
+// host registered with d3p_dev_gemm_trace.  Never compiled into the product library.
+extern unsigned long long* g_trace_buf;
+extern unsigned int g_trace_next, g_trace_cap;
+__device__ __forceinline__ void trace_stamp(const GemmShape& g, int slot) {
+  if (!g.trace) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const size_t cta = (size_t)blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
+  g.trace[cta * 8 + slot] = t;
+}
+#define D3P_TRACE(slot) trace_stamp(g, slot)
+#else
+#define D3P_TRACE(slot)
+#endif
 
 template <int BN>
 struct GemmCfg {
@@ -66,12 +90,64 @@ struct GemmCfg {
   static constexpr uint32_t kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32, 256]");
   static_assert(kRingBytes >= 2 * kStageBytes, "tile too large for a 2-stage pipeline");
+  static_assert(kRingBytes >= 16 * 32 * 36 * 4, "the epilogue scratch (16 warps) lives in the ring");
 };
 
-// EW = number of epilogue warps (multiple of 4): the EW / 4 warps that share a TMEM lane quarter take the
-// 32-column chunks round-robin; Epi::begin/end see `part` in [0, EW / 4) for their row reductions.
+// ---- coalesced row I/O for the epilogues ---------------------------------------------------------------------------
+// tcgen05.ld 32x32b hands lane t the 32 columns of ROW t, so a direct store (or load) of those values touches 32
+// different rows per instruction: 32 half-filled sectors, and the epilogues of the forward / backward GEMMs were
+// bound by exactly that (traced: G5's epilogue 21 us of a 41 us kernel, ~1 sector per clock).  These helpers move a
+// 32 x 32 chunk through the warp's private scratch (32 rows x 36 floats of the operand ring, which is idle once the
+// accumulator is complete) so that every global access is a 16-byte piece of a full 128-byte row segment:
+// 8 lanes x 16 B = one row, 4 rows per instruction.  Row stride 36 floats keeps both phases bank-conflict free.
+constexpr int kEpiScratchLd = 36;
+constexpr int kEpiScratchFloats = 32 * kEpiScratchLd;
+
+// vals[j] = src[(lane) * ld + j] for the warp's 32 rows x 32 columns; rows >= n_rows / cols >= n_cols read as 0.
+// `src` points at (first row of the warp, first column of the chunk), 16-byte aligned, ld % 4 == 0, n_cols % 4 == 0.
+__device__ __forceinline__ void warp_load_rows(float* scratch, const float* __restrict__ src, size_t ld, uint32_t n_rows,
+                                               uint32_t n_cols, float (&vals)[32]) {
+  const int lane = threadIdx.x & 31, sub = lane >> 3, c4 = (lane & 7) * 4;
+  float4 t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t r = (uint32_t)(sub + 4 * i);
+    t[i] = (r < n_rows && (uint32_t)c4 < n_cols) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)r * ld + c4))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(scratch + (sub + 4 * i) * kEpiScratchLd + c4) = t[i];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 q = *reinterpret_cast<const float4*>(scratch + lane * kEpiScratchLd + 4 * j);
+    vals[4 * j] = q.x; vals[4 * j + 1] = q.y; vals[4 * j + 2] = q.z; vals[4 * j + 3] = q.w;
+  }
+  __syncwarp();
+}
+
+// dst[(lane) * ld + j] = vals[j], same geometry; rows >= n_rows and columns >= n_cols are not written.
+__device__ __forceinline__ void warp_store_rows(float* scratch, float* __restrict__ dst, size_t ld, uint32_t n_rows,
+                                                uint32_t n_cols, const float (&vals)[32]) {
+  const int lane = threadIdx.x & 31, sub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(scratch + lane * kEpiScratchLd + 4 * j) =
+        make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t r = (uint32_t)(sub + 4 * i);
+    const float4 q = *reinterpret_cast<const float4*>(scratch + r * kEpiScratchLd + c4);
+    if (r < n_rows && (uint32_t)c4 < n_cols) *reinterpret_cast<float4*>(dst + (size_t)r * ld + c4) = q;
+  }
+  __syncwarp();
+}
+
+// EW = number of warps (multiple of 4), all of which run the epilogue: the EW / 4 warps that share a TMEM lane quarter
+// take the 32-column chunks round-robin; Epi::begin/end see `part` in [0, EW / 4) for their row reductions.
 template <bool A_MN, bool B_MN, int BN, class Epi, int EW = kGemmEpiWarps>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+__global__ void __launch_bounds__(32 * EW, 1)
 tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const typename Epi::Args ea) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::kMaxStages;
@@ -86,6 +162,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t m_tile = blockIdx.x, n_tile = blockIdx.y, split = blockIdx.z;
+  if (threadIdx.x == 0) D3P_TRACE(0);                                  // CTA start
   // balanced k-block ranges: the first (num_k_blocks % split_k) splits get one block more
   const uint32_t base = g.num_k_blocks / g.split_k, rem = g.num_k_blocks % g.split_k;
   const uint32_t kb_begin = split * base + (split < rem ? split : rem);
@@ -109,7 +186,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
   if (warp == 1) {
     if (lane == 0) {
       for (uint32_t s = 0; s < stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-      for (uint32_t l = 0; l < 2; ++l) { mbar_init(&bar_lo_full[l], EW); mbar_init(&bar_lo_empty[l], 1); }
+      for (uint32_t l = 0; l < 2; ++l) { mbar_init(&bar_lo_full[l], EW - 2); mbar_init(&bar_lo_empty[l], 1); }
       mbar_init(&bar_acc, 1);
       fence_barrier_init();
     }
@@ -120,6 +197,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) D3P_TRACE(1);                                  // barriers + TMEM ready
 
   auto stage_ptr = [&](uint32_t s, int which) -> uint8_t* {   // which: 0 a (hi), 1 a_lo (loaded), 2 b (hi), 3 b_lo (loaded)
     uint8_t* p = smem + (size_t)s * stage_bytes;
@@ -167,6 +245,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, A_MN, B_MN);
@@ -182,6 +261,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
         const uint32_t l = it & 1u, lph = (it >> 1) & 1u;
         mbar_wait(any_conv ? &bar_lo_full[l] : &bar_full[s], any_conv ? lph : ph);
         tc_fence_after();
+        if (it == 0) D3P_TRACE(2);                                     // first stage landed (and converted)
         const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(a_conv ? lo_ptr(l, 0) : stage_ptr(s, 1));
         const uint32_t b_hi = smem_u32(stage_ptr(s, 2)), b_lo = smem_u32(b_conv ? lo_ptr(l, 1) : stage_ptr(s, 3));
 #pragma unroll
@@ -203,15 +283,13 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
         if (any_conv) umma_commit(&bar_lo_empty[l]);
       }
       umma_commit(&bar_acc);            // accumulator complete
+      D3P_TRACE(3);                                                    // last MMA issued
     }
+    __syncwarp();
   } else {
-    static_assert(EW % 4 == 0 && EW >= 4, "EW must be a multiple of 4");
-    constexpr int PARTS = EW / 4;
-    const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int part = (warp - 2) >> 2;   // which of the PARTS warps of that quarter
     if (any_conv) {
-      // main-loop duty of the epilogue warps: split the operands of every landed stage (see the file header)
-      const uint32_t ct = (uint32_t)(warp - 2) * 32u + (uint32_t)lane, nct = (uint32_t)EW * 32u;
+      // main-loop duty of warps 2..: split the operands of every landed stage (see the file header)
+      const uint32_t ct = (uint32_t)(warp - 2) * 32u + (uint32_t)lane, nct = (uint32_t)(EW - 2) * 32u;
       auto convert = [&](const uint8_t* raw_p, uint8_t* lo_p, uint32_t bytes) {
 #pragma unroll 4
         for (uint32_t off = ct * 16u; off < bytes; off += nct * 16u) {
@@ -234,14 +312,25 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&bar_lo_full[l])) : "memory");
       }
     }
+  }
+  {
+    // ---- epilogue: every warp (the producer and the MMA issuer have nothing left to do) ----------------------
+    static_assert(EW % 4 == 0 && EW >= 4, "EW must be a multiple of 4");
+    constexpr int PARTS = EW / 4;
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int part = warp >> 2;         // which of the PARTS warps of that quarter
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
+    if (warp == 2 && lane == 0) D3P_TRACE(4);                          // accumulator complete
     const uint32_t row = m_tile * kBM + q * 32 + lane;
     const uint32_t slot = n_tile * PARTS + part;     // row-reduction slot of this (tile, warp)
     typename Epi::RowState rs;
+    // per-warp transpose scratch for coalesced epilogue I/O: the operand ring is idle now (every MMA has completed)
+    float* scratch = reinterpret_cast<float*>(smem) + (size_t)warp * kEpiScratchFloats;
     Epi::begin(ea, g, row, slot, split, rs);
 #pragma unroll 1
     for (int c = part; c < BN / 32; c += PARTS) {
+      if (n_tile * BN + c * 32 >= g.N) break;             // column chunks past N (warp-uniform)
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
       if (has_a_lo || has_b_lo) {                     // + the cross-term accumulator (fp32, round to nearest)
@@ -250,13 +339,34 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(x[j]));
       }
-      Epi::tile(ea, g, row, n_tile * BN + c * 32, split, v, rs);
+      Epi::tile(ea, g, row, n_tile * BN + c * 32, split, v, rs, scratch);
     }
     Epi::end(ea, g, row, slot, split, rs);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) D3P_TRACE(5);                                  // epilogue done
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// 8-byte variant of warp_store_rows for destinations that are only 8-byte aligned (the partial rows of the clipped
+// sums are P + 2 floats apart, so every other K split sits 8 bytes off a 16-byte boundary): 16 lanes x 8 B = one row,
+// 2 rows per instruction.
+__device__ __forceinline__ void warp_store_rows8(float* scratch, float* __restrict__ dst, size_t ld, uint32_t n_rows,
+                                                 uint32_t n_cols, const float (&vals)[32]) {
+  const int lane = threadIdx.x & 31, sub = lane >> 4, c2 = (lane & 15) * 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(scratch + lane * kEpiScratchLd + 4 * j) =
+        make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t r = (uint32_t)(sub + 2 * i);
+    const float2 q = *reinterpret_cast<const float2*>(scratch + r * kEpiScratchLd + c2);
+    if (r < n_rows && (uint32_t)c2 < n_cols) *reinterpret_cast<float2*>(dst + (size_t)r * ld + c2) = q;
+  }
+  __syncwarp();
 }
 
 // ---- plain store epilogue: out[split][m, n] (or transposed) --------------------------------------
@@ -271,7 +381,7 @@ struct EpiStore {
   __device__ static void begin(const Args&, const GemmShape&, uint32_t, uint32_t, uint32_t, RowState&) {}
   __device__ static void end(const Args&, const GemmShape&, uint32_t, uint32_t, uint32_t, RowState&) {}
   __device__ static void tile(const Args& a, const GemmShape& g, uint32_t row, uint32_t col0, uint32_t split,
-                              const uint32_t (&v)[32], RowState&) {
+                              const uint32_t (&v)[32], RowState&, float*) {
     float* out = a.out + (size_t)split * a.split_stride;
     if (!a.transpose) {
       if (row >= g.M) return;
@@ -322,6 +432,19 @@ int32_t launch_tc_gemm(const GemmOperand& A, const GemmOperand& B, uint32_t M, u
   g.a_lo_flag = a_lo_flag;
   g.a_split = A.split ? 1 : 0;
   g.b_split = B.split ? 1 : 0;
+#ifdef D3P_GEMM_TRACE
+  {
+    const unsigned ctas = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN) * g.split_k;
+    g.trace = nullptr; g.trace_id = 0;
+    if (g_trace_buf && g_trace_next + ctas + 1 <= g_trace_cap) {
+      // record header: {id = launch sequence, ctas, M, N, K, BN, split_k, EW} then one 8-word record per CTA
+      unsigned long long hdr[8] = {g_trace_next, ctas, M, N, K, (unsigned long long)BN, g.split_k, (unsigned long long)EW};
+      cudaMemcpyAsync(g_trace_buf + (size_t)g_trace_next * 8, hdr, sizeof(hdr), cudaMemcpyHostToDevice, stream);
+      g.trace = g_trace_buf + (size_t)(g_trace_next + 1) * 8;
+      g_trace_next += ctas + 1;
+    }
+  }
+#endif
   GemmMaps maps;
   bool ok = true;
   if (!A_MN) {
@@ -343,7 +466,7 @@ int32_t launch_tc_gemm(const GemmOperand& A, const GemmOperand& B, uint32_t M, u
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess)
     return D3P_ERR_CUDA;
   dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, g.split_k);
-  kern<<<grid, 64 + 32 * EW, Cfg::kSmemBytes, stream>>>(maps, g, ea);
+  kern<<<grid, 32 * EW, Cfg::kSmemBytes, stream>>>(maps, g, ea);
   return cudaGetLastError() == cudaSuccess ? D3P_OK : D3P_ERR_CUDA;
 }
 

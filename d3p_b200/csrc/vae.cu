@@ -42,21 +42,24 @@ struct EpiFwd1 {   // H1 = softplus(acc + b1)
   struct RowState { float sq; };
   __device__ static void begin(const Args&, const tc::GemmShape&, uint32_t, uint32_t, uint32_t, RowState& rs) { rs.sq = 0.f; }
   __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t,
-                              const uint32_t (&v)[32], RowState& rs) {
+                              const uint32_t (&v)[32], RowState& rs, float*) {
+    // direct 16-byte stores (one row per lane): this epilogue is bound by the softplus arithmetic, not by its stores —
+    // the transposed, fully coalesced form of EpiFwd5 / EpiBwd5 measured slower here (8.5 vs 6.9 us)
     if (row >= g.M) return;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      if (col0 + j >= g.N) break;                 // N is a multiple of 4
-      float h[4], hi[4], lo[4];
+      if (col0 + j < g.N) {                       // N is a multiple of 4; a guard, not a break: the loop must unroll
+        float h[4], hi[4], lo[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        h[t] = softplus_f(__uint_as_float(v[j + t]) + __ldg(a.bias + col0 + j + t));
-        hi[t] = tc::tf32_hi(h[t]);
-        lo[t] = h[t] - hi[t];
-        rs.sq = fmaf(h[t], h[t], rs.sq);
+        for (int t = 0; t < 4; ++t) {
+          h[t] = softplus_f(__uint_as_float(v[j + t]) + __ldg(a.bias + col0 + j + t));
+          hi[t] = tc::tf32_hi(h[t]);
+          lo[t] = h[t] - hi[t];
+          rs.sq = fmaf(h[t], h[t], rs.sq);
+        }
+        *reinterpret_cast<float4*>(a.h_hi + (size_t)row * a.ld + col0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(a.h_lo + (size_t)row * a.ld + col0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
-      *reinterpret_cast<float4*>(a.h_hi + (size_t)row * a.ld + col0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(a.h_lo + (size_t)row * a.ld + col0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
   __device__ static void end(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t n_tile, uint32_t, RowState& rs) {
@@ -66,7 +69,7 @@ struct EpiFwd1 {   // H1 = softplus(acc + b1)
 
 struct EpiFwd5 {   // p = sigmoid(acc + b5); Bernoulli(probs) log-lik (numpyro clamp_probs); delta5 = p - x
   struct Args {
-    const float* bias; const float* x_hi; const float* x_lo; size_t ldx;
+    const float* bias; const float* x_hi; size_t ldx;          // x_hi holds x unmasked
     float* d_hi; float* d_lo; size_t ld; float* rowsq; float* rowloss; uint32_t rows_ld;
   };
   struct RowState { float sq, loss; };
@@ -74,46 +77,33 @@ struct EpiFwd5 {   // p = sigmoid(acc + b5); Bernoulli(probs) log-lik (numpyro c
     rs.sq = 0.f; rs.loss = 0.f;
   }
   __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t,
-                              const uint32_t (&v)[32], RowState& rs) {
-    if (row >= g.M) return;
-    // the 8 row loads of this 32-column chunk are issued before the first use (the x_hi array holds x unmasked, so
-    // one array is read; the earlier form read hi and lo, 64 registers of staging that ended up in local memory)
-    float xs[32];
-    {
-      float4 xh[8];
+                              const uint32_t (&v)[32], RowState& rs, float* scratch) {
+    const uint32_t row0 = row - (threadIdx.x & 31);
+    const uint32_t nr = g.M > row0 ? g.M - row0 : 0, nc = g.N > col0 ? g.N - col0 : 0;
+    // x (held unmasked in x_hi) and delta5 move as full 128-byte row segments through the warp's scratch
+    float xs[32], d[32];
+    tc::warp_load_rows(scratch, a.x_hi + (size_t)row0 * a.ldx + col0, a.ldx, nr, nc, xs);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool ok = col0 + 4 * j < g.N;          // N is a multiple of 4
-        xh[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.x_hi + (size_t)row * a.ldx + col0 + 4 * j)) : make_float4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { xs[4 * j] = xh[j].x; xs[4 * j + 1] = xh[j].y; xs[4 * j + 2] = xh[j].z; xs[4 * j + 3] = xh[j].w; }
+    for (int j = 0; j < 32; ++j) {
+      const bool ok = row < g.M && col0 + j < g.N;
+      const float logit = __uint_as_float(v[j]) + __ldg(a.bias + min(col0 + j, g.N - 1));
+      const float p = __fdividef(1.0f, 1.0f + __expf(-logit));     // MUFU.EX2 / MUFU.RCP: <= 1e-6 relative
+      // numpyro clamps the probabilities (jnp.clip = minimum(maximum(p, tiny), 1 - eps): gradient 1 inside, 1/2 at a
+      // bound, 0 outside)
+      const float wclip = (p > kF32Tiny ? 1.0f : (p == kF32Tiny ? 0.5f : 0.f)) *
+                          (p < kF32OneMinusEps ? 1.0f : (p == kF32OneMinusEps ? 0.5f : 0.f));
+      const float pc = fminf(fmaxf(p, kF32Tiny), kF32OneMinusEps);
+      // log1p(-pc) = log(1 - pc): 1 - pc is exact for pc >= 1/2 (Sterbenz) and within 6e-8 below; MUFU.LG2 logs
+      const float l = xs[j] * __logf(pc) + (1.0f - xs[j]) * __logf(1.0f - pc);
+      const float dj = ok ? wclip * (p - xs[j]) : 0.f;
+      rs.loss -= ok ? l : 0.f;
+      rs.sq = fmaf(dj, dj, rs.sq);
+      d[j] = dj;                          // unmasked: kind::tf32 truncates, and dW5's GEMM splits delta5 itself
     }
+    tc::warp_store_rows(scratch, a.d_hi + (size_t)row0 * a.ld + col0, a.ld, nr, nc, d);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (col0 + j < g.N) {                          // a guard, not a break: the loop must unroll to keep v / xs in registers
-      const float bs[4] = {__ldg(a.bias + col0 + j), __ldg(a.bias + col0 + j + 1), __ldg(a.bias + col0 + j + 2),
-                           __ldg(a.bias + col0 + j + 3)};         // the bias offset need not be 16-byte aligned
-      float hi[4], lo[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float logit = __uint_as_float(v[j + t]) + bs[t];
-        const float p = __fdividef(1.0f, 1.0f + __expf(-logit));     // MUFU.EX2 / MUFU.RCP: <= 1e-6 relative
-        // jnp.clip = minimum(maximum(p, tiny), 1 - eps): gradient 1 inside, 1/2 at a bound, 0 outside
-        const float wclip = (p > kF32Tiny ? 1.0f : (p == kF32Tiny ? 0.5f : 0.f)) *
-                            (p < kF32OneMinusEps ? 1.0f : (p == kF32OneMinusEps ? 0.5f : 0.f));
-        const float pc = fminf(fmaxf(p, kF32Tiny), kF32OneMinusEps);
-        // log1p(-pc) = log(1 - pc): 1 - pc is exact for pc >= 1/2 (Sterbenz) and within 6e-8 below; MUFU.LG2 logs
-        rs.loss -= xs[j + t] * __logf(pc) + (1.0f - xs[j + t]) * __logf(1.0f - pc);
-        const float d = wclip * (p - xs[j + t]);
-        hi[t] = d;                        // unmasked: kind::tf32 truncates, and dW5's GEMM splits delta5 itself
-        lo[t] = d - tc::tf32_hi(d);
-        rs.sq = fmaf(d, d, rs.sq);
-      }
-      *reinterpret_cast<float4*>(a.d_hi + (size_t)row * a.ld + col0 + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(a.d_lo + (size_t)row * a.ld + col0 + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      }
-    }
+    for (int j = 0; j < 32; ++j) d[j] = d[j] - tc::tf32_hi(d[j]);
+    tc::warp_store_rows(scratch, a.d_lo + (size_t)row0 * a.ld + col0, a.ld, nr, nc, d);
   }
   __device__ static void end(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t n_tile, uint32_t, RowState& rs) {
     if (row < g.M) {
@@ -128,27 +118,18 @@ struct EpiBwd5 {   // delta4 = acc * softplus'(pre4) = acc * (1 - exp(-h2))
   struct RowState { float sq; };
   __device__ static void begin(const Args&, const tc::GemmShape&, uint32_t, uint32_t, uint32_t, RowState& rs) { rs.sq = 0.f; }
   __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t,
-                              const uint32_t (&v)[32], RowState& rs) {
-    if (row >= g.M) return;
-    float4 hq[8];                                   // the 8 row loads of the chunk before the first use (h2, unmasked)
+                              const uint32_t (&v)[32], RowState& rs, float* scratch) {
+    const uint32_t row0 = row - (threadIdx.x & 31);
+    const uint32_t nr = g.M > row0 ? g.M - row0 : 0, nc = g.N > col0 ? g.N - col0 : 0;
+    float hs[32], d[32];                                  // h2 (unmasked) in, delta4 out: coalesced through the scratch
+    tc::warp_load_rows(scratch, a.h_hi + (size_t)row0 * a.ld + col0, a.ld, nr, nc, hs);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      hq[j] = col0 + 4 * j < g.N ? __ldg(reinterpret_cast<const float4*>(a.h_hi + (size_t)row * a.ld + col0 + 4 * j))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (col0 + j < g.N) {
-        const float4 hh = hq[j / 4];
-        const float hs[4] = {hh.x, hh.y, hh.z, hh.w};
-        float d[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          d[t] = __uint_as_float(v[j + t]) * (-expm1f(-hs[t]));
-          rs.sq = fmaf(d[t], d[t], rs.sq);
-        }
-        *reinterpret_cast<float4*>(a.d4 + (size_t)row * a.ld + col0 + j) = make_float4(d[0], d[1], d[2], d[3]);
-      }
+    for (int j = 0; j < 32; ++j) {
+      const bool ok = row < g.M && col0 + j < g.N;
+      d[j] = ok ? __uint_as_float(v[j]) * (-expm1f(-hs[j])) : 0.f;
+      rs.sq = fmaf(d[j], d[j], rs.sq);
     }
+    tc::warp_store_rows(scratch, a.d4 + (size_t)row0 * a.ld + col0, a.ld, nr, nc, d);
   }
   __device__ static void end(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t n_tile, uint32_t, RowState& rs) {
     if (row < g.M) a.rowsq[(size_t)n_tile * a.rows_ld + row] = rs.sq;
@@ -169,34 +150,26 @@ struct EpiGrad {   // clipped-sum tile -> partial row `split`: weight block(s) +
   __device__ static void begin(const Args&, const tc::GemmShape&, uint32_t, uint32_t, uint32_t, RowState&) {}
   __device__ static void end(const Args&, const tc::GemmShape&, uint32_t, uint32_t, uint32_t, RowState&) {}
   __device__ static void tile(const Args& a, const tc::GemmShape& g, uint32_t row, uint32_t col0, uint32_t split,
-                              const uint32_t (&v)[32], RowState&) {
-    if (row >= g.M) return;
+                              const uint32_t (&v)[32], RowState&, float* scratch) {
     float* out = a.partials + (size_t)split * a.row_stride;
     if (!a.transpose) {
       const uint32_t sc = a.split_col ? a.split_col : 0xffffffffu;
+      // weight rows of a full chunk (the common case): the warp's 32 rows are w_ld floats apart in the flat vector, so
+      // the chunk goes out as 128-byte row segments through the scratch (16-byte pieces, or 8-byte ones when this
+      // split's partial row sits 8 bytes off); warp-uniform conditions only
+      const uint32_t row0 = row - (threadIdx.x & 31);
+      if (col0 + 32 <= g.N && col0 + 32 <= sc && row0 + 32 <= a.main && row0 + 32 <= g.M && (a.w_ld & 1) == 0) {
+        float* base = out + a.w_off + (size_t)row0 * a.w_ld + col0;
+        const uintptr_t mis = reinterpret_cast<uintptr_t>(base) & 15;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (mis == 0 && (a.w_ld & 3) == 0) { tc::warp_store_rows(scratch, base, a.w_ld, 32, 32, f); return; }
+        if ((mis & 7) == 0) { tc::warp_store_rows8(scratch, base, a.w_ld, 32, 32, f); return; }
+      }
+      if (row >= g.M) return;
       float* p1 = row < a.main ? out + a.w_off + (size_t)row * a.w_ld : out + a.b_off;
       float* p2 = row < a.main ? out + a.w_off2 + (size_t)row * a.w_ld : out + a.b_off2;
-      if (col0 + 32 <= g.N && col0 + 32 <= sc) {
-        const uintptr_t mis = reinterpret_cast<uintptr_t>(p1 + col0) & 15;
-        if (mis == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)      // 128 contiguous bytes per thread
-            *reinterpret_cast<float4*>(p1 + col0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          return;
-        }
-        if (mis == 8) {
-          // the partial rows are P + 2 floats apart, so every other K split starts 8 bytes off a 16-byte boundary: 8 + 7 x 16 + 8
-          // bytes instead of 32 scalar stores (which made the dW1 GEMM the critical path of the clipped-sum wave)
-          *reinterpret_cast<float2*>(p1 + col0) = make_float2(__uint_as_float(v[0]), __uint_as_float(v[1]));
-#pragma unroll
-          for (int j = 2; j < 30; j += 4)
-            *reinterpret_cast<float4*>(p1 + col0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          *reinterpret_cast<float2*>(p1 + col0 + 30) = make_float2(__uint_as_float(v[30]), __uint_as_float(v[31]));
-          return;
-        }
-      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const uint32_t col = col0 + j;
@@ -206,6 +179,7 @@ struct EpiGrad {   // clipped-sum tile -> partial row `split`: weight block(s) +
         }
       }
     } else {
+      if (row >= g.M) return;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const uint32_t col = col0 + j;
@@ -1281,14 +1255,14 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   }
   // G5: logits = H2 W5  (B = W5 stored [K = H, N = D])
   {
-    tc::GemmOperand A{a.h2_hi, a.h2_lo, 0, H}, Bo{w5_hi, w5_lo, 1, D};
-    EpiFwd5::Args ea{params_d + a.off_b5, a.x_hi, a.x_lo, a.ldx, a.d5_hi, a.d5_lo, D, a.sq_d5, a.loss_rec, Bl};
+    tc::GemmOperand A{a.h2_hi, nullptr, 0, H, 1}, Bo{params_d + a.off_w5, nullptr, 1, D, 1};   // both split in the kernel
+    EpiFwd5::Args ea{params_d + a.off_b5, a.x_hi, a.ldx, a.d5_hi, a.d5_lo, D, a.sq_d5, a.loss_rec, Bl};
     if ((rc = tc::launch_tc_gemm<false, true, kVaeBN, EpiFwd5, kHeavyEW>(A, Bo, Bl, D, H, 1, ea, s, nullptr)) != D3P_OK)
       return rc;
   }
   // G5b: dh2 = delta5 W5^T  (B[n = h, k = d] = W5[h, d]: K-major)
   {
-    tc::GemmOperand A{a.d5_hi, a.d5_lo, 0, D}, Bo{w5_hi, w5_lo, 0, D};
+    tc::GemmOperand A{a.d5_hi, a.d5_lo, 0, D}, Bo{w5_hi, w5_lo, 0, D};     // pre-split: the in-kernel split measured slower here
     EpiBwd5::Args ea{a.h2_hi, a.h2_lo, H, a.d4, a.sq_d4, Bl};
     if ((rc = tc::launch_tc_gemm<false, false, kVaeBNH, EpiBwd5, kHeavyEW>(A, Bo, Bl, H, D, 1, ea, s, nullptr)) != D3P_OK)
       return rc;
