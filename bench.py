@@ -297,6 +297,44 @@ class LibEvents:
         return ms.value
 
 
+def quick_workload(name, steps, warmup, device):
+    """A short device-resident run of another BASELINE workload through DPSVI.run_epoch (same kernels, same step
+    definition as the headline), so that the driver's default run also records C3 and C5.  -> dict for `workloads`."""
+    import torch
+    import d3p_b200.random as rng
+    from d3p_b200 import minibatch as mb, models, optimizers, svi as dsvi
+    cfg = dict(WORKLOADS[name])
+    dataset = make_dataset(cfg, device)
+    fam = make_family(cfg)
+    svi = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), cfg["C"], 1.0, num_obs_total=cfg["N"])
+    svi.donate_state = True
+    if cfg["sampler"] == "poisson":
+        init, get_batch = mb.poisson_batchify_data(dataset, cfg["q"], .99)
+    else:
+        init, get_batch = mb.subsample_batchify_data(dataset, batch_size=batch_size_of(cfg), return_mask=True)
+    key, k_init, k_fetch = rng.split(rng.PRNGKey(0), 3)
+    _, bstate = init(k_fetch)
+    batch, mask = get_batch(0, bstate)
+    state = svi.init(k_init, *batch)
+    state, _ = svi.run_epoch(state, get_batch, bstate, max(warmup, 3), first_step=0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    state, stats = svi.run_epoch(state, get_batch, bstate, steps, first_step=16)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if not bool(torch.isfinite(stats[:, 0]).all()):
+        raise RuntimeError(f"workload {name} produced a non-finite loss")
+    out = {"value": float(stats[:, 1].sum().item()) / (ms * 1e-3), "unit": "examples/s", "ms_per_step": ms / steps,
+           "steps": steps, "config": workload_config(name, cfg), "driver": "DPSVI.run_epoch"}
+    if name in ALGO_BYTES_PER_EXAMPLE:
+        out["algorithmic_gbs_whole_step"] = ALGO_BYTES_PER_EXAMPLE[name] * out["value"] / 1e9
+    del dataset, state, svi
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args, cfg):
     import torch
     import torch.distributed as dist
@@ -564,6 +602,12 @@ def run_b200(args, cfg):
             line["driver"] = ("DPSVI.run_epoch: get_batch + update for all K steps inside "
                                         + ("d3p_dpsvi_run_epoch_vae" if is_vae else "d3p_dpsvi_run_epoch_meanfield"))
             line["roofline"]["kernel_share_of_step"] = line["roofline"]["kernel_ms"] / epoch_line["ms_per_step"]
+        if world == 1 and args.workload == "c2" and args.other_workloads:
+            # the default run also records the other single-GPU roofline workloads (short runs, outside the headline)
+            del dataset, batch
+            svi._ws = svi._epoch_ws = None
+            torch.cuda.empty_cache()
+            line["workloads"] = {w: quick_workload(w, min(args.steps, 50), args.warmup, device) for w in ("c3", "c5")}
         if world == 1 and args.cpu_baseline:
             threads = os.cpu_count() or 1
             v, ms, desc = cpu_run(args.workload, cfg, 4, 1, threads)
@@ -587,6 +631,8 @@ def main():
     ap.add_argument("--rows", type=int, default=None, help="override N (development only)")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-other-workloads", dest="other_workloads", action="store_false",
+                    help="default (c2, N = 1) run only: skip the short c3 / c5 runs reported under `workloads`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = dict(WORKLOADS[args.workload])
