@@ -111,7 +111,9 @@ _SIGNATURES = {
     "d3p_comm_timeouts": (C.c_int32, [_vp, _u32p]),
     "d3p_comm_window": (C.c_int32, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "d3p_comm_connect_local": (C.c_int32, [_vp, C.POINTER(C.c_void_p)]),
+    "d3p_comm_timeout_detail": (C.c_int32, [_vp, _u32p]),
     "d3p_comm_set_timeout_ms": (C.c_int32, [_vp, C.c_uint32]),
+    "d3p_comm_set_sampler_margin": (C.c_int32, [_vp, C.c_uint32]),
     "d3p_comm_destroy": (C.c_int32, [_vp]),
     "d3p_perturb_finalize_p2p_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(LeafTable),
                                                  C.c_float, C.c_float, C.c_float, C.c_int32, _vp,

@@ -79,6 +79,7 @@ extern "C" int32_t d3p_comm_create(int32_t rank, int32_t world, uint32_t max_par
   }
   c->total = c->samp_off + 2 * c->samp_stride;
   c->timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;      // d3p_comm_set_timeout_ms changes it
+  c->sampler_margin = 16;                                   // d3p_comm_set_sampler_margin
   void* eh = nullptr;
   if (cudaHostAlloc(&eh, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { delete c; return D3P_ERR_CUDA; }
   memset(eh, 0, 64);
@@ -146,9 +147,27 @@ extern "C" int32_t d3p_comm_timeouts(d3p_comm* c, uint32_t* count_out_h) {
   return D3P_OK;
 }
 
+// out_h[0] = all time-outs, [1] = waits of a finalize kernel for a peer's clipped sums, [2] = waits of the sharded
+// sampler for a peer's tile counts, [3] = 0 (reserved)
+extern "C" int32_t d3p_comm_timeout_detail(d3p_comm* c, uint32_t out_h[4]) {
+  if (!c || !out_h) return D3P_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < 3; ++i) out_h[i] = static_cast<volatile const uint32_t*>(c->err_host)[i];
+  out_h[3] = 0;
+  return D3P_OK;
+}
+
 extern "C" int32_t d3p_comm_set_timeout_ms(d3p_comm* c, uint32_t timeout_ms) {
   if (!c || timeout_ms == 0) return D3P_ERR_INVALID_ARGUMENT;
   c->timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
+  return D3P_OK;
+}
+
+// Sharded Poisson sampler: every rank draws `tiles` extra tiles (4096 records each) on both sides of the slice it
+// owns, so that the tiles its batch positions fall into are local; all ranks must use the same value.  0 forces the
+// re-draw path of the compaction kernel (tests).
+extern "C" int32_t d3p_comm_set_sampler_margin(d3p_comm* c, uint32_t tiles) {
+  if (!c) return D3P_ERR_INVALID_ARGUMENT;
+  c->sampler_margin = tiles;
   return D3P_OK;
 }
 

@@ -27,6 +27,7 @@ struct d3p_comm {
   uint32_t* err_host;                           // pinned, device-mapped mirror of the window's time-out counter
   uint32_t* err_host_dev;                       // device address of err_host
   unsigned long long timeout_ns;                // spin time-out of the waiting kernels
+  uint32_t sampler_margin;                      // sharded sampler: tiles drawn redundantly on each side of the owned slice
   uint8_t* peer[D3P_COMM_MAX_RANKS];            // mapped windows (peer[rank] == local)
   bool connected;
   bool ipc;                                     // peers were mapped with cudaIpcOpenMemHandle (else: same-process pointers)
@@ -78,9 +79,12 @@ D3P_D unsigned long long global_ns() {
 }
 // A peer did not deliver within the time-out (it died, diverged or stalled): count it in the window (device
 // flag, read by every later finalize kernel) and in the host-mapped mirror (read by the next d3p_* call).
-D3P_D void comm_flag_timeout(uint32_t* err, uint32_t* err_host) {
+// `which`: 1 = the clipped-sum exchange of a finalize kernel, 2 = the tile counts of the sharded sampler (the host
+// mirror keeps one counter per kind at words [1], [2]: d3p_comm_timeout_detail).
+D3P_D void comm_flag_timeout(uint32_t* err, uint32_t* err_host, int which) {
   atomicAdd(err, 1u);
   atomicAdd_system(err_host, 1u);
+  atomicAdd_system(err_host + which, 1u);
 }
 // wait for rank src's slot j of this epoch (spins on LOCAL memory).  A slot whose tag never matches is NOT
 // consumed: the result is NaN, which poisons this step's gradient, parameters and loss on this rank and, through
@@ -98,7 +102,7 @@ D3P_D float ll_wait(const CommDev& c, int src, size_t j) {
       else if (now - t0 > c.timeout_ns || ld_relaxed_sys_u32(c.err) != 0u) break;   // once flagged, nobody waits long
     }
   }
-  comm_flag_timeout(c.err, c.err_host);
+  comm_flag_timeout(c.err, c.err_host, 1);
   return __uint_as_float(0x7fc00000u);
 }
 // true when an earlier kernel of this rank has seen a time-out (sampler or exchange): the caller poisons its output
@@ -139,7 +143,7 @@ D3P_D uint32_t samp_wait_count(const SampDev& sd, uint32_t tile) {
       else if (now - t0 > sd.timeout_ns || ld_relaxed_sys_u32(sd.err) != 0u) break;
     }
   }
-  comm_flag_timeout(sd.err, sd.err_host);
+  comm_flag_timeout(sd.err, sd.err_host, 2);
   return 0u;
 }
 

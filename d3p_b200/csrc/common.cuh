@@ -68,6 +68,28 @@ D3P_HD void chacha_derive_key(const uint32_t (&in)[16], uint32_t data, uint32_t 
   out[13] = in[13]; out[14] = in[14]; out[15] = in[15];
 }
 
+// A ChaCha state handed to a kernel either BY VALUE (the host-key entry points: the 16 words travel in the kernel
+// parameters) or BY DEVICE POINTER (the *_dk entry points: the key was produced on the device, e.g. by a split /
+// fold_in inside a jitted loop body, and no host ever sees it).  d == nullptr selects the by-value words.
+struct ChaChaArg {
+  ChaChaState v;
+  const uint32_t* d;
+};
+__device__ __forceinline__ void load_chacha(const ChaChaArg& a, ChaChaState& st) {
+  if (a.d) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st.w[i] = __ldg(a.d + i);
+  } else {
+    st = a.v;
+  }
+}
+inline ChaChaArg chacha_arg(const uint32_t* host_words, const uint32_t* dev_words) {
+  ChaChaArg a;
+  for (int i = 0; i < 16; ++i) a.v.w[i] = host_words ? host_words[i] : 0u;
+  a.d = dev_words;
+  return a;
+}
+
 // Threefry-2x32, 20 rounds (Random123), as used by jax.random (d3p/svi.py:290).
 struct TfKey {
   uint32_t k0, k1, k2;
@@ -90,6 +112,11 @@ D3P_HD void threefry2x32(const TfKey& k, uint32_t c0, uint32_t c1, uint32_t& y0,
   D3P_TF_ROUND(13) D3P_TF_ROUND(15) D3P_TF_ROUND(26) D3P_TF_ROUND(6)
   x0 += k.k2; x1 += k.k0 + 5u;
   y0 = x0; y1 = x1;
+}
+
+// The step kernels take the Threefry key as two words by value, or - the *_dk entry points - from device memory.
+__device__ __forceinline__ TfKey tf_key_arg(uint32_t k0, uint32_t k1, const uint32_t* dev) {
+  return dev ? TfKey(__ldg(dev), __ldg(dev + 1)) : TfKey(k0, k1);
 }
 
 // jax.random.split(key, 2): counts iota(4) -> calls (0,2),(1,3); child0=(a.y0,b.y0), child1=(a.y1,b.y1)

@@ -13,6 +13,7 @@ namespace d3p {
 
 struct EvalArgs {
   const float* params; const float* x; size_t x_stride; const int32_t* y; const int32_t* idx;
+  const uint32_t* key_d;   // *_dk: Threefry key in device memory (else nullptr)
   uint32_t B, k0, k1, d, n_main, half, loc_off, rho_off, b_loc_off, b_rho_off;
   int family, link, has_b;
   float N, inv_var, log_norm_lik;
@@ -26,7 +27,7 @@ __global__ void __launch_bounds__(kEvalThreads) meanfield_eval_kernel(EvalArgs a
   extern __shared__ float th[];             // theta[n_main]
   __shared__ float red[kEvalThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const TfKey K(a.k0, a.k1);
+  const TfKey K = tf_key_arg(a.k0, a.k1, a.key_d);
   TfKey model_seed, guide_seed, rng, k_main;
   tf_split2(K, model_seed, guide_seed);
   tf_split2(guide_seed, rng, k_main);
@@ -125,7 +126,7 @@ extern "C" int32_t d3p_elbo_evaluate_meanfield(const d3p_meanfield_desc* desc, c
   if (ws_bytes < d3p_elbo_evaluate_workspace_bytes()) return D3P_ERR_WORKSPACE;
   EvalArgs a;
   a.params = params_d; a.x = x_d; a.x_stride = x_row_stride; a.y = y_d; a.idx = idx_d; a.B = B;
-  a.k0 = threefry_key_h[0]; a.k1 = threefry_key_h[1];
+  a.k0 = threefry_key_h[0]; a.k1 = threefry_key_h[1]; a.key_d = nullptr;
   a.d = desc->d;
   a.n_main = (desc->joint_site && desc->family == D3P_FAMILY_LOGREG) ? desc->d + 1 : desc->d;
   a.half = (a.n_main + 1) / 2;

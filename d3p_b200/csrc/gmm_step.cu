@@ -31,6 +31,7 @@ struct GmmArgs {
   const float* params; const float* x; size_t x_stride; const int32_t* idx; const uint8_t* mask;
   const int32_t* num_valid;
   uint32_t B, pos_begin, pos_end, k0, k1;
+  const uint32_t* key_d;      // *_dk entry point: Threefry key in device memory (else nullptr)
   uint32_t K, d, P, alpha_off, mus_off;
   float N, inv_S, C;
   float* px_norms; float* px_grads; float* px_loss; float* partials;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kGmmThreads, 2) gmm_step_kernel(GmmArgs a) {
   const float lgamma_K = lgammaf((float)K);
   __syncthreads();
 
-  const TfKey Kk(a.k0, a.k1);
+  const TfKey Kk = tf_key_arg(a.k0, a.k1, a.key_d);
   const uint32_t nv = a.num_valid ? (uint32_t)max(*a.num_valid, 0) : 0xffffffffu;
   const uint32_t half = (n + 1) / 2;
   const float kLogSqrt2Pi = 0.918938533f, kLog10Sqrt2Pi = 3.22152363f;
@@ -387,19 +388,20 @@ extern "C" size_t d3p_gmm_workspace_bytes(const d3p_gmm_desc* desc, uint32_t* n_
   return (size_t)n_part * (desc->n_params + 2) * sizeof(float);
 }
 
-extern "C" int32_t d3p_dpsvi_step_gmm(const d3p_gmm_desc* desc, const float* params_d, const float* x_d,
-                                      size_t x_row_stride, const int32_t* idx_d, const uint8_t* mask_d,
-                                      const int32_t* num_valid_d, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
-                                      const uint32_t threefry_key_h[2], float obs_scale, float C, float* px_norms_d,
-                                      float* px_grads_d, float* px_loss_d, void* ws_d, size_t ws_bytes, void* stream) {
-  if (!desc || !params_d || !x_d || !threefry_key_h || !ws_d) return D3P_ERR_INVALID_ARGUMENT;
+static int32_t step_gmm_impl(const d3p_gmm_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
+                             const int32_t* idx_d, const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                             uint32_t pos_begin, uint32_t pos_end, const uint32_t* threefry_key_h,
+                             const uint32_t* threefry_key_d, float obs_scale, float C, float* px_norms_d,
+                             float* px_grads_d, float* px_loss_d, void* ws_d, size_t ws_bytes, void* stream) {
+  if (!desc || !params_d || !x_d || (!threefry_key_h && !threefry_key_d) || !ws_d) return D3P_ERR_INVALID_ARGUMENT;
   if (!gmm_supported(desc)) return D3P_ERR_UNSUPPORTED;
   if (pos_end > B || pos_begin > pos_end || !(C > 0.f) || !(obs_scale != 0.f)) return D3P_ERR_INVALID_ARGUMENT;
   const uint32_t n_part = 2u * (uint32_t)sm_count();
   if (ws_bytes < (size_t)n_part * (desc->n_params + 2) * sizeof(float)) return D3P_ERR_WORKSPACE;
   GmmArgs a;
   a.params = params_d; a.x = x_d; a.x_stride = x_row_stride; a.idx = idx_d; a.mask = mask_d; a.num_valid = num_valid_d;
-  a.B = B; a.pos_begin = pos_begin; a.pos_end = pos_end; a.k0 = threefry_key_h[0]; a.k1 = threefry_key_h[1];
+  a.B = B; a.pos_begin = pos_begin; a.pos_end = pos_end; a.k0 = threefry_key_h ? threefry_key_h[0] : 0u;
+  a.k1 = threefry_key_h ? threefry_key_h[1] : 0u; a.key_d = threefry_key_d;
   a.K = desc->K; a.d = desc->d; a.P = desc->n_params; a.alpha_off = desc->alpha_off; a.mus_off = desc->mus_off;
   a.N = desc->num_obs_total; a.inv_S = 1.0f / obs_scale; a.C = C;
   a.px_norms = px_norms_d; a.px_grads = px_grads_d; a.px_loss = px_loss_d; a.partials = static_cast<float*>(ws_d);
@@ -409,4 +411,24 @@ extern "C" int32_t d3p_dpsvi_step_gmm(const d3p_gmm_desc* desc, const float* par
     return D3P_ERR_CUDA;
   gmm_step_kernel<<<n_part, kGmmThreads, smem, (cudaStream_t)stream>>>(a);
   return check_launch();
+}
+
+extern "C" int32_t d3p_dpsvi_step_gmm(const d3p_gmm_desc* desc, const float* params_d, const float* x_d,
+                                      size_t x_row_stride, const int32_t* idx_d, const uint8_t* mask_d,
+                                      const int32_t* num_valid_d, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
+                                      const uint32_t threefry_key_h[2], float obs_scale, float C, float* px_norms_d,
+                                      float* px_grads_d, float* px_loss_d, void* ws_d, size_t ws_bytes, void* stream) {
+  if (!threefry_key_h) return D3P_ERR_INVALID_ARGUMENT;
+  return step_gmm_impl(desc, params_d, x_d, x_row_stride, idx_d, mask_d, num_valid_d, B, pos_begin, pos_end, threefry_key_h,
+                       nullptr, obs_scale, C, px_norms_d, px_grads_d, px_loss_d, ws_d, ws_bytes, stream);
+}
+
+extern "C" int32_t d3p_dpsvi_step_gmm_dk(const d3p_gmm_desc* desc, const float* params_d, const float* x_d,
+                                         size_t x_row_stride, const int32_t* idx_d, const uint8_t* mask_d,
+                                         const int32_t* num_valid_d, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
+                                         const uint32_t* threefry_key_d, float obs_scale, float C, float* px_norms_d,
+                                         float* px_grads_d, float* px_loss_d, void* ws_d, size_t ws_bytes, void* stream) {
+  if (!threefry_key_d) return D3P_ERR_INVALID_ARGUMENT;
+  return step_gmm_impl(desc, params_d, x_d, x_row_stride, idx_d, mask_d, num_valid_d, B, pos_begin, pos_end, nullptr,
+                       threefry_key_d, obs_scale, C, px_norms_d, px_grads_d, px_loss_d, ws_d, ws_bytes, stream);
 }

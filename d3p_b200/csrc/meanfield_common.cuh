@@ -17,6 +17,7 @@ struct StepArgs {
   const int32_t* num_valid;
   uint32_t B, pos_begin, pos_end;
   uint32_t k0, k1;
+  const uint32_t* key_d;      // *_dk entry points: the Threefry key lives in device memory (else nullptr)
   float inv_S, L, C, N;
   float inv_var, log_norm_lik;
   uint32_t d, n_main, half, P, loc_off, rho_off, b_loc_off, b_rho_off;

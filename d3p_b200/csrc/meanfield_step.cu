@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
   for (int s = 0; s < NS; ++s) { acc_loc[s] = 0.f; acc_rho[s] = 0.f; }
   float acc_bloc = 0.f, acc_brho = 0.f, acc_loss = 0.f, acc_cnt = 0.f;
 
-  const TfKey K(a.k0, a.k1);
+  const TfKey K = tf_key_arg(a.k0, a.k1, a.key_d);
   const uint32_t npos = a.pos_end - a.pos_begin;
   const uint32_t nv = a.num_valid ? (uint32_t)max(*a.num_valid, 0) : 0xffffffffu;
   const uint32_t total_warps = gridDim.x * kStepWarps;
@@ -334,13 +334,13 @@ size_t d3p_meanfield_workspace_bytes(const d3p_meanfield_desc* desc, uint32_t* n
   return (size_t)n_partials * (desc->n_params + 2) * sizeof(float);
 }
 
-int32_t d3p_dpsvi_step_meanfield(const d3p_meanfield_desc* desc, const float* params_d, const float* x_d,
-                                 size_t x_row_stride, const int32_t* y_d, const int32_t* idx_d,
-                                 const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
-                                 uint32_t pos_begin, uint32_t pos_end, const uint32_t threefry_key_h[2],
-                                 float obs_scale, float C, float* px_norms_d, float* px_grads_d, float* px_loss_d,
-                                 void* ws_d, size_t ws_bytes, void* stream) {
-  if (!desc_ok(desc) || !params_d || !x_d || !threefry_key_h || !ws_d) return D3P_ERR_INVALID_ARGUMENT;
+static int32_t step_meanfield_impl(const d3p_meanfield_desc* desc, const float* params_d, const float* x_d,
+                                   size_t x_row_stride, const int32_t* y_d, const int32_t* idx_d,
+                                   const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                                   uint32_t pos_begin, uint32_t pos_end, const uint32_t* threefry_key_h,
+                                   const uint32_t* threefry_key_d, float obs_scale, float C, float* px_norms_d,
+                                   float* px_grads_d, float* px_loss_d, void* ws_d, size_t ws_bytes, void* stream) {
+  if (!desc_ok(desc) || !params_d || !x_d || (!threefry_key_h && !threefry_key_d) || !ws_d) return D3P_ERR_INVALID_ARGUMENT;
   if (desc->family == D3P_FAMILY_LOGREG && !y_d) return D3P_ERR_INVALID_ARGUMENT;
   if (C == 0.f || obs_scale == 0.f || B == 0 || pos_begin > pos_end || pos_end > B || x_row_stride < desc->d)
     return D3P_ERR_INVALID_ARGUMENT;
@@ -351,7 +351,8 @@ int32_t d3p_dpsvi_step_meanfield(const d3p_meanfield_desc* desc, const float* pa
   StepArgs a;
   a.params = params_d; a.x = x_d; a.x_stride = x_row_stride; a.y = y_d; a.idx = idx_d; a.mask = mask_d;
   a.num_valid = num_valid_d; a.B = B; a.pos_begin = pos_begin; a.pos_end = pos_end;
-  a.k0 = threefry_key_h[0]; a.k1 = threefry_key_h[1];
+  a.k0 = threefry_key_h ? threefry_key_h[0] : 0u; a.k1 = threefry_key_h ? threefry_key_h[1] : 0u;
+  a.key_d = threefry_key_d;
   a.inv_S = 1.0f / obs_scale; a.L = desc->num_obs_total / obs_scale; a.C = C; a.N = desc->num_obs_total;
   a.inv_var = 0.f; a.log_norm_lik = 0.f;
   if (desc->family == D3P_FAMILY_GAUSS) {
@@ -377,6 +378,30 @@ int32_t d3p_dpsvi_step_meanfield(const d3p_meanfield_desc* desc, const float* pa
   }
   if (desc->link == D3P_LINK_EXP) return launch_shape<D3P_FAMILY_GAUSS, D3P_LINK_EXP>(sh, a, smem, n_partials, s);
   return launch_shape<D3P_FAMILY_GAUSS, D3P_LINK_SOFTPLUS>(sh, a, smem, n_partials, s);
+}
+
+int32_t d3p_dpsvi_step_meanfield(const d3p_meanfield_desc* desc, const float* params_d, const float* x_d,
+                                 size_t x_row_stride, const int32_t* y_d, const int32_t* idx_d,
+                                 const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                                 uint32_t pos_begin, uint32_t pos_end, const uint32_t threefry_key_h[2],
+                                 float obs_scale, float C, float* px_norms_d, float* px_grads_d, float* px_loss_d,
+                                 void* ws_d, size_t ws_bytes, void* stream) {
+  if (!threefry_key_h) return D3P_ERR_INVALID_ARGUMENT;
+  return step_meanfield_impl(desc, params_d, x_d, x_row_stride, y_d, idx_d, mask_d, num_valid_d, B, pos_begin, pos_end,
+                             threefry_key_h, nullptr, obs_scale, C, px_norms_d, px_grads_d, px_loss_d, ws_d, ws_bytes, stream);
+}
+
+// Device-key form: the Threefry key (convert_to_jax_rng_key of the step's ChaCha key, d3p_dpsvi_keys_dk) is read from
+// device memory by the kernel, so a jitted caller never brings a key to the host.
+int32_t d3p_dpsvi_step_meanfield_dk(const d3p_meanfield_desc* desc, const float* params_d, const float* x_d,
+                                    size_t x_row_stride, const int32_t* y_d, const int32_t* idx_d,
+                                    const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                                    uint32_t pos_begin, uint32_t pos_end, const uint32_t* threefry_key_d,
+                                    float obs_scale, float C, float* px_norms_d, float* px_grads_d, float* px_loss_d,
+                                    void* ws_d, size_t ws_bytes, void* stream) {
+  if (!threefry_key_d) return D3P_ERR_INVALID_ARGUMENT;
+  return step_meanfield_impl(desc, params_d, x_d, x_row_stride, y_d, idx_d, mask_d, num_valid_d, B, pos_begin, pos_end,
+                             nullptr, threefry_key_d, obs_scale, C, px_norms_d, px_grads_d, px_loss_d, ws_d, ws_bytes, stream);
 }
 
 }  // extern "C"

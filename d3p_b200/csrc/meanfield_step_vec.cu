@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kStepThreads, 2) meanfield_step_vec_kernel(Ste
   for (int i = 0; i < 2 * NCH; ++i) { accL[i] = make_float4(0.f, 0.f, 0.f, 0.f); accR[i] = accL[i]; }
   float acc_bloc = 0.f, acc_brho = 0.f, acc_loss = 0.f, acc_cnt = 0.f;
 
-  const TfKey K(a.k0, a.k1);
+  const TfKey K = tf_key_arg(a.k0, a.k1, a.key_d);
   const uint32_t npos = a.pos_end - a.pos_begin;
   const uint32_t nv = a.num_valid ? (uint32_t)max(*a.num_valid, 0) : 0xffffffffu;
   const uint32_t total_warps = gridDim.x * kStepWarps;

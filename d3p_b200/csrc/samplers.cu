@@ -1,7 +1,5 @@
 // K2 Feistel sampler, K3 Poisson select + ordered compaction, K4 masked row gather.
 // Replace d3p/util.py:216-301 and d3p/minibatch.py:29-39,103-131,210,233,306.
-#include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "comm.cuh"
@@ -78,7 +76,8 @@ D3P_D int tile_count(uint32_t m, int* warp_c) {      // CTA total of popc(m); va
 
 __global__ void __launch_bounds__(kPoisThreads) poisson_select_kernel(ChaChaState st, float q, uint32_t n_records,
                                                                       uint16_t* __restrict__ masks,
-                                                                      int32_t* __restrict__ tile_counts) {
+                                                                      int32_t* __restrict__ tile_counts, uint32_t* ready) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ready = 0u;      // the compaction kernel's "prefix published" flag
   uint32_t blk = blockIdx.x * kPoisThreads + threadIdx.x;
   uint32_t n_blocks = (n_records + 15) / 16;
   uint32_t m = 0;
@@ -99,7 +98,9 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_select_kernel(ChaChaStat
 __global__ void __launch_bounds__(kPoisThreads) poisson_select_sharded_kernel(ChaChaState st, float q,
                                                                               uint32_t n_records, uint32_t cov_lo,
                                                                               uint32_t own_lo, uint32_t own_hi,
-                                                                              uint16_t* __restrict__ masks, SampDev sd) {
+                                                                              uint16_t* __restrict__ masks, SampDev sd,
+                                                                              uint32_t* ready) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ready = 0u;
   const uint32_t tile = cov_lo + blockIdx.x;
   const uint32_t blk = tile * kPoisThreads + threadIdx.x;
   const uint32_t n_blocks = (n_records + 15) / 16;
@@ -118,10 +119,50 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_select_sharded_kernel(Ch
 }
 
 
-// Pass B + C fused: every CTA (one per tile) first adds up the tile counts above it — n_tiles is a few
-// thousand, i.e. ~10 loads per thread — which replaces the former single-CTA scan launch, then compacts its
-// tile in DESCENDING record order: idx[s] for the selected records (s = number of selected records with a
-// larger index), and the unselected ones behind them for the padding slots (d3p/minibatch.py:37).
+// Pass B (CTA 0 of the compaction kernel): the per-tile counts become "selected records in the tiles above" (exclusive
+// prefix in DESCENDING tile order, the output order of d3p/minibatch.py:37) + the total, published to the other CTAs
+// through a ready flag.  Sharded: the counts are the tagged words the tile owners pushed into this rank's window; only
+// this CTA polls them.  (Round 1 had every compaction CTA add up all n_tiles counts itself: n_tiles^2 loads, 15.5 us at
+// N = 10 M, paid in full by every rank of a sharded run.)  A separate scan launch would do the same, but it would put
+// a kernel that waits for the peers in front of a dependent kernel of the same stream, and streams that share a
+// hardware work queue would then block each other; this way the waiting kernel stays the last one of the sampler call.
+template <bool kSharded>
+D3P_D void scan_tiles(const int32_t* __restrict__ tile_counts, uint32_t n_tiles, uint32_t max_b, int suppress,
+                      int32_t* __restrict__ tile_above, int32_t* __restrict__ counts, const SampDev& sd, int* warp_tot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // thread i owns a run of consecutive tiles, runs ordered from the HIGH end: thread 0 has the top tiles
+  const uint32_t per = (n_tiles + kPoisThreads - 1) / kPoisThreads;
+  const uint32_t hi = n_tiles > threadIdx.x * per ? n_tiles - threadIdx.x * per : 0;      // exclusive upper end
+  const uint32_t lo = hi > per ? hi - per : 0;
+  int mine = 0;
+  for (uint32_t t = lo; t < hi; ++t) mine += kSharded ? (int)samp_wait_count(sd, t) : tile_counts[t];
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  int before = 0, total = 0;                                     // sums of the warps before mine / of all warps
+#pragma unroll
+  for (int w = 0; w < kPoisThreads / 32; ++w) { before += w < warp ? warp_tot[w] : 0; total += warp_tot[w]; }
+  int above = incl - mine + before;                              // selected records in the runs of lower thread ids
+  for (uint32_t t = hi; t-- > lo;) {                             // descending inside the run
+    tile_above[t] = above;
+    above += kSharded ? (int)samp_wait_count(sd, t) : tile_counts[t];
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t tot = (uint32_t)total;
+    const uint32_t eff = suppress ? (tot <= max_b ? tot : 0u) : (tot < max_b ? tot : max_b);
+    tile_above[n_tiles] = (int32_t)tot;
+    counts[0] = (int32_t)tot; counts[1] = (int32_t)eff;
+  }
+}
+
+// Pass C: one CTA per tile compacts it in DESCENDING record order: idx[s] for the selected records (s = number of
+// selected records with a larger index = tile_above[tile] + those above it inside the tile), and the unselected ones
+// behind them for the padding slots (d3p/minibatch.py:37).  CTAs whose tile cannot reach a wanted position leave at once.
 // counts[0] = number selected, counts[1] = after truncate / suppress (:119-122), mask = arange(max_b) < counts[1].
 // kSharded (comm.cuh): counts were pushed into the local window by the tile owners, masks are local (or
 // re-drawn), only positions [pos_begin, pos_end) are written and padding slots are left alone.
@@ -130,6 +171,7 @@ constexpr int kCompactTiles = 1;               // tiles per CTA (8 measured slow
 template <bool kSharded>
 __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uint16_t* __restrict__ masks,
                                                                        const int32_t* __restrict__ tile_counts,
+                                                                       int32_t* tile_above_g, uint32_t* ready,
                                                                        uint32_t n_records, uint32_t n_tiles,
                                                                        uint32_t max_b, int suppress, uint32_t pos_begin,
                                                                        uint32_t pos_end, int32_t* __restrict__ idx,
@@ -140,26 +182,27 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uin
   const uint32_t t_first = blockIdx.x * kCompactTiles;                       // this CTA's tiles [t_first, t_end)
   const uint32_t t_end = min(n_tiles, t_first + kCompactTiles);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __shared__ int red[2][kPoisThreads / 32];
   __shared__ int warp_tot[kPoisThreads / 32];
-  __shared__ int own_counts[kCompactTiles];
-  int above = 0, all = 0;                      // above: selected records in tiles >= t_end
-  for (uint32_t t = threadIdx.x; t < n_tiles; t += kPoisThreads) {
-    const int v = kSharded ? (int)samp_wait_count(sd, t) : tile_counts[t];   // sharded: polls the tagged word
-    all += v;
-    above += t >= t_end ? v : 0;
-    if (t >= t_first && t < t_end) own_counts[t - t_first] = v;
+  static_assert(kCompactTiles == 1, "one tile per CTA");
+  // CTA 0 (always dispatched first) scans the tile counts and raises `ready` (reset by the selector kernel, which
+  // precedes this one on the stream); the others wait for it
+  if (blockIdx.x == 0) {
+    scan_tiles<kSharded>(tile_counts, n_tiles, max_b, suppress, tile_above_g, counts, sd, warp_tot);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ready), "r"(1u) : "memory");
+  } else {
+    if (threadIdx.x == 0) {
+      uint32_t v;
+      do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory"); } while (v != 1u);
+    }
+    __syncthreads();
   }
-  above = __reduce_add_sync(0xffffffffu, above);
-  all = __reduce_add_sync(0xffffffffu, all);
-  if (lane == 0) { red[0][warp] = above; red[1][warp] = all; }
-  __syncthreads();
-  above = 0; all = 0;
-#pragma unroll
-  for (int w = 0; w < kPoisThreads / 32; ++w) { above += red[0][w]; all += red[1][w]; }
-  const uint32_t total = (uint32_t)all;
+  const uint32_t total = (uint32_t)__ldcg(tile_above_g + n_tiles);
+  const int above = __ldcg(tile_above_g + t_first);
+  // this tile's count = the next-lower tile's "above" minus ours (the lowest tile: total - above)
+  const uint32_t own_count = (t_first > 0 ? (uint32_t)__ldcg(tile_above_g + t_first - 1) : total) - (uint32_t)above;
   const uint32_t eff = suppress ? (total <= max_b ? total : 0u) : (total < max_b ? total : max_b);
-  if (blockIdx.x == 0 && threadIdx.x == 0) { counts[0] = (int32_t)total; counts[1] = (int32_t)eff; }
   if (mask) {                                  // this CTA's slice of the mask, 4 bytes per store when aligned
     const uint32_t words = (max_b + 3) / 4, per = (words + gridDim.x - 1) / gridDim.x;
     const bool aligned = (reinterpret_cast<uintptr_t>(mask) & 3) == 0;
@@ -179,7 +222,7 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uin
   const uint32_t n_blocks = (n_records + 15) / 16;
   uint32_t tile_above = (uint32_t)above;       // selected records in tiles above the current one
   for (uint32_t tile = t_end; tile-- > t_first;) {                           // descending: running offset
-    const uint32_t cnt = (uint32_t)own_counts[tile - t_first];
+    const uint32_t cnt = own_count;
     const uint32_t base = tile_above;
     tile_above += cnt;
     // CTA-uniform early outs: nothing of this tile lands in the wanted positions
@@ -272,6 +315,7 @@ struct PoissonWs {
   uint16_t* masks;
   int32_t* tile_counts;
   int32_t* tile_off;
+  uint32_t* ready;
   size_t bytes;
 };
 
@@ -286,7 +330,9 @@ static PoissonWs carve_poisson_ws(void* ws, uint32_t n_records) {
   w.masks = reinterpret_cast<uint16_t*>(base + o_masks);
   w.tile_counts = reinterpret_cast<int32_t*>(base + o_counts);
   w.tile_off = reinterpret_cast<int32_t*>(base + o_off);
-  w.bytes = o_off + align_up(n_tiles * sizeof(int32_t), 256);
+  size_t o_ready = o_off + align_up((n_tiles + 1) * sizeof(int32_t), 256);      // tile_off: n_tiles prefixes + the total
+  w.ready = reinterpret_cast<uint32_t*>(base + o_ready);
+  w.bytes = o_ready + 256;
   return w;
 }
 
@@ -337,12 +383,12 @@ int32_t d3p_poisson_sample(const uint32_t state_h[16], float q, uint32_t n_recor
   uint32_t n_blocks = (n_records + 15) / 16;
   uint32_t n_tiles = (n_blocks + kPoisThreads - 1) / kPoisThreads;
   cudaStream_t s = (cudaStream_t)stream;
-  poisson_select_kernel<<<n_tiles, kPoisThreads, 0, s>>>(load_state(state_h), q, n_records, w.masks, w.tile_counts);
+  poisson_select_kernel<<<n_tiles, kPoisThreads, 0, s>>>(load_state(state_h), q, n_records, w.masks, w.tile_counts, w.ready);
   SampDev none;
   memset(&none, 0, sizeof(none));
-  poisson_compact_kernel<false><<<(n_tiles + kCompactTiles - 1) / kCompactTiles, kPoisThreads, 0, s>>>(w.masks, w.tile_counts, n_records, n_tiles, max_b,
-                                                                 suppress, 0, max_b, idx_d, counts_d, mask_d, none,
-                                                                 load_state(state_h), q, 0, n_tiles);
+  poisson_compact_kernel<false><<<n_tiles, kPoisThreads, 0, s>>>(w.masks, w.tile_counts, w.tile_off, w.ready, n_records, n_tiles, max_b, suppress, 0,
+                                                                 max_b, idx_d, counts_d, mask_d, none, load_state(state_h),
+                                                                 q, 0, n_tiles);
   return check_launch();
 }
 
@@ -368,34 +414,15 @@ int32_t d3p_poisson_sample_sharded(d3p_comm* comm, const uint32_t state_h[16], f
   // slices in DESCENDING record order: rank 0 draws the top tiles, whose records fill the first positions
   const uint32_t hi = n_tiles > (uint32_t)sd.rank * sd.tiles_per_rank ? n_tiles - (uint32_t)sd.rank * sd.tiles_per_rank : 0;
   const uint32_t lo = hi > sd.tiles_per_rank ? hi - sd.tiles_per_rank : 0;
-  // D3P_SAMPLER_PROFILE=1: per-kernel timings of calls 100..199 on stderr (development aid; synchronises once)
-  static const bool prof = getenv("D3P_SAMPLER_PROFILE") != nullptr;
-  static int calls = 0;
-  static cudaEvent_t pe[100][4];
-  const bool rec = prof && calls >= 100 && calls < 200;
-  auto mark = [&](int k) { if (rec) { cudaEventCreate(&pe[calls - 100][k]); cudaEventRecord(pe[calls - 100][k], s); } };
-  mark(0);
-  // tiles (4096 records each) drawn redundantly on each side; D3P_SAMPLER_MARGIN overrides it (tests use 0 to
-  // force the re-draw path of the compaction kernel)
-  static const char* margin_env = getenv("D3P_SAMPLER_MARGIN");
-  const uint32_t margin = margin_env ? (uint32_t)atoi(margin_env) : 16u;
+  // tiles (4096 records each) drawn redundantly on each side of the owned slice (d3p_comm_set_sampler_margin; tests
+  // use 0 to force the re-draw path of the compaction kernel)
+  const uint32_t margin = comm->sampler_margin;
   const uint32_t cov_lo = lo > margin ? lo - margin : 0, cov_hi = hi + margin < n_tiles ? hi + margin : n_tiles;
   poisson_select_sharded_kernel<<<cov_hi - cov_lo, kPoisThreads, 0, s>>>(load_state(state_h), q, n_records, cov_lo, lo,
-                                                                         hi, w.masks, sd);
-  mark(1);
-  mark(2);
-  poisson_compact_kernel<true><<<(n_tiles + kCompactTiles - 1) / kCompactTiles, kPoisThreads, 0, s>>>(w.masks, nullptr, n_records, n_tiles, max_b, suppress,
+                                                                         hi, w.masks, sd, w.ready);
+  poisson_compact_kernel<true><<<n_tiles, kPoisThreads, 0, s>>>(w.masks, nullptr, w.tile_off, w.ready, n_records, n_tiles, max_b, suppress,
                                                                 pos_begin, pos_end, idx_d, counts_d, mask_d, sd,
                                                                 load_state(state_h), q, cov_lo, cov_hi);
-  mark(3);
-  if (prof && ++calls == 200) {
-    cudaStreamSynchronize(s);
-    double t[3] = {0, 0, 0};
-    for (int c = 0; c < 100; ++c)
-      for (int k = 0; k < 3; ++k) { float ms; cudaEventElapsedTime(&ms, pe[c][k], pe[c][k + 1]); t[k] += ms; }
-    fprintf(stderr, "[d3p sampler profile] rank %d: select %.4f  scan %.4f  scatter %.4f ms\n", sd.rank, t[0] / 100,
-            t[1] / 100, t[2] / 100);
-  }
   return check_launch();
 }
 

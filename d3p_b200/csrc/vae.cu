@@ -198,6 +198,7 @@ struct VaeArgs {
   uint32_t off_w4, off_b4, off_w5, off_b5, off_w1, off_b1, off_w2, off_b2, off_w3, off_b3, P;
   const float* x; size_t x_stride; const int32_t* idx; const uint8_t* mask; const int32_t* num_valid;
   uint32_t k0, k1;
+  const uint32_t* key_d;              // *_dk entry point: Threefry key in device memory (else nullptr)
   float site_scale, inv_S, C;
   uint32_t ns_h, ns_d;                // row-reduction slots over H and over D (N tiles x epilogue parts)
   uint32_t S;                         // partial rows
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
   for (uint32_t i = threadIdx.x; i < Z; i += blockDim.x) { b23s[i] = a.params[a.off_b2 + i]; b23s[Z + i] = a.params[a.off_b3 + i]; }
   for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) b4s[i] = a.params[a.off_b4 + i];
   __syncthreads();
-  const TfKey K(a.k0, a.k1);
+  const TfKey K = tf_key_arg(a.k0, a.k1, a.key_d);
   const uint32_t half = (Z + 1) / 2;
   const uint32_t groups = (a.Bl + kMidE - 1) / kMidE;
   for (uint32_t gidx = blockIdx.x * kMidWarps + warp; gidx < groups; gidx += gridDim.x * kMidWarps) {
@@ -725,7 +726,7 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_fwd_mma_kernel(VaeArgs a)
   // ---- phase 0: guide noise: key_p -> (_, guide_seed) -> (rng, k_plate) -> (_, k_z); eps = normal(k_z, (Z,)) ----
   for (uint32_t j = j8; j < 32; j += kMmaTpe) { s_z[0][e8][j] = 0.f; s_z[1][e8][j] = 0.f; }
   if (r0 + e8 < a.Bl) {
-    const TfKey K(a.k0, a.k1);
+    const TfKey K = tf_key_arg(a.k0, a.k1, a.key_d);
     TfKey kp = tf_example_key(K, a.B, a.pos_begin + r0 + e8);
     TfKey model_seed, guide_seed, rng, k_plate, rng2, k_z;
     tf_split2(kp, model_seed, guide_seed);
@@ -1154,13 +1155,12 @@ extern "C" size_t d3p_vae_workspace_bytes(const d3p_vae_desc* desc, uint32_t bat
   return L.total;
 }
 
-extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* params_d, const float* x_d,
-                                      size_t x_row_stride, const int32_t* idx_d, const uint8_t* mask_d,
-                                      const int32_t* num_valid_d, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
-                                      const uint32_t threefry_key_h[2], float obs_scale, float C, float* px_norms_d,
-                                      float* px_loss_d, void* ws_d, size_t ws_bytes, void* const* profile_events_h,
-                                      void* stream) {
-  if (!desc || !params_d || !x_d || !threefry_key_h || !ws_d) return D3P_ERR_INVALID_ARGUMENT;
+static int32_t step_vae_impl(const d3p_vae_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
+                             const int32_t* idx_d, const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                             uint32_t pos_begin, uint32_t pos_end, const uint32_t* threefry_key_h,
+                             const uint32_t* threefry_key_d, float obs_scale, float C, float* px_norms_d,
+                             float* px_loss_d, void* ws_d, size_t ws_bytes, void* const* profile_events_h, void* stream) {
+  if (!desc || !params_d || !x_d || (!threefry_key_h && !threefry_key_d) || !ws_d) return D3P_ERR_INVALID_ARGUMENT;
   if (!vae_supported(desc)) return D3P_ERR_UNSUPPORTED;
   if (pos_end > B || pos_begin >= pos_end || !(C > 0.f) || !(obs_scale != 0.f)) return D3P_ERR_INVALID_ARGUMENT;
   if (reinterpret_cast<uintptr_t>(ws_d) & 255) return D3P_ERR_INVALID_ARGUMENT;
@@ -1181,7 +1181,8 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   a.off_w1 = desc->off_w1; a.off_b1 = desc->off_b1; a.off_w2 = desc->off_w2; a.off_b2 = desc->off_b2;
   a.off_w3 = desc->off_w3; a.off_b3 = desc->off_b3; a.P = P;
   a.x = x_d; a.x_stride = x_row_stride; a.idx = idx_d; a.mask = mask_d; a.num_valid = num_valid_d;
-  a.k0 = threefry_key_h[0]; a.k1 = threefry_key_h[1];
+  a.k0 = threefry_key_h ? threefry_key_h[0] : 0u; a.k1 = threefry_key_h ? threefry_key_h[1] : 0u;
+  a.key_d = threefry_key_d;
   a.site_scale = desc->site_scale; a.inv_S = 1.0f / obs_scale; a.C = C;
   a.ns_h = L.ns_h; a.ns_d = L.ns_d; a.S = L.S;
   a.x_hi = F(L.x_hi); a.x_lo = F(L.x_lo); a.x_lo_flag = reinterpret_cast<int*>(ws + L.flag);
@@ -1326,4 +1327,27 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
   if (profile_events_h && cudaEventRecord((cudaEvent_t)profile_events_h[1], s) != cudaSuccess) return D3P_ERR_CUDA;
   vae_loss_kernel<<<L.S, 256, 0, s>>>(a);
   return check_launch();
+}
+
+extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* params_d, const float* x_d,
+                                      size_t x_row_stride, const int32_t* idx_d, const uint8_t* mask_d,
+                                      const int32_t* num_valid_d, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
+                                      const uint32_t threefry_key_h[2], float obs_scale, float C, float* px_norms_d,
+                                      float* px_loss_d, void* ws_d, size_t ws_bytes, void* const* profile_events_h,
+                                      void* stream) {
+  if (!threefry_key_h) return D3P_ERR_INVALID_ARGUMENT;
+  return step_vae_impl(desc, params_d, x_d, x_row_stride, idx_d, mask_d, num_valid_d, B, pos_begin, pos_end, threefry_key_h,
+                       nullptr, obs_scale, C, px_norms_d, px_loss_d, ws_d, ws_bytes, profile_events_h, stream);
+}
+
+// Device-key form (see d3p_dpsvi_step_meanfield_dk).
+extern "C" int32_t d3p_dpsvi_step_vae_dk(const d3p_vae_desc* desc, const float* params_d, const float* x_d,
+                                         size_t x_row_stride, const int32_t* idx_d, const uint8_t* mask_d,
+                                         const int32_t* num_valid_d, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
+                                         const uint32_t* threefry_key_d, float obs_scale, float C, float* px_norms_d,
+                                         float* px_loss_d, void* ws_d, size_t ws_bytes, void* const* profile_events_h,
+                                         void* stream) {
+  if (!threefry_key_d) return D3P_ERR_INVALID_ARGUMENT;
+  return step_vae_impl(desc, params_d, x_d, x_row_stride, idx_d, mask_d, num_valid_d, B, pos_begin, pos_end, nullptr,
+                       threefry_key_d, obs_scale, C, px_norms_d, px_loss_d, ws_d, ws_bytes, profile_events_h, stream);
 }

@@ -80,7 +80,10 @@ class PeerWindow:
         if self.world_size > 1:
             dist.barrier(group=self.group)
         self.close()
-        return PeerWindow(self.rank, self.world_size, self.max_params, self.group, max_records=n_records)
+        new = PeerWindow(self.rank, self.world_size, self.max_params, self.group, max_records=n_records)
+        if getattr(self, "sampler_margin", None) is not None:
+            new.set_sampler_margin(self.sampler_margin)
+        return new
 
     def timeouts(self):
         """Exchanges that timed out on this rank so far (host-mapped counter, no device synchronisation: covers
@@ -91,9 +94,21 @@ class PeerWindow:
         _n.check(_n.lib().d3p_comm_timeouts(self._comm, C.byref(out)), "comm_timeouts")
         return out.value
 
+    def timeout_detail(self):
+        """(all, clipped-sum exchange, sampler counts) time-outs seen by this rank's kernels."""
+        import ctypes as C
+        out = (C.c_uint32 * 4)()
+        _n.check(_n.lib().d3p_comm_timeout_detail(self._comm, out), "comm_timeout_detail")
+        return tuple(out)[:3]
+
     def set_timeout_ms(self, ms):
         """How long a kernel waits for a peer's words before it gives up (default 10 s)."""
         _n.check(_n.lib().d3p_comm_set_timeout_ms(self._comm, int(ms)), "comm_set_timeout_ms")
+
+    def set_sampler_margin(self, tiles):
+        """Sharded Poisson sampler: tiles drawn redundantly on each side of a rank's slice (same on all ranks)."""
+        _n.check(_n.lib().d3p_comm_set_sampler_margin(self._comm, int(tiles)), "comm_set_sampler_margin")
+        self.sampler_margin = int(tiles)
 
     def check(self, synchronize=True):
         """Raise on every rank's own evidence if an exchange timed out (``synchronize=True`` drains the device first)."""
@@ -101,7 +116,8 @@ class PeerWindow:
             torch.cuda.synchronize()
         n = self.timeouts()
         if n:
-            raise _n.D3PNativeError(f"rank {self.rank}: {n} peer-memory exchange time-out(s); this step was poisoned "
+            raise _n.D3PNativeError(f"rank {self.rank}: {n} peer-memory exchange time-out(s) {self.timeout_detail()} "
+                                    "(all, clipped sums, sampler counts); this step was poisoned "
                                     "(NaN) and the replicas can no longer be trusted")
 
     def close(self):

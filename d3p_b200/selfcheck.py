@@ -14,6 +14,7 @@ import torch.distributed as dist
 
 from . import minibatch as mb, models, optimizers, parallel, random as rng, svi as dsvi
 
+SAMPLER_MARGIN = None   # tests set 0: the sharded sampler draws no redundant tiles, which exercises its re-draw path
 REL_TOL = 1e-5
 ABS_FLOOR = 1e-3      # |got - ref| / max(|ref|, ABS_FLOOR): parameters below 1e-3 are compared at 1e-8 absolute
 LOSS_RTOL = 2e-5
@@ -29,6 +30,8 @@ def _run(make_family, dataset, clip, sharded, steps, epoch, q):
                    num_obs_total=len(dataset[0]))
     if sharded:
         parallel.shard_dpsvi(s, backend=sharded)
+        if SAMPLER_MARGIN is not None and s.peer_window is not None:
+            s.peer_window.set_sampler_margin(SAMPLER_MARGIN)
     init, get = mb.poisson_batchify_data(dataset, q, .99)
     key = rng.PRNGKey(5)
     key, k_init, k_fetch = rng.split(key, 3)

@@ -286,7 +286,10 @@ int32_t d3p_comm_connect(d3p_comm* comm, const uint8_t* handles_h);
 int32_t d3p_comm_window(d3p_comm* comm, void** window_out_h, size_t* bytes_out_h);
 int32_t d3p_comm_connect_local(d3p_comm* comm, void* const* windows_h);
 int32_t d3p_comm_timeouts(d3p_comm* comm, uint32_t* count_out_h);
+int32_t d3p_comm_timeout_detail(d3p_comm* comm, uint32_t out_h[4]); /* [0] all, [1] clipped-sum exchange, [2] sampler counts */
 int32_t d3p_comm_set_timeout_ms(d3p_comm* comm, uint32_t timeout_ms);
+/* sharded sampler: tiles (4096 records) drawn redundantly on each side of a rank's slice (default 16; same on all ranks) */
+int32_t d3p_comm_set_sampler_margin(d3p_comm* comm, uint32_t tiles);
 int32_t d3p_comm_destroy(d3p_comm* comm);
 /* d3p_poisson_sample with the selector draw (the expensive part: N / 16 ChaCha blocks) split over the
  * ranks: rank r draws its slice of the records, publishes 16-bit selection masks and per-tile counts in

@@ -14,6 +14,9 @@ import d3p_b200.random as rng  # noqa: E402
 from d3p_b200 import minibatch as mb, models, optimizers, parallel, svi as dsvi  # noqa: E402
 
 
+MARGIN = int(os.environ["D3P_TEST_SAMPLER_MARGIN"]) if "D3P_TEST_SAMPLER_MARGIN" in os.environ else None
+
+
 def check_local_rows(dev, rank, world):
     """minibatch.LocalRows: feeding only this rank's rows must equal feeding the whole batch (bit for bit)."""
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -51,6 +54,8 @@ def check_sharded_sampler(dev, rank, world):
     from d3p_b200 import _native as _n
     N = 300_000
     win = parallel.PeerWindow(rank, world, 16, max_records=N)
+    if MARGIN is not None:
+        win.set_sampler_margin(MARGIN)
     need = _n.lib().d3p_poisson_workspace_bytes(N)
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
     ok = True
@@ -88,6 +93,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
     from d3p_b200 import selfcheck
+    selfcheck.SAMPLER_MARGIN = MARGIN
     res = selfcheck.sharded_parity_check(dev, which=("logreg", "gauss", "vae"),
                                          modes=(("nccl", False), ("p2p", False), ("p2p", True)), verbose=True)
     ok = res["ok"]

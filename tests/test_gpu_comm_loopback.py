@@ -91,7 +91,7 @@ def _run(make_fam, dataset, clip, world, epoch, steps=3):
                 losses[r].append(float(out[r]))
     torch.cuda.synchronize()
     for w in wins:
-        assert w.timeouts() == 0, "peer exchange timed out"
+        assert w.timeouts() == 0, f"peer exchange timed out: {[x.timeout_detail() for x in wins]}"
     flats = [st.optim_state.flat.clone() for st in states]
     keys = [np.asarray(st.rng_key).copy() for st in states]
     for w in wins:
@@ -116,11 +116,16 @@ def test_sharded_equals_unsharded_on_one_device(cuda, world, epoch):
         assert np.allclose(losses[0], l1, rtol=2e-5), (name, losses[0], l1)
 
 
-def test_sharded_sampler_bit_exact_on_one_device(cuda):
+@pytest.mark.parametrize("margin", [None, 0], ids=["margin16", "margin0-redraw"])
+def test_sharded_sampler_bit_exact_on_one_device(cuda, margin):
     import d3p_b200.random as rng
     from d3p_b200 import _native as _n, minibatch as mb, parallel
     N, world = 300_000, 3
     wins = parallel.PeerWindow.local_group(world, 16, max_records=N)
+    for w in wins:
+        w.set_timeout_ms(4000)
+        if margin is not None:
+            w.set_sampler_margin(margin)
     need = _n.lib().d3p_poisson_workspace_bytes(N)
     streams = [torch.cuda.Stream() for _ in range(world)]
     for it, (q, max_b, suppress) in enumerate([(0.01, 3200, 0), (0.01, 2900, 0), (0.01, 2900, 1), (0.02, 6500, 0),

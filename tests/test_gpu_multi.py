@@ -19,7 +19,7 @@ def test_sharded_equals_single_gpu(cuda, margin):
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ)
     if margin is not None:
-        env["D3P_SAMPLER_MARGIN"] = margin
+        env["D3P_TEST_SAMPLER_MARGIN"] = margin
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "helpers", "multi_rank_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
