@@ -121,9 +121,43 @@ _SIGNATURES = {
                                                  C.POINTER(C.c_float), _vp, _vp]),
     "d3p_reduce_partials_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "d3p_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.c_uint32, _u32p]),
+    "d3p_vae_ctx_create": (C.c_int32, [C.POINTER(C.c_void_p)]),
+    "d3p_vae_ctx_destroy": (C.c_int32, [_vp]),
     "d3p_dpsvi_step_vae": (C.c_int32, [C.POINTER(VaeDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
                                        C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, C.c_size_t,
-                                       C.POINTER(C.c_void_p), _vp]),
+                                       C.POINTER(C.c_void_p), _vp, _vp]),
+    # ---- device-key forms: every key argument is a device pointer (c_void_p) ----
+    "d3p_chacha_split_dk": (C.c_int32, [_vp, C.c_int32, _vp, _vp]),
+    "d3p_chacha_fold_in_dk": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp]),
+    "d3p_chacha_random_bits_dk": (C.c_int32, [_vp, C.c_uint64, _vp, C.c_size_t, _vp]),
+    "d3p_chacha_uniform_f32_dk": (C.c_int32, [_vp, C.c_uint64, C.c_float, C.c_float, _vp, C.c_size_t, _vp]),
+    "d3p_chacha_normal_f32_dk": (C.c_int32, [_vp, C.c_uint64, _vp, C.c_size_t, _vp]),
+    "d3p_dpsvi_keys_dk": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, _vp]),
+    "d3p_feistel_round_constants_dk": (C.c_int32, [_vp, _vp, _vp]),
+    "d3p_feistel_sample_dk": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "d3p_poisson_sample_dk": (C.c_int32, [_vp, C.c_float, C.c_uint32, C.c_uint32, C.c_int32, _vp, _vp, _vp, _vp,
+                                          C.c_size_t, _vp]),
+    "d3p_poisson_sample_sharded_dk": (C.c_int32, [_vp, _vp, C.c_float, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32,
+                                                  C.c_uint32, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_dpsvi_step_meanfield_dk": (C.c_int32, [C.POINTER(MeanfieldDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp,
+                                                C.c_uint32, C.c_uint32, C.c_uint32, _vp, C.c_float, C.c_float,
+                                                _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_dpsvi_step_vae_dk": (C.c_int32, [C.POINTER(VaeDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
+                                          C.c_uint32, _vp, C.c_float, C.c_float, _vp, _vp, _vp, C.c_size_t,
+                                          C.POINTER(C.c_void_p), _vp, _vp]),
+    "d3p_dpsvi_step_gmm_dk": (C.c_int32, [C.POINTER(GmmDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
+                                          C.c_uint32, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_perturb_finalize_dk_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(LeafTable), _vp,
+                                                C.c_float, C.c_float, C.c_float, _vp, C.POINTER(OptimDesc), _vp, _vp,
+                                                _vp, _vp, _vp, _vp]),
+    "d3p_dpsvi_run_epoch_meanfield_dk": (C.c_int32, [C.POINTER(MeanfieldDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
+                                                     _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
+                                                     C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
+                                                     _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_dpsvi_run_epoch_vae_dk": (C.c_int32, [C.POINTER(VaeDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
+                                               _vp, _vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
+                                               C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
+                                               _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "d3p_gmm_workspace_bytes": (C.c_size_t, [C.POINTER(GmmDesc), _u32p]),
     "d3p_dpsvi_step_gmm": (C.c_int32, [C.POINTER(GmmDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
                                        C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),

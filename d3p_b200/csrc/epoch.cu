@@ -32,6 +32,11 @@ struct EpochWs {
   int32_t* counts[2]; // [2]
   uint8_t* mask[2];   // [batch]
   float* step;        // [n_partials, P + 2]
+  // device-key mode (*_dk): per-step keys made on the device
+  uint32_t* bkey[2];  // fold_in(batch_key, step) per sampler buffer
+  uint32_t* rc[2];    // Feistel round constants per sampler buffer
+  uint32_t* tf;       // Threefry key of the step
+  uint32_t* sites;    // [D3P_MAX_LEAVES][16] per-leaf noise keys of the step
 };
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -46,6 +51,7 @@ bool layout_ws(size_t step_bytes, const d3p_sampler_desc* s, void* base, EpochWs
   const size_t o_poi = take(w.poisson_bytes), o_step = take(w.step_bytes);
   size_t o_idx[2], o_cnt[2], o_mask[2];
   for (int b = 0; b < 2; ++b) { o_idx[b] = take((size_t)s->batch * 4); o_cnt[b] = take(8); o_mask[b] = take(s->batch); }
+  const size_t o_keys = take((2 * 16 + 2 * 32 + 64 + D3P_MAX_LEAVES * 16) * sizeof(uint32_t));
   w.total = off;
   if (base) {
     w.poisson = w.base + o_poi;
@@ -55,6 +61,8 @@ bool layout_ws(size_t step_bytes, const d3p_sampler_desc* s, void* base, EpochWs
       w.counts[b] = reinterpret_cast<int32_t*>(w.base + o_cnt[b]);
       w.mask[b] = w.base + o_mask[b];
     }
+    uint32_t* k = reinterpret_cast<uint32_t*>(w.base + o_keys);
+    w.bkey[0] = k; w.bkey[1] = k + 16; w.rc[0] = k + 32; w.rc[1] = k + 64; w.tf = k + 96; w.sites = k + 160;
   }
   return true;
 }
@@ -77,13 +85,17 @@ uint32_t rows_per_rank(uint32_t B, int world) { return world > 1 ? (B + (uint32_
 struct StepLauncher {
   size_t step_bytes;      // workspace of one step (partial rows first)
   uint32_t n_part, P;
+  // tf_h: Threefry key on the host, or nullptr and tf_d: the key in device memory
   virtual int32_t launch(const int32_t* idx, const uint8_t* mask, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
-                         const uint32_t tf[2], float obs_scale, float C, void* ws, cudaStream_t s) const = 0;
+                         const uint32_t* tf_h, const uint32_t* tf_d, float obs_scale, float C, void* ws,
+                         cudaStream_t s) const = 0;
   virtual ~StepLauncher() {}
 };
 
-int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, const uint32_t batch_key_h[16],
-                  uint32_t rng_key_io_h[16], uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
+// keys: host words (batch_key_h, rng_key_io_h) or, for the *_dk entry points, device words (batch_key_d, rng_key_io_d)
+int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, const uint32_t* batch_key_h,
+                  uint32_t* rng_key_io_h, const uint32_t* batch_key_d, uint32_t* rng_key_io_d, uint32_t first_step,
+                  uint32_t n_steps, float obs_scale, float C,
                   float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d, float* m_d,
                   float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream);
 
@@ -108,18 +120,26 @@ namespace {
 struct MeanfieldLauncher : StepLauncher {
   const d3p_meanfield_desc* desc; const float* x; size_t stride; const int32_t* y;
   int32_t launch(const int32_t* idx, const uint8_t* mask, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
-                 const uint32_t tf[2], float obs_scale, float C, void* ws, cudaStream_t s) const override {
-    return d3p_dpsvi_step_meanfield(desc, params, x, stride, y, idx, mask, nullptr, B, pos_begin, pos_end, tf, obs_scale, C,
-                                    nullptr, nullptr, nullptr, ws, step_bytes, s);
+                 const uint32_t* tf_h, const uint32_t* tf_d, float obs_scale, float C, void* ws, cudaStream_t s) const override {
+    if (tf_h)
+      return d3p_dpsvi_step_meanfield(desc, params, x, stride, y, idx, mask, nullptr, B, pos_begin, pos_end, tf_h, obs_scale,
+                                      C, nullptr, nullptr, nullptr, ws, step_bytes, s);
+    return d3p_dpsvi_step_meanfield_dk(desc, params, x, stride, y, idx, mask, nullptr, B, pos_begin, pos_end, tf_d, obs_scale,
+                                       C, nullptr, nullptr, nullptr, ws, step_bytes, s);
   }
   const float* params;
 };
 struct VaeLauncher : StepLauncher {
   const d3p_vae_desc* desc; const float* x; size_t stride; const float* params;
+  d3p_vae_ctx* ctx = nullptr;      // side streams of this epoch call (created by the entry point, released at its end)
+  ~VaeLauncher() override { if (ctx) d3p_vae_ctx_destroy(ctx); }
   int32_t launch(const int32_t* idx, const uint8_t* mask, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
-                 const uint32_t tf[2], float obs_scale, float C, void* ws, cudaStream_t s) const override {
-    return d3p_dpsvi_step_vae(desc, params, x, stride, idx, mask, nullptr, B, pos_begin, pos_end, tf, obs_scale, C, nullptr,
-                              nullptr, ws, step_bytes, nullptr, s);
+                 const uint32_t* tf_h, const uint32_t* tf_d, float obs_scale, float C, void* ws, cudaStream_t s) const override {
+    if (tf_h)
+      return d3p_dpsvi_step_vae(desc, params, x, stride, idx, mask, nullptr, B, pos_begin, pos_end, tf_h, obs_scale, C,
+                                nullptr, nullptr, ws, step_bytes, nullptr, ctx, s);
+    return d3p_dpsvi_step_vae_dk(desc, params, x, stride, idx, mask, nullptr, B, pos_begin, pos_end, tf_d, obs_scale, C,
+                                 nullptr, nullptr, ws, step_bytes, nullptr, ctx, s);
   }
 };
 }  // namespace
@@ -138,8 +158,28 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
   fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.y = y_d; fam.params = params_d;
   fam.step_bytes = d3p_meanfield_workspace_bytes(desc, &fam.n_part);
   fam.P = desc->n_params;
-  return run_epoch(fam, sampler, batch_key_h, rng_key_io_h, first_step, n_steps, obs_scale, C, dp_scale, leaves_h,
-                   optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+  return run_epoch(fam, sampler, batch_key_h, rng_key_io_h, nullptr, nullptr, first_step, n_steps, obs_scale, C, dp_scale,
+                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+}
+
+// Device-key form: the batchifier key and the DPSVI state key live in device memory (rng_key_io_d is advanced in place),
+// every per-step key is derived by one-block kernels on the stream: the loop body of a jitted fori_loop with traced
+// keys (examples/logistic_regression.py:149-160) without a host round trip.  Same kernels, same results.
+extern "C" int32_t d3p_dpsvi_run_epoch_meanfield_dk(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler,
+                                                    const float* x_d, size_t x_row_stride, const int32_t* y_d,
+                                                    const uint32_t* batch_key_d, uint32_t* rng_key_io_d,
+                                                    uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
+                                                    float dp_scale, const d3p_leaf_table* leaves_h,
+                                                    d3p_optim_desc* optim_io_h, float* params_d, float* m_d, float* v_d,
+                                                    float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes,
+                                                    void* stream) {
+  if (!desc || !x_d || !params_d || !batch_key_d || !rng_key_io_d) return D3P_ERR_INVALID_ARGUMENT;
+  MeanfieldLauncher fam;
+  fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.y = y_d; fam.params = params_d;
+  fam.step_bytes = d3p_meanfield_workspace_bytes(desc, &fam.n_part);
+  fam.P = desc->n_params;
+  return run_epoch(fam, sampler, nullptr, nullptr, batch_key_d, rng_key_io_d, first_step, n_steps, obs_scale, C, dp_scale,
+                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
 }
 
 // The same loop for the VAE family (examples/vae.py:216-233 runs fori_loop(get_batch -> update) per epoch).
@@ -155,16 +195,36 @@ extern "C" int32_t d3p_dpsvi_run_epoch_vae(const d3p_vae_desc* desc, const d3p_s
   fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.params = params_d;
   fam.step_bytes = d3p_vae_workspace_bytes(desc, rows_per_rank(sampler->batch, comm ? comm->world : 1), &fam.n_part);
   fam.P = desc->n_params;
-  return run_epoch(fam, sampler, batch_key_h, rng_key_io_h, first_step, n_steps, obs_scale, C, dp_scale, leaves_h,
-                   optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+  if (d3p_vae_ctx_create(&fam.ctx) != D3P_OK) return D3P_ERR_CUDA;
+  return run_epoch(fam, sampler, batch_key_h, rng_key_io_h, nullptr, nullptr, first_step, n_steps, obs_scale, C, dp_scale,
+                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+}
+
+extern "C" int32_t d3p_dpsvi_run_epoch_vae_dk(const d3p_vae_desc* desc, const d3p_sampler_desc* sampler, const float* x_d,
+                                              size_t x_row_stride, const uint32_t* batch_key_d, uint32_t* rng_key_io_d,
+                                              uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
+                                              float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h,
+                                              float* params_d, float* m_d, float* v_d, float* stats_out_d, d3p_comm* comm,
+                                              void* ws_d, size_t ws_bytes, void* stream) {
+  if (!desc || !x_d || !params_d || !sampler_ok(sampler) || !batch_key_d || !rng_key_io_d) return D3P_ERR_INVALID_ARGUMENT;
+  if (reinterpret_cast<uintptr_t>(ws_d) & 255) return D3P_ERR_INVALID_ARGUMENT;
+  VaeLauncher fam;
+  fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.params = params_d;
+  fam.step_bytes = d3p_vae_workspace_bytes(desc, rows_per_rank(sampler->batch, comm ? comm->world : 1), &fam.n_part);
+  fam.P = desc->n_params;
+  if (d3p_vae_ctx_create(&fam.ctx) != D3P_OK) return D3P_ERR_CUDA;
+  return run_epoch(fam, sampler, nullptr, nullptr, batch_key_d, rng_key_io_d, first_step, n_steps, obs_scale, C, dp_scale,
+                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
 }
 
 namespace {
-int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, const uint32_t batch_key_h[16],
-                  uint32_t rng_key_io_h[16], uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
+int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, const uint32_t* batch_key_h,
+                  uint32_t* rng_key_io_h, const uint32_t* batch_key_d, uint32_t* rng_key_io_d, uint32_t first_step,
+                  uint32_t n_steps, float obs_scale, float C,
                   float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d, float* m_d,
                   float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream) {
-  if (!batch_key_h || !rng_key_io_h || !leaves_h || !optim_io_h || !params_d || !ws_d)
+  const bool dk = batch_key_d != nullptr;            // keys in device memory
+  if ((dk ? !rng_key_io_d : (!batch_key_h || !rng_key_io_h)) || !leaves_h || !optim_io_h || !params_d || !ws_d)
     return D3P_ERR_INVALID_ARGUMENT;
   if (!sampler_ok(sampler) || leaves_h->n_leaves == 0 || leaves_h->n_leaves > D3P_MAX_LEAVES)
     return D3P_ERR_INVALID_ARGUMENT;
@@ -185,8 +245,13 @@ int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, cons
   }
   // D3P_EPOCH_PROFILE=1: per-phase CUDA-event timings of this call on stderr (synchronises at the end; the
   // sampler then stays on the main stream so that the three phases are disjoint in time)
+#ifdef D3P_DEV_SWITCHES      // development builds only (D3P_NVCC_DEFINES=D3P_DEV_SWITCHES): the product reads no environment
   const bool prof = getenv("D3P_EPOCH_PROFILE") != nullptr;
   const bool fork = !prof && getenv("D3P_EPOCH_SERIAL") == nullptr && n_steps > 1;
+#else
+  const bool prof = false;
+  const bool fork = n_steps > 1;
+#endif
   cudaStream_t main_s = (cudaStream_t)stream, samp_s = main_s;
   cudaEvent_t ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_fork = nullptr;
   if (fork) {
@@ -211,10 +276,25 @@ int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, cons
   auto queue_sampler = [&](uint32_t s) -> int32_t {
     const int b = s & 1;
     uint32_t bkey[16];
-    int32_t r = d3p_chacha_fold_in_h(batch_key_h, first_step + s, bkey);
-    if (r != D3P_OK) return r;
+    int32_t r = D3P_OK;
+    if (!dk && (r = d3p_chacha_fold_in_h(batch_key_h, first_step + s, bkey)) != D3P_OK) return r;
     if (fork && s >= 2 && cudaStreamWaitEvent(samp_s, ev_consumed[b], 0) != cudaSuccess) return D3P_ERR_CUDA;
-    if (sampler->kind == D3P_SAMPLER_POISSON) {
+    if (dk) {
+      // the same get_batch with the key derived on the device (buffers of parity b: free once step s - 2 has consumed them)
+      if ((r = d3p_chacha_fold_in_dk(batch_key_d, nullptr, first_step + s, w.bkey[b], samp_s)) != D3P_OK) return r;
+      if (sampler->kind == D3P_SAMPLER_POISSON) {
+        r = D3P_ERR_UNSUPPORTED;
+        if (comm && comm->world > 1)
+          r = d3p_poisson_sample_sharded_dk(comm, w.bkey[b], sampler->q, sampler->n_records, B, sampler->suppress, pos_begin,
+                                            pos_end, w.idx[b], w.counts[b], w.mask[b], w.poisson, w.poisson_bytes, samp_s);
+        if (r == D3P_ERR_UNSUPPORTED)
+          r = d3p_poisson_sample_dk(w.bkey[b], sampler->q, sampler->n_records, B, sampler->suppress, w.idx[b], w.counts[b],
+                                    w.mask[b], w.poisson, w.poisson_bytes, samp_s);
+      } else {
+        if ((r = d3p_feistel_round_constants_dk(w.bkey[b], w.rc[b], samp_s)) != D3P_OK) return r;
+        r = d3p_feistel_sample_dk(w.rc[b], sampler->n_records, 0, B, w.idx[b], samp_s);
+      }
+    } else if (sampler->kind == D3P_SAMPLER_POISSON) {
       r = D3P_ERR_UNSUPPORTED;
       if (comm && comm->world > 1)             // selector draw split over the ranks (samplers.cu)
         r = d3p_poisson_sample_sharded(comm, bkey, sampler->q, sampler->n_records, B, sampler->suppress, pos_begin,
@@ -245,22 +325,31 @@ int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, cons
     mark();
     // ---- DPSVI.update (svi.py:395-434) ----------------------------------------------------------------------
     uint32_t keys[3][16], tf[2];
-    if ((rc = d3p_chacha_split_h(rng_key_io_h, 3, &keys[0][0])) != D3P_OK) break;           // carry, k_grad, k_noise
-    if ((rc = d3p_chacha_random_bits_h(keys[1], 0, tf, 2)) != D3P_OK) break;                // convert_to_jax_rng_key
-    rc = fam.launch(w.idx[b], mask, B, pos_begin, pos_end, tf, obs_scale, C, w.step, main_s);
-    if (rc != D3P_OK) break;
-    mark();
-    if ((rc = d3p_chacha_split_h(keys[2], (int32_t)lt.n_leaves, &lt.site_state[0][0])) != D3P_OK) break;
-    rc = d3p_perturb_finalize_p2p_f32(w.step, n_part, P, B, &lt, dp_scale, C, obs_scale, 1, nullptr, optim_io_h,
-                                      params_d, m_d, v_d, stats_out_d ? stats_out_d + 3 * (size_t)s : nullptr, nullptr,
-                                      comm, main_s);
+    if (dk) {
+      // carry / k_grad -> Threefry key / k_noise -> per-leaf keys, all on the device, the state key advanced in place
+      if ((rc = d3p_dpsvi_keys_dk(rng_key_io_d, lt.n_leaves, w.tf, w.sites, main_s)) != D3P_OK) break;
+      if ((rc = fam.launch(w.idx[b], mask, B, pos_begin, pos_end, nullptr, w.tf, obs_scale, C, w.step, main_s)) != D3P_OK) break;
+      mark();
+      rc = d3p_perturb_finalize_dk_f32(w.step, n_part, P, B, &lt, w.sites, dp_scale, C, obs_scale, nullptr, optim_io_h,
+                                       params_d, m_d, v_d, stats_out_d ? stats_out_d + 3 * (size_t)s : nullptr, comm, main_s);
+    } else {
+      if ((rc = d3p_chacha_split_h(rng_key_io_h, 3, &keys[0][0])) != D3P_OK) break;           // carry, k_grad, k_noise
+      if ((rc = d3p_chacha_random_bits_h(keys[1], 0, tf, 2)) != D3P_OK) break;                // convert_to_jax_rng_key
+      rc = fam.launch(w.idx[b], mask, B, pos_begin, pos_end, tf, nullptr, obs_scale, C, w.step, main_s);
+      if (rc != D3P_OK) break;
+      mark();
+      if ((rc = d3p_chacha_split_h(keys[2], (int32_t)lt.n_leaves, &lt.site_state[0][0])) != D3P_OK) break;
+      rc = d3p_perturb_finalize_p2p_f32(w.step, n_part, P, B, &lt, dp_scale, C, obs_scale, 1, nullptr, optim_io_h,
+                                        params_d, m_d, v_d, stats_out_d ? stats_out_d + 3 * (size_t)s : nullptr, nullptr,
+                                        comm, main_s);
+    }
     if (rc != D3P_OK) break;
     // recorded after the finalize launch so that nothing sits between the step kernel and its programmatic dependent
     if (fork && cudaEventRecord(ev_consumed[b], main_s) != cudaSuccess) { rc = D3P_ERR_CUDA; break; }
     if (optim_io_h->kind == D3P_OPT_ADADP && (optim_io_h->step & 1))
       if ((rc = d3p_adadp_finish_f32(optim_io_h, P, params_d, v_d, main_s)) != D3P_OK) break;
     optim_io_h->step += 1;
-    memcpy(rng_key_io_h, keys[0], sizeof(keys[0]));
+    if (!dk) memcpy(rng_key_io_h, keys[0], sizeof(keys[0]));
     mark();
   }
   if (fork) {

@@ -53,8 +53,10 @@ constexpr int kFinThreads = 512;   // 16 warps share the partial rows of a 32-co
 // site states live in constant-bank kernel parameters next to the leaf table
 struct SiteStates { uint32_t w[D3P_MAX_LEAVES][16]; };
 
+// `sites_d` (the *_dk entry point): the per-leaf ChaCha states live in device memory ([n_leaves][16] words, written by
+// d3p_dpsvi_keys_dk) instead of the kernel parameters.
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites,
-                                                               CommDev comm) {
+                                                               const uint32_t* __restrict__ sites_d, CommDev comm) {
   __shared__ float red[2][kFinThreads / 32];
   __shared__ float s_n, s_loss;
   const uint32_t stride = a.P + 2;
@@ -135,8 +137,10 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, L
         if (j >= leaves.off[l] && j < leaves.off[l] + leaves.len[l]) leaf = (int)l;
       if (leaf >= 0) {
         uint32_t e = j - leaves.off[leaf];
-        uint32_t ks[16];
-        chacha20_block(sites.w[leaf], sites.w[leaf][12] + (e >> 4), ks);
+        uint32_t ks[16], st[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st[i] = sites_d ? __ldg(sites_d + 16 * leaf + i) : sites.w[leaf][i];
+        chacha20_block(st, st[12] + (e >> 4), ks);
         uint32_t bits = ks[0];
 #pragma unroll
         for (int i = 1; i < 16; ++i) bits = ((e & 15u) == (uint32_t)i) ? ks[i] : bits;
@@ -180,7 +184,8 @@ struct ChunkTable { uint32_t n_chunks; uint32_t chunk_start[D3P_MAX_LEAVES + 1];
 D3P_D void quad_qr(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) { D3P_QR(a, b, c, d) }
 
 __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites,
-                                                            ChunkTable ct, CommDev comm) {
+                                                            const uint32_t* __restrict__ sites_d, ChunkTable ct,
+                                                            CommDev comm) {
   __shared__ float red[2][8];
   __shared__ float s_n, s_loss;
   const uint32_t stride = a.P + 2;
@@ -237,8 +242,9 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
     for (int i = 0; i < 4; ++i) sum[i] += ok[i] ? __ldg(parts + (size_t)p * stride + jj[i]) : 0.f;
   }
   // column q of the state: rows 0..3
-  const uint32_t i0 = sites.w[leaf][q], i1 = sites.w[leaf][4 + q], i2 = sites.w[leaf][8 + q];
-  const uint32_t i3 = (q == 0) ? sites.w[leaf][12] + b : sites.w[leaf][12 + q];
+  const uint32_t* sw = sites_d ? sites_d + 16 * leaf : sites.w[leaf];
+  const uint32_t i0 = sw[q], i1 = sw[4 + q], i2 = sw[8 + q];
+  const uint32_t i3 = (q == 0) ? sw[12] + b : sw[12 + q];
   uint32_t x0 = i0, x1 = i1, x2 = i2, x3 = i3;
   const int base = lane & ~3;
 #pragma unroll
@@ -258,8 +264,8 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
     const float my_n = s_n, my_loss = s_loss;
     const size_t jn = comm.extra_off + 2 * (size_t)blockIdx.x;
     float mine[4];
-#pragma unroll
     const float zero = comm_poisoned(comm) ? __uint_as_float(0x7fc00000u) : 0.f;   // see finalize_kernel
+#pragma unroll
     for (int i = 0; i < 4; ++i) { mine[i] = sum[i]; if (ok[i]) ll_push(comm, jj[i], mine[i]); sum[i] = zero; }
     if (threadIdx.x == 0) { ll_push(comm, jn, my_n); ll_push(comm, jn + 1, my_loss); }
     n_all = 0.f; loss_all = zero;
@@ -388,12 +394,12 @@ extern "C" int32_t d3p_perturb_finalize_f32(const float* partials_d, uint32_t n_
                                       grad_out_d, optim_h, params_d, m_d, v_d, stats_d, nf_override_h, nullptr, stream);
 }
 
-extern "C" int32_t d3p_perturb_finalize_p2p_f32(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
-                                                const d3p_leaf_table* leaves_h, float dp_scale, float C,
-                                                float obs_scale, int32_t add_noise, float* grad_out_d,
-                                                const d3p_optim_desc* optim_h, float* params_d, float* m_d,
-                                                float* v_d, float* stats_d, const float* nf_override_h,
-                                                d3p_comm* comm, void* stream) {
+static int32_t perturb_finalize_impl(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
+                                     const d3p_leaf_table* leaves_h, const uint32_t* site_states_d, float dp_scale, float C,
+                                     float obs_scale, int32_t add_noise, float* grad_out_d,
+                                     const d3p_optim_desc* optim_h, float* params_d, float* m_d,
+                                     float* v_d, float* stats_d, const float* nf_override_h,
+                                     d3p_comm* comm, void* stream) {
   if (!partials_d || n_partials == 0 || B == 0) return D3P_ERR_INVALID_ARGUMENT;
   if (add_noise && !leaves_h) return D3P_ERR_INVALID_ARGUMENT;
   if (leaves_h && leaves_h->n_leaves > D3P_MAX_LEAVES) return D3P_ERR_UNSUPPORTED;
@@ -433,6 +439,18 @@ extern "C" int32_t d3p_perturb_finalize_p2p_f32(const float* partials_d, uint32_
       for (int i = 0; i < 16; ++i) ss.w[l][i] = leaves_h->site_state[l][i];
     }
   }
+  if (add_noise) {
+    // every coordinate must get its noise: the leaves have to tile [0, P) exactly (disjoint, no gap).  A table that
+    // leaves a coordinate uncovered would release that clipped sum un-noised (round-1 ADVICE)
+    uint64_t covered = 0;
+    for (uint32_t l = 0; l < lt.n_leaves; ++l) {
+      covered += lt.len[l];
+      for (uint32_t k = 0; k < l; ++k)
+        if (lt.off[l] < lt.off[k] + lt.len[k] && lt.off[k] < lt.off[l] + lt.len[l] && lt.len[l] && lt.len[k])
+          return D3P_ERR_INVALID_ARGUMENT;
+    }
+    if (covered != P) return D3P_ERR_INVALID_ARGUMENT;
+  }
   // large parameter vectors with a leaf table that tiles [0, P): one thread per keystream block
   if (add_noise && leaves_h && P >= 32768 && n_partials <= 64) {
     ChunkTable ct;
@@ -449,7 +467,7 @@ extern "C" int32_t d3p_perturb_finalize_p2p_f32(const float* partials_d, uint32_
     if (covered == P && nc > 0) {
       const unsigned qgrid = (nc * 4 + 255) / 256;
       if (comm) { const int32_t rc = comm_next(comm, P, qgrid, &cd); if (rc != D3P_OK) return rc; }
-      finalize_quad_kernel<<<qgrid, 256, 0, (cudaStream_t)stream>>>(a, lt, ss, ct, cd);
+      finalize_quad_kernel<<<qgrid, 256, 0, (cudaStream_t)stream>>>(a, lt, ss, site_states_d, ct, cd);
       return check_launch();
     }
   }
@@ -466,8 +484,30 @@ extern "C" int32_t d3p_perturb_finalize_p2p_f32(const float* partials_d, uint32_
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, finalize_kernel, a, lt, ss, cd) != cudaSuccess) return D3P_ERR_CUDA;
+  if (cudaLaunchKernelEx(&cfg, finalize_kernel, a, lt, ss, site_states_d, cd) != cudaSuccess) return D3P_ERR_CUDA;
   return check_launch();
+}
+
+extern "C" int32_t d3p_perturb_finalize_p2p_f32(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
+                                                const d3p_leaf_table* leaves_h, float dp_scale, float C,
+                                                float obs_scale, int32_t add_noise, float* grad_out_d,
+                                                const d3p_optim_desc* optim_h, float* params_d, float* m_d,
+                                                float* v_d, float* stats_d, const float* nf_override_h,
+                                                d3p_comm* comm, void* stream) {
+  return perturb_finalize_impl(partials_d, n_partials, P, B, leaves_h, nullptr, dp_scale, C, obs_scale, add_noise,
+                               grad_out_d, optim_h, params_d, m_d, v_d, stats_d, nf_override_h, comm, stream);
+}
+
+// Device-key form: leaves_h carries the leaf layout only (its site_state words are ignored); the per-leaf ChaCha states
+// are read from site_states_d ([n_leaves][16] words, e.g. written by d3p_dpsvi_keys_dk).
+extern "C" int32_t d3p_perturb_finalize_dk_f32(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
+                                               const d3p_leaf_table* leaves_h, const uint32_t* site_states_d,
+                                               float dp_scale, float C, float obs_scale, float* grad_out_d,
+                                               const d3p_optim_desc* optim_h, float* params_d, float* m_d, float* v_d,
+                                               float* stats_d, d3p_comm* comm, void* stream) {
+  if (!leaves_h || !site_states_d) return D3P_ERR_INVALID_ARGUMENT;
+  return perturb_finalize_impl(partials_d, n_partials, P, B, leaves_h, site_states_d, dp_scale, C, obs_scale, 1, grad_out_d,
+                               optim_h, params_d, m_d, v_d, stats_d, nullptr, comm, stream);
 }
 
 extern "C" size_t d3p_adadp_workspace_floats(uint32_t P) { return (size_t)(P + 31) / 32 + 2; }

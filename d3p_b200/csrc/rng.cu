@@ -11,8 +11,10 @@ enum { kBits = 0, kUniform = 1, kNormal = 2 };
 // One thread per 64-byte block; a warp writes 32 consecutive blocks.  Each lane owns 16
 // consecutive words, stored as four 16-byte vectors (each lane writes a full 64 B line half).
 template <int kMode>
-__global__ void __launch_bounds__(256) chacha_stream_kernel(ChaChaState st, uint32_t first_block, void* out,
+__global__ void __launch_bounds__(256) chacha_stream_kernel(ChaChaArg key, uint32_t first_block, void* out,
                                                             size_t n_words, float lo, float hi) {
+  ChaChaState st;
+  load_chacha(key, st);
   size_t n_blocks = (n_words + 15) / 16;
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks;
        b += (size_t)gridDim.x * blockDim.x) {
@@ -39,8 +41,10 @@ __global__ void __launch_bounds__(256) chacha_stream_kernel(ChaChaState st, uint
   }
 }
 
-__global__ void __launch_bounds__(256) randint_round_kernel(ChaChaState st, uint32_t bitmask, uint32_t delta,
+__global__ void __launch_bounds__(256) randint_round_kernel(ChaChaArg key, uint32_t bitmask, uint32_t delta,
                                                             int first, uint32_t* vals, size_t n, int* pending) {
+  ChaChaState st;
+  load_chacha(key, st);
   size_t n_blocks = (n + 15) / 16;
   int local = 0;
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks;
@@ -67,16 +71,73 @@ __global__ void randint_finish_kernel(const uint32_t* vals, int32_t minval, int3
     out[i] = (int32_t)vals[i] + minval;
 }
 
-static ChaChaState load_state(const uint32_t* s) {
-  ChaChaState st;
-  for (int i = 0; i < 16; ++i) st.w[i] = s[i];
-  return st;
+// ---- device-resident keys (the *_dk entry points) -------------------------------------------------------------------
+// The reference runs get_batch + update as the body of a jitted fori_loop with TRACED keys
+// (examples/logistic_regression.py:149-160, d3p/random/__init__.py:28-32): a key there is a device value no host ever
+// sees.  These one-block kernels are rng_suite.split / fold_in / convert_to_jax_rng_key and the per-step key plumbing
+// of DPSVI.update (d3p/svi.py:208-211,413-414,490-491) on such keys.
+__global__ void chacha_split_dk_kernel(const uint32_t* __restrict__ in, uint32_t num, uint32_t* __restrict__ out) {
+  uint32_t parent[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) parent[i] = in[i];
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < num; k += gridDim.x * blockDim.x) {
+    uint32_t child[16];
+    chacha_derive_key(parent, k, D3P_DERIVE_SPLIT, child);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[16 * (size_t)k + i] = child[i];
+  }
+}
+
+__global__ void chacha_fold_in_dk_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ data_d,
+                                         uint32_t data_imm, uint32_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t parent[16], child[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) parent[i] = in[i];
+  chacha_derive_key(parent, (data_d ? *data_d : 0u) + data_imm, D3P_DERIVE_FOLD_IN, child);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[i] = child[i];
+}
+
+// One DPSVI.update worth of keys from the state key, in place: (carry, k_grad, k_noise) = split(key, 3); key := carry;
+// tf_key_out = convert_to_jax_rng_key(k_grad) = its first two keystream words; site_out = split(k_noise, n_leaves).
+__global__ void dpsvi_keys_dk_kernel(uint32_t* __restrict__ key_io, uint32_t n_leaves, uint32_t* __restrict__ tf_key_out,
+                                     uint32_t* __restrict__ site_out) {
+  __shared__ uint32_t s_noise[16];
+  uint32_t parent[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) parent[i] = key_io[i];
+  __syncthreads();                                   // everybody has read the old key before thread 0 replaces it
+  if (threadIdx.x < 3) {
+    uint32_t child[16];
+    chacha_derive_key(parent, threadIdx.x, D3P_DERIVE_SPLIT, child);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) key_io[i] = child[i];
+    } else if (threadIdx.x == 1) {
+      uint32_t ks[16];
+      chacha20_block(child, child[12], ks);
+      tf_key_out[0] = ks[0]; tf_key_out[1] = ks[1];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s_noise[i] = child[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_leaves) {
+    uint32_t noise[16], child[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) noise[i] = s_noise[i];
+    chacha_derive_key(noise, threadIdx.x, D3P_DERIVE_SPLIT, child);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) site_out[16 * threadIdx.x + i] = child[i];
+  }
 }
 
 template <int kMode>
-static int32_t launch_stream(const uint32_t* state_h, uint64_t first_block, void* out_d, size_t n, float lo,
-                             float hi, void* stream) {
-  if (!state_h || (!out_d && n)) return D3P_ERR_INVALID_ARGUMENT;
+static int32_t launch_stream(const uint32_t* state_h, const uint32_t* state_d, uint64_t first_block, void* out_d, size_t n,
+                             float lo, float hi, void* stream) {
+  if ((!state_h && !state_d) || (!out_d && n)) return D3P_ERR_INVALID_ARGUMENT;
   if (n == 0) return D3P_OK;
   size_t n_blocks = (n + 15) / 16;
   if (first_block + n_blocks > 0x100000000ull) return D3P_ERR_INVALID_ARGUMENT;  // 32-bit block counter
@@ -84,7 +145,7 @@ static int32_t launch_stream(const uint32_t* state_h, uint64_t first_block, void
   size_t grid = (n_blocks + threads - 1) / threads;
   if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
   chacha_stream_kernel<kMode><<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(
-      load_state(state_h), (uint32_t)first_block, out_d, n, lo, hi);
+      chacha_arg(state_h, state_d), (uint32_t)first_block, out_d, n, lo, hi);
   return check_launch();
 }
 
@@ -177,17 +238,17 @@ int32_t d3p_chacha_random_bits_h(const uint32_t state_h[16], uint64_t first_bloc
 
 int32_t d3p_chacha_random_bits(const uint32_t state_h[16], uint64_t first_block, uint32_t* out_d,
                                size_t n_words, void* stream) {
-  return launch_stream<kBits>(state_h, first_block, out_d, n_words, 0.f, 1.f, stream);
+  return launch_stream<kBits>(state_h, nullptr, first_block, out_d, n_words, 0.f, 1.f, stream);
 }
 
 int32_t d3p_chacha_uniform_f32(const uint32_t state_h[16], uint64_t first_block, float lo, float hi,
                                float* out_d, size_t n, void* stream) {
-  return launch_stream<kUniform>(state_h, first_block, out_d, n, lo, hi, stream);
+  return launch_stream<kUniform>(state_h, nullptr, first_block, out_d, n, lo, hi, stream);
 }
 
 int32_t d3p_chacha_normal_f32(const uint32_t state_h[16], uint64_t first_block, float* out_d, size_t n,
                               void* stream) {
-  return launch_stream<kNormal>(state_h, first_block, out_d, n, 0.f, 1.f, stream);
+  return launch_stream<kNormal>(state_h, nullptr, first_block, out_d, n, 0.f, 1.f, stream);
 }
 
 int32_t d3p_chacha_randint_round_u32(const uint32_t round_state_h[16], uint32_t bitmask, uint32_t delta,
@@ -199,8 +260,8 @@ int32_t d3p_chacha_randint_round_u32(const uint32_t round_state_h[16], uint32_t 
   size_t n_blocks = (n + 15) / 16;
   size_t grid = (n_blocks + 255) / 256;
   if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
-  randint_round_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(load_state(round_state_h), bitmask, delta,
-                                                                         first, vals_d, n, pending_d);
+  randint_round_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(chacha_arg(round_state_h, nullptr), bitmask,
+                                                                         delta, first, vals_d, n, pending_d);
   return check_launch();
 }
 
@@ -210,6 +271,45 @@ int32_t d3p_randint_finish_i32(const uint32_t* vals_d, int32_t minval, int32_t* 
   size_t grid = (n + 255) / 256;
   if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
   randint_finish_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(vals_d, minval, out_d, n);
+  return check_launch();
+}
+
+
+// ---- device-key forms (keys never leave the device) ------------------------------------------------------------------
+int32_t d3p_chacha_split_dk(const uint32_t* in_d, int32_t num, uint32_t* out_d, void* stream) {
+  if (!in_d || num < 0 || (!out_d && num)) return D3P_ERR_INVALID_ARGUMENT;
+  if (num == 0) return D3P_OK;
+  const unsigned threads = 128, grid = ((unsigned)num + threads - 1) / threads;
+  chacha_split_dk_kernel<<<grid > 1024 ? 1024 : grid, threads, 0, (cudaStream_t)stream>>>(in_d, (uint32_t)num, out_d);
+  return check_launch();
+}
+
+int32_t d3p_chacha_fold_in_dk(const uint32_t* in_d, const uint32_t* data_d, uint32_t data_imm, uint32_t* out_d,
+                              void* stream) {
+  if (!in_d || !out_d) return D3P_ERR_INVALID_ARGUMENT;
+  chacha_fold_in_dk_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(in_d, data_d, data_imm, out_d);
+  return check_launch();
+}
+
+int32_t d3p_chacha_random_bits_dk(const uint32_t* state_d, uint64_t first_block, uint32_t* out_d, size_t n_words,
+                                  void* stream) {
+  return launch_stream<kBits>(nullptr, state_d, first_block, out_d, n_words, 0.f, 1.f, stream);
+}
+
+int32_t d3p_chacha_uniform_f32_dk(const uint32_t* state_d, uint64_t first_block, float lo, float hi, float* out_d,
+                                  size_t n, void* stream) {
+  return launch_stream<kUniform>(nullptr, state_d, first_block, out_d, n, lo, hi, stream);
+}
+
+int32_t d3p_chacha_normal_f32_dk(const uint32_t* state_d, uint64_t first_block, float* out_d, size_t n, void* stream) {
+  return launch_stream<kNormal>(nullptr, state_d, first_block, out_d, n, 0.f, 1.f, stream);
+}
+
+int32_t d3p_dpsvi_keys_dk(uint32_t* rng_key_io_d, uint32_t n_leaves, uint32_t* threefry_key_out_d,
+                          uint32_t* site_states_out_d, void* stream) {
+  if (!rng_key_io_d || !threefry_key_out_d || n_leaves > D3P_MAX_LEAVES || (n_leaves && !site_states_out_d))
+    return D3P_ERR_INVALID_ARGUMENT;
+  dpsvi_keys_dk_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rng_key_io_d, n_leaves, threefry_key_out_d, site_states_out_d);
   return check_launch();
 }
 

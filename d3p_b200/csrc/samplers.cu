@@ -16,6 +16,20 @@ struct FeistelParams {
   uint32_t capacity, bits_lower, bits_upper, mask_lower, mask_upper;
 };
 
+// round constants from device memory (d3p_feistel_sample_dk): 30 keystream words of the batch key, rc[3j] |= 1
+__global__ void feistel_rc_dk_kernel(const uint32_t* __restrict__ state_d, uint32_t* __restrict__ rc_out) {
+  if (threadIdx.x >= 2) return;
+  uint32_t st[16], ks[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) st[i] = state_d[i];
+  chacha20_block(st, st[12] + threadIdx.x, ks);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t w = 16u * threadIdx.x + i;
+    if (w < 30) rc_out[w] = (w % 3 == 0) ? (ks[i] | 1u) : ks[i];
+  }
+}
+
 D3P_D uint32_t feistel_rounds(const FeistelParams& p, uint32_t x) {
 #pragma unroll
   for (int j = 0; j < 10; ++j) {
@@ -29,8 +43,12 @@ D3P_D uint32_t feistel_rounds(const FeistelParams& p, uint32_t x) {
   return x;
 }
 
-__global__ void __launch_bounds__(256) feistel_kernel(FeistelParams p, uint32_t first_pos, uint32_t n,
-                                                      int32_t* __restrict__ idx) {
+__global__ void __launch_bounds__(256) feistel_kernel(FeistelParams p, const uint32_t* __restrict__ rc_d,
+                                                      uint32_t first_pos, uint32_t n, int32_t* __restrict__ idx) {
+  if (rc_d) {
+#pragma unroll
+    for (int j = 0; j < 30; ++j) p.rc[j] = __ldg(rc_d + j);
+  }
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t x = feistel_rounds(p, first_pos + i);
     while (x >= p.capacity) x = feistel_rounds(p, x);
@@ -74,10 +92,12 @@ D3P_D int tile_count(uint32_t m, int* warp_c) {      // CTA total of popc(m); va
   return t;
 }
 
-__global__ void __launch_bounds__(kPoisThreads) poisson_select_kernel(ChaChaState st, float q, uint32_t n_records,
+__global__ void __launch_bounds__(kPoisThreads) poisson_select_kernel(ChaChaArg key, float q, uint32_t n_records,
                                                                       uint16_t* __restrict__ masks,
                                                                       int32_t* __restrict__ tile_counts, uint32_t* ready) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *ready = 0u;      // the compaction kernel's "prefix published" flag
+  ChaChaState st;
+  load_chacha(key, st);
   uint32_t blk = blockIdx.x * kPoisThreads + threadIdx.x;
   uint32_t n_blocks = (n_records + 15) / 16;
   uint32_t m = 0;
@@ -95,12 +115,14 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_select_kernel(ChaChaStat
 // both sides, so that the tiles its batch positions fall into are (with overwhelming probability) local and
 // no selection mask ever crosses NVLink.  Only the owner pushes a tile's tagged count {count, epoch & 0xffff}
 // into every window (posted stores: no fence and no flag, the tag validates the word).
-__global__ void __launch_bounds__(kPoisThreads) poisson_select_sharded_kernel(ChaChaState st, float q,
+__global__ void __launch_bounds__(kPoisThreads) poisson_select_sharded_kernel(ChaChaArg key, float q,
                                                                               uint32_t n_records, uint32_t cov_lo,
                                                                               uint32_t own_lo, uint32_t own_hi,
                                                                               uint16_t* __restrict__ masks, SampDev sd,
                                                                               uint32_t* ready) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *ready = 0u;
+  ChaChaState st;
+  load_chacha(key, st);
   const uint32_t tile = cov_lo + blockIdx.x;
   const uint32_t blk = tile * kPoisThreads + threadIdx.x;
   const uint32_t n_blocks = (n_records + 15) / 16;
@@ -177,7 +199,7 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uin
                                                                        uint32_t pos_end, int32_t* __restrict__ idx,
                                                                        int32_t* __restrict__ counts,
                                                                        uint8_t* __restrict__ mask, SampDev sd,
-                                                                       ChaChaState st, float q, uint32_t cov_lo,
+                                                                       ChaChaArg key, float q, uint32_t cov_lo,
                                                                        uint32_t cov_hi) {
   const uint32_t t_first = blockIdx.x * kCompactTiles;                       // this CTA's tiles [t_first, t_end)
   const uint32_t t_end = min(n_tiles, t_first + kCompactTiles);
@@ -233,7 +255,13 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uin
     if (blk < n_blocks) {
       // sharded: inside the locally drawn range the masks are in this rank's scratch; a tile outside it (a
       // position boundary further off than the margin: many standard deviations) is simply drawn again
-      m = (!kSharded || (tile >= cov_lo && tile < cov_hi)) ? masks[blk] : poisson_block_mask(st, q, n_records, blk);
+      if (!kSharded || (tile >= cov_lo && tile < cov_hi)) {
+        m = masks[blk];
+      } else {
+        ChaChaState st;
+        load_chacha(key, st);
+        m = poisson_block_mask(st, q, n_records, blk);
+      }
     }
     const int c = __popc(m);
     int incl = c;                              // exclusive scan over threads in DESCENDING thread order
@@ -305,12 +333,6 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const V* __restrict__ 
   }
 }
 
-static ChaChaState load_state(const uint32_t* s) {
-  ChaChaState st;
-  for (int i = 0; i < 16; ++i) st.w[i] = s[i];
-  return st;
-}
-
 struct PoissonWs {
   uint16_t* masks;
   int32_t* tile_counts;
@@ -350,13 +372,13 @@ int32_t d3p_feistel_round_constants_h(const uint32_t state_h[16], uint32_t rc_h[
   return D3P_OK;
 }
 
-int32_t d3p_feistel_sample(const uint32_t rc_h[30], uint32_t capacity, uint32_t first_pos, uint32_t n,
-                           int32_t* idx_d, void* stream) {
-  if (!rc_h || capacity == 0 || (!idx_d && n)) return D3P_ERR_INVALID_ARGUMENT;
+static int32_t feistel_sample_impl(const uint32_t* rc_h, const uint32_t* rc_d, uint32_t capacity, uint32_t first_pos,
+                                   uint32_t n, int32_t* idx_d, void* stream) {
+  if ((!rc_h && !rc_d) || capacity == 0 || (!idx_d && n)) return D3P_ERR_INVALID_ARGUMENT;
   if ((uint64_t)first_pos + n > (uint64_t)capacity) return D3P_ERR_INVALID_ARGUMENT;
   if (n == 0) return D3P_OK;
   FeistelParams p;
-  for (int i = 0; i < 30; ++i) p.rc[i] = rc_h[i];
+  for (int i = 0; i < 30; ++i) p.rc[i] = rc_h ? rc_h[i] : 0u;
   uint32_t bits = 0;
   for (uint32_t c = capacity - 1; c; c >>= 1) ++bits;   // (capacity - 1).bit_length()
   p.capacity = capacity;
@@ -367,36 +389,71 @@ int32_t d3p_feistel_sample(const uint32_t rc_h[30], uint32_t capacity, uint32_t 
   unsigned grid = (n + 255) / 256;
   unsigned cap = (unsigned)sm_count() * 16;
   if (grid > cap) grid = cap;
-  feistel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, first_pos, n, idx_d);
+  feistel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, rc_d, first_pos, n, idx_d);
   return check_launch();
+}
+
+int32_t d3p_feistel_sample(const uint32_t rc_h[30], uint32_t capacity, uint32_t first_pos, uint32_t n,
+                           int32_t* idx_d, void* stream) {
+  if (!rc_h) return D3P_ERR_INVALID_ARGUMENT;
+  return feistel_sample_impl(rc_h, nullptr, capacity, first_pos, n, idx_d, stream);
+}
+
+// Device-key forms: the round constants are derived on the device from a key in device memory (rc_out_d: 30 words)
+int32_t d3p_feistel_round_constants_dk(const uint32_t* state_d, uint32_t* rc_out_d, void* stream) {
+  if (!state_d || !rc_out_d) return D3P_ERR_INVALID_ARGUMENT;
+  feistel_rc_dk_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state_d, rc_out_d);
+  return check_launch();
+}
+
+int32_t d3p_feistel_sample_dk(const uint32_t* rc_d, uint32_t capacity, uint32_t first_pos, uint32_t n, int32_t* idx_d,
+                              void* stream) {
+  if (!rc_d) return D3P_ERR_INVALID_ARGUMENT;
+  return feistel_sample_impl(nullptr, rc_d, capacity, first_pos, n, idx_d, stream);
 }
 
 size_t d3p_poisson_workspace_bytes(uint32_t n_records) { return carve_poisson_ws(nullptr, n_records).bytes; }
 
-int32_t d3p_poisson_sample(const uint32_t state_h[16], float q, uint32_t n_records, uint32_t max_b,
-                           int32_t suppress, int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d,
-                           size_t ws_bytes, void* stream) {
-  if (!state_h || !counts_d || !ws_d || (!idx_d && max_b) || n_records == 0 || max_b > n_records)
+static int32_t poisson_sample_impl(const uint32_t* state_h, const uint32_t* state_d, float q, uint32_t n_records,
+                                   uint32_t max_b, int32_t suppress, int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d,
+                                   void* ws_d, size_t ws_bytes, void* stream) {
+  if ((!state_h && !state_d) || !counts_d || !ws_d || (!idx_d && max_b) || n_records == 0 || max_b > n_records)
     return D3P_ERR_INVALID_ARGUMENT;
+  const ChaChaArg key = chacha_arg(state_h, state_d);
   PoissonWs w = carve_poisson_ws(ws_d, n_records);
   if (ws_bytes < w.bytes) return D3P_ERR_WORKSPACE;
   uint32_t n_blocks = (n_records + 15) / 16;
   uint32_t n_tiles = (n_blocks + kPoisThreads - 1) / kPoisThreads;
   cudaStream_t s = (cudaStream_t)stream;
-  poisson_select_kernel<<<n_tiles, kPoisThreads, 0, s>>>(load_state(state_h), q, n_records, w.masks, w.tile_counts, w.ready);
+  poisson_select_kernel<<<n_tiles, kPoisThreads, 0, s>>>(key, q, n_records, w.masks, w.tile_counts, w.ready);
   SampDev none;
   memset(&none, 0, sizeof(none));
   poisson_compact_kernel<false><<<n_tiles, kPoisThreads, 0, s>>>(w.masks, w.tile_counts, w.tile_off, w.ready, n_records, n_tiles, max_b, suppress, 0,
-                                                                 max_b, idx_d, counts_d, mask_d, none, load_state(state_h),
+                                                                 max_b, idx_d, counts_d, mask_d, none, key,
                                                                  q, 0, n_tiles);
   return check_launch();
 }
 
-int32_t d3p_poisson_sample_sharded(d3p_comm* comm, const uint32_t state_h[16], float q, uint32_t n_records,
-                                   uint32_t max_b, int32_t suppress, uint32_t pos_begin, uint32_t pos_end,
-                                   int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d, size_t ws_bytes,
-                                   void* stream) {
-  if (!comm || !state_h || !counts_d || !ws_d || (!idx_d && max_b) || n_records == 0 || max_b > n_records ||
+int32_t d3p_poisson_sample(const uint32_t state_h[16], float q, uint32_t n_records, uint32_t max_b,
+                           int32_t suppress, int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d,
+                           size_t ws_bytes, void* stream) {
+  if (!state_h) return D3P_ERR_INVALID_ARGUMENT;
+  return poisson_sample_impl(state_h, nullptr, q, n_records, max_b, suppress, idx_d, counts_d, mask_d, ws_d, ws_bytes, stream);
+}
+
+int32_t d3p_poisson_sample_dk(const uint32_t* state_d, float q, uint32_t n_records, uint32_t max_b, int32_t suppress,
+                              int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d, size_t ws_bytes,
+                              void* stream) {
+  if (!state_d) return D3P_ERR_INVALID_ARGUMENT;
+  return poisson_sample_impl(nullptr, state_d, q, n_records, max_b, suppress, idx_d, counts_d, mask_d, ws_d, ws_bytes, stream);
+}
+
+static int32_t poisson_sample_sharded_impl(d3p_comm* comm, const uint32_t* state_h, const uint32_t* state_d, float q,
+                                           uint32_t n_records, uint32_t max_b, int32_t suppress, uint32_t pos_begin,
+                                           uint32_t pos_end, int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d,
+                                           void* ws_d, size_t ws_bytes, void* stream) {
+  const ChaChaArg key = chacha_arg(state_h, state_d);
+  if (!comm || (!state_h && !state_d) || !counts_d || !ws_d || (!idx_d && max_b) || n_records == 0 || max_b > n_records ||
       pos_begin > pos_end || pos_end > max_b)
     return D3P_ERR_INVALID_ARGUMENT;
   PoissonWs w = carve_poisson_ws(ws_d, n_records);
@@ -418,12 +475,30 @@ int32_t d3p_poisson_sample_sharded(d3p_comm* comm, const uint32_t state_h[16], f
   // use 0 to force the re-draw path of the compaction kernel)
   const uint32_t margin = comm->sampler_margin;
   const uint32_t cov_lo = lo > margin ? lo - margin : 0, cov_hi = hi + margin < n_tiles ? hi + margin : n_tiles;
-  poisson_select_sharded_kernel<<<cov_hi - cov_lo, kPoisThreads, 0, s>>>(load_state(state_h), q, n_records, cov_lo, lo,
+  poisson_select_sharded_kernel<<<cov_hi - cov_lo, kPoisThreads, 0, s>>>(key, q, n_records, cov_lo, lo,
                                                                          hi, w.masks, sd, w.ready);
   poisson_compact_kernel<true><<<n_tiles, kPoisThreads, 0, s>>>(w.masks, nullptr, w.tile_off, w.ready, n_records, n_tiles, max_b, suppress,
                                                                 pos_begin, pos_end, idx_d, counts_d, mask_d, sd,
-                                                                load_state(state_h), q, cov_lo, cov_hi);
+                                                                key, q, cov_lo, cov_hi);
   return check_launch();
+}
+
+int32_t d3p_poisson_sample_sharded(d3p_comm* comm, const uint32_t state_h[16], float q, uint32_t n_records,
+                                   uint32_t max_b, int32_t suppress, uint32_t pos_begin, uint32_t pos_end,
+                                   int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d, size_t ws_bytes,
+                                   void* stream) {
+  if (!state_h) return D3P_ERR_INVALID_ARGUMENT;
+  return poisson_sample_sharded_impl(comm, state_h, nullptr, q, n_records, max_b, suppress, pos_begin, pos_end, idx_d,
+                                     counts_d, mask_d, ws_d, ws_bytes, stream);
+}
+
+int32_t d3p_poisson_sample_sharded_dk(d3p_comm* comm, const uint32_t* state_d, float q, uint32_t n_records,
+                                      uint32_t max_b, int32_t suppress, uint32_t pos_begin, uint32_t pos_end,
+                                      int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d, size_t ws_bytes,
+                                      void* stream) {
+  if (!state_d) return D3P_ERR_INVALID_ARGUMENT;
+  return poisson_sample_sharded_impl(comm, nullptr, state_d, q, n_records, max_b, suppress, pos_begin, pos_end, idx_d,
+                                     counts_d, mask_d, ws_d, ws_bytes, stream);
 }
 
 int32_t d3p_gather_rows_masked(const void* src_d, size_t row_bytes, const int32_t* idx_d,

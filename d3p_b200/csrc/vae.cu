@@ -1112,31 +1112,19 @@ static size_t mid_bwd_smem_bytes(uint32_t H, uint32_t Z) {
   return (3 * (size_t)Z * H + (size_t)kMidWarps * kMidE * (H + 128)) * sizeof(float);
 }
 
-// Side streams for the four independent clipped-sum GEMMs: one set per device, created on first use and kept (the
-// step path must not create or destroy streams).  `mu` serialises the fork / join bookkeeping of concurrent callers.
-struct VaeSideStreams {
+}  // namespace d3p
+
+// Side streams for the four independent clipped-sum GEMMs (and the small preparation kernels): CALLER-OWNED
+// (d3p_vae_ctx_create / _destroy; the library keeps no global state).  `mu` serialises the fork / join bookkeeping
+// should two host threads share one context.
+struct d3p_vae_ctx {
   std::mutex mu;
   cudaStream_t s[3];
   cudaEvent_t fork, join[3];
-  bool ok = false;
 };
-static VaeSideStreams* vae_side_streams() {
-  static std::mutex tab_mu;
-  static VaeSideStreams* tab[64] = {nullptr};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lk(tab_mu);
-  if (!tab[dev]) {
-    VaeSideStreams* v = new VaeSideStreams();
-    bool ok = cudaEventCreateWithFlags(&v->fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 3 && ok; ++i)
-      ok = cudaStreamCreateWithFlags(&v->s[i], cudaStreamNonBlocking) == cudaSuccess &&
-           cudaEventCreateWithFlags(&v->join[i], cudaEventDisableTiming) == cudaSuccess;
-    v->ok = ok;
-    tab[dev] = v;
-  }
-  return tab[dev]->ok ? tab[dev] : nullptr;
-}
+
+namespace d3p {
+using VaeSideStreams = d3p_vae_ctx;
 
 static bool vae_supported(const d3p_vae_desc* d) {
   return d && d->out_dim >= 4 && d->hidden_dim >= 4 && d->z_dim >= 1 && d->z_dim <= 32 && (d->out_dim % 4) == 0 &&
@@ -1155,11 +1143,41 @@ extern "C" size_t d3p_vae_workspace_bytes(const d3p_vae_desc* desc, uint32_t bat
   return L.total;
 }
 
+extern "C" int32_t d3p_vae_ctx_create(d3p_vae_ctx** ctx_out) {
+  if (!ctx_out) return D3P_ERR_INVALID_ARGUMENT;
+  d3p_vae_ctx* v = new (std::nothrow) d3p_vae_ctx();
+  if (!v) return D3P_ERR_CUDA;
+  bool ok = cudaEventCreateWithFlags(&v->fork, cudaEventDisableTiming) == cudaSuccess;
+  int made = 0;
+  for (int i = 0; i < 3 && ok; ++i) {
+    ok = cudaStreamCreateWithFlags(&v->s[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&v->join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ++made;
+  }
+  if (!ok) {
+    for (int i = 0; i < made; ++i) { cudaStreamDestroy(v->s[i]); cudaEventDestroy(v->join[i]); }
+    delete v;
+    return D3P_ERR_CUDA;
+  }
+  *ctx_out = v;
+  return D3P_OK;
+}
+
+// Returns at once; streams and events are released by the runtime when the work queued on them has drained.
+extern "C" int32_t d3p_vae_ctx_destroy(d3p_vae_ctx* ctx) {
+  if (!ctx) return D3P_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < 3; ++i) { cudaStreamDestroy(ctx->s[i]); cudaEventDestroy(ctx->join[i]); }
+  cudaEventDestroy(ctx->fork);
+  delete ctx;
+  return D3P_OK;
+}
+
 static int32_t step_vae_impl(const d3p_vae_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
                              const int32_t* idx_d, const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
                              uint32_t pos_begin, uint32_t pos_end, const uint32_t* threefry_key_h,
                              const uint32_t* threefry_key_d, float obs_scale, float C, float* px_norms_d,
-                             float* px_loss_d, void* ws_d, size_t ws_bytes, void* const* profile_events_h, void* stream) {
+                             float* px_loss_d, void* ws_d, size_t ws_bytes, void* const* profile_events_h,
+                             d3p_vae_ctx* ctx, void* stream) {
   if (!desc || !params_d || !x_d || (!threefry_key_h && !threefry_key_d) || !ws_d) return D3P_ERR_INVALID_ARGUMENT;
   if (!vae_supported(desc)) return D3P_ERR_UNSUPPORTED;
   if (pos_end > B || pos_begin >= pos_end || !(C > 0.f) || !(obs_scale != 0.f)) return D3P_ERR_INVALID_ARGUMENT;
@@ -1197,14 +1215,14 @@ static int32_t step_vae_impl(const d3p_vae_desc* desc, const float* params_d, co
   a.wf23 = reinterpret_cast<float4*>(ws + L.wf23); a.wf4 = reinterpret_cast<float4*>(ws + L.wf4);
   a.wf4t = reinterpret_cast<float4*>(ws + L.wf4t); a.wf23t = reinterpret_cast<float4*>(ws + L.wf23t);
   // thin layers: warp-MMA kernels for the shapes they tile (H % 8 == 0, Z % 4 == 0), SIMT kernels otherwise
-  const bool mid_mma = (H % 8) == 0 && (Z % 4) == 0 && Z <= 32 && getenv("D3P_VAE_MID_SIMT") == nullptr;
+  const bool mid_mma = (H % 8) == 0 && (Z % 4) == 0 && Z <= 32;
   float* w1_hi = F(L.w1_hi); float* w1_lo = F(L.w1_lo); float* w5_hi = F(L.w5_hi); float* w5_lo = F(L.w5_lo);
 
   const int sms = sm_count();
   int32_t rc;
   // parameter splits + X preparation: four independent small kernels; the weight splits and the thin-layer fragments
   // run on side streams beside the X preparation (the longest of them)
-  VaeSideStreams* ss = vae_side_streams();
+  VaeSideStreams* ss = ctx;               // nullptr: everything on the caller's stream
   {
     std::unique_lock<std::mutex> lk;
     cudaStream_t sw = s, sm = s;
@@ -1334,10 +1352,10 @@ extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* par
                                       const int32_t* num_valid_d, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
                                       const uint32_t threefry_key_h[2], float obs_scale, float C, float* px_norms_d,
                                       float* px_loss_d, void* ws_d, size_t ws_bytes, void* const* profile_events_h,
-                                      void* stream) {
+                                      d3p_vae_ctx* ctx, void* stream) {
   if (!threefry_key_h) return D3P_ERR_INVALID_ARGUMENT;
   return step_vae_impl(desc, params_d, x_d, x_row_stride, idx_d, mask_d, num_valid_d, B, pos_begin, pos_end, threefry_key_h,
-                       nullptr, obs_scale, C, px_norms_d, px_loss_d, ws_d, ws_bytes, profile_events_h, stream);
+                       nullptr, obs_scale, C, px_norms_d, px_loss_d, ws_d, ws_bytes, profile_events_h, ctx, stream);
 }
 
 // Device-key form (see d3p_dpsvi_step_meanfield_dk).
@@ -1346,8 +1364,8 @@ extern "C" int32_t d3p_dpsvi_step_vae_dk(const d3p_vae_desc* desc, const float* 
                                          const int32_t* num_valid_d, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
                                          const uint32_t* threefry_key_d, float obs_scale, float C, float* px_norms_d,
                                          float* px_loss_d, void* ws_d, size_t ws_bytes, void* const* profile_events_h,
-                                         void* stream) {
+                                         d3p_vae_ctx* ctx, void* stream) {
   if (!threefry_key_d) return D3P_ERR_INVALID_ARGUMENT;
   return step_vae_impl(desc, params_d, x_d, x_row_stride, idx_d, mask_d, num_valid_d, B, pos_begin, pos_end, nullptr,
-                       threefry_key_d, obs_scale, C, px_norms_d, px_loss_d, ws_d, ws_bytes, profile_events_h, stream);
+                       threefry_key_d, obs_scale, C, px_norms_d, px_loss_d, ws_d, ws_bytes, profile_events_h, ctx, stream);
 }

@@ -271,6 +271,25 @@ class VAE(Family):
         d.site_scale = self.site_scale(num_obs_total)
         return d
 
+    def _side_streams(self):
+        """This family object's ``d3p_vae_ctx`` on the current device (caller-owned side streams: the four clipped-sum
+        GEMMs of a step run concurrently on them); created on first use, released with the object."""
+        import ctypes as C
+        dev = torch.cuda.current_device()
+        ctxs = self.__dict__.setdefault("_ctx", {})
+        if dev not in ctxs:
+            h = C.c_void_p()
+            _n.check(_n.lib().d3p_vae_ctx_create(C.byref(h)), "vae_ctx_create")
+            ctxs[dev] = h
+        return ctxs[dev]
+
+    def __del__(self):
+        for h in self.__dict__.get("_ctx", {}).values():
+            try:
+                _n.lib().d3p_vae_ctx_destroy(h)
+            except Exception:
+                pass
+
     def run_step(self, svi, state, tf_key, args, mask, B, pos_begin, pos_end, px_norms, px_grads, px_loss):
         import ctypes as C
         if px_grads is not None:
@@ -292,7 +311,7 @@ class VAE(Family):
             C.byref(desc), _n.ptr(state.optim_state.flat), _n.ptr(Xsrc), stride, _n.ptr(idx), _n.ptr(mask_t), None, B,
             pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
             float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_loss), _n.ptr(ws_al), need,
-            self.profile_events, _n.stream_ptr()), "dpsvi_step_vae")
+            self.profile_events, self._side_streams(), _n.stream_ptr()), "dpsvi_step_vae")
         if svi.event_hook is not None:
             svi.event_hook("step_end")
         return ws_al, n_part.value, B, desc.n_params

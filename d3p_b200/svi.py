@@ -348,7 +348,7 @@ class DPSVI:
         new_os = OptimState(os_.step + 1, new_flat, new_m, new_v, os_.layout, new_lr)
         return DPSVIState(new_os, svi_state.rng_key, svi_state.observation_scale), stats[0]
 
-    def run_epoch(self, svi_state, get_batch, batchifier_state, num_steps, first_step=0):
+    def run_epoch(self, svi_state, get_batch, batchifier_state, num_steps, first_step=0, device_keys=False):
         """The examples' ``lax.fori_loop(first_step, first_step + num_steps, body, state)`` with
         ``body = lambda i, s: update(s, *get_batch(i, batchifier_state))``
         (``examples/logistic_regression.py:149-160``): returns ``(new_state, stats)`` where
@@ -358,7 +358,12 @@ class DPSVI:
         ``subsample_batchify_data`` the whole loop runs inside ``d3p_dpsvi_run_epoch_meanfield`` /
         ``d3p_dpsvi_run_epoch_vae`` (no interpreter between launches); the result is bit-identical to
         the step-by-step calls, which remain the path for everything else (NCCL-backend sharded runs,
-        GMM, custom batchifiers)."""
+        GMM, custom batchifiers).
+
+        ``device_keys=True`` drives the ``*_dk`` entry points: the batchifier key and the state key are uploaded once
+        and every per-step key is derived on the device (what a jitted caller with traced keys binds to, see
+        INTEGRATION.md); the results are bit-identical.  This facade then reads the final state key back, which
+        synchronises; a binding that keeps its keys on the device does not."""
         from .models import MeanFieldFamily, VAE
         spec = getattr(get_batch, "spec", None)
         is_vae = isinstance(self.family, VAE)
@@ -408,7 +413,23 @@ class DPSVI:
         rkey = np.array(np.asarray(svi_state.rng_key, dtype=np.uint32).reshape(16), copy=True)
         u32p = C.POINTER(C.c_uint32)
         comm = self.peer_window.ptr if self.shard is not None else None
-        if is_vae:
+        if device_keys:
+            bkey_d = torch.as_tensor(bkey.view(np.int32)).to(_dev())
+            rkey_d = torch.as_tensor(rkey.view(np.int32)).to(_dev())
+            if is_vae:
+                _n.check(_n.lib().d3p_dpsvi_run_epoch_vae_dk(
+                    C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, _n.ptr(bkey_d), _n.ptr(rkey_d), int(first_step),
+                    int(num_steps), float(svi_state.observation_scale), float(self._clipping_threshold),
+                    float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m), _n.ptr(v), _n.ptr(stats), comm,
+                    _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch_vae_dk")
+            else:
+                _n.check(_n.lib().d3p_dpsvi_run_epoch_meanfield_dk(
+                    C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, _n.ptr(ysrc), _n.ptr(bkey_d), _n.ptr(rkey_d),
+                    int(first_step), int(num_steps), float(svi_state.observation_scale), float(self._clipping_threshold),
+                    float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m), _n.ptr(v), _n.ptr(stats), comm,
+                    _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch_dk")
+            rkey = rkey_d.cpu().numpy().view(np.uint32).copy()
+        elif is_vae:
             _n.check(_n.lib().d3p_dpsvi_run_epoch_vae(
                 C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, bkey.ctypes.data_as(u32p),
                 rkey.ctypes.data_as(u32p), int(first_step), int(num_steps), float(svi_state.observation_scale),

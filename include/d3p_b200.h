@@ -8,7 +8,10 @@
  *     with suffix `_d` are DEVICE pointers, suffix `_h` HOST pointers; scratch space comes
  *     from the caller, sized by the matching `*_workspace_bytes` query),
  *   - enqueues its kernels on `stream` (a `cudaStream_t` passed as `void*`; NULL = default),
- *   - keeps no global mutable state and is re-entrant across streams and threads.
+ *   - keeps no global mutable state (the only statics are write-once caches of immutable facts: the SM count of a
+ *     device, the driver's cuTensorMapEncodeTiled entry point) and is re-entrant across streams and threads;
+ *     handles (d3p_comm, d3p_vae_ctx) are caller-owned and serve one caller at a time.
+ *     d3p_dpsvi_run_epoch_* create and release one sampler stream (and, for the VAE, one d3p_vae_ctx) per call.
  * One process per GPU; the caller selects the device with cudaSetDevice before calling.
  *
  * ChaCha states are 16 x uint32 in RFC 8439 layout (constants | 8 key words | counter |
@@ -34,7 +37,8 @@ extern "C" {
 #define D3P_MAX_LEAVES 16
 
 /* Library / build identification. */
-typedef struct d3p_comm d3p_comm; /* peer-memory window of a sharded run, see d3p_comm_create */
+typedef struct d3p_comm d3p_comm;       /* peer-memory window of a sharded run, see d3p_comm_create */
+typedef struct d3p_vae_ctx d3p_vae_ctx; /* side streams of the VAE step, see d3p_vae_ctx_create */
 
 int32_t d3p_abi_version(void);
 const char* d3p_error_string(int32_t code);
@@ -366,12 +370,17 @@ size_t d3p_vae_workspace_bytes(const d3p_vae_desc* desc, uint32_t batch_rows, ui
  * through idx_d when given; positions [pos_begin, pos_end) of a batch of B; per-example Threefry keys by
  * position.  ws_d must be 256-byte aligned.  px_norms_d[B] / px_loss_d[B] (may be NULL) receive the
  * pre-clip gradient norms and obs_scale * loss_p.  profile_events_h (may be NULL) = two events
- * (d3p_event_create) recorded immediately before and after the two tcgen05 clipped-sum GEMMs. */
+ * (d3p_event_create) recorded immediately before and after the two tcgen05 clipped-sum GEMMs.
+ * ctx (may be NULL): caller-owned side streams on which the four independent clipped-sum GEMMs and the small
+ * preparation kernels run concurrently (forked from / joined to `stream`); NULL runs everything on `stream`.
+ * One context serves one caller at a time (one per DPSVI object / per stream). */
+int32_t d3p_vae_ctx_create(d3p_vae_ctx** ctx_out);
+int32_t d3p_vae_ctx_destroy(d3p_vae_ctx* ctx); /* returns at once; resources go when the queued work has drained */
 int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
                            const int32_t* idx_d, const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
                            uint32_t pos_begin, uint32_t pos_end, const uint32_t threefry_key_h[2], float obs_scale,
                            float C, float* px_norms_d, float* px_loss_d, void* ws_d, size_t ws_bytes,
-                           void* const* profile_events_h, void* stream);
+                           void* const* profile_events_h, d3p_vae_ctx* ctx, void* stream);
 
 /* The same loop for the VAE family (examples/vae.py:216-233: lax.fori_loop over get_batch -> update for one epoch;
  * d3p/svi.py:395-434 per step).  `world` = number of ranks sharing the batch (1 without `comm`); ws_d must be
@@ -418,6 +427,81 @@ int32_t d3p_elbo_evaluate_meanfield(const d3p_meanfield_desc* desc, const float*
                                     size_t x_row_stride, const int32_t* y_d, const int32_t* idx_d, uint32_t B,
                                     const uint32_t threefry_key_h[2], float* loss_d, void* ws_d, size_t ws_bytes,
                                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-key forms (*_dk).  The reference runs get_batch + update as the body of a jitted lax.fori_loop with TRACED
+ * keys (examples/logistic_regression.py:149-160; README.md:119-126; d3p/random/__init__.py:28-32): a key there is a
+ * device value that no host code ever sees.  Every entry point above that takes a key as HOST words has a twin that
+ * takes it as a DEVICE pointer (16 uint32 ChaCha state words, or 2 Threefry words), and the key plumbing itself
+ * (split / fold_in / convert_to_jax_rng_key, the per-step keys of DPSVI.update) runs as one-block kernels on the
+ * stream, so an XLA custom call bound to these needs no host synchronisation.  Same kernels, bit-identical results
+ * (tests/test_gpu_device_keys.py).
+ * ------------------------------------------------------------------------------------------ */
+/* rng_suite.split (d3p/random/__init__.py:29): out_d = num x 16 words. */
+int32_t d3p_chacha_split_dk(const uint32_t* in_d, int32_t num, uint32_t* out_d, void* stream);
+/* rng_suite.fold_in(key, *data_d + data_imm) (d3p/random/__init__.py:30); data_d may be NULL (a loop index that
+ * lives on the device, e.g. the `i` of fori_loop, or an immediate). */
+int32_t d3p_chacha_fold_in_dk(const uint32_t* in_d, const uint32_t* data_d, uint32_t data_imm, uint32_t* out_d,
+                              void* stream);
+/* rng_suite.random_bits / uniform / normal with the key in device memory; random_bits with n_words = 2 is
+ * convert_to_jax_rng_key (d3p/random/__init__.py:149-155). */
+int32_t d3p_chacha_random_bits_dk(const uint32_t* state_d, uint64_t first_block, uint32_t* out_d, size_t n_words,
+                                  void* stream);
+int32_t d3p_chacha_uniform_f32_dk(const uint32_t* state_d, uint64_t first_block, float lo, float hi, float* out_d,
+                                  size_t n, void* stream);
+int32_t d3p_chacha_normal_f32_dk(const uint32_t* state_d, uint64_t first_block, float* out_d, size_t n, void* stream);
+/* The keys of one DPSVI.update (d3p/svi.py:208-211,413-414,490-491) from the state key, which is advanced in place:
+ * (carry, k_grad, k_noise) = split(key, 3); key := carry; threefry_key_out_d[2] = convert_to_jax_rng_key(k_grad);
+ * site_states_out_d[n_leaves][16] = split(k_noise, n_leaves). */
+int32_t d3p_dpsvi_keys_dk(uint32_t* rng_key_io_d, uint32_t n_leaves, uint32_t* threefry_key_out_d,
+                          uint32_t* site_states_out_d, void* stream);
+/* Samplers.  rc_out_d / rc_d: 30 words (32 allocated is fine). */
+int32_t d3p_feistel_round_constants_dk(const uint32_t* state_d, uint32_t* rc_out_d, void* stream);
+int32_t d3p_feistel_sample_dk(const uint32_t* rc_d, uint32_t capacity, uint32_t first_pos, uint32_t n, int32_t* idx_d,
+                              void* stream);
+int32_t d3p_poisson_sample_dk(const uint32_t* state_d, float q, uint32_t n_records, uint32_t max_b, int32_t suppress,
+                              int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d, size_t ws_bytes,
+                              void* stream);
+int32_t d3p_poisson_sample_sharded_dk(d3p_comm* comm, const uint32_t* state_d, float q, uint32_t n_records,
+                                      uint32_t max_b, int32_t suppress, uint32_t pos_begin, uint32_t pos_end,
+                                      int32_t* idx_d, int32_t* counts_d, uint8_t* mask_d, void* ws_d, size_t ws_bytes,
+                                      void* stream);
+/* Fused steps with the Threefry key (2 words) in device memory. */
+int32_t d3p_dpsvi_step_meanfield_dk(const d3p_meanfield_desc* desc, const float* params_d, const float* x_d,
+                                    size_t x_row_stride, const int32_t* y_d, const int32_t* idx_d,
+                                    const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                                    uint32_t pos_begin, uint32_t pos_end, const uint32_t* threefry_key_d,
+                                    float obs_scale, float C, float* px_norms_d, float* px_grads_d, float* px_loss_d,
+                                    void* ws_d, size_t ws_bytes, void* stream);
+int32_t d3p_dpsvi_step_vae_dk(const d3p_vae_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
+                              const int32_t* idx_d, const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                              uint32_t pos_begin, uint32_t pos_end, const uint32_t* threefry_key_d, float obs_scale,
+                              float C, float* px_norms_d, float* px_loss_d, void* ws_d, size_t ws_bytes,
+                              void* const* profile_events_h, d3p_vae_ctx* ctx, void* stream);
+int32_t d3p_dpsvi_step_gmm_dk(const d3p_gmm_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
+                              const int32_t* idx_d, const uint8_t* mask_d, const int32_t* num_valid_d, uint32_t B,
+                              uint32_t pos_begin, uint32_t pos_end, const uint32_t* threefry_key_d, float obs_scale,
+                              float C, float* px_norms_d, float* px_grads_d, float* px_loss_d, void* ws_d,
+                              size_t ws_bytes, void* stream);
+/* d3p_perturb_finalize_p2p_f32 with the per-leaf noise keys in device memory (leaves_h: layout only). */
+int32_t d3p_perturb_finalize_dk_f32(const float* partials_d, uint32_t n_partials, uint32_t P, uint32_t B,
+                                    const d3p_leaf_table* leaves_h, const uint32_t* site_states_d, float dp_scale, float C,
+                                    float obs_scale, float* grad_out_d, const d3p_optim_desc* optim_h, float* params_d,
+                                    float* m_d, float* v_d, float* stats_d, d3p_comm* comm, void* stream);
+/* The epoch loops with the batchifier key and the DPSVI state key in device memory (rng_key_io_d advanced in place). */
+int32_t d3p_dpsvi_run_epoch_meanfield_dk(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler,
+                                         const float* x_d, size_t x_row_stride, const int32_t* y_d,
+                                         const uint32_t* batch_key_d, uint32_t* rng_key_io_d, uint32_t first_step,
+                                         uint32_t n_steps, float obs_scale, float C, float dp_scale,
+                                         const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d,
+                                         float* m_d, float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d,
+                                         size_t ws_bytes, void* stream);
+int32_t d3p_dpsvi_run_epoch_vae_dk(const d3p_vae_desc* desc, const d3p_sampler_desc* sampler, const float* x_d,
+                                   size_t x_row_stride, const uint32_t* batch_key_d, uint32_t* rng_key_io_d,
+                                   uint32_t first_step, uint32_t n_steps, float obs_scale, float C, float dp_scale,
+                                   const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d,
+                                   float* m_d, float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d,
+                                   size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }
