@@ -164,6 +164,15 @@ _SIGNATURES = {
     "d3p_elbo_evaluate_workspace_bytes": (C.c_size_t, []),
     "d3p_elbo_evaluate_meanfield": (C.c_int32, [C.POINTER(MeanfieldDesc), _vp, _vp, C.c_size_t, _vp, _vp, C.c_uint32,
                                                 _u32p, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_elbo_evaluate_vae": (C.c_int32, [C.POINTER(VaeDesc), _vp, _vp, C.c_size_t, _vp, C.c_uint32, _u32p, _vp, _vp,
+                                          C.c_size_t, _vp, _vp]),
+    "d3p_elbo_evaluate_gmm_workspace_bytes": (C.c_size_t, [C.POINTER(GmmDesc)]),
+    "d3p_elbo_evaluate_gmm": (C.c_int32, [C.POINTER(GmmDesc), _vp, _vp, C.c_size_t, _vp, C.c_uint32, _u32p, _vp, _vp,
+                                          C.c_size_t, _vp]),
+    "d3p_threefry_random_bits": (C.c_int32, [_u32p, _vp, C.c_size_t, _vp]),
+    "d3p_threefry_uniform_f32": (C.c_int32, [_u32p, C.c_float, C.c_float, _vp, C.c_size_t, _vp]),
+    "d3p_threefry_normal_f32": (C.c_int32, [_u32p, _vp, C.c_size_t, _vp]),
+    "d3p_threefry_gamma_f32": (C.c_int32, [_u32p, _vp, C.c_uint32, C.c_uint32, C.c_int32, _vp, _vp]),
     "d3p_split_tf32": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_size_t, _vp]),
     "d3p_gemm_f32x3": (C.c_int32, [_vp, C.c_int32, C.c_size_t, _vp, C.c_int32, C.c_size_t, C.c_uint32, C.c_uint32,
                                    C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, C.c_size_t, C.c_int32, _vp]),

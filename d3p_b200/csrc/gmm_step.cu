@@ -20,6 +20,7 @@
 // Every (k, j) is owned by one thread, so the partial row is accumulated without atomics and the
 // result is run-to-run deterministic.
 #include "common.cuh"
+#include "jrandom.cuh"
 #include "launch.cuh"
 
 namespace d3p {
@@ -36,55 +37,6 @@ struct GmmArgs {
   float N, inv_S, C;
   float* px_norms; float* px_grads; float* px_loss; float* partials;
 };
-
-// jax.random.split(key, 3): words 0..5 from calls (0,3), (1,4), (2,5)
-D3P_D void tf_split3(const TfKey& k, TfKey& a, TfKey& b, TfKey& c) {
-  uint32_t a0, a1, b0, b1, c0, c1;
-  threefry2x32(k, 0u, 3u, a0, a1);
-  threefry2x32(k, 1u, 4u, b0, b1);
-  threefry2x32(k, 2u, 5u, c0, c1);
-  a = TfKey(a0, b0); b = TfKey(c0, a1); c = TfKey(b1, c1);
-}
-D3P_D float tf_scalar_bits_normal(const TfKey& k) { uint32_t y0, y1; threefry2x32(k, 0u, 0u, y0, y1); return bits_to_normal<false>(y0); }
-D3P_D float tf_scalar_uniform(const TfKey& k) { uint32_t y0, y1; threefry2x32(k, 0u, 0u, y0, y1); return bits_to_unit_float(y0); }
-
-// One pass of the outer loop of jax's _gamma_one: proposes (X, V, U) and advances the key.
-D3P_D void mt_propose(TfKey& key, float c, float& X, float& V, float& U) {
-  TfKey nk, x_key, U_key;
-  tf_split3(key, nk, x_key, U_key);
-  key = nk;
-  float x = 0.f, v = -1.0f;
-  while (v <= 0.f) {
-    TfKey xk2, sub;
-    tf_split2(x_key, xk2, sub);
-    x_key = xk2;
-    x = tf_scalar_bits_normal(sub);
-    v = 1.0f + x * c;
-  }
-  X = x * x;
-  V = (v * v) * v;
-  U = tf_scalar_uniform(U_key);
-}
-// the loop continues (= the proposal is rejected) while this holds
-D3P_D bool mt_reject(float X, float V, float U, float d) {
-  return (U >= 1.0f - 0.0331f * (X * X)) && (logf(U) >= X * 0.5f + d * ((1.0f - V) + logf(V)));
-}
-
-// jax _gamma_one(key, alpha, log_space = true): log of a Gamma(alpha, 1) draw
-D3P_D float loggamma_one(TfKey key, float alpha_orig) {
-  const bool boost_mask = alpha_orig >= 1.0f;
-  const float alpha = boost_mask ? alpha_orig : alpha_orig + 1.0f;
-  const float d = alpha - (1.0f / 3.0f);
-  const float c = (1.0f / 3.0f) / sqrtf(d);
-  TfKey k2, subkey;
-  tf_split2(key, k2, subkey);
-  const float u_boost = tf_scalar_uniform(subkey);
-  float X = 0.f, V = 1.0f, U = 2.0f;
-  while (mt_reject(X, V, U, d)) mt_propose(k2, c, X, V, U);
-  const float log_samples = log1pf(-u_boost);
-  const float log_boost = (boost_mask || log_samples == 0.f) ? 0.f : log_samples * (1.0f / alpha_orig);
-  return (logf(d) + logf(V)) + log_boost;
-}
 
 D3P_D float digamma_f32(float x) {      // x > 0
   float r = 0.f;
@@ -369,6 +321,195 @@ __global__ void __launch_bounds__(kGmmThreads, 2) gmm_step_kernel(GmmArgs a) {
   if (tid == 0) { part[a.P] = acc_loss; part[a.P + 1] = acc_cnt; }
 }
 
+// ---- DPSVI.evaluate for the mixture (d3p/svi.py:436-449 -> numpyro SVI.evaluate -> Trace_ELBO.loss on the whole batch) --
+// ONE guide draw (pis, mus, sigs) from numpyro's rng_key_eval, then the log-likelihood of every example of the batch under
+// it, plate scale N / B:   loss = -[log p(pis) + log p(mus) + (N / B) sum_i log p(x_i | pis, mus, sigs) - log q(pis) - log q(mus)].
+struct GmmEvalArgs {
+  const float* params; const float* x; size_t x_stride; const int32_t* idx;
+  uint32_t B, k0, k1;
+  uint32_t K, d, alpha_off, mus_off;
+  float N;
+  float* aT;        // [d][K]  -1 / (2 sig^2)
+  float* muT;       // [d][K]
+  float* ck;        // [K]     sum_j -log(sqrt(2 pi) sig_kj) + log pi_k
+  float* terms;     // [1]     log p(pis) + log p(mus) - log q(pis) - log q(mus)
+  float* partial;   // [grid]  per-CTA sums of log p(x_i | ...)
+  float* loss;
+};
+
+// one CTA: the guide draw, with the same device samplers (and the same key plumbing) as the step kernel
+__global__ void __launch_bounds__(kGmmThreads) gmm_eval_draw_kernel(GmmEvalArgs a) {
+  extern __shared__ float smem[];
+  constexpr int NW = kGmmThreads / 32;
+  const uint32_t K = a.K, d = a.d, n = a.K * a.d;
+  float* S = smem;              // [n] sig, then -log(sqrt(2 pi) sig)
+  float* alpha_s = S + n;       // [K]
+  float* comp = alpha_s + K;    // [K] log g, then row sums
+  float* lpi = comp + K;        // [K]
+  float* red = lpi + K;         // [NW + 4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float asum_part = 0.f, lgam_part = 0.f;
+  for (uint32_t k = tid; k < K; k += kGmmThreads) {
+    const float al = expf(a.params[a.alpha_off + k]);
+    alpha_s[k] = al;
+    asum_part += al;
+    lgam_part += lgammaf(al);
+  }
+  const float alpha_sum = block_sum<NW>(asum_part, red, lane, warp);
+  const float lgam_sum = block_sum<NW>(lgam_part, red, lane, warp);
+  const float log_norm_q_pis = lgammaf(alpha_sum) - lgam_sum;
+  __syncthreads();
+  const TfKey Ke(a.k0, a.k1);
+  TfKey model_seed, guide_seed, rng1, k_pis, rng2, k_mus, rng3, k_sigs;
+  tf_split2(Ke, model_seed, guide_seed);
+  tf_split2(guide_seed, rng1, k_pis);
+  tf_split2(rng1, rng2, k_mus);
+  tf_split2(rng2, rng3, k_sigs);
+  {   // sigs[m] = 1 / gamma(split(k_sigs, n)[m], 1): lane-level work queue (see gmm_step_kernel A1)
+    const float dd = 1.0f - 1.0f / 3.0f, cc = (1.0f / 3.0f) / sqrtf(dd);
+    uint32_t m = tid;
+    TfKey key;
+    bool have = m < n;
+    if (have) {
+      TfKey ek(tf_split_word(k_sigs, n, 2u * m), tf_split_word(k_sigs, n, 2u * m + 1u)), sub;
+      tf_split2(ek, key, sub);
+    }
+    while (__any_sync(0xffffffffu, have)) {
+      if (have) {
+        float X, V, U;
+        mt_propose(key, cc, X, V, U);
+        if (!mt_reject(X, V, U, dd)) {
+          S[m] = 1.0f / (dd * V);
+          m += kGmmThreads;
+          have = m < n;
+          if (have) {
+            TfKey ek(tf_split_word(k_sigs, n, 2u * m), tf_split_word(k_sigs, n, 2u * m + 1u)), sub;
+            tf_split2(ek, key, sub);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t half = (n + 1) / 2;
+  float s_mu2 = 0.f, s_e2 = 0.f;
+  for (uint32_t c = tid; c < half; c += kGmmThreads) {
+    uint32_t y0, y1;
+    const uint32_t m1 = c + half;
+    threefry2x32(k_mus, c, m1 < n ? m1 : 0u, y0, y1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t m = h ? m1 : c;
+      if (m >= n) break;
+      const float eps = bits_to_normal_fast(h ? y1 : y0);
+      const uint32_t k = m / d, j = m % d;
+      const float mu = a.params[a.mus_off + m] + eps;
+      const float sg = S[m];
+      a.muT[(size_t)j * K + k] = mu;
+      a.aT[(size_t)j * K + k] = -0.5f / (sg * sg);
+      S[m] = -logf(2.50662827f * sg);
+      s_mu2 = fmaf(mu, mu, s_mu2);
+      s_e2 = fmaf(eps, eps, s_e2);
+    }
+  }
+  for (uint32_t k = tid; k < K; k += kGmmThreads) {
+    TfKey ek(tf_split_word(k_pis, K, 2u * k), tf_split_word(k_pis, K, 2u * k + 1u));
+    comp[k] = loggamma_one(ek, alpha_s[k]);
+  }
+  const float sum_mu2 = block_sum<NW>(s_mu2, red, lane, warp);
+  const float sum_e2 = block_sum<NW>(s_e2, red, lane, warp);
+  const float lg_own = tid < K ? comp[tid] : -3.4e38f;
+  const float mx = block_max<NW>(lg_own, red, lane, warp);
+  const float den = block_sum<NW>(tid < K ? expf(lg_own - mx) : 0.f, red, lane, warp);
+  __syncthreads();
+  float lq_own = 0.f;
+  for (uint32_t k = tid; k < K; k += kGmmThreads) {
+    const float pi = expf(comp[k] - mx) / den;
+    const float pc = fminf(fmaxf(pi, 1.17549435e-38f), 0.99999988079071044921875f);
+    lpi[k] = logf(pc);
+    lq_own += (alpha_s[k] - 1.0f) * lpi[k];
+  }
+  const float lq_pis = block_sum<NW>(lq_own, red, lane, warp) + log_norm_q_pis;
+  __syncthreads();
+  for (uint32_t k = warp; k < K; k += NW) {
+    float s = 0.f;
+    for (uint32_t j = lane; j < d; j += 32) s += S[k * d + j];
+    s = group_sum<32>(s);
+    if (lane == 0) a.ck[k] = s + lpi[k];
+  }
+  if (tid == 0) {
+    const float kLogSqrt2Pi = 0.918938533f, kLog10Sqrt2Pi = 3.22152363f;
+    const float log_p_mus = -0.5f * sum_mu2 * 0.01f - (float)n * kLog10Sqrt2Pi;
+    const float log_q_mus = -0.5f * sum_e2 - (float)n * kLogSqrt2Pi;
+    a.terms[0] = lgammaf((float)K) + log_p_mus - lq_pis - log_q_mus;
+  }
+}
+
+// warp per example, lanes over the components: comp_k = ck_k + sum_j aT[j][k] (x_j - muT[j][k])^2, logsumexp over k
+constexpr int kGmmEvalMaxKPerLane = kGmmMaxK / 32;
+__global__ void __launch_bounds__(kGmmThreads) gmm_eval_loglik_kernel(GmmEvalArgs a) {
+  extern __shared__ float smem[];
+  constexpr int NW = kGmmThreads / 32;
+  const uint32_t K = a.K, d = a.d, n = a.K * a.d;
+  float* aT = smem;             // [d][K]
+  float* muT = aT + n;          // [d][K]
+  float* ck = muT + n;          // [K]
+  float* xs = ck + K;           // [NW][d]
+  __shared__ float wsum[NW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t i = tid; i < n; i += kGmmThreads) { aT[i] = a.aT[i]; muT[i] = a.muT[i]; }
+  for (uint32_t k = tid; k < K; k += kGmmThreads) ck[k] = a.ck[k];
+  __syncthreads();
+  float* x_w = xs + (size_t)warp * d;
+  float acc_ll = 0.f;
+  for (uint32_t p = blockIdx.x * NW + warp; p < a.B; p += gridDim.x * NW) {
+    const uint32_t row = a.idx ? (uint32_t)a.idx[p] : p;
+    __syncwarp();
+    for (uint32_t j = lane; j < d; j += 32) x_w[j] = a.x[(size_t)row * a.x_stride + j];
+    __syncwarp();
+    float acc[kGmmEvalMaxKPerLane];
+#pragma unroll
+    for (int t = 0; t < kGmmEvalMaxKPerLane; ++t) acc[t] = 0.f;
+    for (uint32_t j = 0; j < d; ++j) {
+      const float xj = x_w[j];
+#pragma unroll
+      for (int t = 0; t < kGmmEvalMaxKPerLane; ++t) {
+        const uint32_t k = lane + 32u * t;
+        if (k < K) { const float df = xj - muT[j * K + k]; acc[t] = fmaf(aT[j * K + k] * df, df, acc[t]); }
+      }
+    }
+    float mx = -3.4e38f;
+#pragma unroll
+    for (int t = 0; t < kGmmEvalMaxKPerLane; ++t) {
+      const uint32_t k = lane + 32u * t;
+      acc[t] = k < K ? acc[t] + ck[k] : -3.4e38f;
+      mx = fmaxf(mx, acc[t]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+#pragma unroll
+    for (int t = 0; t < kGmmEvalMaxKPerLane; ++t) se += (lane + 32u * t < K) ? expf(acc[t] - mx) : 0.f;
+    se = group_sum<32>(se);
+    acc_ll += mx + logf(se);
+  }
+  if (lane == 0) wsum[warp] = acc_ll;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += wsum[w];
+    a.partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void gmm_eval_finish_kernel(GmmEvalArgs a, uint32_t n_partial) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float s = 0.f;
+  for (uint32_t i = 0; i < n_partial; ++i) s += a.partial[i];
+  *a.loss = -(a.terms[0] + (a.N / (float)a.B) * s);
+}
+
 static size_t gmm_smem_bytes(uint32_t K, uint32_t d) {
   return ((size_t)3 * K * d + d + 9 * (size_t)K + kGmmThreads / 32 + 4) * sizeof(float);
 }
@@ -431,4 +572,43 @@ extern "C" int32_t d3p_dpsvi_step_gmm_dk(const d3p_gmm_desc* desc, const float* 
   if (!threefry_key_d) return D3P_ERR_INVALID_ARGUMENT;
   return step_gmm_impl(desc, params_d, x_d, x_row_stride, idx_d, mask_d, num_valid_d, B, pos_begin, pos_end, nullptr,
                        threefry_key_d, obs_scale, C, px_norms_d, px_grads_d, px_loss_d, ws_d, ws_bytes, stream);
+}
+
+extern "C" size_t d3p_elbo_evaluate_gmm_workspace_bytes(const d3p_gmm_desc* desc) {
+  if (!gmm_supported(desc)) return 0;
+  return ((size_t)2 * desc->K * desc->d + desc->K + 4 + 2 * (size_t)sm_count()) * sizeof(float);
+}
+
+// DPSVI.evaluate for the mixture: threefry_key_h = numpyro's rng_key_eval (d3p/svi.py:447 + SVI.evaluate's split).
+extern "C" int32_t d3p_elbo_evaluate_gmm(const d3p_gmm_desc* desc, const float* params_d, const float* x_d,
+                                         size_t x_row_stride, const int32_t* idx_d, uint32_t B,
+                                         const uint32_t threefry_key_h[2], float* loss_d, void* ws_d, size_t ws_bytes,
+                                         void* stream) {
+  if (!desc || !params_d || !x_d || !threefry_key_h || !loss_d || !ws_d || B == 0) return D3P_ERR_INVALID_ARGUMENT;
+  if (!gmm_supported(desc)) return D3P_ERR_UNSUPPORTED;
+  if (ws_bytes < d3p_elbo_evaluate_gmm_workspace_bytes(desc)) return D3P_ERR_WORKSPACE;
+  const uint32_t K = desc->K, d = desc->d, n = K * d;
+  GmmEvalArgs a;
+  a.params = params_d; a.x = x_d; a.x_stride = x_row_stride; a.idx = idx_d; a.B = B;
+  a.k0 = threefry_key_h[0]; a.k1 = threefry_key_h[1];
+  a.K = K; a.d = d; a.alpha_off = desc->alpha_off; a.mus_off = desc->mus_off; a.N = desc->num_obs_total;
+  float* w = static_cast<float*>(ws_d);
+  a.aT = w; a.muT = w + n; a.ck = w + 2 * (size_t)n; a.terms = a.ck + K; a.partial = a.terms + 4; a.loss = loss_d;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem1 = ((size_t)n + 3 * K + kGmmThreads / 32 + 4) * sizeof(float);
+  const size_t smem2 = ((size_t)2 * n + K + (size_t)(kGmmThreads / 32) * d) * sizeof(float);
+  if (smem2 > 200 * 1024) return D3P_ERR_UNSUPPORTED;
+  if (smem1 > 48 * 1024 &&
+      cudaFuncSetAttribute(gmm_eval_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1) != cudaSuccess)
+    return D3P_ERR_CUDA;
+  if (smem2 > 48 * 1024 &&
+      cudaFuncSetAttribute(gmm_eval_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess)
+    return D3P_ERR_CUDA;
+  gmm_eval_draw_kernel<<<1, kGmmThreads, smem1, s>>>(a);
+  unsigned grid = (B + kGmmThreads / 32 - 1) / (kGmmThreads / 32);
+  const unsigned cap = 2u * (unsigned)sm_count();
+  if (grid > cap) grid = cap;
+  gmm_eval_loglik_kernel<<<grid, kGmmThreads, smem2, s>>>(a);
+  gmm_eval_finish_kernel<<<1, 32, 0, s>>>(a, grid);
+  return check_launch();
 }

@@ -199,6 +199,7 @@ struct VaeArgs {
   const float* x; size_t x_stride; const int32_t* idx; const uint8_t* mask; const int32_t* num_valid;
   uint32_t k0, k1;
   const uint32_t* key_d;              // *_dk entry point: Threefry key in device memory (else nullptr)
+  int eval_mode;                      // DPSVI.evaluate: the key is numpyro's rng_key_eval, z [B, Z] is ONE draw (see vae_eval_eps)
   float site_scale, inv_S, C;
   uint32_t ns_h, ns_d;                // row-reduction slots over H and over D (N tiles x epilogue parts)
   uint32_t S;                         // partial rows
@@ -256,6 +257,25 @@ __global__ void vae_prep_x_kernel(VaeArgs a) {
     if (lane == 0) a.sq_x[r] = sq;
   }
   if (__any_sync(0xffffffffu, any_lo) && lane == 0) atomicOr(a.x_lo_flag, 1);
+}
+
+// DPSVI.evaluate (d3p/svi.py:436-449 -> numpyro SVI.evaluate -> Trace_ELBO.loss on the whole batch): one guide trace,
+// so z ~ Normal(z_loc, z_std).to_event(1) of shape [B, Z] is drawn with ONE key: rng_key_eval -> (_, guide_seed) ->
+// (rng, k_plate) -> (_, k_z); eps = jax.random.normal(k_z, (B, Z)), i.e. element e = p Z + j of B Z variates in the
+// legacy Threefry layout (call c yields elements c and c + half).
+D3P_D float vae_eval_eps(const TfKey& K_eval, uint32_t B, uint32_t Z, uint32_t p, uint32_t j) {
+  TfKey model_seed, guide_seed, rng, k_plate, rng2, k_z;
+  tf_split2(K_eval, model_seed, guide_seed);
+  tf_split2(guide_seed, rng, k_plate);
+  tf_split2(rng, rng2, k_z);
+  const uint32_t n = B * Z, half = (n + 1) / 2, e = p * Z + j;
+  uint32_t y0, y1;
+  if (e < half) {
+    threefry2x32(k_z, e, e + half < n ? e + half : 0u, y0, y1);
+    return bits_to_normal<false>(y0);
+  }
+  threefry2x32(k_z, e - half, e, y0, y1);
+  return bits_to_normal<false>(y1);
 }
 
 // S1: encoder heads, guide sample, KL part of the loss, decoder hidden layer.  The three thin weight
@@ -324,7 +344,9 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
         }
       }
       // guide noise: key_p -> (_, guide_seed) -> (rng, k_plate) -> (_, k_z); eps = normal(k_z, (Z,))
-      if (r < a.Bl) {
+      if (r < a.Bl && a.eval_mode) {
+        for (uint32_t j = lane; j < Z; j += 32) es[e * 64 + j] = vae_eval_eps(K, a.B, Z, a.pos_begin + r, j);
+      } else if (r < a.Bl) {
         TfKey kp = tf_example_key(K, a.B, a.pos_begin + r);
         TfKey model_seed, guide_seed, rng, k_plate, rng2, k_z;
         tf_split2(kp, model_seed, guide_seed);
@@ -337,6 +359,8 @@ __global__ void __launch_bounds__(kMidWarps * 32) vae_mid_fwd_kernel(VaeArgs a) 
           es[e * 64 + j] = bits_to_normal<false>(y0);
           if (j + half < Z) es[e * 64 + j + half] = bits_to_normal<false>(y1);
         }
+      }
+      if (r < a.Bl) {
         if (lane < 4) {     // ones column of [H1 | 1] (bias row of the dW2 / dW3 clipped-sum GEMM)
           a.h1_hi[(size_t)r * a.ldh + H + lane] = lane == 0 ? 1.0f : 0.f;
           a.h1_lo[(size_t)r * a.ldh + H + lane] = 0.f;
@@ -725,7 +749,10 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_fwd_mma_kernel(VaeArgs a)
   const uint32_t e8 = threadIdx.x / kMmaTpe, j8 = threadIdx.x % kMmaTpe;     // phase 0 / 2 mapping: kMmaTpe threads per example
   // ---- phase 0: guide noise: key_p -> (_, guide_seed) -> (rng, k_plate) -> (_, k_z); eps = normal(k_z, (Z,)) ----
   for (uint32_t j = j8; j < 32; j += kMmaTpe) { s_z[0][e8][j] = 0.f; s_z[1][e8][j] = 0.f; }
-  if (r0 + e8 < a.Bl) {
+  if (r0 + e8 < a.Bl && a.eval_mode) {
+    const TfKey K = tf_key_arg(a.k0, a.k1, a.key_d);
+    for (uint32_t j = j8; j < Z; j += kMmaTpe) s_eps[e8][j] = vae_eval_eps(K, a.B, Z, a.pos_begin + r0 + e8, j);
+  } else if (r0 + e8 < a.Bl) {
     const TfKey K = tf_key_arg(a.k0, a.k1, a.key_d);
     TfKey kp = tf_example_key(K, a.B, a.pos_begin + r0 + e8);
     TfKey model_seed, guide_seed, rng, k_plate, rng2, k_z;
@@ -1026,6 +1053,27 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_bwd_mma_kernel(VaeArgs a)
   }
 }
 
+// DPSVI.evaluate: loss = site scale of the evaluation trace (N / B) * (1 / N) = 1 / B, times sum_i (kl_i + rec_i);
+// one CTA, fixed order.
+__global__ void __launch_bounds__(1024) vae_eval_reduce_kernel(VaeArgs a, float* __restrict__ loss_out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (uint32_t r = threadIdx.x; r < a.Bl; r += 1024) {
+    float l = a.loss_kl[r];
+    for (uint32_t t = 0; t < a.ns_d; ++t) l += a.loss_rec[(size_t)t * a.Bl + r];
+    s += l;
+  }
+  s = group_sum<32>(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) tot += red[w];
+    *loss_out = tot * (a.site_scale / (float)a.B);
+  }
+}
+
 // loss / count columns of the partial rows: slab s = a contiguous range of examples, summed in a fixed order
 __global__ void __launch_bounds__(256) vae_loss_kernel(VaeArgs a) {
   __shared__ float red[2][8];
@@ -1177,7 +1225,7 @@ static int32_t step_vae_impl(const d3p_vae_desc* desc, const float* params_d, co
                              uint32_t pos_begin, uint32_t pos_end, const uint32_t* threefry_key_h,
                              const uint32_t* threefry_key_d, float obs_scale, float C, float* px_norms_d,
                              float* px_loss_d, void* ws_d, size_t ws_bytes, void* const* profile_events_h,
-                             d3p_vae_ctx* ctx, void* stream) {
+                             d3p_vae_ctx* ctx, void* stream, float* eval_loss_d = nullptr) {
   if (!desc || !params_d || !x_d || (!threefry_key_h && !threefry_key_d) || !ws_d) return D3P_ERR_INVALID_ARGUMENT;
   if (!vae_supported(desc)) return D3P_ERR_UNSUPPORTED;
   if (pos_end > B || pos_begin >= pos_end || !(C > 0.f) || !(obs_scale != 0.f)) return D3P_ERR_INVALID_ARGUMENT;
@@ -1201,6 +1249,7 @@ static int32_t step_vae_impl(const d3p_vae_desc* desc, const float* params_d, co
   a.x = x_d; a.x_stride = x_row_stride; a.idx = idx_d; a.mask = mask_d; a.num_valid = num_valid_d;
   a.k0 = threefry_key_h ? threefry_key_h[0] : 0u; a.k1 = threefry_key_h ? threefry_key_h[1] : 0u;
   a.key_d = threefry_key_d;
+  a.eval_mode = eval_loss_d ? 1 : 0;
   a.site_scale = desc->site_scale; a.inv_S = 1.0f / obs_scale; a.C = C;
   a.ns_h = L.ns_h; a.ns_d = L.ns_d; a.S = L.S;
   a.x_hi = F(L.x_hi); a.x_lo = F(L.x_lo); a.x_lo_flag = reinterpret_cast<int*>(ws + L.flag);
@@ -1278,6 +1327,10 @@ static int32_t step_vae_impl(const d3p_vae_desc* desc, const float* params_d, co
     EpiFwd5::Args ea{params_d + a.off_b5, a.x_hi, a.ldx, a.d5_hi, a.d5_lo, D, a.sq_d5, a.loss_rec, Bl};
     if ((rc = tc::launch_tc_gemm<false, true, kVaeBN, EpiFwd5, kHeavyEW>(A, Bo, Bl, D, H, 1, ea, s, nullptr)) != D3P_OK)
       return rc;
+  }
+  if (eval_loss_d) {       // DPSVI.evaluate: the forward pass is all there is; loss = (1 / B) sum_i (kl_i + rec_i) * N * (1 / N)
+    vae_eval_reduce_kernel<<<1, 1024, 0, s>>>(a, eval_loss_d);
+    return check_launch();
   }
   // G5b: dh2 = delta5 W5^T  (B[n = h, k = d] = W5[h, d]: K-major)
   {
@@ -1368,4 +1421,16 @@ extern "C" int32_t d3p_dpsvi_step_vae_dk(const d3p_vae_desc* desc, const float* 
   if (!threefry_key_d) return D3P_ERR_INVALID_ARGUMENT;
   return step_vae_impl(desc, params_d, x_d, x_row_stride, idx_d, mask_d, num_valid_d, B, pos_begin, pos_end, nullptr,
                        threefry_key_d, obs_scale, C, px_norms_d, px_loss_d, ws_d, ws_bytes, profile_events_h, ctx, stream);
+}
+
+// DPSVI.evaluate for the VAE (d3p/svi.py:436-449; examples/vae.py:236-247 evaluates the test loss every epoch): the
+// forward half of the step on the whole batch with ONE guide draw z [B, Z] from `threefry_key_h` = numpyro's
+// rng_key_eval; *loss_d = -ELBO under the evaluation trace's scale (N / B) * (1 / N).  Workspace as for the step.
+extern "C" int32_t d3p_elbo_evaluate_vae(const d3p_vae_desc* desc, const float* params_d, const float* x_d,
+                                         size_t x_row_stride, const int32_t* idx_d, uint32_t B,
+                                         const uint32_t threefry_key_h[2], float* loss_d, void* ws_d, size_t ws_bytes,
+                                         d3p_vae_ctx* ctx, void* stream) {
+  if (!loss_d || !threefry_key_h || B == 0) return D3P_ERR_INVALID_ARGUMENT;
+  return step_vae_impl(desc, params_d, x_d, x_row_stride, idx_d, nullptr, nullptr, B, 0, B, threefry_key_h, nullptr, 1.0f, 1.0f,
+                       nullptr, nullptr, ws_d, ws_bytes, nullptr, ctx, stream, loss_d);
 }

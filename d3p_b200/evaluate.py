@@ -1,14 +1,13 @@
 """``DPSVI.evaluate`` (``d3p/svi.py:436-449``) on the device: numpyro's ``SVI.evaluate`` draws one guide
 sample for the whole batch from ``split(rng_key)[1]`` and returns ``Trace_ELBO.loss`` with the plate scale
-``N / B``.  Implemented for the mean-field families (``d3p_elbo_evaluate_meanfield``); the GMM and VAE
-families raise ``NotImplementedError`` (listed under "next" in DESIGN.md)."""
+``N / B``.  ``d3p_elbo_evaluate_meanfield`` / ``_vae`` / ``_gmm``: all four model families."""
 import ctypes as C
 
 import numpy as np
 import torch
 
 from . import _native as _n
-from .models import MeanFieldFamily
+from .models import VAE, GaussianMixture, MeanFieldFamily
 
 
 def _threefry_split_second(key):
@@ -36,15 +35,32 @@ def _threefry_split_second(key):
 
 def evaluate_elbo(svi, svi_state, jax_key, args):
     fam = svi.family
-    if not isinstance(fam, MeanFieldFamily):
-        raise NotImplementedError("DPSVI.evaluate is implemented for the mean-field families only")
     Xsrc, stride, ysrc, idx, B = svi._resolve_args(args)
+    if getattr(svi, "_local_rows", None) is not None:
+        raise NotImplementedError("DPSVI.evaluate takes whole batches (LocalRows are a sharded-update input)")
     desc = fam.desc(svi._num_obs_total())
     key = _threefry_split_second(np.asarray(jax_key, dtype=np.uint32).reshape(2))    # SVI.evaluate: _, rng_key_eval
     lib = _n.lib()
+    kp = key.ctypes.data_as(C.POINTER(C.c_uint32))
+    loss = torch.empty(1, dtype=torch.float32, device=Xsrc.device)
+    flat = svi_state.optim_state.flat
+    if isinstance(fam, VAE):
+        need = lib.d3p_vae_workspace_bytes(C.byref(desc), B, None)
+        ws = svi._workspace(need + 256)
+        ws_al = ws[((-ws.data_ptr()) % 256) // 4:]
+        _n.check(lib.d3p_elbo_evaluate_vae(C.byref(desc), _n.ptr(flat), _n.ptr(Xsrc), stride, _n.ptr(idx), B, kp, _n.ptr(loss),
+                                           _n.ptr(ws_al), need, fam._side_streams(), _n.stream_ptr()), "elbo_evaluate_vae")
+        return loss[0]
+    if isinstance(fam, GaussianMixture):
+        need = lib.d3p_elbo_evaluate_gmm_workspace_bytes(C.byref(desc))
+        ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=Xsrc.device)
+        _n.check(lib.d3p_elbo_evaluate_gmm(C.byref(desc), _n.ptr(flat), _n.ptr(Xsrc), stride, _n.ptr(idx), B, kp, _n.ptr(loss),
+                                           _n.ptr(ws), need, _n.stream_ptr()), "elbo_evaluate_gmm")
+        return loss[0]
+    if not isinstance(fam, MeanFieldFamily):
+        raise NotImplementedError(f"DPSVI.evaluate: unknown family {type(fam).__name__}")
     need = lib.d3p_elbo_evaluate_workspace_bytes()
     ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=Xsrc.device)
-    loss = torch.empty(1, dtype=torch.float32, device=Xsrc.device)
     _n.check(lib.d3p_elbo_evaluate_meanfield(C.byref(desc), _n.ptr(svi_state.optim_state.flat), _n.ptr(Xsrc), stride,
                                              _n.ptr(ysrc), _n.ptr(idx), B, key.ctypes.data_as(C.POINTER(C.c_uint32)),
                                              _n.ptr(loss), _n.ptr(ws), need, _n.stream_ptr()), "elbo_evaluate")

@@ -427,6 +427,28 @@ int32_t d3p_elbo_evaluate_meanfield(const d3p_meanfield_desc* desc, const float*
                                     size_t x_row_stride, const int32_t* y_d, const int32_t* idx_d, uint32_t B,
                                     const uint32_t threefry_key_h[2], float* loss_d, void* ws_d, size_t ws_bytes,
                                     void* stream);
+/* The same for the VAE (examples/vae.py:236-247 evaluates the test loss every epoch): the forward half of the step on
+ * the whole batch with ONE guide draw z [B, Z]; scale (N / B) * (1 / N).  Workspace: d3p_vae_workspace_bytes(desc, B). */
+int32_t d3p_elbo_evaluate_vae(const d3p_vae_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
+                              const int32_t* idx_d, uint32_t B, const uint32_t threefry_key_h[2], float* loss_d,
+                              void* ws_d, size_t ws_bytes, d3p_vae_ctx* ctx, void* stream);
+/* ... and for the mixture: one guide draw (pis, mus, sigs), then the log-likelihood of every example under it. */
+size_t d3p_elbo_evaluate_gmm_workspace_bytes(const d3p_gmm_desc* desc);
+int32_t d3p_elbo_evaluate_gmm(const d3p_gmm_desc* desc, const float* params_d, const float* x_d, size_t x_row_stride,
+                              const int32_t* idx_d, uint32_t B, const uint32_t threefry_key_h[2], float* loss_d,
+                              void* ws_d, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * jax.random with Threefry keys (2 words) on the device, for predictive sampling (d3p/modelling.py:39-223 runs numpyro
+ * models under the `seed` handler, whose sites draw jax.random.normal / bernoulli / gamma ...): jax's legacy layout,
+ * n variates from ceil(n / 2) Threefry-2x32-20 calls; gamma / loggamma with per-element keys split(key, n)
+ * (alpha_n = 1: one shared concentration, else alpha_n = n).
+ * ------------------------------------------------------------------------------------------ */
+int32_t d3p_threefry_random_bits(const uint32_t key_h[2], uint32_t* out_d, size_t n_words, void* stream);
+int32_t d3p_threefry_uniform_f32(const uint32_t key_h[2], float lo, float hi, float* out_d, size_t n, void* stream);
+int32_t d3p_threefry_normal_f32(const uint32_t key_h[2], float* out_d, size_t n, void* stream);
+int32_t d3p_threefry_gamma_f32(const uint32_t key_h[2], const float* alpha_d, uint32_t alpha_n, uint32_t n,
+                               int32_t log_space, float* out_d, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Device-key forms (*_dk).  The reference runs get_batch + update as the body of a jitted lax.fori_loop with TRACED

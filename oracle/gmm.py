@@ -53,8 +53,10 @@ class GaussianMixture:
         return {"logg": logg.astype(np.float32), "dlogg": dlogg.astype(np.float32), "eps_mus": eps_mus, "sigs": sigs}
 
     def neg_elbo(self, p, eps, x):
+        """x: one example [d] / [1, d] (per-example path) or a batch [B, d] with B > 1 (DPSVI.evaluate: one guide draw
+        for the whole batch, log-likelihood summed over the plate)."""
         K, N = self.K, self.num_obs_total
-        x = x.reshape(-1)
+        x = x.reshape(-1, self.d)
         alpha = torch.exp(p["alpha_log"])
         logg = eps["logg"] + eps["dlogg"] * (alpha - alpha.detach())
         un = torch.exp(logg - logg.max().detach())
@@ -69,7 +71,7 @@ class GaussianMixture:
         # model
         log_p_pis = (torch.log(pis) * 0.0).sum() - (0.0 - math.lgamma(K))
         log_p_mus = normal_log_prob(mus, torch.zeros_like(mus), 10.0).sum()
-        comp = normal_log_prob(x[None, :], mus, sigs).sum(dim=1) + torch.log(pis)      # d3p/gmm.py:71-86
-        loglik = torch.logsumexp(comp, dim=0)
+        comp = normal_log_prob(x[:, None, :], mus[None], sigs[None]).sum(dim=2) + torch.log(pis)[None]      # d3p/gmm.py:71-86
+        loglik = torch.logsumexp(comp, dim=1).sum()
         elbo = log_p_pis + log_p_mus + N * loglik - log_q_pis - log_q_mus
         return -elbo

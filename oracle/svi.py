@@ -282,8 +282,13 @@ class DPSVI:
         key = self._rng_suite.convert_to_jax_rng_key(self._rng_suite.split(svi_state.rng_key, 1)[0])
         # numpyro SVI.evaluate: _, rng_key_eval = split(rng_key); Trace_ELBO.loss(rng_key_eval, ...)
         rng_key_eval = threefry.split(key, 2)[1]
-        eps = fam.sample_eps(rng_key_eval.reshape(1, 2))
         params = self.optim.get_params(svi_state.optim_state)
+        if hasattr(fam, "evaluate_loss"):      # families whose guide has batch-shaped sites (VAE: z [B, Z])
+            return float(fam.evaluate_loss(rng_key_eval, params, *args))
+        if getattr(fam, "needs_params_for_eps", False):
+            eps = fam.sample_eps(rng_key_eval.reshape(1, 2), params)
+        else:
+            eps = fam.sample_eps(rng_key_eval.reshape(1, 2))
         tparams = {k: torch.tensor(np.asarray(v, np.float32)) for k, v in params.items()}
         teps = {k: torch.tensor(v[0]) for k, v in eps.items()}
         targs = tuple(torch.tensor(np.asarray(a)) for a in args)

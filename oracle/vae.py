@@ -102,6 +102,28 @@ class VAE:
     def flat_param_order(self):
         return list(NAMES)
 
+    def evaluate_loss(self, rng_key_eval, params, X):
+        """numpyro ``SVI.evaluate`` -> ``Trace_ELBO.loss(rng_key_eval, ...)`` on a whole batch (``d3p/svi.py:436-449``):
+        ONE guide trace, ``z ~ Normal(z_loc, z_std).to_event(1)`` of shape [B, Z] drawn from one key inside the
+        subsampling plate (scale N / B) under the ``scale(1 / N)`` handler of ``examples/vae.py:193-194``."""
+        B = X.shape[0]
+        _plate_key, z_key = guide_site_keys(np.asarray(rng_key_eval, np.uint32).reshape(1, 2), 2)
+        eps = torch.tensor(threefry.normal(z_key[0], (B * self.z_dim,)).reshape(B, self.z_dim))
+        p = {k: torch.tensor(np.asarray(v, np.float32)) for k, v in params.items()}
+        sp = torch.nn.functional.softplus
+        x = torch.tensor(np.asarray(X, np.float32)).reshape(B, -1)
+        h1 = sp(x @ p[W1] + p[B1])
+        z_loc = h1 @ p[W2] + p[B2]
+        z_std = torch.exp(h1 @ p[W3] + p[B3])
+        z = z_loc + z_std * eps
+        log_q = normal_log_prob(z, z_loc, z_std).sum()
+        log_pz = normal_log_prob(z, torch.zeros_like(z), torch.ones_like(z)).sum()
+        h2 = sp(z @ p[W4] + p[B4])
+        probs = clamp_probs(torch.sigmoid(h2 @ p[W5] + p[B5]))
+        log_px = (x * torch.log(probs) + (1.0 - x) * torch.log1p(-probs)).sum()
+        s = float(np.float32((1.0 / self.num_obs_total) * (self.num_obs_total / B)))
+        return -(s * (log_pz + log_px) - s * log_q)
+
 
 def explicit_clipped_sum(params, X, eps_z, clip, mask, site_scale=1.0, obs_scale=1.0):
     """The same per-example gradients WITHOUT autodiff, in float64, at any batch size: forward and delta

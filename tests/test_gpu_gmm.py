@@ -116,3 +116,12 @@ def test_gmm_full_shape_properties(cuda):
     norms = torch.zeros(B, device=cuda)
     s._run_step(st1, keys[0], (X,), True, px_norms=norms)
     assert float(norms.min()) > 0 and bool(torch.isfinite(norms).all())
+
+
+@pytest.mark.parametrize("K,d,B", [(3, 2, 24), (8, 5, 400), (64, 128, 300)])
+def test_gmm_evaluate_matches_oracle(cuda, K, d, B):
+    """DPSVI.evaluate (d3p/svi.py:436-449): one guide draw (pis, mus, sigs) for the whole batch, plate scale N / B."""
+    X, o, ost, s, st = make(K, d, 2000, B, 20.0, 1.0)
+    want = o.evaluate(ost, X)
+    got = float(s.evaluate(st, torch.as_tensor(X).cuda()))
+    assert np.isclose(got, want, rtol=REL), (got, want)

@@ -166,3 +166,15 @@ def test_vae_full_shape_matches_explicit_oracle(cuda, init_std, C):
         # element-wise with floor = rms(leaf).  2e-5, not 1e-5: the accumulators of tcgen05.mma truncate (DESIGN.md
         # section 7, scripts/gemm_accuracy.py), ~2^-24 per 8-deep k-step over the 1024-example contraction of a split
         assert ew_rel_err(got, ref) < 2e-5, (name, ew_rel_err(got, ref))
+
+
+@pytest.mark.parametrize("D,H,Z,B", [(36, 24, 4, 50), (36, 20, 3, 19), (64, 40, 20, 333), (784, 400, 20, 1000)])
+def test_vae_evaluate_matches_oracle(cuda, D, H, Z, B):
+    """DPSVI.evaluate (d3p/svi.py:436-449; examples/vae.py:236-247): one guide draw z [B, Z] for the whole batch,
+    scale (N / B) (1 / N)."""
+    X, o, ost, s, st = make(D, H, Z, 60000, B, 10.0, 1.0)
+    want = o.evaluate(ost, X)
+    got = float(s.evaluate(st, torch.as_tensor(X).cuda()))
+    assert np.isclose(got, want, rtol=REL), (got, want)
+    # evaluate does not touch the state; a second call gives the same number
+    assert float(s.evaluate(st, torch.as_tensor(X).cuda())) == got
