@@ -50,10 +50,10 @@ class OptimDesc(C.Structure):
 
 class SamplerDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("q", C.c_float), ("n_records", C.c_uint32), ("batch", C.c_uint32),
-                ("suppress", C.c_int32)]
+                ("suppress", C.c_int32), ("perm_d", C.c_void_p)]
 
 
-SAMPLER_POISSON, SAMPLER_SUBSAMPLE = 0, 1
+SAMPLER_POISSON, SAMPLER_SUBSAMPLE, SAMPLER_SPLIT = 0, 1, 2
 
 _u32p = C.POINTER(C.c_uint32)
 _vp = C.c_void_p
@@ -81,6 +81,7 @@ _SIGNATURES = {
                                        C.c_size_t, _vp]),
     "d3p_gather_rows_masked": (C.c_int32, [_vp, C.c_size_t, _vp, _vp, C.c_uint32, _vp, _vp]),
     "d3p_clip_rows_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, C.c_float, _vp, _vp]),
+    "d3p_vector_norm_f32": (C.c_int32, [_vp, C.c_size_t, C.c_float, _vp, _vp]),
     "d3p_clip_and_sum_workspace_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32]),
     "d3p_clip_and_sum_f32": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_float, _vp, _vp, C.c_size_t, _vp]),
     "d3p_meanfield_workspace_bytes": (C.c_size_t, [C.POINTER(MeanfieldDesc), _u32p]),
@@ -98,6 +99,11 @@ _SIGNATURES = {
                                                   _vp, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                                   C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
                                                   _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "d3p_dpsvi_epoch_gmm_workspace_bytes": (C.c_size_t, [C.POINTER(GmmDesc), C.POINTER(SamplerDesc)]),
+    "d3p_dpsvi_run_epoch_gmm": (C.c_int32, [C.POINTER(GmmDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
+                                            _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
+                                            C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
+                                            _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "d3p_dpsvi_epoch_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.POINTER(SamplerDesc), C.c_int32]),
     "d3p_dpsvi_run_epoch_vae": (C.c_int32, [C.POINTER(VaeDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
                                             _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,

@@ -71,6 +71,8 @@ def _composed(pld, sigma, q, ncomp, nx, L):
         raise ValueError("non-finite privacy loss density: increase sigma or change L / nx")
     half = nx // 2
     fx = np.concatenate([fx[half:], fx[:half]])                        # put s = 0 at index 0
+    # ncomp may be fractional (DPSVI.get_epsilon passes num_epochs / q, d3p/svi.py:451-468): the reference hands the
+    # float straight to this power, so no rounding (in either direction) happens here
     cfx = np.fft.ifft(np.fft.fft(fx * dx) ** ncomp)
     cfx = np.real(np.concatenate([cfx[half:], cfx[:half]])) / dx
     mass = np.sum(cfx) * dx
@@ -89,15 +91,22 @@ def _delta_and_slope(x, dx, cfx, eps):
     return delta, slope
 
 
+def _ncomp(ncomp):
+    """An integral count as int (exact integer power), anything else as the float it is: like fourier-accountant, and
+    never rounded down, which would under-report epsilon / delta (round-1 ADVICE)."""
+    f = float(ncomp)
+    return int(f) if f == int(f) else f
+
+
 def _get_delta(pld, target_eps, sigma, q, ncomp, nx, L):
-    x, dx, cfx = _composed(pld, sigma, q, int(round(ncomp)), nx, L)
+    x, dx, cfx = _composed(pld, sigma, q, _ncomp(ncomp), nx, L)
     if not -L < target_eps < L:
         raise ValueError("target_eps outside of [-L, L]")
     return float(_delta_and_slope(x, dx, cfx, float(target_eps))[0])
 
 
 def _get_epsilon(pld, target_delta, sigma, q, ncomp, nx, L):
-    x, dx, cfx = _composed(pld, sigma, q, int(round(ncomp)), nx, L)
+    x, dx, cfx = _composed(pld, sigma, q, _ncomp(ncomp), nx, L)
     eps = 0.0
     for _ in range(200):
         delta, slope = _delta_and_slope(x, dx, cfx, eps)

@@ -135,6 +135,37 @@ static uint32_t pick_splits(uint32_t B, uint32_t P) {
   return want;
 }
 
+
+// full_norm(vector_parts, ord) for ord != 2 (d3p/svi.py:68-87 -> jnp.linalg.norm of the concatenated leaves):
+// inf -> max |x|, -inf -> min |x|, 0 -> number of non-zeros, p -> (sum |x|^p)^(1/p).  One CTA, fixed order.
+__global__ void __launch_bounds__(1024) vector_norm_kernel(const float* __restrict__ x, size_t n, float ord, float* out) {
+  __shared__ float red[32];
+  const bool is_max = isinf(ord) && ord > 0, is_min = isinf(ord) && ord < 0;
+  float acc = is_min ? __int_as_float(0x7f800000) : 0.f;
+  for (size_t i = threadIdx.x; i < n; i += 1024) {
+    const float a = fabsf(x[i]);
+    if (is_max) acc = fmaxf(acc, a);
+    else if (is_min) acc = fminf(acc, a);
+    else if (ord == 0.f) acc += a != 0.f ? 1.f : 0.f;
+    else if (ord == 1.f) acc += a;
+    else acc += powf(a, ord);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v = __shfl_xor_sync(0xffffffffu, acc, o);
+    acc = is_max ? fmaxf(acc, v) : is_min ? fminf(acc, v) : acc + v;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+#pragma unroll
+    for (int w = 1; w < 32; ++w) t = is_max ? fmaxf(t, red[w]) : is_min ? fminf(t, red[w]) : t + red[w];
+    if (n == 0) t = 0.f;
+    *out = (is_max || is_min || ord == 0.f || ord == 1.f) ? t : powf(t, 1.0f / ord);
+  }
+}
+
 }  // namespace d3p
 
 using namespace d3p;
@@ -147,6 +178,12 @@ int32_t d3p_clip_rows_f32(float* px_grads_d, uint32_t B, uint32_t P, float C, fl
   if (B == 0) return D3P_OK;
   unsigned grid = B < (unsigned)sm_count() * 8 ? B : (unsigned)sm_count() * 8;
   clip_rows_kernel<<<grid, kClipThreads, 0, (cudaStream_t)stream>>>(px_grads_d, B, P, C, norms_d);
+  return check_launch();
+}
+
+int32_t d3p_vector_norm_f32(const float* x_d, size_t n, float ord, float* out_d, void* stream) {
+  if ((!x_d && n) || !out_d || ord != ord) return D3P_ERR_INVALID_ARGUMENT;
+  vector_norm_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x_d, n, ord, out_d);
   return check_launch();
 }
 

@@ -71,6 +71,7 @@ bool sampler_ok(const d3p_sampler_desc* s) {
   if (!s || s->n_records == 0 || s->batch == 0) return false;
   if (s->kind == D3P_SAMPLER_POISSON) return s->q >= 0.f && s->q <= 1.f;
   if (s->kind == D3P_SAMPLER_SUBSAMPLE) return s->batch <= s->n_records;
+  if (s->kind == D3P_SAMPLER_SPLIT) return s->batch <= s->n_records && s->perm_d != nullptr;
   return false;
 }
 
@@ -129,6 +130,17 @@ struct MeanfieldLauncher : StepLauncher {
   }
   const float* params;
 };
+struct GmmLauncher : StepLauncher {
+  const d3p_gmm_desc* desc; const float* x; size_t stride; const float* params;
+  int32_t launch(const int32_t* idx, const uint8_t* mask, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
+                 const uint32_t* tf_h, const uint32_t* tf_d, float obs_scale, float C, void* ws, cudaStream_t s) const override {
+    if (tf_h)
+      return d3p_dpsvi_step_gmm(desc, params, x, stride, idx, mask, nullptr, B, pos_begin, pos_end, tf_h, obs_scale, C,
+                                nullptr, nullptr, nullptr, ws, step_bytes, s);
+    return d3p_dpsvi_step_gmm_dk(desc, params, x, stride, idx, mask, nullptr, B, pos_begin, pos_end, tf_d, obs_scale, C,
+                                 nullptr, nullptr, nullptr, ws, step_bytes, s);
+  }
+};
 struct VaeLauncher : StepLauncher {
   const d3p_vae_desc* desc; const float* x; size_t stride; const float* params;
   d3p_vae_ctx* ctx = nullptr;      // side streams of this epoch call (created by the entry point, released at its end)
@@ -182,6 +194,29 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield_dk(const d3p_meanfield_desc* de
                    leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
 }
 
+// The same loop for the mixture model (examples/gaussian_mixture_model.py:205-218).
+extern "C" size_t d3p_dpsvi_epoch_gmm_workspace_bytes(const d3p_gmm_desc* desc, const d3p_sampler_desc* sampler) {
+  EpochWs w;
+  uint32_t n_part = 0;
+  if (!desc || !sampler_ok(sampler) || !layout_ws(d3p_gmm_workspace_bytes(desc, &n_part), sampler, nullptr, w)) return 0;
+  return w.total;
+}
+
+extern "C" int32_t d3p_dpsvi_run_epoch_gmm(const d3p_gmm_desc* desc, const d3p_sampler_desc* sampler, const float* x_d,
+                                           size_t x_row_stride, const uint32_t batch_key_h[16],
+                                           uint32_t rng_key_io_h[16], uint32_t first_step, uint32_t n_steps,
+                                           float obs_scale, float C, float dp_scale, const d3p_leaf_table* leaves_h,
+                                           d3p_optim_desc* optim_io_h, float* params_d, float* m_d, float* v_d,
+                                           float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream) {
+  if (!desc || !x_d || !params_d) return D3P_ERR_INVALID_ARGUMENT;
+  GmmLauncher fam;
+  fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.params = params_d;
+  fam.step_bytes = d3p_gmm_workspace_bytes(desc, &fam.n_part);
+  fam.P = desc->n_params;
+  return run_epoch(fam, sampler, batch_key_h, rng_key_io_h, nullptr, nullptr, first_step, n_steps, obs_scale, C, dp_scale,
+                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+}
+
 // The same loop for the VAE family (examples/vae.py:216-233 runs fori_loop(get_batch -> update) per epoch).
 extern "C" int32_t d3p_dpsvi_run_epoch_vae(const d3p_vae_desc* desc, const d3p_sampler_desc* sampler, const float* x_d,
                                            size_t x_row_stride, const uint32_t batch_key_h[16],
@@ -223,9 +258,12 @@ int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, cons
                   uint32_t n_steps, float obs_scale, float C,
                   float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d, float* m_d,
                   float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream) {
-  const bool dk = batch_key_d != nullptr;            // keys in device memory
-  if ((dk ? !rng_key_io_d : (!batch_key_h || !rng_key_io_h)) || !leaves_h || !optim_io_h || !params_d || !ws_d)
+  const bool dk = rng_key_io_d != nullptr;           // keys in device memory
+  const bool split = sampler && sampler->kind == D3P_SAMPLER_SPLIT;      // pre-shuffled epoch: no sampler, no batch key
+  if ((dk ? (!split && !batch_key_d) : ((!split && !batch_key_h) || !rng_key_io_h)) || !leaves_h || !optim_io_h ||
+      !params_d || !ws_d)
     return D3P_ERR_INVALID_ARGUMENT;
+  if (split && (uint64_t)(first_step + n_steps) * sampler->batch > sampler->n_records) return D3P_ERR_INVALID_ARGUMENT;
   if (!sampler_ok(sampler) || leaves_h->n_leaves == 0 || leaves_h->n_leaves > D3P_MAX_LEAVES)
     return D3P_ERR_INVALID_ARGUMENT;
   EpochWs w;
@@ -250,7 +288,7 @@ int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, cons
   const bool fork = !prof && getenv("D3P_EPOCH_SERIAL") == nullptr && n_steps > 1;
 #else
   const bool prof = false;
-  const bool fork = n_steps > 1;
+  const bool fork = n_steps > 1 && !split;
 #endif
   cudaStream_t main_s = (cudaStream_t)stream, samp_s = main_s;
   cudaEvent_t ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_fork = nullptr;
@@ -315,27 +353,30 @@ int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, cons
   for (uint32_t s = 0; s < n_steps && rc == D3P_OK; ++s) {
     const int b = s & 1;
     mark();
-    if (fork) {
+    if (split) {
+      // nothing to sample: this step's records are a slice of the epoch's shuffle
+    } else if (fork) {
       if (s + 1 < n_steps && (rc = queue_sampler(s + 1)) != D3P_OK) break;      // runs ahead on the sampler stream
       if (cudaStreamWaitEvent(main_s, ev_sampled[b], 0) != cudaSuccess) { rc = D3P_ERR_CUDA; break; }
     } else if ((rc = queue_sampler(s)) != D3P_OK) {
       break;
     }
     const uint8_t* mask = sampler->kind == D3P_SAMPLER_POISSON ? w.mask[b] : nullptr;
+    const int32_t* idx = split ? sampler->perm_d + (size_t)(first_step + s) * B : w.idx[b];
     mark();
     // ---- DPSVI.update (svi.py:395-434) ----------------------------------------------------------------------
     uint32_t keys[3][16], tf[2];
     if (dk) {
       // carry / k_grad -> Threefry key / k_noise -> per-leaf keys, all on the device, the state key advanced in place
       if ((rc = d3p_dpsvi_keys_dk(rng_key_io_d, lt.n_leaves, w.tf, w.sites, main_s)) != D3P_OK) break;
-      if ((rc = fam.launch(w.idx[b], mask, B, pos_begin, pos_end, nullptr, w.tf, obs_scale, C, w.step, main_s)) != D3P_OK) break;
+      if ((rc = fam.launch(idx, mask, B, pos_begin, pos_end, nullptr, w.tf, obs_scale, C, w.step, main_s)) != D3P_OK) break;
       mark();
       rc = d3p_perturb_finalize_dk_f32(w.step, n_part, P, B, &lt, w.sites, dp_scale, C, obs_scale, nullptr, optim_io_h,
                                        params_d, m_d, v_d, stats_out_d ? stats_out_d + 3 * (size_t)s : nullptr, comm, main_s);
     } else {
       if ((rc = d3p_chacha_split_h(rng_key_io_h, 3, &keys[0][0])) != D3P_OK) break;           // carry, k_grad, k_noise
       if ((rc = d3p_chacha_random_bits_h(keys[1], 0, tf, 2)) != D3P_OK) break;                // convert_to_jax_rng_key
-      rc = fam.launch(w.idx[b], mask, B, pos_begin, pos_end, tf, nullptr, obs_scale, C, w.step, main_s);
+      rc = fam.launch(idx, mask, B, pos_begin, pos_end, tf, nullptr, obs_scale, C, w.step, main_s);
       if (rc != D3P_OK) break;
       mark();
       if ((rc = d3p_chacha_split_h(keys[2], (int32_t)lt.n_leaves, &lt.site_state[0][0])) != D3P_OK) break;

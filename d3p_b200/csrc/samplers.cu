@@ -504,14 +504,18 @@ int32_t d3p_poisson_sample_sharded_dk(d3p_comm* comm, const uint32_t* state_d, f
 int32_t d3p_gather_rows_masked(const void* src_d, size_t row_bytes, const int32_t* idx_d,
                                const int32_t* num_valid_d, uint32_t b, void* dst_d, void* stream) {
   if ((!src_d || !idx_d || !dst_d) && b) return D3P_ERR_INVALID_ARGUMENT;
-  if (row_bytes == 0 || (row_bytes & 3)) return D3P_ERR_INVALID_ARGUMENT;
+  if (row_bytes == 0) return D3P_ERR_INVALID_ARGUMENT;
   if (b == 0) return D3P_OK;
   unsigned grid = (b + 7) / 8;
   unsigned cap = (unsigned)sm_count() * 8;
   if (grid > cap) grid = cap;
   cudaStream_t s = (cudaStream_t)stream;
-  bool vec16 = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src_d) | reinterpret_cast<uintptr_t>(dst_d)) % 16 == 0);
-  if (vec16)
+  const uintptr_t both = reinterpret_cast<uintptr_t>(src_d) | reinterpret_cast<uintptr_t>(dst_d);
+  bool vec16 = (row_bytes % 16 == 0) && (both % 16 == 0);
+  if ((row_bytes & 3) || (both & 3))       // odd row sizes (int8 labels, 3-byte pixels, ...): byte granularity
+    gather_rows_kernel<uint8_t><<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(src_d), row_bytes, idx_d,
+                                                     num_valid_d, b, reinterpret_cast<uint8_t*>(dst_d));
+  else if (vec16)
     gather_rows_kernel<uint4><<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(src_d), row_bytes / 16, idx_d,
                                                    num_valid_d, b, reinterpret_cast<uint4*>(dst_d));
   else

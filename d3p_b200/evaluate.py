@@ -35,6 +35,10 @@ def _threefry_split_second(key):
 
 def evaluate_elbo(svi, svi_state, jax_key, args):
     fam = svi.family
+    # the reference's evaluate has no mask: a Poisson batch enters with its padding rows zero-filled
+    # (d3p/minibatch.py:126-131), so those are materialised rather than read through the index list
+    from .minibatch import BatchView
+    args = tuple(a.tensor() if (isinstance(a, BatchView) and a.num_valid is not None) else a for a in args)
     Xsrc, stride, ysrc, idx, B = svi._resolve_args(args)
     if getattr(svi, "_local_rows", None) is not None:
         raise NotImplementedError("DPSVI.evaluate takes whole batches (LocalRows are a sharded-update input)")

@@ -39,12 +39,6 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, num_valid: torch.Tensor = 
     out = torch.empty((b,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     if b == 0 or row_bytes == 0:
         return out
-    if row_bytes % 4:
-        taken = src.index_select(0, idx.to(torch.int64))
-        if num_valid is not None:
-            m = torch.arange(b, device=src.device) < num_valid
-            taken = taken * m.reshape((-1,) + (1,) * (taken.dim() - 1)).to(taken.dtype)
-        return taken
     _n.check(_n.lib().d3p_gather_rows_masked(_n.ptr(src), row_bytes, _n.ptr(idx), _n.ptr(num_valid), b,
                                              _n.ptr(out), _n.stream_ptr()), "gather_rows_masked")
     return out
@@ -247,4 +241,7 @@ def split_batchify_data(dataset, batch_size=None, q=None, rng_suite=strong_rng, 
             return batch, torch.ones(batch_size, dtype=torch.bool, device=ret_idx.device)
         return batch
 
+    # DPSVI.run_epoch: the epoch's shuffle (the state `init` returns) is the index list of every step
+    get_batch.spec = dict(kind=_n.SAMPLER_SPLIT, q=0.0, n_records=num_records, batch=int(batch_size), suppress=False,
+                          dataset=dataset, rng_suite=rng_suite)
     return init, get_batch

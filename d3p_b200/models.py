@@ -139,7 +139,7 @@ class MeanFieldFamily(Family):
         if svi.event_hook is not None:
             svi.event_hook("step_begin")
         _n.check(_n.lib().d3p_dpsvi_step_meanfield(
-            C.byref(desc), _n.ptr(flat), x_p, stride, y_p, _n.ptr(idx), m_p, None,
+            C.byref(desc), _n.ptr(flat), x_p, stride, y_p, _n.ptr(idx), m_p, _n.ptr(getattr(svi, "_num_valid", None)),
             B, pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
             float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_grads), _n.ptr(px_loss), _n.ptr(ws), need,
             _n.stream_ptr()), "dpsvi_step_meanfield")
@@ -308,7 +308,8 @@ class VAE(Family):
         if svi.event_hook is not None:
             svi.event_hook("step_begin")
         _n.check(_n.lib().d3p_dpsvi_step_vae(
-            C.byref(desc), _n.ptr(state.optim_state.flat), _n.ptr(Xsrc), stride, _n.ptr(idx), _n.ptr(mask_t), None, B,
+            C.byref(desc), _n.ptr(state.optim_state.flat), _n.ptr(Xsrc), stride, _n.ptr(idx), _n.ptr(mask_t),
+            _n.ptr(getattr(svi, "_num_valid", None)), B,
             pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
             float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_loss), _n.ptr(ws_al), need,
             self.profile_events, self._side_streams(), _n.stream_ptr()), "dpsvi_step_vae")
@@ -361,7 +362,8 @@ class GaussianMixture(Family):
         if svi.event_hook is not None:
             svi.event_hook("step_begin")
         _n.check(_n.lib().d3p_dpsvi_step_gmm(
-            C.byref(desc), _n.ptr(state.optim_state.flat), _n.ptr(Xsrc), stride, _n.ptr(idx), _n.ptr(mask_t), None, B,
+            C.byref(desc), _n.ptr(state.optim_state.flat), _n.ptr(Xsrc), stride, _n.ptr(idx), _n.ptr(mask_t),
+            _n.ptr(getattr(svi, "_num_valid", None)), B,
             pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
             float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_grads), _n.ptr(px_loss), _n.ptr(ws), need,
             _n.stream_ptr()), "dpsvi_step_gmm")

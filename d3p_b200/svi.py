@@ -95,9 +95,11 @@ def full_norm(vector_parts, ord=2):
     if len(parts) == 0:
         return 0.
     mat, _, _ = _concat_rows(parts, batched=False)
-    if ord != 2:
-        return torch.linalg.vector_norm(mat.reshape(-1), ord=ord)
     norms = torch.empty(1, dtype=torch.float32, device=mat.device)
+    if ord != 2:
+        _n.check(_n.lib().d3p_vector_norm_f32(_n.ptr(mat), mat.numel(), float(ord), _n.ptr(norms), _n.stream_ptr()),
+                 "vector_norm")
+        return norms[0]
     scratch = mat.clone()
     _n.check(_n.lib().d3p_clip_rows_f32(_n.ptr(scratch), 1, mat.shape[1], float("inf"), _n.ptr(norms),
                                         _n.stream_ptr()), "full_norm")
@@ -216,6 +218,9 @@ class DPSVI:
         X = args[0]
         idx = None
         self._local_rows = None
+        # a Poisson BatchView knows how many of its slots are real: the kernels skip the padding slots even when the
+        # caller does not pass mask= (the reference zero-fills those rows, d3p/minibatch.py:126-131)
+        self._num_valid = X.num_valid if isinstance(X, BatchView) else None
         if isinstance(X, LocalRows):
             # rank-local slice of the batch: (first, n_local); the step kernel addresses rows by global
             # position, so the family shifts the base pointers back by `first` rows
@@ -239,6 +244,7 @@ class DPSVI:
                     ysrc = Y.source
                 else:   # mixed: materialise everything
                     idx, Xsrc = None, X.tensor()
+                    self._num_valid = None          # the gather zero-filled the padding rows
                     ysrc = Y.tensor() if isinstance(Y, BatchView) else Y
         else:
             Xsrc = X
@@ -260,6 +266,12 @@ class DPSVI:
             if ysrc.dtype != torch.int32:
                 ysrc = ysrc.to(torch.int32)
             ysrc = ysrc.contiguous()
+            rows_needed = Xsrc.shape[0] if idx is not None else B       # labels are read at the same rows as X
+            if ysrc.dim() == 0 or ysrc.shape[0] < rows_needed:
+                raise ValueError(f"the label array has {0 if ysrc.dim() == 0 else ysrc.shape[0]} entries, "
+                                 f"{rows_needed} are needed")
+        if idx is None and Xsrc.shape[0] < B:
+            raise ValueError(f"the batch array has {Xsrc.shape[0]} rows, {B} are needed")
         return Xsrc, int(Xsrc.stride(0)), ysrc, idx, B
 
     @staticmethod
@@ -267,9 +279,12 @@ class DPSVI:
         """-> (mask_uint8_tensor_or_None, all_masked)."""
         if isinstance(mask, (bool, np.bool_)):
             return (None, False) if mask else (torch.zeros(B, dtype=torch.uint8, device=_dev()), True)
-        if isinstance(mask, LocalRows):
+        local = isinstance(mask, LocalRows)
+        if local:
             mask = mask.tensor
         m = mask if isinstance(mask, torch.Tensor) else torch.as_tensor(np.asarray(mask))
+        if not local and m.numel() != B:
+            raise ValueError(f"mask has {m.numel()} entries for a batch of {B}")
         m = m.to(_dev())
         if m.dtype == torch.bool:
             m = m.view(torch.uint8)
@@ -364,10 +379,13 @@ class DPSVI:
         and every per-step key is derived on the device (what a jitted caller with traced keys binds to, see
         INTEGRATION.md); the results are bit-identical.  This facade then reads the final state key back, which
         synchronises; a binding that keeps its keys on the device does not."""
-        from .models import MeanFieldFamily, VAE
+        from .models import GaussianMixture, MeanFieldFamily, VAE
         spec = getattr(get_batch, "spec", None)
-        is_vae = isinstance(self.family, VAE)
-        fused = (spec is not None and (isinstance(self.family, MeanFieldFamily) or is_vae)
+        is_vae, is_gmm = isinstance(self.family, VAE), isinstance(self.family, GaussianMixture)
+        is_split = spec is not None and spec["kind"] == _n.SAMPLER_SPLIT
+        if is_gmm and (device_keys or self.shard is not None):
+            spec = None         # the mixture's epoch driver: single GPU, host keys
+        fused = (spec is not None and (isinstance(self.family, MeanFieldFamily) or is_vae or is_gmm)
                  and (self.shard is None or self.shard[2] is None) and self._rng_suite is strong_rng and spec["rng_suite"] is strong_rng and self.event_hook is None
                  and num_steps > 0)
         if not fused:
@@ -381,9 +399,17 @@ class DPSVI:
         fam = self.family
         Xsrc, stride, ysrc, _, _ = self._resolve_args(spec["dataset"])
         desc = fam.desc(self._num_obs_total())
-        sd = _n.SamplerDesc(spec["kind"], spec["q"], spec["n_records"], spec["batch"], 1 if spec["suppress"] else 0)
+        perm = None
+        if is_split:        # split_batchify_data: the state IS the epoch's shuffled index list (no key)
+            perm = torch.as_tensor(batchifier_state).to(device=_dev(), dtype=torch.int32).contiguous()
+            if (first_step + num_steps) * spec["batch"] > perm.numel():
+                raise ValueError("run_epoch: the split batchifier has only num_records // batch_size batches per epoch")
+        sd = _n.SamplerDesc(spec["kind"], spec["q"], spec["n_records"], spec["batch"], 1 if spec["suppress"] else 0,
+                            perm.data_ptr() if perm is not None else None)
         world = self.shard[1] if self.shard is not None else 1
-        if is_vae:
+        if is_gmm:
+            need = _n.lib().d3p_dpsvi_epoch_gmm_workspace_bytes(C.byref(desc), C.byref(sd))
+        elif is_vae:
             need = _n.lib().d3p_dpsvi_epoch_vae_workspace_bytes(C.byref(desc), C.byref(sd), world)
         else:
             need = _n.lib().d3p_dpsvi_epoch_workspace_bytes(C.byref(desc), C.byref(sd))
@@ -409,7 +435,8 @@ class DPSVI:
             lt.leaf_len[l] = int(np.prod(shape)) if len(shape) else 1
         od = self.optim.desc(os_.step, lr, desc.n_params)
         stats = torch.empty(num_steps, 3, dtype=torch.float32, device=_dev())
-        bkey = np.ascontiguousarray(np.asarray(batchifier_state, dtype=np.uint32).reshape(16))
+        bkey = (np.zeros(16, np.uint32) if is_split else
+                np.ascontiguousarray(np.asarray(batchifier_state, dtype=np.uint32).reshape(16)))
         rkey = np.array(np.asarray(svi_state.rng_key, dtype=np.uint32).reshape(16), copy=True)
         u32p = C.POINTER(C.c_uint32)
         comm = self.peer_window.ptr if self.shard is not None else None
@@ -429,6 +456,12 @@ class DPSVI:
                     float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m), _n.ptr(v), _n.ptr(stats), comm,
                     _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch_dk")
             rkey = rkey_d.cpu().numpy().view(np.uint32).copy()
+        elif is_gmm:
+            _n.check(_n.lib().d3p_dpsvi_run_epoch_gmm(
+                C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, bkey.ctypes.data_as(u32p),
+                rkey.ctypes.data_as(u32p), int(first_step), int(num_steps), float(svi_state.observation_scale),
+                float(self._clipping_threshold), float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m),
+                _n.ptr(v), _n.ptr(stats), comm, _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch_gmm")
         elif is_vae:
             _n.check(_n.lib().d3p_dpsvi_run_epoch_vae(
                 C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, bkey.ctypes.data_as(u32p),
@@ -537,6 +570,18 @@ class DPSVI:
             a = _as_dev_f32(a)
             out.append(a + rng_suite.normal(site_rng, tuple(a.shape)) * perturbation_scale)
         return tree_unflatten_like(values, out)
+
+    def evaluate_epoch(self, svi_state, get_batch, batchifier_state, num_batches, first_batch=0):
+        """The evaluation loops of the examples (``examples/logistic_regression.py:162-180``, ``vae.py:236-247``:
+        ``fori_loop`` over ``test_fetch(i, state)`` -> ``svi.evaluate``), typically fed by ``split_batchify_data``:
+        returns the ``num_batches`` losses as one device tensor.  Every ``evaluate`` is a few asynchronous launches
+        and nothing here synchronises, so the loop runs at kernel speed without a C driver of its own."""
+        out = torch.empty(max(num_batches, 0), dtype=torch.float32, device=_dev())
+        for i in range(num_batches):
+            b = get_batch(first_batch + i, batchifier_state)
+            batch = b[0] if (isinstance(b, tuple) and len(b) == 2 and isinstance(b[0], tuple)) else b
+            out[i] = self.evaluate(svi_state, *batch)
+        return out
 
     def evaluate(self, svi_state, *args, **kwargs):
         """``d3p/svi.py:436-449``: non-private batch ELBO with one guide sample."""

@@ -45,4 +45,8 @@ def sample_from_array(rng_key, x: torch.Tensor, n: int, axis: int, rng_suite=str
     """Samples ``n`` elements from ``x`` along ``axis`` without replacement (``d3p/util.py:216-301``)."""
     capacity = x.shape[axis]
     idxs = sample_indices(rng_key, capacity, n, rng_suite)
-    return torch.index_select(x, axis, idxs.to(torch.int64))
+    from .minibatch import gather_rows
+    x = torch.as_tensor(x)
+    axis = axis % x.dim()
+    rows = x.movedim(axis, 0).contiguous().to(idxs.device)          # the sampled axis first: one row per element
+    return gather_rows(rows, idxs).movedim(0, axis)

@@ -104,7 +104,8 @@ int32_t d3p_poisson_sample(const uint32_t state_h[16], float q, uint32_t n_recor
                            size_t ws_bytes, void* stream);
 
 /* mask * take(a, idxs, axis=0) (d3p/minibatch.py:126-131,210,233,306).
- * dst[r, :] = (num_valid_d == NULL || r < *num_valid_d) ? src[idx[r], :] : 0 ; row_bytes % 4 == 0. */
+ * dst[r, :] = (num_valid_d == NULL || r < *num_valid_d) ? src[idx[r], :] : 0 ; any row_bytes > 0 (16-byte vectors
+ * when rows and pointers allow, else 4-byte words, else bytes). */
 int32_t d3p_gather_rows_masked(const void* src_d, size_t row_bytes, const int32_t* idx_d,
                                const int32_t* num_valid_d, uint32_t b, void* dst_d, void* stream);
 
@@ -116,6 +117,8 @@ int32_t d3p_gather_rows_masked(const void* src_d, size_t row_bytes, const int32_
 /* DPSVI._clip_gradients (d3p/svi.py:310-325): rows scaled in place by 1/max(1, norm/C).
  * norms_d (may be NULL) receives the pre-clip L2 norms (full_norm, d3p/svi.py:68-87). */
 int32_t d3p_clip_rows_f32(float* px_grads_d, uint32_t B, uint32_t P, float C, float* norms_d, void* stream);
+/* full_norm(parts, ord) for ord != 2 (d3p/svi.py:68-87): out_d[0] = ||x||_ord of n floats; ord = +-inf, 0, 1 or p. */
+int32_t d3p_vector_norm_f32(const float* x_d, size_t n, float ord, float* out_d, void* stream);
 /* Fused clip + sum over examples (d3p/svi.py:310-348 without the [B,P] round trip):
  * sum_d[P + 2] = { sum_i m_i c_i g_i , sum_i m_i loss_i (px_loss_d may be NULL), sum_i m_i }. */
 size_t d3p_clip_and_sum_workspace_bytes(uint32_t B, uint32_t P);
@@ -219,13 +222,17 @@ int32_t d3p_adadp_finish_f32(const d3p_optim_desc* optim_h, uint32_t P, float* p
  * ------------------------------------------------------------------------------------------ */
 #define D3P_SAMPLER_POISSON 0   /* poisson_batchify_data: q, batch = max_batch_size, suppress */
 #define D3P_SAMPLER_SUBSAMPLE 1 /* subsample_batchify_data(with_replacement=False): batch     */
+#define D3P_SAMPLER_SPLIT 2     /* split_batchify_data (d3p/minibatch.py:242-312): step i takes records
+                                   perm_d[i * batch, (i + 1) * batch) of the epoch's shuffle; no sampler kernel, the batch
+                                   key is unused */
 
 typedef struct {
-  int32_t kind;       /* D3P_SAMPLER_*                                            */
-  float q;            /* Poisson selection probability                            */
-  uint32_t n_records; /* N                                                        */
-  uint32_t batch;     /* structural batch size B (Poisson: max_batch_size)        */
-  int32_t suppress;   /* Poisson: handle_oversized_batch == 'suppress'            */
+  int32_t kind;          /* D3P_SAMPLER_*                                            */
+  float q;               /* Poisson selection probability                            */
+  uint32_t n_records;    /* N                                                        */
+  uint32_t batch;        /* structural batch size B (Poisson: max_batch_size)        */
+  int32_t suppress;      /* Poisson: handle_oversized_batch == 'suppress'            */
+  const int32_t* perm_d; /* SPLIT: the state `init` returned = shuffled record indices [n_records] (device) */
 } d3p_sampler_desc;
 
 size_t d3p_dpsvi_epoch_workspace_bytes(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler);
@@ -416,6 +423,16 @@ int32_t d3p_dpsvi_step_gmm(const d3p_gmm_desc* desc, const float* params_d, cons
                            uint32_t pos_begin, uint32_t pos_end, const uint32_t threefry_key_h[2], float obs_scale,
                            float C, float* px_norms_d, float* px_grads_d, float* px_loss_d, void* ws_d, size_t ws_bytes,
                            void* stream);
+
+/* The same loop for the mixture model (examples/gaussian_mixture_model.py:205-218). */
+size_t d3p_dpsvi_epoch_gmm_workspace_bytes(const d3p_gmm_desc* desc, const d3p_sampler_desc* sampler);
+int32_t d3p_dpsvi_run_epoch_gmm(const d3p_gmm_desc* desc, const d3p_sampler_desc* sampler, const float* x_d,
+                                size_t x_row_stride, const uint32_t batch_key_h[16], uint32_t rng_key_io_h[16],
+                                uint32_t first_step, uint32_t n_steps, float obs_scale, float C, float dp_scale,
+                                const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d,
+                                float* m_d, float* v_d, float* stats_out_d, d3p_comm* comm /* NULL = single GPU */,
+                                void* ws_d, size_t ws_bytes, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------
  * DPSVI.evaluate (d3p/svi.py:436-449 -> numpyro SVI.evaluate) for the mean-field families: the

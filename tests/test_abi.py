@@ -78,7 +78,11 @@ def test_argument_validation_without_gpu(lib):
     # invalid-argument paths return before any CUDA call
     assert lib.d3p_chacha_split_h(None, 2, None) == -1
     assert lib.d3p_clip_rows_f32(None, 4, 4, 0.0, None, None) == -1          # C == 0 (svi.py:119)
-    assert lib.d3p_gather_rows_masked(None, 6, None, None, 0, None, None) == -1
+    assert lib.d3p_gather_rows_masked(None, 0, None, None, 0, None, None) == -1          # row_bytes == 0
+    assert lib.d3p_gather_rows_masked(None, 6, None, None, 4, None, None) == -1          # rows wanted, no buffers
+    assert lib.d3p_chacha_split_dk(None, 2, None, None) == -1
+    assert lib.d3p_dpsvi_keys_dk(None, 4, None, None, None) == -1
+    assert lib.d3p_vector_norm_f32(None, 4, 2.0, None, None) == -1
     assert lib.d3p_poisson_workspace_bytes(10_000_000) > 10_000_000 // 8
 
 

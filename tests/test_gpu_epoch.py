@@ -157,3 +157,78 @@ def test_run_epoch_vae_equals_stepwise(cuda, sampler):
     assert torch.equal(st_e.optim_state.flat, st.optim_state.flat), "run_epoch must be bit-identical to stepwise"
     assert np.array_equal(stats[:, 0].cpu().numpy(), np.asarray(losses, np.float32))
     assert st0.optim_state.step == 0
+
+
+def _stepwise(s, st, get, bst, first_step, n_steps):
+    losses = []
+    for i in range(first_step, first_step + n_steps):
+        out = get(i, bst)
+        batch, mask = out if (isinstance(out, tuple) and len(out) == 2 and isinstance(out[0], tuple)) else (out, True)
+        st, loss = s.update(st, *batch, mask=mask)
+        losses.append(float(loss))
+    return st, losses
+
+
+@pytest.mark.parametrize("return_mask", [False, True])
+def test_run_epoch_split_batchifier(cuda, return_mask):
+    """split_batchify_data (d3p/minibatch.py:242-312) in the epoch driver: step i takes slice i of the epoch's shuffle;
+    bit-identical to calling get_batch / update step by step."""
+    from d3p_b200 import minibatch as mb, models, optimizers, svi
+    import d3p_b200.random as rng
+    rs = np.random.RandomState(3)
+    N, d = 5000, 256
+    data = (torch.as_tensor(rs.randn(N, d).astype(np.float32)).cuda(), torch.as_tensor((rs.rand(N) < .5).astype(np.int32)).cuda())
+    fam = models.LogisticRegression(d)
+    s = svi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-2), models.Trace_ELBO(), 1.0, 0.7, num_obs_total=N)
+    init, get = mb.split_batchify_data(data, batch_size=300, return_mask=return_mask)
+    key, k_init, k_fetch = rng.split(rng.PRNGKey(4), 3)
+    nb, perm = init(k_fetch)
+    assert nb == N // 300 and len(torch.unique(perm)) == N
+    b0 = get(0, perm)
+    st0 = s.init(k_init, *(b0[0] if return_mask else b0))
+    a, la = _stepwise(s, st0, get, perm, 3, 6)
+    b, stats = s.run_epoch(st0, get, perm, 6, first_step=3)
+    assert torch.equal(a.optim_state.flat, b.optim_state.flat)
+    assert [float(v) for v in stats[:, 0].cpu()] == la
+    assert np.array_equal(np.asarray(a.rng_key), np.asarray(b.rng_key))
+    with pytest.raises(ValueError):
+        s.run_epoch(st0, get, perm, 3, first_step=nb - 1)      # runs past the epoch's batches
+
+
+def test_run_epoch_gmm(cuda):
+    """d3p_dpsvi_run_epoch_gmm (examples/gaussian_mixture_model.py:205-218): bit-identical to the step-by-step calls."""
+    from d3p_b200 import minibatch as mb, models, optimizers, svi
+    import d3p_b200.random as rng
+    rs = np.random.RandomState(5)
+    K, d, N = 4, 3, 4000
+    centers = rs.randn(K, d).astype(np.float32) * 3
+    X = torch.as_tensor((centers[rs.randint(0, K, N)] + rs.randn(N, d)).astype(np.float32)).cuda()
+    fam = models.GaussianMixture(K, d)
+    s = svi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), 20.0, 1.0, num_obs_total=N)
+    init, get = mb.poisson_batchify_data((X,), 0.02, .99)
+    key, k_init, k_fetch = rng.split(rng.PRNGKey(6), 3)
+    _, bst = init(k_fetch)
+    batch, mask = get(0, bst)
+    st0 = s.init(k_init, *batch)
+    a, la = _stepwise(s, st0, get, bst, 1, 5)
+    b, stats = s.run_epoch(st0, get, bst, 5, first_step=1)
+    assert torch.equal(a.optim_state.flat, b.optim_state.flat)
+    assert [float(v) for v in stats[:, 0].cpu()] == la
+
+
+def test_evaluate_epoch(cuda):
+    """The examples' evaluation loop: evaluate over the batches of a split epoch == the individual evaluate calls."""
+    from d3p_b200 import minibatch as mb, models, optimizers, svi
+    import d3p_b200.random as rng
+    rs = np.random.RandomState(8)
+    N, d = 2000, 12
+    data = (torch.as_tensor(rs.randn(N, d).astype(np.float32)).cuda(), torch.as_tensor((rs.rand(N) < .5).astype(np.int32)).cuda())
+    fam = models.LogisticRegression(d)
+    s = svi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-2), models.Trace_ELBO(), 1.0, 0.7, num_obs_total=N)
+    init, get = mb.split_batchify_data(data, batch_size=250)
+    nb, perm = init(rng.PRNGKey(1))
+    st = s.init(rng.PRNGKey(2), *get(0, perm))
+    losses = s.evaluate_epoch(st, get, perm, nb)
+    assert losses.shape == (nb,)
+    for i in range(nb):
+        assert float(losses[i]) == float(s.evaluate(st, *get(i, perm)))

@@ -442,3 +442,53 @@ def test_c3_full_batch_properties(cuda):
     assert np.max(np.abs(norms[sel] - ref) / ref) < 1e-5
     ref_loss = vals.numpy() * N            # px_loss is reported on the observation scale (svi.py:306)
     assert np.allclose(losses[sel], ref_loss, rtol=2e-5), (losses[sel][:4], ref_loss[:4])
+
+
+def test_full_norm_orders_and_gather_of_odd_rows(cuda):
+    """full_norm(parts, ord) for ord != 2 (d3p/svi.py:68-87 -> jnp.linalg.norm) and the byte-granular row gather
+    (int8 rows of 3 bytes): native kernels, no library fallback."""
+    from d3p_b200 import minibatch as mb, svi, util
+    import d3p_b200.random as rng
+    rs = np.random.RandomState(0)
+    tree = {"a": rs.randn(7, 3).astype(np.float32), "b": (rs.randn(5).astype(np.float32), np.float32(-2.5))}
+    flat = np.concatenate([tree["a"].ravel(), tree["b"][0], [tree["b"][1]]])
+    for ord_ in (1, 3, np.inf, -np.inf, 0, 2.5):
+        assert np.isclose(float(svi.full_norm(tree, ord=ord_)), np.linalg.norm(flat, ord=ord_), rtol=1e-6), ord_
+    src = torch.as_tensor(rs.randint(-100, 100, (50, 3)).astype(np.int8)).cuda()
+    idx = torch.as_tensor(rs.randint(0, 50, 20).astype(np.int32)).cuda()
+    nv = torch.tensor([13], dtype=torch.int32, device=cuda)
+    out = mb.gather_rows(src, idx, nv)
+    want = src.cpu().numpy()[idx.cpu().numpy()]
+    want[13:] = 0
+    assert np.array_equal(out.cpu().numpy(), want)
+    x = torch.arange(30, device=cuda, dtype=torch.float32).reshape(5, 6)
+    got = util.sample_from_array(rng.PRNGKey(1), x, 4, 1)
+    cols = util.sample_indices(rng.PRNGKey(1), 6, 4).cpu().numpy()
+    assert got.shape == (5, 4) and np.array_equal(got.cpu().numpy(), x.cpu().numpy()[:, cols])
+
+
+def test_argument_validation_and_padding_slots(cuda):
+    """A short mask or label array raises instead of reading out of bounds; a Poisson batch without mask= does not
+    process its padding slots (round-1 ADVICE)."""
+    from d3p_b200 import minibatch as mb, models, optimizers, svi
+    import d3p_b200.random as rng
+    rs = np.random.RandomState(2)
+    N, d = 4000, 8
+    X = torch.as_tensor(rs.randn(N, d).astype(np.float32)).cuda()
+    y = torch.as_tensor((rs.rand(N) < .5).astype(np.int32)).cuda()
+    fam = models.LogisticRegression(d)
+    s = svi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), 1.0, 1.0, num_obs_total=N)
+    st = s.init(rng.PRNGKey(0), X[:100], y[:100])
+    with pytest.raises(ValueError, match="mask"):
+        s.update(st, X[:100], y[:100], mask=torch.ones(99, dtype=torch.bool, device=cuda))
+    with pytest.raises(ValueError, match="label"):
+        s.update(st, X[:100], y[:50])
+    init, get = mb.poisson_batchify_data((X, y), 0.02, .99)
+    _, bst = init(rng.PRNGKey(3))
+    batch, mask = get(0, bst)
+    a, la = s.update(st, *batch, mask=mask)
+    b, lb = s.update(st, *batch)                      # mask omitted: num_valid of the BatchView still applies
+    n_valid = int(mask.sum())
+    assert 0 < n_valid < len(mask)
+    # the padding slots are skipped either way (and counted out of n), so both calls are the same step
+    assert float(la) == float(lb) and torch.equal(a.optim_state.flat, b.optim_state.flat)
