@@ -297,6 +297,46 @@ class LibEvents:
         return ms.value
 
 
+def ncu_side_run(workload, elements_per_example):
+    """Measures, in THIS bench invocation, the instruction count and issue activity of the dominant step kernel: one
+    launch of a child `bench.py --ncu-child` under `ncu --metrics ...` (outside every timed region; a number printed by
+    the child under the profiler is never a bench value).  -> dict or None when ncu is not on the box / fails."""
+    import shutil
+    import subprocess
+    ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.exists("/usr/local/cuda/bin/ncu") else None)
+    if ncu is None:
+        return None
+    metrics = "smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum"
+    # child launch order of the step kernel: 3 warm-up steps, then 2 timed steps: skip 4 = the second timed step
+    cmd = [ncu, "--metrics", metrics, "--clock-control", "none", "-k", "regex:meanfield_step", "-s", "4", "-c", "1", "--csv",
+           sys.executable, os.path.abspath(__file__), "--workload", workload, "--steps", "2", "--warmup", "3", "--no-e2e",
+           "--no-cpu-baseline", "--no-other-workloads", "--ncu-child"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    except Exception:
+        return None
+    vals, child = {}, None
+    for ln in r.stdout.splitlines():
+        if ln.startswith("{") and "per_step_examples" in ln:
+            child = json.loads(ln)
+        parts = [p.strip('"') for p in ln.split('","')]
+        for m in metrics.split(","):
+            if m in parts:
+                try:
+                    vals[m] = float(parts[-1].replace(",", ""))
+                except ValueError:
+                    pass
+    if child is None or "smsp__inst_executed.sum" not in vals:
+        return None
+    examples = child["per_step_examples"][1]
+    return {"warp_instr_per_launch": vals["smsp__inst_executed.sum"], "examples_in_launch": examples,
+            "warp_instr_per_element": vals["smsp__inst_executed.sum"] * 32.0 / (examples * elements_per_example),
+            "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "kernel_us_under_ncu": vals.get("gpu__time_duration.sum", 0.0) / 1e3,
+            "how": "ncu --metrics smsp__inst_executed.sum,smsp__issue_active... -k regex:meanfield_step -s 4 -c 1 on a "
+                   "child run of this script (same workload, 5 steps), launched by this bench run"}
+
+
 def quick_workload(name, steps, warmup, device):
     """A short device-resident run of another BASELINE workload through DPSVI.run_epoch (same kernels, same step
     definition as the headline), so that the driver's default run also records C3 and C5.  -> dict for `workloads`."""
@@ -421,6 +461,9 @@ def run_b200(args, cfg):
     t_end.record()
     sync_all()
     svi.event_hook = None
+    if args.ncu_child:      # profiled child of ncu_side_run: report which launch held how many examples, nothing else
+        print(json.dumps({"per_step_examples": [int(c) if isinstance(c, int) else int(c.reshape(()).item()) for c in counts]}))
+        return
     elapsed_ms = t_begin.elapsed_time(t_end)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=device)
@@ -528,6 +571,10 @@ def run_b200(args, cfg):
                        + ("; each rank uploads the rows of its own position range, bytes are summed over ranks"
                           if local else "")}
 
+    ncu_side_run_result = None
+    if (rank == 0 and world == 1 and args.ncu_side_run and not args.ncu_child and cfg["family"] in ("logreg", "gauss")
+            and cfg["d"] >= 256):
+        ncu_side_run_result = ncu_side_run(args.workload, cfg["d"] + (1 if cfg["family"] == "logreg" else 0))
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         step_ms = elapsed_ms / args.steps
@@ -565,16 +612,19 @@ def run_b200(args, cfg):
                                  if cfg["family"] == "gmm" else
                                  "issue-bound, not HBM-bound: one Threefry-2x32-20 normal per data float "
                                  "(~83 warp-instructions per element, DESIGN.md section 5)")}
-            if kname == "meanfield_step_vec_kernel" and cfg["family"] == "logreg" and clocks.get("sm_mhz"):
-                # the bound that does apply: issue slots.  Instruction count per element from the committed ncu
-                # capture (profiles/r1_step_vec_c2_ncu_full_v7.csv: smsp__inst_executed.sum / (examples * 1025 / 32));
-                # the slots offered are SMs x 4 schedulers x measured SM clock x kernel time.
-                wi_per_elem = 82.9
-                elems = per_rank_examples * (cfg["d"] + 1)
-                slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * kern_ms_avg * 1e-3
-                roofline["issue_slots"] = {"warp_instr_per_element": wi_per_elem,
-                                           "frac_of_issue_slots": (wi_per_elem * elems / 32) / slots,
-                                           "min_instr_per_element_at_70pct_hbm": 31}
+            if kname == "meanfield_step_vec_kernel" and world == 1 and args.ncu_side_run and clocks.get("sm_mhz"):
+                # the bound that does apply: issue slots.  The instruction count per element is MEASURED by this run
+                # (ncu side run of a child process, see ncu_side_run); the slots offered are SMs x 4 schedulers x
+                # measured SM clock x the kernel time measured above with CUDA events (not the profiler's).
+                epe = cfg["d"] + (1 if cfg["family"] == "logreg" else 0)
+                side = ncu_side_run_result
+                if side is not None:
+                    elems = per_rank_examples * epe
+                    slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * kern_ms_avg * 1e-3
+                    roofline["issue_slots"] = dict(side, frac_of_issue_slots=(side["warp_instr_per_element"] * elems / 32) / slots,
+                                                   min_instr_per_element_at_70pct_hbm=31)
+                else:
+                    roofline["issue_slots"] = {"unavailable": "ncu side run failed or ncu is not on this box"}
         line = {
             "metric": "DPSVI.update examples/sec", "value": value, "unit": "examples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
@@ -631,6 +681,9 @@ def main():
     ap.add_argument("--rows", type=int, default=None, help="override N (development only)")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-ncu-side-run", dest="ncu_side_run", action="store_false",
+                    help="skip the ncu child run that measures instructions per element of the step kernel")
+    ap.add_argument("--ncu-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-other-workloads", dest="other_workloads", action="store_false",
                     help="default (c2, N = 1) run only: skip the short c3 / c5 runs reported under `workloads`")
     args = ap.parse_args()

@@ -8,7 +8,7 @@ import torch
 from torch.profiler import ProfilerActivity, profile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.argv = [os.path.join(ROOT, "bench.py")] + sys.argv[1:] + ["--no-e2e", "--no-cpu-baseline", "--no-other-workloads", "--steps", "50", "--warmup", "5"]
+sys.argv = [os.path.join(ROOT, "bench.py")] + sys.argv[1:] + ["--no-e2e", "--no-cpu-baseline", "--no-other-workloads", "--no-ncu-side-run", "--steps", "50", "--warmup", "5"]
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     try:
         runpy.run_path(sys.argv[0], run_name="__main__")
