@@ -98,17 +98,17 @@ _SIGNATURES = {
     "d3p_dpsvi_run_epoch_meanfield": (C.c_int32, [C.POINTER(MeanfieldDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
                                                   _vp, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                                   C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
-                                                  _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+                                                  _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
     "d3p_dpsvi_epoch_gmm_workspace_bytes": (C.c_size_t, [C.POINTER(GmmDesc), C.POINTER(SamplerDesc)]),
     "d3p_dpsvi_run_epoch_gmm": (C.c_int32, [C.POINTER(GmmDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
                                             _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                             C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
-                                            _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+                                            _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
     "d3p_dpsvi_epoch_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.POINTER(SamplerDesc), C.c_int32]),
     "d3p_dpsvi_run_epoch_vae": (C.c_int32, [C.POINTER(VaeDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
                                             _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                             C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
-                                            _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+                                            _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
     "d3p_comm_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_uint8)]),
     "d3p_poisson_sample_sharded": (C.c_int32, [_vp, _u32p, C.c_float, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32,
@@ -128,6 +128,8 @@ _SIGNATURES = {
     "d3p_reduce_partials_f32": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "d3p_vae_workspace_bytes": (C.c_size_t, [C.POINTER(VaeDesc), C.c_uint32, _u32p]),
     "d3p_vae_ctx_create": (C.c_int32, [C.POINTER(C.c_void_p)]),
+    "d3p_epoch_ctx_create": (C.c_int32, [C.POINTER(C.c_void_p)]),
+    "d3p_epoch_ctx_destroy": (C.c_int32, [_vp]),
     "d3p_vae_ctx_destroy": (C.c_int32, [_vp]),
     "d3p_dpsvi_step_vae": (C.c_int32, [C.POINTER(VaeDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
                                        C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, C.c_size_t,
@@ -159,11 +161,11 @@ _SIGNATURES = {
     "d3p_dpsvi_run_epoch_meanfield_dk": (C.c_int32, [C.POINTER(MeanfieldDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
                                                      _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                                      C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
-                                                     _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+                                                     _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
     "d3p_dpsvi_run_epoch_vae_dk": (C.c_int32, [C.POINTER(VaeDesc), C.POINTER(SamplerDesc), _vp, C.c_size_t,
                                                _vp, _vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                                C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
-                                               _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+                                               _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
     "d3p_gmm_workspace_bytes": (C.c_size_t, [C.POINTER(GmmDesc), _u32p]),
     "d3p_dpsvi_step_gmm": (C.c_int32, [C.POINTER(GmmDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
                                        C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
 #include <vector>
 
 #include "comm.cuh"
@@ -77,7 +78,53 @@ bool sampler_ok(const d3p_sampler_desc* s) {
 
 }  // namespace
 
+// Caller-owned resources of the epoch drivers: the forked sampler stream with its events and (VAE) the side streams of
+// the step.  Creating a stream costs tens of microseconds, so a caller that runs many short epochs keeps one context;
+// entry points called with ctx = NULL make a temporary one.
+struct d3p_epoch_ctx {
+  cudaStream_t samp = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  d3p_vae_ctx* vae = nullptr;
+};
+
+extern "C" int32_t d3p_epoch_ctx_destroy(d3p_epoch_ctx* c) {
+  if (!c) return D3P_OK;
+  for (int b = 0; b < 2; ++b) {
+    if (c->ev_sampled[b]) cudaEventDestroy(c->ev_sampled[b]);
+    if (c->ev_consumed[b]) cudaEventDestroy(c->ev_consumed[b]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->samp) cudaStreamDestroy(c->samp);     // returns at once; the stream is released when its work has drained
+  if (c->vae) d3p_vae_ctx_destroy(c->vae);
+  delete c;
+  return D3P_OK;
+}
+
+extern "C" int32_t d3p_epoch_ctx_create(d3p_epoch_ctx** out) {
+  if (!out) return D3P_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  d3p_epoch_ctx* c = new (std::nothrow) d3p_epoch_ctx();
+  if (!c) return D3P_ERR_CUDA;
+  bool ok = cudaStreamCreateWithFlags(&c->samp, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int b = 0; b < 2 && ok; ++b)
+    ok = cudaEventCreateWithFlags(&c->ev_sampled[b], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_consumed[b], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { d3p_epoch_ctx_destroy(c); return D3P_ERR_CUDA; }
+  *out = c;
+  return D3P_OK;
+}
+
 namespace {
+// a context for the duration of one call when the caller passed none
+struct CtxGuard {
+  d3p_epoch_ctx* ctx; bool own = false;
+  explicit CtxGuard(d3p_epoch_ctx* c, bool needed = true) : ctx(c) {
+    if (!ctx && needed) own = d3p_epoch_ctx_create(&ctx) == D3P_OK;
+  }
+  ~CtxGuard() { if (own) d3p_epoch_ctx_destroy(ctx); }
+};
+
 // rows of the batch handled by one rank of `world` (contiguous position ranges, the last one may be shorter)
 uint32_t rows_per_rank(uint32_t B, int world) { return world > 1 ? (B + (uint32_t)world - 1) / (uint32_t)world : B; }
 
@@ -98,7 +145,8 @@ int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, cons
                   uint32_t* rng_key_io_h, const uint32_t* batch_key_d, uint32_t* rng_key_io_d, uint32_t first_step,
                   uint32_t n_steps, float obs_scale, float C,
                   float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d, float* m_d,
-                  float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream);
+                  float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, d3p_epoch_ctx* ctx,
+                  void* stream);
 
 }  // namespace
 
@@ -143,8 +191,7 @@ struct GmmLauncher : StepLauncher {
 };
 struct VaeLauncher : StepLauncher {
   const d3p_vae_desc* desc; const float* x; size_t stride; const float* params;
-  d3p_vae_ctx* ctx = nullptr;      // side streams of this epoch call (created by the entry point, released at its end)
-  ~VaeLauncher() override { if (ctx) d3p_vae_ctx_destroy(ctx); }
+  d3p_vae_ctx* ctx = nullptr;      // side streams of the step: owned by the d3p_epoch_ctx
   int32_t launch(const int32_t* idx, const uint8_t* mask, uint32_t B, uint32_t pos_begin, uint32_t pos_end,
                  const uint32_t* tf_h, const uint32_t* tf_d, float obs_scale, float C, void* ws, cudaStream_t s) const override {
     if (tf_h)
@@ -164,14 +211,14 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc,
                                                  float dp_scale, const d3p_leaf_table* leaves_h,
                                                  d3p_optim_desc* optim_io_h, float* params_d, float* m_d, float* v_d,
                                                  float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes,
-                                                 void* stream) {
+                                                 d3p_epoch_ctx* ctx, void* stream) {
   if (!desc || !x_d || !params_d) return D3P_ERR_INVALID_ARGUMENT;
   MeanfieldLauncher fam;
   fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.y = y_d; fam.params = params_d;
   fam.step_bytes = d3p_meanfield_workspace_bytes(desc, &fam.n_part);
   fam.P = desc->n_params;
   return run_epoch(fam, sampler, batch_key_h, rng_key_io_h, nullptr, nullptr, first_step, n_steps, obs_scale, C, dp_scale,
-                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, ctx, stream);
 }
 
 // Device-key form: the batchifier key and the DPSVI state key live in device memory (rng_key_io_d is advanced in place),
@@ -184,14 +231,14 @@ extern "C" int32_t d3p_dpsvi_run_epoch_meanfield_dk(const d3p_meanfield_desc* de
                                                     float dp_scale, const d3p_leaf_table* leaves_h,
                                                     d3p_optim_desc* optim_io_h, float* params_d, float* m_d, float* v_d,
                                                     float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes,
-                                                    void* stream) {
+                                                    d3p_epoch_ctx* ctx, void* stream) {
   if (!desc || !x_d || !params_d || !batch_key_d || !rng_key_io_d) return D3P_ERR_INVALID_ARGUMENT;
   MeanfieldLauncher fam;
   fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.y = y_d; fam.params = params_d;
   fam.step_bytes = d3p_meanfield_workspace_bytes(desc, &fam.n_part);
   fam.P = desc->n_params;
   return run_epoch(fam, sampler, nullptr, nullptr, batch_key_d, rng_key_io_d, first_step, n_steps, obs_scale, C, dp_scale,
-                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, ctx, stream);
 }
 
 // The same loop for the mixture model (examples/gaussian_mixture_model.py:205-218).
@@ -207,14 +254,15 @@ extern "C" int32_t d3p_dpsvi_run_epoch_gmm(const d3p_gmm_desc* desc, const d3p_s
                                            uint32_t rng_key_io_h[16], uint32_t first_step, uint32_t n_steps,
                                            float obs_scale, float C, float dp_scale, const d3p_leaf_table* leaves_h,
                                            d3p_optim_desc* optim_io_h, float* params_d, float* m_d, float* v_d,
-                                           float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream) {
+                                           float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, d3p_epoch_ctx* ctx,
+                                           void* stream) {
   if (!desc || !x_d || !params_d) return D3P_ERR_INVALID_ARGUMENT;
   GmmLauncher fam;
   fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.params = params_d;
   fam.step_bytes = d3p_gmm_workspace_bytes(desc, &fam.n_part);
   fam.P = desc->n_params;
   return run_epoch(fam, sampler, batch_key_h, rng_key_io_h, nullptr, nullptr, first_step, n_steps, obs_scale, C, dp_scale,
-                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, ctx, stream);
 }
 
 // The same loop for the VAE family (examples/vae.py:216-233 runs fori_loop(get_batch -> update) per epoch).
@@ -223,16 +271,20 @@ extern "C" int32_t d3p_dpsvi_run_epoch_vae(const d3p_vae_desc* desc, const d3p_s
                                            uint32_t rng_key_io_h[16], uint32_t first_step, uint32_t n_steps,
                                            float obs_scale, float C, float dp_scale, const d3p_leaf_table* leaves_h,
                                            d3p_optim_desc* optim_io_h, float* params_d, float* m_d, float* v_d,
-                                           float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream) {
+                                           float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, d3p_epoch_ctx* ctx,
+                                           void* stream) {
   if (!desc || !x_d || !params_d || !sampler_ok(sampler)) return D3P_ERR_INVALID_ARGUMENT;
   if (reinterpret_cast<uintptr_t>(ws_d) & 255) return D3P_ERR_INVALID_ARGUMENT;   // the VAE step wants 256-byte alignment
   VaeLauncher fam;
   fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.params = params_d;
   fam.step_bytes = d3p_vae_workspace_bytes(desc, rows_per_rank(sampler->batch, comm ? comm->world : 1), &fam.n_part);
   fam.P = desc->n_params;
-  if (d3p_vae_ctx_create(&fam.ctx) != D3P_OK) return D3P_ERR_CUDA;
+  CtxGuard g(ctx);
+  if (!g.ctx || (!g.ctx->vae && d3p_vae_ctx_create(&g.ctx->vae) != D3P_OK)) return D3P_ERR_CUDA;
+  fam.ctx = g.ctx->vae;
+  ctx = g.ctx;
   return run_epoch(fam, sampler, batch_key_h, rng_key_io_h, nullptr, nullptr, first_step, n_steps, obs_scale, C, dp_scale,
-                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, ctx, stream);
 }
 
 extern "C" int32_t d3p_dpsvi_run_epoch_vae_dk(const d3p_vae_desc* desc, const d3p_sampler_desc* sampler, const float* x_d,
@@ -240,16 +292,20 @@ extern "C" int32_t d3p_dpsvi_run_epoch_vae_dk(const d3p_vae_desc* desc, const d3
                                               uint32_t first_step, uint32_t n_steps, float obs_scale, float C,
                                               float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h,
                                               float* params_d, float* m_d, float* v_d, float* stats_out_d, d3p_comm* comm,
-                                              void* ws_d, size_t ws_bytes, void* stream) {
+                                              void* ws_d, size_t ws_bytes, d3p_epoch_ctx* ctx,
+                                           void* stream) {
   if (!desc || !x_d || !params_d || !sampler_ok(sampler) || !batch_key_d || !rng_key_io_d) return D3P_ERR_INVALID_ARGUMENT;
   if (reinterpret_cast<uintptr_t>(ws_d) & 255) return D3P_ERR_INVALID_ARGUMENT;
   VaeLauncher fam;
   fam.desc = desc; fam.x = x_d; fam.stride = x_row_stride; fam.params = params_d;
   fam.step_bytes = d3p_vae_workspace_bytes(desc, rows_per_rank(sampler->batch, comm ? comm->world : 1), &fam.n_part);
   fam.P = desc->n_params;
-  if (d3p_vae_ctx_create(&fam.ctx) != D3P_OK) return D3P_ERR_CUDA;
+  CtxGuard g(ctx);
+  if (!g.ctx || (!g.ctx->vae && d3p_vae_ctx_create(&g.ctx->vae) != D3P_OK)) return D3P_ERR_CUDA;
+  fam.ctx = g.ctx->vae;
+  ctx = g.ctx;
   return run_epoch(fam, sampler, nullptr, nullptr, batch_key_d, rng_key_io_d, first_step, n_steps, obs_scale, C, dp_scale,
-                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, stream);
+                   leaves_h, optim_io_h, params_d, m_d, v_d, stats_out_d, comm, ws_d, ws_bytes, ctx, stream);
 }
 
 namespace {
@@ -257,7 +313,8 @@ int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, cons
                   uint32_t* rng_key_io_h, const uint32_t* batch_key_d, uint32_t* rng_key_io_d, uint32_t first_step,
                   uint32_t n_steps, float obs_scale, float C,
                   float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d, float* m_d,
-                  float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, void* stream) {
+                  float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d, size_t ws_bytes, d3p_epoch_ctx* ctx,
+                  void* stream) {
   const bool dk = rng_key_io_d != nullptr;           // keys in device memory
   const bool split = sampler && sampler->kind == D3P_SAMPLER_SPLIT;      // pre-shuffled epoch: no sampler, no batch key
   if ((dk ? (!split && !batch_key_d) : ((!split && !batch_key_h) || !rng_key_io_h)) || !leaves_h || !optim_io_h ||
@@ -292,15 +349,15 @@ int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, cons
 #endif
   cudaStream_t main_s = (cudaStream_t)stream, samp_s = main_s;
   cudaEvent_t ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_fork = nullptr;
+  CtxGuard guard(ctx, fork);          // no context needed without the fork
   if (fork) {
-    bool ok = cudaStreamCreateWithFlags(&samp_s, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int b = 0; b < 2 && ok; ++b)
-      ok = cudaEventCreateWithFlags(&ev_sampled[b], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&ev_consumed[b], cudaEventDisableTiming) == cudaSuccess;
+    if (!guard.ctx) return D3P_ERR_CUDA;
+    samp_s = guard.ctx->samp;
+    ev_fork = guard.ctx->ev_fork;
+    for (int b = 0; b < 2; ++b) { ev_sampled[b] = guard.ctx->ev_sampled[b]; ev_consumed[b] = guard.ctx->ev_consumed[b]; }
     // the sampler stream starts after everything already queued on the caller's stream
-    ok = ok && cudaEventRecord(ev_fork, main_s) == cudaSuccess && cudaStreamWaitEvent(samp_s, ev_fork, 0) == cudaSuccess;
-    if (!ok) return D3P_ERR_CUDA;
+    if (cudaEventRecord(ev_fork, main_s) != cudaSuccess || cudaStreamWaitEvent(samp_s, ev_fork, 0) != cudaSuccess)
+      return D3P_ERR_CUDA;
   }
   std::vector<cudaEvent_t> ev;
   auto mark = [&]() {
@@ -396,9 +453,6 @@ int32_t run_epoch(const StepLauncher& fam, const d3p_sampler_desc* sampler, cons
   if (fork) {
     // join: whatever is still queued on the sampler stream (only after an error) precedes later work of the caller
     if (cudaEventRecord(ev_fork, samp_s) == cudaSuccess) cudaStreamWaitEvent(main_s, ev_fork, 0);
-    for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_sampled[b]); cudaEventDestroy(ev_consumed[b]); }
-    cudaEventDestroy(ev_fork);
-    cudaStreamDestroy(samp_s);       // returns at once; the stream is released when its work has drained
   }
   if (prof && rc == D3P_OK && ev.size() == 4 * (size_t)n_steps) {
     cudaStreamSynchronize((cudaStream_t)stream);

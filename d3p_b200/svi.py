@@ -57,9 +57,15 @@ def tree_unflatten_like(tree, leaves):
     return rec(tree)
 
 
+_CUDA_OK = False
+
+
 def _dev():
-    if not torch.cuda.is_available():
-        raise _n.D3PNativeError("d3p_b200 needs a CUDA device (no CPU fallback)")
+    global _CUDA_OK
+    if not _CUDA_OK:
+        if not torch.cuda.is_available():
+            raise _n.D3PNativeError("d3p_b200 needs a CUDA device (no CPU fallback)")
+        _CUDA_OK = True
     return torch.device("cuda", torch.cuda.current_device())
 
 
@@ -363,6 +369,24 @@ class DPSVI:
         new_os = OptimState(os_.step + 1, new_flat, new_m, new_v, os_.layout, new_lr)
         return DPSVIState(new_os, svi_state.rng_key, svi_state.observation_scale), stats[0]
 
+    def _epoch_ctx(self, dev_index):
+        """This object's ``d3p_epoch_ctx`` on the device (the epoch drivers' sampler stream, events and VAE side streams:
+        caller-owned, created on first use, released with the object)."""
+        ctxs = self.__dict__.setdefault("_epoch_ctxs", {})
+        h = ctxs.get(dev_index)
+        if h is None:
+            h = C.c_void_p()
+            _n.check(_n.lib().d3p_epoch_ctx_create(C.byref(h)), "epoch_ctx_create")
+            ctxs[dev_index] = h
+        return h
+
+    def __del__(self):
+        for h in self.__dict__.get("_epoch_ctxs", {}).values():
+            try:
+                _n.lib().d3p_epoch_ctx_destroy(h)
+            except Exception:
+                pass
+
     def run_epoch(self, svi_state, get_batch, batchifier_state, num_steps, first_step=0, device_keys=False):
         """The examples' ``lax.fori_loop(first_step, first_step + num_steps, body, state)`` with
         ``body = lambda i, s: update(s, *get_batch(i, batchifier_state))``
@@ -397,29 +421,41 @@ class DPSVI:
                 stats[s, 0] = loss
             return svi_state, stats
         fam = self.family
-        Xsrc, stride, ysrc, _, _ = self._resolve_args(spec["dataset"])
-        desc = fam.desc(self._num_obs_total())
+        dev = _dev()
+        world = self.shard[1] if self.shard is not None else 1
+        # everything about an epoch call that depends only on (batchifier, family, device) is worked out once
+        plan_key = (id(spec), dev.index, world, self._num_obs_total())
+        plan = getattr(self, "_epoch_plan", None)
+        if plan is None or plan[0] != plan_key:
+            Xsrc, stride, ysrc, _, _ = self._resolve_args(spec["dataset"])
+            desc = fam.desc(self._num_obs_total())
+            sd = _n.SamplerDesc(spec["kind"], spec["q"], spec["n_records"], spec["batch"], 1 if spec["suppress"] else 0, None)
+            probe = sd
+            if is_split:        # the size query wants a non-null shuffle pointer; the real one is set per call
+                probe = _n.SamplerDesc(spec["kind"], spec["q"], spec["n_records"], spec["batch"], 0, 256)
+            if is_gmm:
+                need = _n.lib().d3p_dpsvi_epoch_gmm_workspace_bytes(C.byref(desc), C.byref(probe))
+            elif is_vae:
+                need = _n.lib().d3p_dpsvi_epoch_vae_workspace_bytes(C.byref(desc), C.byref(probe), world)
+            else:
+                need = _n.lib().d3p_dpsvi_epoch_workspace_bytes(C.byref(desc), C.byref(probe))
+            if need == 0:
+                raise _n.D3PNativeError("unsupported family / sampler configuration for run_epoch")
+            plan = (plan_key, spec, Xsrc, stride, ysrc, desc, sd, need)      # keeps `spec` (and its id) alive
+            self._epoch_plan = plan
+        _, _, Xsrc, stride, ysrc, desc, sd, need = plan
         perm = None
         if is_split:        # split_batchify_data: the state IS the epoch's shuffled index list (no key)
-            perm = torch.as_tensor(batchifier_state).to(device=_dev(), dtype=torch.int32).contiguous()
+            perm = torch.as_tensor(batchifier_state).to(device=dev, dtype=torch.int32).contiguous()
             if (first_step + num_steps) * spec["batch"] > perm.numel():
                 raise ValueError("run_epoch: the split batchifier has only num_records // batch_size batches per epoch")
-        sd = _n.SamplerDesc(spec["kind"], spec["q"], spec["n_records"], spec["batch"], 1 if spec["suppress"] else 0,
-                            perm.data_ptr() if perm is not None else None)
-        world = self.shard[1] if self.shard is not None else 1
-        if is_gmm:
-            need = _n.lib().d3p_dpsvi_epoch_gmm_workspace_bytes(C.byref(desc), C.byref(sd))
-        elif is_vae:
-            need = _n.lib().d3p_dpsvi_epoch_vae_workspace_bytes(C.byref(desc), C.byref(sd), world)
-        else:
-            need = _n.lib().d3p_dpsvi_epoch_workspace_bytes(C.byref(desc), C.byref(sd))
-        if need == 0:
-            raise _n.D3PNativeError("unsupported family / sampler configuration for run_epoch")
-        if getattr(self, "_epoch_ws", None) is None or self._epoch_ws.numel() < need + 256 or self._epoch_ws.device != _dev():
-            self._epoch_ws = torch.empty(need + 256, dtype=torch.uint8, device=_dev())
+            sd = _n.SamplerDesc(spec["kind"], spec["q"], spec["n_records"], spec["batch"], 0, perm.data_ptr())
+        if getattr(self, "_epoch_ws", None) is None or self._epoch_ws.numel() < need + 256 or self._epoch_ws.device != dev:
+            self._epoch_ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
         ws_al = self._epoch_ws[(-self._epoch_ws.data_ptr()) % 256:]          # the VAE step wants 256-byte alignment
         if self.peer_window is not None and spec["kind"] == _n.SAMPLER_POISSON:
             self.peer_window = self.peer_window.with_records(spec["n_records"])   # sharded selector draw
+        ectx = self._epoch_ctx(dev.index)
         os_ = svi_state.optim_state
         if self.donate_state:
             flat, m, v, lr = os_.flat, os_.m, os_.v, os_.lr
@@ -428,52 +464,56 @@ class DPSVI:
             m = os_.m.clone() if os_.m is not None else None
             v = os_.v.clone() if os_.v is not None else None
             lr = os_.lr.clone() if os_.lr is not None else None
-        lt = _n.LeafTable()
-        lt.n_leaves = len(os_.layout)
-        for l, (name, off, shape) in enumerate(os_.layout):
-            lt.leaf_off[l] = off
-            lt.leaf_len[l] = int(np.prod(shape)) if len(shape) else 1
+        lt_c = getattr(self, "_epoch_lt", None)
+        if lt_c is None or lt_c[0] is not os_.layout:
+            lt = _n.LeafTable()
+            lt.n_leaves = len(os_.layout)
+            for l, (name, off, shape) in enumerate(os_.layout):
+                lt.leaf_off[l] = off
+                lt.leaf_len[l] = int(np.prod(shape)) if len(shape) else 1
+            self._epoch_lt = lt_c = (os_.layout, lt)
+        lt = lt_c[1]
         od = self.optim.desc(os_.step, lr, desc.n_params)
-        stats = torch.empty(num_steps, 3, dtype=torch.float32, device=_dev())
+        stats = torch.empty(num_steps, 3, dtype=torch.float32, device=dev)
         bkey = (np.zeros(16, np.uint32) if is_split else
                 np.ascontiguousarray(np.asarray(batchifier_state, dtype=np.uint32).reshape(16)))
         rkey = np.array(np.asarray(svi_state.rng_key, dtype=np.uint32).reshape(16), copy=True)
         u32p = C.POINTER(C.c_uint32)
         comm = self.peer_window.ptr if self.shard is not None else None
         if device_keys:
-            bkey_d = torch.as_tensor(bkey.view(np.int32)).to(_dev())
-            rkey_d = torch.as_tensor(rkey.view(np.int32)).to(_dev())
+            bkey_d = torch.as_tensor(bkey.view(np.int32)).to(dev)
+            rkey_d = torch.as_tensor(rkey.view(np.int32)).to(dev)
             if is_vae:
                 _n.check(_n.lib().d3p_dpsvi_run_epoch_vae_dk(
                     C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, _n.ptr(bkey_d), _n.ptr(rkey_d), int(first_step),
                     int(num_steps), float(svi_state.observation_scale), float(self._clipping_threshold),
                     float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m), _n.ptr(v), _n.ptr(stats), comm,
-                    _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch_vae_dk")
+                    _n.ptr(ws_al), need, ectx, _n.stream_ptr()), "run_epoch_vae_dk")
             else:
                 _n.check(_n.lib().d3p_dpsvi_run_epoch_meanfield_dk(
                     C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, _n.ptr(ysrc), _n.ptr(bkey_d), _n.ptr(rkey_d),
                     int(first_step), int(num_steps), float(svi_state.observation_scale), float(self._clipping_threshold),
                     float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m), _n.ptr(v), _n.ptr(stats), comm,
-                    _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch_dk")
+                    _n.ptr(ws_al), need, ectx, _n.stream_ptr()), "run_epoch_dk")
             rkey = rkey_d.cpu().numpy().view(np.uint32).copy()
         elif is_gmm:
             _n.check(_n.lib().d3p_dpsvi_run_epoch_gmm(
                 C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, bkey.ctypes.data_as(u32p),
                 rkey.ctypes.data_as(u32p), int(first_step), int(num_steps), float(svi_state.observation_scale),
                 float(self._clipping_threshold), float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m),
-                _n.ptr(v), _n.ptr(stats), comm, _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch_gmm")
+                _n.ptr(v), _n.ptr(stats), comm, _n.ptr(ws_al), need, ectx, _n.stream_ptr()), "run_epoch_gmm")
         elif is_vae:
             _n.check(_n.lib().d3p_dpsvi_run_epoch_vae(
                 C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, bkey.ctypes.data_as(u32p),
                 rkey.ctypes.data_as(u32p), int(first_step), int(num_steps), float(svi_state.observation_scale),
                 float(self._clipping_threshold), float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m),
-                _n.ptr(v), _n.ptr(stats), comm, _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch_vae")
+                _n.ptr(v), _n.ptr(stats), comm, _n.ptr(ws_al), need, ectx, _n.stream_ptr()), "run_epoch_vae")
         else:
             _n.check(_n.lib().d3p_dpsvi_run_epoch_meanfield(
                 C.byref(desc), C.byref(sd), _n.ptr(Xsrc), stride, _n.ptr(ysrc), bkey.ctypes.data_as(u32p),
                 rkey.ctypes.data_as(u32p), int(first_step), int(num_steps), float(svi_state.observation_scale),
                 float(self._clipping_threshold), float(self._dp_scale), C.byref(lt), C.byref(od), _n.ptr(flat), _n.ptr(m),
-                _n.ptr(v), _n.ptr(stats), comm, _n.ptr(ws_al), need, _n.stream_ptr()), "run_epoch")
+                _n.ptr(v), _n.ptr(stats), comm, _n.ptr(ws_al), need, ectx, _n.stream_ptr()), "run_epoch")
         new_os = OptimState(os_.step + num_steps, flat, m, v, os_.layout, lr)
         return DPSVIState(new_os, rkey.reshape(np.asarray(svi_state.rng_key).shape), svi_state.observation_scale), stats
 

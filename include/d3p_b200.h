@@ -10,8 +10,7 @@
  *   - enqueues its kernels on `stream` (a `cudaStream_t` passed as `void*`; NULL = default),
  *   - keeps no global mutable state (the only statics are write-once caches of immutable facts: the SM count of a
  *     device, the driver's cuTensorMapEncodeTiled entry point) and is re-entrant across streams and threads;
- *     handles (d3p_comm, d3p_vae_ctx) are caller-owned and serve one caller at a time.
- *     d3p_dpsvi_run_epoch_* create and release one sampler stream (and, for the VAE, one d3p_vae_ctx) per call.
+ *     handles (d3p_comm, d3p_vae_ctx, d3p_epoch_ctx) are caller-owned and serve one caller at a time.
  * One process per GPU; the caller selects the device with cudaSetDevice before calling.
  *
  * ChaCha states are 16 x uint32 in RFC 8439 layout (constants | 8 key words | counter |
@@ -38,6 +37,7 @@ extern "C" {
 
 /* Library / build identification. */
 typedef struct d3p_comm d3p_comm;       /* peer-memory window of a sharded run, see d3p_comm_create */
+typedef struct d3p_epoch_ctx d3p_epoch_ctx; /* streams / events of the epoch drivers, see d3p_epoch_ctx_create */
 typedef struct d3p_vae_ctx d3p_vae_ctx; /* side streams of the VAE step, see d3p_vae_ctx_create */
 
 int32_t d3p_abi_version(void);
@@ -236,6 +236,13 @@ typedef struct {
 } d3p_sampler_desc;
 
 size_t d3p_dpsvi_epoch_workspace_bytes(const d3p_meanfield_desc* desc, const d3p_sampler_desc* sampler);
+/* The epoch drivers run the index sampler of step i + 1 on a forked stream beside step i (and the VAE step forks its
+ * independent GEMMs).  Those streams and their events live in a caller-owned context, created once per device on the
+ * current device: creating a stream costs tens of microseconds, which a caller running many short epochs should not pay
+ * per call.  Every d3p_dpsvi_run_epoch_* takes `ctx`; NULL = make a temporary one for this call.  One context serves
+ * one epoch call at a time. */
+int32_t d3p_epoch_ctx_create(d3p_epoch_ctx** ctx_out);
+int32_t d3p_epoch_ctx_destroy(d3p_epoch_ctx* ctx); /* returns at once; resources go when the queued work has drained */
 /* batch_key_h: the batchifier state (the key `init` returned); step i uses fold_in(batch_key, i),
  * i = first_step .. first_step + n_steps - 1.  rng_key_io_h: DPSVIState.rng_key, advanced in place.
  * leaves_h: leaf offsets / lengths (site states are derived per step).  optim_io_h->step is advanced.
@@ -249,7 +256,7 @@ int32_t d3p_dpsvi_run_epoch_meanfield(const d3p_meanfield_desc* desc, const d3p_
                                       float dp_scale, const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h,
                                       float* params_d, float* m_d, float* v_d, float* stats_out_d,
                                       d3p_comm* comm /* NULL = single GPU */, void* ws_d, size_t ws_bytes,
-                                      void* stream);
+                                      d3p_epoch_ctx* ctx /* NULL = temporary */, void* stream);
 
 /* partials_d is [n_partials, P + 2] (grad sum | loss sum | count).  With n = total count,
  * f = (n == 0 ? 0 : B / n):
@@ -398,7 +405,7 @@ int32_t d3p_dpsvi_run_epoch_vae(const d3p_vae_desc* desc, const d3p_sampler_desc
                                 uint32_t first_step, uint32_t n_steps, float obs_scale, float C, float dp_scale,
                                 const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d,
                                 float* m_d, float* v_d, float* stats_out_d, d3p_comm* comm /* NULL = single GPU */,
-                                void* ws_d, size_t ws_bytes, void* stream);
+                                void* ws_d, size_t ws_bytes, d3p_epoch_ctx* ctx, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------
@@ -431,7 +438,7 @@ int32_t d3p_dpsvi_run_epoch_gmm(const d3p_gmm_desc* desc, const d3p_sampler_desc
                                 uint32_t first_step, uint32_t n_steps, float obs_scale, float C, float dp_scale,
                                 const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d,
                                 float* m_d, float* v_d, float* stats_out_d, d3p_comm* comm /* NULL = single GPU */,
-                                void* ws_d, size_t ws_bytes, void* stream);
+                                void* ws_d, size_t ws_bytes, d3p_epoch_ctx* ctx, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------
@@ -534,13 +541,13 @@ int32_t d3p_dpsvi_run_epoch_meanfield_dk(const d3p_meanfield_desc* desc, const d
                                          uint32_t n_steps, float obs_scale, float C, float dp_scale,
                                          const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d,
                                          float* m_d, float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d,
-                                         size_t ws_bytes, void* stream);
+                                         size_t ws_bytes, d3p_epoch_ctx* ctx, void* stream);
 int32_t d3p_dpsvi_run_epoch_vae_dk(const d3p_vae_desc* desc, const d3p_sampler_desc* sampler, const float* x_d,
                                    size_t x_row_stride, const uint32_t* batch_key_d, uint32_t* rng_key_io_d,
                                    uint32_t first_step, uint32_t n_steps, float obs_scale, float C, float dp_scale,
                                    const d3p_leaf_table* leaves_h, d3p_optim_desc* optim_io_h, float* params_d,
                                    float* m_d, float* v_d, float* stats_out_d, d3p_comm* comm, void* ws_d,
-                                   size_t ws_bytes, void* stream);
+                                   size_t ws_bytes, d3p_epoch_ctx* ctx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,30 @@
+#!/bin/bash
+# Round-2 evidence pass on one B200 (run through gpurun; outputs land in gpurun_out/ and are condensed into profiles/ here):
+#   launch lists of the C2 and C5 steps, ncu --set full of the dominant kernels (C2 / C3 step kernels, the VAE GEMMs, the
+#   thin-layer kernels, finalize, the Poisson sampler, the GMM step), in-pipeline kernel times of the C5 step.
+# Numbers printed by a run under ncu are never bench values.
+TAG=${1:-r2}
+O=gpurun_out
+mkdir -p $O
+COMMON="--no-e2e --no-cpu-baseline --no-other-workloads --no-ncu-side-run"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${TAG}_c2_launches.csv \
+  python bench.py --steps 20 --warmup 3 $COMMON > $O/${TAG}_c2_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_c5_launches.csv \
+  python bench.py --workload c5 --steps 10 --warmup 3 $COMMON > $O/${TAG}_c5_launches.log 2>&1
+full() {   # name, kernel regex, skip, count, bench args...
+  local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
+  ncu --set full --clock-control none --import-source on -k "regex:$rx" -s $skip -c $cnt -f -o $O/${TAG}_$name \
+    python bench.py "$@" --steps 3 --warmup 3 $COMMON > $O/${TAG}_$name.log 2>&1
+  ncu -i $O/${TAG}_$name.ncu-rep --page raw --csv > $O/${TAG}_${name}_raw.csv 2>/dev/null
+  rm -f $O/${TAG}_$name.ncu-rep
+}
+full step_vec_c2 meanfield_step_vec 4 2 --workload c2
+full step_vec_c3 meanfield_step_vec 4 2 --workload c3
+full vae_gemms tc_gemm_kernel 21 7 --workload c5
+full vae_mid "vae_mid_(fwd|bwd)_mma" 6 2 --workload c5
+full finalize_c2 "finalize_(quad_)?kernel" 4 2 --workload c2
+full finalize_c5 "finalize_(quad_)?kernel" 3 2 --workload c5
+full poisson "poisson_(select|compact)" 8 2 --workload c2
+full gmm gmm_step_kernel 2 1 --workload c4 --rows 2000000
+python scripts/kernel_times.py --workload c5 > $O/${TAG}_c5_kernel_times.txt 2> $O/${TAG}_c5_kernel_times.err
+ls -la $O | tail -30
