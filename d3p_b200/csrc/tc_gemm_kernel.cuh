@@ -321,6 +321,10 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmShape g, const t
     const int part = warp >> 2;         // which of the PARTS warps of that quarter
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
+    // The scratch below reuses the operand ring.  Its last readers (the split pass of the final k-block) are ordered
+    // before this point through bar_lo_full -> MMA -> tcgen05.commit -> bar_acc; the CTA barrier states the same
+    // ordering in a form compute-sanitizer's racecheck can follow (once per CTA, every warp is here anyway).
+    __syncthreads();
     if (warp == 2 && lane == 0) D3P_TRACE(4);                          // accumulator complete
     const uint32_t row = m_tile * kBM + q * 32 + lane;
     const uint32_t slot = n_tile * PARTS + part;     // row-reduction slot of this (tile, warp)

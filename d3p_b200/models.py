@@ -65,6 +65,25 @@ class Family:
     def constrain(self, name, value):
         return value
 
+    @staticmethod
+    def _local_row_pointers(svi, Xsrc, stride, mask_t, pos_begin, pos_end):
+        """Base pointers of X and of the mask as the step kernels want them.  With ``minibatch.LocalRows`` the tensors
+        hold only rows [first, first + n) of the batch: the pointers are shifted back so that the kernel's global
+        position p addresses local row p - first (the kernels touch positions [pos_begin, pos_end) only)."""
+        import ctypes as C
+        x_p, m_p = _n.ptr(Xsrc), _n.ptr(mask_t)
+        if getattr(svi, "_local_rows", None) is not None:
+            first, n_local = svi._local_rows
+            if (first, first + n_local) != (pos_begin, pos_end):
+                raise ValueError(f"LocalRows [{first}, {first + n_local}) is not this rank's position range "
+                                 f"[{pos_begin}, {pos_end})")
+            x_p = C.c_void_p(Xsrc.data_ptr() - first * stride * 4)
+            if mask_t is not None:
+                if mask_t.numel() != n_local:
+                    raise ValueError("with LocalRows the mask must be the matching LocalRows slice")
+                m_p = C.c_void_p(mask_t.data_ptr() - first)
+        return x_p, m_p
+
     def observation_scale(self, num_obs_total):
         """``get_observations_scale`` (d3p/svi.py:43-65) on a one-element batch: the plate scale N / 1."""
         return float(num_obs_total)
@@ -295,8 +314,6 @@ class VAE(Family):
         if px_grads is not None:
             raise NotImplementedError("the VAE path never materialises [B, P] per-example gradients")
         Xsrc, stride, _, idx, B = svi._resolve_args(args)
-        if getattr(svi, "_local_rows", None) is not None:
-            raise NotImplementedError("LocalRows batches are supported by the mean-field families only")
         desc = self.desc(svi._num_obs_total())
         n_part = C.c_uint32(0)
         need = _n.lib().d3p_vae_workspace_bytes(C.byref(desc), pos_end - pos_begin, C.byref(n_part))
@@ -305,10 +322,11 @@ class VAE(Family):
         shift = (-base) % 256                    # the library wants a 256-byte aligned workspace
         ws_al = ws[shift // 4:]
         mask_t, _ = svi._mask_arg(mask, B)
+        x_p, m_p = self._local_row_pointers(svi, Xsrc, stride, mask_t, pos_begin, pos_end)
         if svi.event_hook is not None:
             svi.event_hook("step_begin")
         _n.check(_n.lib().d3p_dpsvi_step_vae(
-            C.byref(desc), _n.ptr(state.optim_state.flat), _n.ptr(Xsrc), stride, _n.ptr(idx), _n.ptr(mask_t),
+            C.byref(desc), _n.ptr(state.optim_state.flat), x_p, stride, _n.ptr(idx), m_p,
             _n.ptr(getattr(svi, "_num_valid", None)), B,
             pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
             float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_loss), _n.ptr(ws_al), need,
@@ -352,17 +370,16 @@ class GaussianMixture(Family):
     def run_step(self, svi, state, tf_key, args, mask, B, pos_begin, pos_end, px_norms, px_grads, px_loss):
         import ctypes as C
         Xsrc, stride, _, idx, B = svi._resolve_args(args)
-        if getattr(svi, "_local_rows", None) is not None:
-            raise NotImplementedError("LocalRows batches are supported by the mean-field families only")
         desc = self.desc(svi._num_obs_total())
         n_part = C.c_uint32(0)
         need = _n.lib().d3p_gmm_workspace_bytes(C.byref(desc), C.byref(n_part))
         ws = svi._workspace(need)
         mask_t, _ = svi._mask_arg(mask, B)
+        x_p, m_p = self._local_row_pointers(svi, Xsrc, stride, mask_t, pos_begin, pos_end)
         if svi.event_hook is not None:
             svi.event_hook("step_begin")
         _n.check(_n.lib().d3p_dpsvi_step_gmm(
-            C.byref(desc), _n.ptr(state.optim_state.flat), _n.ptr(Xsrc), stride, _n.ptr(idx), _n.ptr(mask_t),
+            C.byref(desc), _n.ptr(state.optim_state.flat), x_p, stride, _n.ptr(idx), m_p,
             _n.ptr(getattr(svi, "_num_valid", None)), B,
             pos_begin, pos_end, tf_key.ctypes.data_as(C.POINTER(C.c_uint32)), float(state.observation_scale),
             float(svi._clipping_threshold), _n.ptr(px_norms), _n.ptr(px_grads), _n.ptr(px_loss), _n.ptr(ws), need,

@@ -38,7 +38,7 @@ def _families(dev):
             ("vae", lambda: models.VAE(256, 64, 8, init_std=0.1), (Xv,), 5.0, False)]
 
 
-def _run(make_fam, dataset, clip, world, epoch, steps=3):
+def _run(make_fam, dataset, clip, world, epoch, steps=3, local_rows=False):
     """world == 1: plain DPSVI; else `world` logical ranks on one device.  -> (flat params per rank, losses per rank,
     rng keys per rank)"""
     import d3p_b200.random as rng
@@ -88,9 +88,20 @@ def _run(make_fam, dataset, clip, world, epoch, steps=3):
             # all ranks' step kernels, then all ranks' finalize kernels: on ONE device a spinning finalize kernel holds
             # a little shared memory on every SM, which keeps a peer's max-shared-memory GEMM CTAs (VAE) from being
             # placed; with one GPU per rank (the real layout) `update` runs as a whole
+            if local_rows:
+                # minibatch.LocalRows: every rank is handed only the rows of its own position range (what a sharded
+                # caller with host-resident batches uploads)
+                full = [a.tensor() for a in batch]
+                B = int(full[0].shape[0])
+                torch.cuda.synchronize()
             for r in range(world):
                 with torch.cuda.stream(streams[r]):
-                    ctx[r] = svis[r]._update_launch_step(states[r], batch, mask)
+                    if local_rows:
+                        pb, pe = parallel.position_range(B, r, world)
+                        args = tuple(mb.LocalRows(a[pb:pe].clone(), pb, B) for a in full)
+                        ctx[r] = svis[r]._update_launch_step(states[r], args, mb.LocalRows(mask[pb:pe].clone(), pb, B))
+                    else:
+                        ctx[r] = svis[r]._update_launch_step(states[r], batch, mask)
             torch.cuda.synchronize()
             for r in range(world):
                 with torch.cuda.stream(streams[r]):
@@ -125,6 +136,22 @@ def test_sharded_equals_unsharded_on_one_device(cuda, world, epoch):
         err = _rel_err(flats[0], p1, floor=1e-3)
         assert err < 1e-5, (name, err)
         assert np.allclose(losses[0], l1, rtol=2e-5), (name, losses[0], l1)
+
+
+def test_local_rows_equal_full_batch_on_one_device(cuda):
+    """``minibatch.LocalRows`` for every family (the mixture and the VAE too): a rank fed only its own rows computes
+    bit for bit what it computes from the whole batch."""
+    from d3p_b200 import models
+    g = torch.Generator(device="cuda").manual_seed(4)
+    Xm = torch.randn((3000, 16), device=cuda, generator=g)
+    fams = _families(cuda) + [("gmm", lambda: models.GaussianMixture(4, 16), (Xm,), 20.0, False)]
+    for name, make_fam, data, clip, _ in fams:
+        data = tuple(a[:3000] for a in data)
+        a, la, ka = _run(make_fam, data, clip, 2, False)
+        b, lb, kb = _run(make_fam, data, clip, 2, False, local_rows=True)
+        for r in range(2):
+            assert torch.equal(a[r], b[r]), name
+            assert la[r] == lb[r] and np.array_equal(ka[r], kb[r]), name
 
 
 @pytest.mark.parametrize("margin", [None, 0], ids=["margin16", "margin0-redraw"])

@@ -232,3 +232,42 @@ def test_evaluate_epoch(cuda):
     assert losses.shape == (nb,)
     for i in range(nb):
         assert float(losses[i]) == float(s.evaluate(st, *get(i, perm)))
+
+
+@pytest.mark.parametrize("kind", ["logreg", "vae"])
+def test_run_epoch_context_is_optional_and_reusable(cuda, kind, monkeypatch):
+    """``d3p_epoch_ctx`` only carries streams and events: a NULL context (the library makes a temporary one per call) and
+    one context reused over many calls give bit-identical results, also when calls of different lengths alternate."""
+    from d3p_b200 import minibatch as mb, models, optimizers, svi
+    import d3p_b200.random as rng
+    g = torch.Generator(device="cuda").manual_seed(3)
+    if kind == "logreg":
+        N = 20_000
+        data = (torch.randn((N, 256), device=cuda, generator=g), (torch.rand(N, device=cuda, generator=g) < .5).to(torch.int32))
+        fam, clip = models.LogisticRegression(256), 1.0
+        init, get = mb.poisson_batchify_data(data, .02, .99)
+    else:
+        N = 4000
+        data = ((torch.rand((N, 64), device=cuda, generator=g) < .3).float(),)
+        fam, clip = models.VAE(64, 40, 8, init_std=.1), 5.0
+        init, get = mb.subsample_batchify_data(data, batch_size=200, return_mask=True)
+    s = svi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), clip, 1.0, num_obs_total=N)
+    k_init, k_fetch = rng.split(rng.PRNGKey(11), 2)
+    _, bst = init(k_fetch)
+    st0 = s.init(k_init, *get(0, bst)[0])
+
+    def run(state):
+        out = []
+        for first, n in ((0, 1), (1, 4), (5, 2), (7, 1), (8, 3)):
+            state, stats = s.run_epoch(state, get, bst, n, first_step=first)
+            out.append(stats.clone())
+        return state, torch.cat(out)
+
+    a, sa = run(st0)                                                    # one context, reused
+    assert len(s.__dict__["_epoch_ctxs"]) == 1
+    monkeypatch.setattr(svi.DPSVI, "_epoch_ctx", lambda self, dev: None)   # NULL: temporary context per call
+    b, sb = run(st0)
+    assert torch.equal(a.optim_state.flat, b.optim_state.flat) and torch.equal(sa, sb)
+    assert np.array_equal(np.asarray(a.rng_key), np.asarray(b.rng_key))
+    c, sc = s.run_epoch(st0, get, bst, 11, first_step=0)               # and both equal one long call
+    assert torch.equal(a.optim_state.flat, c.optim_state.flat) and torch.equal(sa, sc)
