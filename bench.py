@@ -611,7 +611,8 @@ def run_b200(args, cfg):
                                  "samples at ~10 Threefry calls each) per 512-byte row, DESIGN.md section 6"
                                  if cfg["family"] == "gmm" else
                                  "issue-bound, not HBM-bound: one Threefry-2x32-20 normal per data float "
-                                 "(~83 warp-instructions per element, DESIGN.md section 5)")}
+                                 "(~84 warp-instructions per element, measured by this run under issue_slots when "
+                                 "the ncu side run is on; DESIGN.md section 5)")}
             if kname == "meanfield_step_vec_kernel" and world == 1 and args.ncu_side_run and clocks.get("sm_mhz"):
                 # the bound that does apply: issue slots.  The instruction count per element is MEASURED by this run
                 # (ncu side run of a child process, see ncu_side_run); the slots offered are SMs x 4 schedulers x
