@@ -19,6 +19,7 @@ oracle port of the same step on the host cores (the reference itself needs jax/n
 jax-chacha-prng, none of which can be installed here — see DESIGN.md).
 """
 import argparse
+import gc
 import ctypes as C
 import json
 import os
@@ -432,6 +433,9 @@ def run_b200(args, cfg):
         return state, loss, (nv if nv is not None else max_b)
 
     def sync_all():
+        # garbage of the set-up phase (parity check, data generation) is collected here, outside the timed regions: a
+        # collection that runs finalisers with CUDA calls in the middle of a timed loop is a multi-millisecond host stall
+        gc.collect()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

@@ -302,12 +302,21 @@ class VAE(Family):
             ctxs[dev] = h
         return ctxs[dev]
 
-    def __del__(self):
-        for h in self.__dict__.get("_ctx", {}).values():
+    def close(self):
+        """Release the side streams now (re-created on demand)."""
+        ctxs = self.__dict__.get("_ctx", {})
+        while ctxs:
+            _, h = ctxs.popitem()
             try:
                 _n.lib().d3p_vae_ctx_destroy(h)
             except Exception:
                 pass
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def run_step(self, svi, state, tf_key, args, mask, B, pos_begin, pos_end, px_norms, px_grads, px_loss):
         import ctypes as C

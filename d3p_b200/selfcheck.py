@@ -8,6 +8,8 @@ prints the result as ``parity_check``; ``tests/helpers/multi_rank_check.py`` run
 The reference is single-device (``d3p/svi.py:395-434``); "the unsharded run" is this package's own single-GPU
 path, which the ``-m gpu`` tests hold against the oracle.
 """
+import gc
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -53,6 +55,7 @@ def _run(make_family, dataset, clip, sharded, steps, epoch, q):
         timeouts = s.peer_window.timeouts()
         dist.barrier()
         s.peer_window.close()
+    s.close()       # streams / events now, not at some later garbage collection inside the caller's timed region
     return st.optim_state.flat.clone(), losses, np.asarray(st.rng_key).copy(), timeouts
 
 
@@ -100,4 +103,5 @@ def sharded_parity_check(device, which=("logreg", "vae"), modes=(("p2p", False),
             if verbose and rank == 0:
                 print(f"{tag}: sharded-vs-single rel err {err:.2e}, replicas identical {same}, "
                       f"losses {l_sh} vs {l_1}, ok={good}", flush=True)
+    gc.collect()
     return out

@@ -380,12 +380,27 @@ class DPSVI:
             ctxs[dev_index] = h
         return h
 
-    def __del__(self):
-        for h in self.__dict__.get("_epoch_ctxs", {}).values():
+    def _release_epoch_ctxs(self):
+        ctxs = self.__dict__.get("_epoch_ctxs", {})
+        while ctxs:
+            _, h = ctxs.popitem()
             try:
                 _n.lib().d3p_epoch_ctx_destroy(h)
             except Exception:
                 pass
+
+    def close(self):
+        """Release the native resources behind this object (the epoch drivers' streams and events, the family's side
+        streams) now rather than when the garbage collector gets to them; everything is re-created on demand.  Not to
+        be called while another DPSVI object sharing the family is in the middle of a call."""
+        self._release_epoch_ctxs()
+        self._epoch_plan = None
+        fam = getattr(self, "family", None)
+        if fam is not None and hasattr(fam, "close"):
+            fam.close()
+
+    def __del__(self):
+        self._release_epoch_ctxs()      # only what this object alone owns: the family may be shared
 
     def run_epoch(self, svi_state, get_batch, batchifier_state, num_steps, first_step=0, device_keys=False):
         """The examples' ``lax.fori_loop(first_step, first_step + num_steps, body, state)`` with
