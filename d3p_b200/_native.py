@@ -74,6 +74,8 @@ _SIGNATURES = {
     "d3p_chacha_normal_f32": (C.c_int32, [_u32p, C.c_uint64, _vp, C.c_size_t, _vp]),
     "d3p_chacha_randint_round_u32": (C.c_int32, [_u32p, C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, _vp, _vp]),
     "d3p_randint_finish_i32": (C.c_int32, [_vp, C.c_int32, _vp, C.c_size_t, _vp]),
+    "d3p_chacha_randint_round": (C.c_int32, [_u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, _vp, C.c_size_t, _vp, _vp]),
+    "d3p_randint_finish": (C.c_int32, [_vp, C.c_int32, C.c_uint32, _vp, C.c_size_t, _vp]),
     "d3p_feistel_round_constants_h": (C.c_int32, [_u32p, _u32p]),
     "d3p_feistel_sample": (C.c_int32, [_u32p, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp]),
     "d3p_poisson_workspace_bytes": (C.c_size_t, [C.c_uint32]),
@@ -166,6 +168,7 @@ _SIGNATURES = {
                                                _vp, _vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                                C.c_float, C.POINTER(LeafTable), C.POINTER(OptimDesc), _vp, _vp,
                                                _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
+    "d3p_gmm_log_prob_f32": (C.c_int32, [_vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp]),
     "d3p_gmm_workspace_bytes": (C.c_size_t, [C.POINTER(GmmDesc), _u32p]),
     "d3p_dpsvi_step_gmm": (C.c_int32, [C.POINTER(GmmDesc), _vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_uint32, C.c_uint32,
                                        C.c_uint32, _u32p, C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),

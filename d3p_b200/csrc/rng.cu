@@ -41,22 +41,27 @@ __global__ void __launch_bounds__(256) chacha_stream_kernel(ChaChaArg key, uint3
   }
 }
 
+// One rejection round of rng_suite.randint (d3p/random/__init__.py:127-142) for NBITS-wide draws: element e takes bit
+// field e of the keystream (random_bits(key, NBITS, shape): the words viewed as little-endian NBITS-bit integers).
+template <int NBITS>
 __global__ void __launch_bounds__(256) randint_round_kernel(ChaChaArg key, uint32_t bitmask, uint32_t delta,
                                                             int first, uint32_t* vals, size_t n, int* pending) {
+  constexpr int kPerWord = 32 / NBITS, kPerBlock = 16 * kPerWord;
+  constexpr uint32_t kFieldMask = NBITS == 32 ? 0xFFFFFFFFu : ((1u << (NBITS & 31)) - 1u);
   ChaChaState st;
   load_chacha(key, st);
-  size_t n_blocks = (n + 15) / 16;
+  size_t n_blocks = (n + kPerBlock - 1) / kPerBlock;
   int local = 0;
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks;
        b += (size_t)gridDim.x * blockDim.x) {
     uint32_t ks[16];
     chacha20_block(st.w, st.w[12] + (uint32_t)b, ks);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      size_t e = b * 16 + i;
+    for (int i = 0; i < kPerBlock; ++i) {
+      size_t e = b * kPerBlock + i;
       if (e < n) {
         uint32_t v = first ? 0xFFFFFFFFu : vals[e];
-        if (first || v > delta) v = ks[i] & bitmask;
+        if (first || v > delta) v = ((ks[i / kPerWord] >> ((i % kPerWord) * NBITS)) & kFieldMask) & bitmask;
         vals[e] = v;
         local += (v > delta);
       }
@@ -66,9 +71,11 @@ __global__ void __launch_bounds__(256) randint_round_kernel(ChaChaArg key, uint3
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(pending, local);
 }
 
-__global__ void randint_finish_kernel(const uint32_t* vals, int32_t minval, int32_t* out, size_t n) {
+// vals + minval in the arithmetic of the result type (wraps like vdtype(uvals) + minval, d3p/random/__init__.py:145)
+template <typename T>
+__global__ void randint_finish_kernel(const uint32_t* vals, int32_t minval, T* out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    out[i] = (int32_t)vals[i] + minval;
+    out[i] = (T)(uint32_t)(vals[i] + (uint32_t)minval);
 }
 
 // ---- device-resident keys (the *_dk entry points) -------------------------------------------------------------------
@@ -251,27 +258,48 @@ int32_t d3p_chacha_normal_f32(const uint32_t state_h[16], uint64_t first_block, 
   return launch_stream<kNormal>(state_h, nullptr, first_block, out_d, n, 0.f, 1.f, stream);
 }
 
+int32_t d3p_chacha_randint_round(const uint32_t round_state_h[16], uint32_t nbits, uint32_t bitmask, uint32_t delta,
+                                 int32_t first, uint32_t* vals_d, size_t n, int32_t* pending_d, void* stream) {
+  if (!round_state_h || !pending_d || (!vals_d && n)) return D3P_ERR_INVALID_ARGUMENT;
+  if (nbits != 8 && nbits != 16 && nbits != 32) return D3P_ERR_UNSUPPORTED;
+  cudaMemsetAsync(pending_d, 0, sizeof(int32_t), (cudaStream_t)stream);
+  if (n == 0) return check_launch();
+  const size_t per_block = 512 / nbits;
+  size_t n_blocks = (n + per_block - 1) / per_block;
+  size_t grid = (n_blocks + 255) / 256;
+  if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
+  const ChaChaArg key = chacha_arg(round_state_h, nullptr);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nbits == 8)
+    randint_round_kernel<8><<<(unsigned)grid, 256, 0, s>>>(key, bitmask, delta, first, vals_d, n, pending_d);
+  else if (nbits == 16)
+    randint_round_kernel<16><<<(unsigned)grid, 256, 0, s>>>(key, bitmask, delta, first, vals_d, n, pending_d);
+  else
+    randint_round_kernel<32><<<(unsigned)grid, 256, 0, s>>>(key, bitmask, delta, first, vals_d, n, pending_d);
+  return check_launch();
+}
+
 int32_t d3p_chacha_randint_round_u32(const uint32_t round_state_h[16], uint32_t bitmask, uint32_t delta,
                                      int32_t first, uint32_t* vals_d, size_t n, int32_t* pending_d,
                                      void* stream) {
-  if (!round_state_h || !pending_d || (!vals_d && n)) return D3P_ERR_INVALID_ARGUMENT;
-  cudaMemsetAsync(pending_d, 0, sizeof(int32_t), (cudaStream_t)stream);
-  if (n == 0) return check_launch();
-  size_t n_blocks = (n + 15) / 16;
-  size_t grid = (n_blocks + 255) / 256;
+  return d3p_chacha_randint_round(round_state_h, 32, bitmask, delta, first, vals_d, n, pending_d, stream);
+}
+
+int32_t d3p_randint_finish(const uint32_t* vals_d, int32_t minval, uint32_t nbits, void* out_d, size_t n, void* stream) {
+  if ((!vals_d || !out_d) && n) return D3P_ERR_INVALID_ARGUMENT;
+  if (nbits != 8 && nbits != 16 && nbits != 32) return D3P_ERR_UNSUPPORTED;
+  if (n == 0) return D3P_OK;
+  size_t grid = (n + 255) / 256;
   if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
-  randint_round_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(chacha_arg(round_state_h, nullptr), bitmask,
-                                                                         delta, first, vals_d, n, pending_d);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nbits == 8) randint_finish_kernel<int8_t><<<(unsigned)grid, 256, 0, s>>>(vals_d, minval, (int8_t*)out_d, n);
+  else if (nbits == 16) randint_finish_kernel<int16_t><<<(unsigned)grid, 256, 0, s>>>(vals_d, minval, (int16_t*)out_d, n);
+  else randint_finish_kernel<int32_t><<<(unsigned)grid, 256, 0, s>>>(vals_d, minval, (int32_t*)out_d, n);
   return check_launch();
 }
 
 int32_t d3p_randint_finish_i32(const uint32_t* vals_d, int32_t minval, int32_t* out_d, size_t n, void* stream) {
-  if ((!vals_d || !out_d) && n) return D3P_ERR_INVALID_ARGUMENT;
-  if (n == 0) return D3P_OK;
-  size_t grid = (n + 255) / 256;
-  if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
-  randint_finish_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(vals_d, minval, out_d, n);
-  return check_launch();
+  return d3p_randint_finish(vals_d, minval, 32, out_d, n, stream);
 }
 
 

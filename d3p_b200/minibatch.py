@@ -235,6 +235,9 @@ def split_batchify_data(dataset, batch_size=None, q=None, rng_suite=strong_rng, 
         return num_records // batch_size, sample_indices(rng_key, num_records, num_records, rng_suite)
 
     def get_batch(i, idxs):
+        if not isinstance(idxs, torch.Tensor) or idxs.dtype != torch.int32 or not idxs.is_cuda:
+            idxs = torch.as_tensor(np.asarray(idxs.cpu() if isinstance(idxs, torch.Tensor) else idxs)).to(
+                device=_device(), dtype=torch.int32)           # any permutation the caller built itself
         ret_idx = idxs[i * batch_size:(i + 1) * batch_size]
         batch = tuple(BatchView(a, ret_idx) for a in dataset)
         if return_mask:

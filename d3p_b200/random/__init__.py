@@ -130,18 +130,30 @@ def normal(key: PRNGState, shape: Sequence[int] = (), dtype=torch.float32) -> to
     return out[:size].reshape(shape)
 
 
+_INT_DTYPES = {torch.int8: (8, torch.int8), np.int8: (8, torch.int8), "int8": (8, torch.int8),
+               torch.int16: (16, torch.int16), np.int16: (16, torch.int16), "int16": (16, torch.int16),
+               torch.int32: (32, torch.int32), np.int32: (32, torch.int32), "int32": (32, torch.int32), int: (32, torch.int32),
+               # jax.dtypes.canonicalize_dtype with x64 disabled (the default the reference runs under): int64 -> int32
+               torch.int64: (32, torch.int32), np.int64: (32, torch.int32), "int64": (32, torch.int32)}
+
+
 def randint(key: PRNGState, shape: Sequence[int], minval, maxval, dtype=torch.int32) -> torch.Tensor:
-    """``d3p/random/__init__.py:84-146`` (32-bit path): power-of-two mask + rejection, one fresh
-    key pair per round.  The loop condition needs one 4-byte device->host read per round."""
-    if dtype not in (torch.int32, np.int32, "int32"):
-        if dtype in (torch.int8, torch.int16, torch.int64, np.int8, np.int16, np.int64):
-            raise TypeError("d3p_b200 implements the int32 path of rng_suite.randint only")
+    """``d3p/random/__init__.py:84-146``: power-of-two mask + rejection on ``random_bits(round_key, nbits, shape)`` with
+    nbits the width of the result type, one fresh key pair per round.  The loop condition needs one 4-byte
+    device->host read per round."""
+    try:
+        np_dt = np.dtype(dtype) if not isinstance(dtype, torch.dtype) else None
+    except TypeError:
+        np_dt = None
+    if dtype not in _INT_DTYPES and not (np_dt is not None and np_dt.type in _INT_DTYPES):
         raise TypeError(f"dtype argument to `randint` must be an integer dtype, got {dtype}")
+    nbits, out_dtype = _INT_DTYPES[dtype] if dtype in _INT_DTYPES else _INT_DTYPES[np_dt.type]
+    full = (1 << nbits) - 1
     shape = _shape(shape)
     size = int(np.prod(shape)) if len(shape) else 1
-    delta = (int(maxval) - 1 - int(minval)) & 0xFFFFFFFF
-    log_po2 = min(int(np.float32(np.log2(np.float32(delta))) + np.float32(1)) if delta > 0 else 0, 32)
-    bitmask = ((1 << log_po2) - 1) & 0xFFFFFFFF
+    delta = (int(maxval) - 1 - int(minval)) & full
+    log_po2 = min(int(np.float32(np.log2(np.float32(delta))) + np.float32(1)) if delta > 0 else 0, nbits)
+    bitmask = ((1 << log_po2) - 1) & full
     dev = _device()
     vals = torch.empty(max(size, 1), dtype=torch.int32, device=dev)
     pending = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -150,14 +162,14 @@ def randint(key: PRNGState, shape: Sequence[int], minval, maxval, dtype=torch.in
         ks = split(key, 2)
         key, round_key = ks[0], ks[1]
         a, p = _state(round_key)
-        _n.check(_n.lib().d3p_chacha_randint_round_u32(p, bitmask, delta, first, _n.ptr(vals), size, _n.ptr(pending),
-                                                       _n.stream_ptr()), "randint")
+        _n.check(_n.lib().d3p_chacha_randint_round(p, nbits, bitmask, delta, first, _n.ptr(vals), size, _n.ptr(pending),
+                                                   _n.stream_ptr()), "randint")
         first = 0
         if int(pending.item()) == 0:
             break
-    out = torch.empty(max(size, 1), dtype=torch.int32, device=dev)
-    _n.check(_n.lib().d3p_randint_finish_i32(_n.ptr(vals), int(minval), _n.ptr(out), size, _n.stream_ptr()),
-             "randint")
+    out = torch.empty(max(size, 1), dtype=out_dtype, device=dev)
+    minval32 = ((int(minval) + (1 << 31)) & 0xFFFFFFFF) - (1 << 31)      # the addition wraps in the result type
+    _n.check(_n.lib().d3p_randint_finish(_n.ptr(vals), minval32, nbits, _n.ptr(out), size, _n.stream_ptr()), "randint")
     return out[:size].reshape(shape)
 
 

@@ -81,6 +81,12 @@ int32_t d3p_chacha_randint_round_u32(const uint32_t round_state_h[16], uint32_t 
                                      void* stream);
 /* vals -> int32 indices: idx = int32(vals) + minval. */
 int32_t d3p_randint_finish_i32(const uint32_t* vals_d, int32_t minval, int32_t* out_d, size_t n, void* stream);
+/* The same pair for the other result widths of d3p.random.randint (d3p/random/__init__.py:113-124: nbits = bits of
+ * the result dtype, draws are random_bits(round_key, nbits, shape)): nbits = 8, 16 or 32; vals_d stays uint32 per
+ * element; out_d is int8 / int16 / int32 and the addition wraps in that type. */
+int32_t d3p_chacha_randint_round(const uint32_t round_state_h[16], uint32_t nbits, uint32_t bitmask, uint32_t delta,
+                                 int32_t first, uint32_t* vals_d, size_t n, int32_t* pending_d, void* stream);
+int32_t d3p_randint_finish(const uint32_t* vals_d, int32_t minval, uint32_t nbits, void* out_d, size_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Minibatch samplers — replace d3p/util.py:216-301 and d3p/minibatch.py:29-39,103-131,217-237.
@@ -430,6 +436,11 @@ int32_t d3p_dpsvi_step_gmm(const d3p_gmm_desc* desc, const float* params_d, cons
                            uint32_t pos_begin, uint32_t pos_end, const uint32_t threefry_key_h[2], float obs_scale,
                            float C, float* px_norms_d, float* px_grads_d, float* px_loss_d, void* ws_d, size_t ws_bytes,
                            void* stream);
+
+/* d3p.gmm.GaussianMixture.log_prob (d3p/gmm.py:71-86) for a batch of rows: out[b] = logsumexp_k(log pis[k] +
+ * sum_e log N(x[b, e]; locs[k, e], scales[k, e])); locs / scales are [K, E] (event dimensions flattened), pis [K]. */
+int32_t d3p_gmm_log_prob_f32(const float* x_d, size_t x_row_stride, const float* locs_d, const float* scales_d,
+                             const float* pis_d, uint32_t B, uint32_t K, uint32_t E, float* out_d, void* stream);
 
 /* The same loop for the mixture model (examples/gaussian_mixture_model.py:205-218). */
 size_t d3p_dpsvi_epoch_gmm_workspace_bytes(const d3p_gmm_desc* desc, const d3p_sampler_desc* sampler);
