@@ -83,6 +83,8 @@ class PeerWindow:
         new = PeerWindow(self.rank, self.world_size, self.max_params, self.group, max_records=n_records)
         if getattr(self, "sampler_margin", None) is not None:
             new.set_sampler_margin(self.sampler_margin)
+        if getattr(self, "timeout_ms", None) is not None:
+            new.set_timeout_ms(self.timeout_ms)
         return new
 
     def timeouts(self):
@@ -104,6 +106,7 @@ class PeerWindow:
     def set_timeout_ms(self, ms):
         """How long a kernel waits for a peer's words before it gives up (default 10 s)."""
         _n.check(_n.lib().d3p_comm_set_timeout_ms(self._comm, int(ms)), "comm_set_timeout_ms")
+        self.timeout_ms = int(ms)
 
     def set_sampler_margin(self, tiles):
         """Sharded Poisson sampler: tiles drawn redundantly on each side of a rank's slice (same on all ranks)."""
