@@ -1,0 +1,173 @@
+"""Randomised differential tests of the bit-exact pieces against the oracle: seeded, so reproducible, with shapes drawn
+to hit the edges the fixed-shape tests do not enumerate (sizes around tile / block / word boundaries, empty and
+one-element cases, first_block offsets, odd row sizes, every randint width, sharded position ranges)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import chacha, minibatch as omb, threefry
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def _sizes(rs, n, edges=(1, 2, 15, 16, 17, 31, 32, 33, 255, 256, 257, 4095, 4096, 4097, 65535, 65536, 65537), hi=300_000):
+    """n sizes: half of them next to a boundary, the rest log-uniform"""
+    out = []
+    for _ in range(n):
+        if rs.rand() < .5:
+            out.append(int(edges[rs.randint(len(edges))]))
+        else:
+            out.append(int(np.exp(rs.uniform(0, np.log(hi)))))
+    return out
+
+
+def test_fuzz_feistel(cuda):
+    from d3p_b200.util import sample_indices
+    rs = np.random.RandomState(101)
+    for cap in _sizes(rs, 40, hi=5_000_000):
+        n = int(rs.randint(1, min(cap, 3000) + 1))
+        first = int(rs.randint(0, cap - n + 1))
+        key = chacha.fold_in(chacha.PRNGKey(cap), n)
+        want = omb.sample_indices(key, cap, cap)[first:first + n] if cap <= 70_000 else None
+        got = _np(sample_indices(key, cap, n, first_pos=first)).astype(np.uint32)
+        if want is None:      # large capacity: the oracle walks only the requested positions
+            rc = omb.feistel_round_constants(key)
+            want = omb.feistel_permute(np.arange(first, first + n, dtype=np.uint32), cap, rc)
+        assert np.array_equal(got, want), (cap, n, first)
+        assert got.max() < cap and len(np.unique(got)) == n
+
+
+def test_fuzz_poisson(cuda):
+    from d3p_b200.minibatch import poisson_sample_idxs
+    rs = np.random.RandomState(202)
+    for N in _sizes(rs, 40, hi=400_000):
+        q = float(rs.choice([0.0, 1.0, rs.uniform(0, 1), rs.uniform(0, .05), 1.0 / max(N, 1)]))
+        cut = int(rs.randint(1, N + 1))
+        suppress = bool(rs.rand() < .3)
+        key = chacha.fold_in(chacha.PRNGKey(N), cut)
+        idx, counts, mask = poisson_sample_idxs(key, q, N, cutoff_size=cut, suppress=suppress)
+        ref_idx, ref_num = omb.poisson_sample_idxs(key, np.float32(q), N, cutoff_size=cut)
+        num = int(ref_num)
+        eff = (0 if num > cut else num) if suppress else min(num, cut)
+        c = _np(counts)
+        assert int(c[0]) == num and int(c[1]) == eff, (N, q, cut, suppress, c, num)
+        assert np.array_equal(_np(mask), np.arange(cut) < eff)
+        k = min(num, cut)                                    # the selected records, in the reference's (descending) order
+        assert np.array_equal(_np(idx)[:k], np.asarray(ref_idx)[:k]), (N, q, cut)
+
+
+def test_fuzz_keystream_and_transforms(cuda):
+    import d3p_b200.random as rng
+    from d3p_b200 import _native as _n
+    rs = np.random.RandomState(303)
+    lib = _n.lib()
+    for n in _sizes(rs, 30, hi=200_000):
+        key = chacha.fold_in(chacha.PRNGKey(7), n)
+        first_block = int(rs.choice([0, 1, 2 ** 16, 2 ** 32 - 5, rs.randint(0, 2 ** 31)]))
+        if first_block + (n + 15) // 16 >= 2 ** 32:
+            first_block = 0
+        out = torch.empty(n, dtype=torch.int32, device=cuda)
+        a = np.ascontiguousarray(np.asarray(key, np.uint32).reshape(16))
+        _n.check(lib.d3p_chacha_random_bits(a.ctypes.data_as(C.POINTER(C.c_uint32)), first_block, _n.ptr(out), n, _n.stream_ptr()))
+        assert np.array_equal(_np(out).view(np.uint32), chacha.keystream_words(key, n, first_block=first_block)), (n, first_block)
+        width = int(rs.choice([8, 16, 32, 64]))
+        shape = (n,) if rs.rand() < .5 else (max(n // 7, 1), 7)
+        got = _np(rng.random_bits(key, width, shape))
+        assert np.array_equal(got, chacha.random_bits(key, width, shape)), (n, width)
+        lo, hi = (0.0, 1.0) if rs.rand() < .5 else (float(rs.uniform(-5, 0)), float(rs.uniform(0.1, 9)))
+        assert np.array_equal(_np(rng.uniform(key, (n,), minval=lo, maxval=hi)), chacha.uniform(key, (n,), minval=lo, maxval=hi))
+        z, zr = _np(rng.normal(key, (n,))), chacha.normal(key, (n,))
+        assert np.allclose(z, zr, rtol=2e-6, atol=2e-7)
+
+
+def test_fuzz_randint(cuda):
+    import d3p_b200.random as rng
+    rs = np.random.RandomState(404)
+    info = {np.int8: 8, np.int16: 16, np.int32: 32}
+    for _ in range(40):
+        dt = [np.int8, np.int16, np.int32][rs.randint(3)]
+        nb = info[dt]
+        lo = int(rs.randint(-2 ** (nb - 1), 2 ** (nb - 1) - 1))
+        span = int(rs.choice([1, 2, 3, 2 ** (nb - 2), 2 ** (nb - 2) + 1, rs.randint(1, 2 ** (nb - 1))]))
+        hi = min(lo + span, 2 ** (nb - 1))
+        n = _sizes(rs, 1, hi=20_000)[0]
+        key = chacha.fold_in(chacha.PRNGKey(nb), lo & 0xFFFF)
+        got = _np(rng.randint(key, (n,), lo, hi, dt))
+        want = chacha.randint(key, (n,), lo, hi, dt)
+        assert got.dtype == want.dtype and np.array_equal(got, want), (dt, lo, hi, n)
+        assert got.min() >= lo and got.max() < hi
+
+
+def test_fuzz_gather(cuda):
+    from d3p_b200.minibatch import gather_rows
+    rs = np.random.RandomState(505)
+    for _ in range(40):
+        dtype = [torch.float32, torch.int32, torch.uint8, torch.int64, torch.float16][rs.randint(5)]
+        n_rows = int(rs.randint(1, 5000))
+        trailing = tuple(int(x) for x in rs.randint(1, 9, size=rs.randint(0, 3)))
+        src = torch.randint(0, 100, (n_rows,) + trailing, device=cuda).to(dtype)
+        b = int(rs.randint(1, 3000))
+        idx = torch.as_tensor(rs.randint(0, n_rows, size=b).astype(np.int32)).to(cuda)
+        nv = int(rs.randint(0, b + 1))
+        num_valid = torch.tensor([nv], dtype=torch.int32, device=cuda) if rs.rand() < .7 else None
+        got = gather_rows(src, idx, num_valid)
+        want = src[idx.long()]
+        if num_valid is not None:
+            want = want.clone()
+            want[nv:] = 0
+        assert got.dtype == src.dtype and torch.equal(got, want), (dtype, n_rows, trailing, b, nv)
+
+
+def test_fuzz_threefry_streams(cuda):
+    from d3p_b200 import jrandom as jr
+    rs = np.random.RandomState(606)
+    for n in _sizes(rs, 25, hi=100_000):
+        key = threefry.fold_in(threefry.PRNGKey(11), n)
+        shape = (n,) if rs.rand() < .5 else (max(n // 3, 1), 3)
+        size = int(np.prod(shape))
+        assert np.array_equal(_np(jr.random_bits(key, shape)).view(np.uint32).ravel(), threefry.threefry_random_bits(key, size))
+        assert np.array_equal(_np(jr.uniform(key, shape)), threefry.uniform(key, shape))
+        assert np.allclose(_np(jr.normal(key, shape)), threefry.normal(key, shape), rtol=2e-6, atol=2e-7)
+        ks = jr.split(key, 5)
+        assert np.array_equal(np.asarray(ks), threefry.split(key, 5))
+
+
+def test_fuzz_device_key_twins(cuda):
+    """*_dk entry points on random keys / sizes: bit-identical to the host-key forms."""
+    import d3p_b200.random as rng
+    from d3p_b200 import _native as _n, minibatch as mb, util
+    rs = np.random.RandomState(707)
+    lib = _n.lib()
+    for _ in range(15):
+        key = rng.fold_in(rng.PRNGKey(int(rs.randint(1 << 30))), int(rs.randint(1 << 30)))
+        kd = torch.as_tensor(np.ascontiguousarray(np.asarray(key, np.uint32).reshape(-1)).view(np.int32)).cuda()
+        n = int(rs.randint(1, 40))
+        out = torch.empty(n * 16, dtype=torch.int32, device=cuda)
+        _n.check(lib.d3p_chacha_split_dk(_n.ptr(kd), n, _n.ptr(out), _n.stream_ptr()))
+        assert np.array_equal(_np(out).view(np.uint32).reshape(n, 16), np.asarray(rng.split(key, n), np.uint32).reshape(n, 16))
+        N = _sizes(rs, 1, hi=200_000)[0]
+        q, cut = float(rs.uniform(0, .2)), int(rs.randint(1, N + 1))
+        need = lib.d3p_poisson_workspace_bytes(N)
+        ws = torch.empty(need, dtype=torch.uint8, device=cuda)
+        idx = torch.full((cut,), -1, dtype=torch.int32, device=cuda)
+        counts = torch.empty(2, dtype=torch.int32, device=cuda)
+        mask = torch.empty(cut, dtype=torch.uint8, device=cuda)
+        _n.check(lib.d3p_poisson_sample_dk(_n.ptr(kd), float(np.float32(q)), N, cut, 0, _n.ptr(idx), _n.ptr(counts), _n.ptr(mask),
+                                           _n.ptr(ws), need, _n.stream_ptr()))
+        r_idx, r_counts, r_mask = mb.poisson_sample_idxs(key, q, N, cutoff_size=cut)
+        k = int(min(int(r_counts[0]), cut))
+        assert torch.equal(counts, r_counts) and torch.equal(mask.view(torch.bool), r_mask) and torch.equal(idx[:k], r_idx[:k])
+        rc = torch.empty(32, dtype=torch.int32, device=cuda)
+        _n.check(lib.d3p_feistel_round_constants_dk(_n.ptr(kd), _n.ptr(rc), _n.stream_ptr()))
+        cap = _sizes(rs, 1, hi=3_000_000)[0]
+        m = int(rs.randint(1, min(cap, 2000) + 1))
+        first = int(rs.randint(0, cap - m + 1))
+        fi = torch.empty(m, dtype=torch.int32, device=cuda)
+        _n.check(lib.d3p_feistel_sample_dk(_n.ptr(rc), cap, first, m, _n.ptr(fi), _n.stream_ptr()))
+        assert torch.equal(fi, util.sample_indices(key, cap, m, first_pos=first))
