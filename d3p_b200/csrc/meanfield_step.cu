@@ -13,6 +13,8 @@
 // it is part of a joint `_auto_latent` site (e == d).  With theta_e = loc_e + eps_e * s_e:
 //   gl_e = d loss / d loc_e = theta_e / S + h_e,   h_e = (N/S) * d(-loglik)/d theta_e
 //   gs_e = d loss / d rho_e = gl_e * eps_e * s'_e - (1/S) * s'_e / s_e
+#include <type_traits>
+
 #include "common.cuh"
 #include "launch.cuh"
 #include "meanfield_common.cuh"
@@ -25,6 +27,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
   constexpr int TILE = G < 8 ? G : 8;         // examples per group between key-derivation rounds
   constexpr int NS = 2 * NQ;                  // latent elements owned by a lane
   constexpr int NALLOC = 2 * G * NQ;          // padded element count
+  static_assert(NS <= 64, "the slot validity mask has 64 bits");
   extern __shared__ float smem[];
   float* s_loc = smem;
   float* s_scl = s_loc + NALLOC;
@@ -67,13 +70,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
   for (int w = 0; w < kStepWarps; ++w) sum_log_s += s_red[w];
 
   // validity of the lane's slots
-  uint32_t vmask = 0;
+  using mask_t = typename std::conditional<(NS > 32), uint64_t, uint32_t>::type;
+  mask_t vmask = 0;          // one bit per slot (NS <= 64)
 #pragma unroll
   for (int k = 0; k < NQ; ++k) {
     uint32_t q = glane + G * k;
     if (q < a.half) {
-      vmask |= 1u << (2 * k);
-      if (q + a.half < a.n_main) vmask |= 1u << (2 * k + 1);
+      vmask |= (mask_t)1 << (2 * k);
+      if (q + a.half < a.n_main) vmask |= (mask_t)1 << (2 * k + 1);
     }
   }
 
@@ -124,19 +128,19 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
 #pragma unroll
       for (int k = 0; k < NQ; ++k) {
         const uint32_t e0 = glane + G * k, e1 = e0 + a.half;
-        xv[2 * k] = ((vmask >> (2 * k)) & 1u) ? (e0 < a.d ? __ldg(xr + e0) : 1.0f) : 0.f;
-        xv[2 * k + 1] = ((vmask >> (2 * k + 1)) & 1u) ? (e1 < a.d ? __ldg(xr + e1) : 1.0f) : 0.f;
+        xv[2 * k] = ((vmask >> (2 * k)) & (mask_t)1) ? (e0 < a.d ? __ldg(xr + e0) : 1.0f) : 0.f;
+        xv[2 * k + 1] = ((vmask >> (2 * k + 1)) & (mask_t)1) ? (e1 < a.d ? __ldg(xr + e1) : 1.0f) : 0.f;
       }
       const TfKey km(kw0, kw1);
 #pragma unroll
       for (int k = 0; k < NQ; ++k) {
         const uint32_t e0 = glane + G * k, e1 = e0 + a.half;
         ev[2 * k] = 0.f; ev[2 * k + 1] = 0.f;
-        if ((vmask >> (2 * k)) & 1u) {
+        if ((vmask >> (2 * k)) & (mask_t)1) {
           uint32_t y0, y1;
           threefry2x32(km, e0, (e1 < a.n_main) ? e1 : 0u, y0, y1);
           ev[2 * k] = bits_to_normal_fast(y0);
-          if ((vmask >> (2 * k + 1)) & 1u) ev[2 * k + 1] = bits_to_normal_fast(y1);
+          if ((vmask >> (2 * k + 1)) & (mask_t)1) ev[2 * k + 1] = bits_to_normal_fast(y1);
         }
       }
       // ---- pass 1: theta, sums -----------------------------------------------------------------
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const int e = glane + G * (s >> 1) + ((s & 1) ? (int)a.half : 0);
-        const bool ok = (vmask >> s) & 1u;
+        const bool ok = (vmask >> s) & (mask_t)1;
         const int es = ok ? e : 0;
         const float th = fmaf(ev[s], s_scl[es], s_loc[es]);
         s_e2 = fmaf(ev[s], ev[s], s_e2);
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const int e = glane + G * (s >> 1) + ((s & 1) ? (int)a.half : 0);
-        const bool ok = (vmask >> s) & 1u;
+        const bool ok = (vmask >> s) & (mask_t)1;
         const int es = ok ? e : 0;
         const float th = (LINK == D3P_LINK_EXP) ? (s_loc[es] + ev[s]) : fmaf(ev[s], s_sa[es], s_loc[es]);
         float h;
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const int e = glane + G * (s >> 1) + ((s & 1) ? (int)a.half : 0);
-        const bool ok = (vmask >> s) & 1u;
+        const bool ok = (vmask >> s) & (mask_t)1;
         const float bt = (LINK == D3P_LINK_EXP) ? a.inv_S : s_bt[ok ? e : 0];
         const float gs = fmaf(xv[s], ev[s], -bt);
         acc_loc[s] = fmaf(c, xv[s], acc_loc[s]);
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) meanfield_step_kernel(StepArg
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
           const uint32_t e = glane + G * (s >> 1) + ((s & 1) ? a.half : 0u);
-          if ((vmask >> s) & 1u) {
+          if ((vmask >> s) & (mask_t)1) {
             s_acc[a.loc_off + e] += acc_loc[s];
             s_acc[a.rho_off + e] += acc_rho[s];
           }
@@ -274,7 +278,10 @@ int32_t launch_meanfield_vec(int family, int link, const StepArgs& a, unsigned g
 struct Shape { int G, NQ; };
 
 static bool pick_shape(uint32_t half, Shape& sh) {
-  static const Shape table[] = {{1, 4}, {2, 4}, {4, 4}, {8, 4}, {16, 4}, {32, 4}, {32, 8}, {32, 16}};
+  // {32, 32}: latent sites of 1025 .. 2048 elements (e.g. the joint AutoDiagonalNormal site of a d = 1024 logistic
+  // regression): 64 elements per lane do not fit the register file, the accumulators live in local memory - a
+  // correct, slower path for shapes outside the tuned ones
+  static const Shape table[] = {{1, 4}, {2, 4}, {4, 4}, {8, 4}, {16, 4}, {32, 4}, {32, 8}, {32, 16}, {32, 32}};
   for (const Shape& s : table)
     if ((uint32_t)(s.G * s.NQ) >= half) { sh = s; return true; }
   return false;
@@ -316,7 +323,7 @@ template <int FAMILY, int LINK>
 static int32_t launch_shape(const Shape& sh, const StepArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
 #define D3P_CASE(g, nq) if (sh.G == g && sh.NQ == nq) return launch_one<FAMILY, LINK, g, nq>(a, smem, grid, s);
   D3P_CASE(1, 4) D3P_CASE(2, 4) D3P_CASE(4, 4) D3P_CASE(8, 4) D3P_CASE(16, 4) D3P_CASE(32, 4) D3P_CASE(32, 8)
-  D3P_CASE(32, 16)
+  D3P_CASE(32, 16) D3P_CASE(32, 32)
 #undef D3P_CASE
   return D3P_ERR_UNSUPPORTED;
 }

@@ -171,3 +171,96 @@ def test_fuzz_device_key_twins(cuda):
         fi = torch.empty(m, dtype=torch.int32, device=cuda)
         _n.check(lib.d3p_feistel_sample_dk(_n.ptr(rc), cap, first, m, _n.ptr(fi), _n.stream_ptr()))
         assert torch.equal(fi, util.sample_indices(key, cap, m, first_pos=first))
+
+
+# ---- floating-point paths: shapes the fixed-shape tests do not enumerate, against the autodiff oracle at 1e-5 -------------
+@pytest.mark.parametrize("D,H,Z,B,C", [(28, 12, 1, 1, 0.5), (28, 12, 1, 129, 0.5), (100, 52, 3, 70, 1.0), (20, 8, 4, 257, 0.3),
+                                        (64, 16, 2, 128, 0.7), (200, 72, 10, 40, 2.0), (784, 96, 5, 33, 5.0), (48, 400, 20, 130, 1.0),
+                                        (36, 20, 31, 5, 1.0), (4, 4, 32, 3, 0.2)])
+def test_fuzz_vae_shapes(cuda, D, H, Z, B, C):
+    """Layer widths at the edges of what the VAE kernels take (D % 8 != 0, H % 8 != 0, Z = 1 ... 32, the minimum 4-4),
+    batches of one example and batches that straddle the 128-row GEMM tile: one clipped-sum SGD step (dp_scale = 0)
+    moves the parameters by exactly the clipped-sum gradient."""
+    from helpers.tolerance import rel_err as ew_rel_err
+    from test_gpu_vae import make
+    X, o, ost, s, st = make(D, H, Z, 60000, B, C, 0.0, optim="sgd", seed=D + B)
+    mask = np.ones(B, dtype=bool)
+    if B > 2:
+        mask[1::4] = False
+    ost2, oloss = o.update(ost, X, mask=mask)
+    st2, loss = s.update(st, torch.as_tensor(X).cuda(), mask=torch.as_tensor(mask).cuda())
+    assert np.isclose(float(loss), float(oloss), rtol=1e-5), (float(loss), float(oloss))
+    oref, got = o.get_params(ost2), s.get_params(st2)
+    for k in oref:
+        assert ew_rel_err(got[k], oref[k]) < 1e-5, (k, ew_rel_err(got[k], oref[k]))
+
+
+def test_vae_unsupported_shapes_fail_loudly(cuda):
+    """The tcgen05 / TMA path needs 16-byte row strides (out_dim % 4 == 0, hidden_dim % 4 == 0) and z_dim <= 32; other
+    shapes are refused with D3P_ERR_UNSUPPORTED, never computed some other way."""
+    from d3p_b200 import _native as _n
+    from test_gpu_vae import make
+    for D, H, Z in ((30, 12, 2), (28, 13, 2), (28, 12, 33)):
+        X, o, ost, s, st = make(D, H, Z, 1000, 8, 1.0, 0.0, optim="sgd")
+        with pytest.raises(_n.D3PNativeError, match="unsupported"):
+            s.update(st, torch.as_tensor(X).cuda())
+
+
+def test_meanfield_unsupported_width_fails_loudly(cuda):
+    """latent sites beyond 2048 elements are refused (D3P_ERR_UNSUPPORTED), never computed some other way"""
+    from d3p_b200 import _native as _n
+    from test_gpu_svi import _data, _pair
+    s, o, fam = _pair("gauss", 4000, 1000, "hand")
+    (X,) = _data("gauss", 4, 4000)
+    Xd = torch.as_tensor(X).to(cuda)
+    st = s.init(chacha.PRNGKey(0), Xd)
+    with pytest.raises(_n.D3PNativeError, match="unsupported"):
+        s.update(st, Xd)
+
+
+def test_fuzz_meanfield_shapes(cuda):
+    """Random (family, guide, d, B) incl. d around the 256 / 512 / 1024 kernel selection, batches of one example, batches
+    fed as index lists with a device-side valid count: one clipped-sum SGD step against the oracle."""
+    from helpers.tolerance import rel_err as ew_rel_err
+    from test_gpu_svi import _data, _pair, _rand_params
+    from d3p_b200.minibatch import BatchView
+    rs = np.random.RandomState(808)
+    ds = [2, 13, 100, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2000]
+    for trial in range(16):
+        kind = ["logreg", "gauss"][rs.randint(2)]
+        guide = ["hand", "auto"][rs.randint(2)]
+        d = int(ds[rs.randint(len(ds))])
+        B = int(rs.choice([1, 2, 31, 32, 33, 100]))
+        N = 20000
+        C = 1.0 if kind == "logreg" else 40.0
+        s, o, fam = _pair(kind, d, N, guide, optim="sgd", C=C, dp_scale=0.0)
+        o.grad_dtype = np.float64
+        args = _data(kind, B, d, seed=trial)
+        p = _rand_params(fam, seed=trial, scale=.2)
+        key = chacha.PRNGKey(trial)
+        n_valid = int(rs.randint(1, B + 1))
+        mask = np.arange(B) < n_valid
+        ost = o.init(key, *args, params=p)
+        ost2, oloss = o.update(ost, *args, mask=mask)
+        if rs.rand() < .5:      # the batch as (resident array, index list, device-side valid count)
+            perm = rs.permutation(B).astype(np.int32)
+            inv = np.argsort(perm).astype(np.int32)
+            srcs = [torch.as_tensor(a[perm]).to(cuda) for a in args]          # source row perm[i] holds... a[perm][inv] = a
+            idx = torch.as_tensor(inv).to(cuda)
+            nv = torch.tensor([n_valid], dtype=torch.int32, device=cuda)
+            targs = [BatchView(src, idx, nv) for src in srcs]
+            tmask = torch.as_tensor(mask).to(cuda)
+        else:
+            targs = [torch.as_tensor(a).to(cuda) for a in args]
+            tmask = torch.as_tensor(mask).to(cuda)
+        st = s.init(key, *[torch.as_tensor(a).to(cuda) for a in args], params=p)
+        st2, loss = s.update(st, *targs, mask=tmask)
+        assert np.isclose(float(loss), float(oloss), rtol=1e-5), (trial, kind, guide, d, B, float(loss), float(oloss))
+        # The update as ONE vector (every coordinate receives DP noise of the same scale, so that is the scale errors are
+        # measured against): element-wise, floor = rms of the whole update.  A per-leaf floor is unfair to a scalar leaf
+        # whose clipped sum cancels (the intercept: 28 terms of +-0.015 adding up to 1e-3 amplifies 6e-7 to 4e-5).
+        got_flat = st2.optim_state.flat.cpu().numpy().astype(np.float64)
+        ref_flat = np.concatenate([np.asarray(o.get_params(ost2)[name], np.float64).ravel() for name, _, _ in fam.layout()])
+        p_flat = st.optim_state.flat.cpu().numpy().astype(np.float64)
+        err = ew_rel_err(got_flat - p_flat, ref_flat - p_flat)
+        assert err < 1e-5, (trial, kind, guide, d, B, err)

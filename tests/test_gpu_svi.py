@@ -55,7 +55,9 @@ def _rand_params(fam, seed=1, scale=.3):
 CASES = [("logreg", 8, "hand"), ("logreg", 8, "auto"), ("logreg", 3, "hand"), ("logreg", 1, "hand"),
          ("logreg", 5, "auto"), ("logreg", 64, "hand"), ("logreg", 250, "hand"), ("logreg", 256, "auto"),
          ("logreg", 1024, "hand"), ("gauss", 8, "hand"), ("gauss", 7, "auto"), ("gauss", 256, "hand"),
-         ("gauss", 1024, "hand")]
+         ("gauss", 1024, "hand"),
+         # latent sites of 1025 .. 2048 elements: the joint AutoDiagonalNormal site of the d = 1024 regression (1025)
+         ("logreg", 1024, "auto"), ("gauss", 1500, "hand")]
 
 
 @pytest.mark.parametrize("kind,d,guide", CASES)
