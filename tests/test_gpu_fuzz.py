@@ -264,3 +264,34 @@ def test_fuzz_meanfield_shapes(cuda):
         p_flat = st.optim_state.flat.cpu().numpy().astype(np.float64)
         err = ew_rel_err(got_flat - p_flat, ref_flat - p_flat)
         assert err < 1e-5, (trial, kind, guide, d, B, err)
+
+
+@pytest.mark.parametrize("K,d,B,C", [(1, 3, 10, 5.0), (2, 1, 9, 0.5), (17, 7, 33, 20.0), (5, 33, 20, 2.0), (33, 40, 12, 20.0),
+                                      (64, 1, 8, 1.0), (3, 130, 1, 10.0)])
+def test_fuzz_gmm_shapes(cuda, K, d, B, C):
+    """Mixture shapes off the beaten path (one component, one dimension, widths that are not multiples of the warp,
+    a batch of one): per-example gradients and one clipped-sum step against the oracle."""
+    from helpers.tolerance import rel_err as ew_rel_err
+    from test_gpu_gmm import make
+    X, o, ost, s, st = make(K, d, 3000, B, C, 0.0, optim="sgd", seed=K * 100 + d)
+    ost1, okeys = o._split_rng_key(ost, 2)
+    _, opx_loss, opx_grads, n, f = o._compute_per_example_gradients(ost1, okeys[0], X)
+    st1, keys = s._split_rng_key(st, 2)
+    _, px_loss, px_grads, n2, f2 = s._compute_per_example_gradients(st1, keys[0], torch.as_tensor(X).cuda())
+    assert n == n2
+    np.testing.assert_allclose(px_loss.cpu().numpy(), opx_loss, rtol=1e-5)
+    # a row's gradient as one vector (both leaves): element-wise, floor = rms of that row
+    got = np.concatenate([px_grads[k].cpu().numpy().reshape(B, -1) for k in sorted(opx_grads)], axis=1)
+    ref = np.concatenate([np.asarray(opx_grads[k]).reshape(B, -1) for k in sorted(opx_grads)], axis=1)
+    assert ew_rel_err(got, ref, axis=0) < 1e-5
+    mask = np.ones(B, dtype=bool)
+    if B > 2:
+        mask[::3] = False
+    ost2, oloss = o.update(ost, X, mask=mask)
+    st2, loss = s.update(st, torch.as_tensor(X).cuda(), mask=torch.as_tensor(mask).cuda())
+    assert np.isclose(float(loss), float(oloss), rtol=1e-5)
+    got_flat = st2.optim_state.flat.cpu().numpy().astype(np.float64) - st.optim_state.flat.cpu().numpy().astype(np.float64)
+    names = [name for name, _, _ in s.family.layout()]
+    ref_flat = np.concatenate([(np.asarray(o.get_params(ost2)[k], np.float64) - np.asarray(o.get_params(ost)[k], np.float64)).ravel()
+                               for k in names])
+    assert ew_rel_err(got_flat, ref_flat) < 1e-5
