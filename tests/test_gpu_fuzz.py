@@ -295,3 +295,70 @@ def test_fuzz_gmm_shapes(cuda, K, d, B, C):
     ref_flat = np.concatenate([(np.asarray(o.get_params(ost2)[k], np.float64) - np.asarray(o.get_params(ost)[k], np.float64)).ravel()
                                for k in names])
     assert ew_rel_err(got_flat, ref_flat) < 1e-5
+
+
+def test_fuzz_finalize(cuda):
+    """d3p_perturb_finalize_f32 on random leaf tables / partial-row counts / optimizers, P on both sides of the
+    32 768-parameter switch between finalize_kernel and finalize_quad_kernel: reduce -> per-leaf ChaCha noise ->
+    rescale -> SGD / Adam (d3p/svi.py:350-393, 470-498) against a numpy restatement built on the oracle's normals."""
+    from d3p_b200 import _native as _n
+    rs = np.random.RandomState(909)
+    lib = _n.lib()
+    for trial in range(14):
+        n_leaves = int(rs.randint(1, 11))
+        big = trial % 3 == 0
+        lens = [int(x) for x in (rs.randint(1, 30000, size=n_leaves) if big else rs.randint(1, 700, size=n_leaves))]
+        if trial == 1:
+            n_leaves, lens = 1, [1]
+        P = sum(lens)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(int)
+        n_part = int(rs.choice([1, 2, 4, 37, 296]))
+        B = int(rs.randint(1, 5000))
+        n = int(rs.randint(1, B + 1))
+        part = rs.randn(n_part, P + 2).astype(np.float32)
+        part[:, P + 1] = 0
+        part[0, P + 1] = n                                        # the count column sums to n
+        dp_scale, C_, obs = float(rs.uniform(.1, 3)), float(rs.uniform(.1, 5)), float(rs.choice([1.0, 20000.0, .3]))
+        key = chacha.fold_in(chacha.PRNGKey(trial), P)
+        site_keys = chacha.split(key, n_leaves)
+        lt = _n.LeafTable()
+        lt.n_leaves = n_leaves
+        for l in range(n_leaves):
+            lt.leaf_off[l], lt.leaf_len[l] = int(offs[l]), lens[l]
+            for i in range(16):
+                lt.site_state[l][i] = int(np.asarray(site_keys[l], np.uint32).reshape(16)[i])
+        kind = [_n.OPT_SGD, _n.OPT_ADAM][trial % 2]
+        step = int(rs.randint(0, 50))
+        od = _n.OptimDesc(kind, 1e-2, 0.9, 0.999, 1e-8, step)
+        x0 = rs.randn(P).astype(np.float32)
+        m0, v0 = (rs.randn(P) * .1).astype(np.float32), (rs.rand(P) * .1).astype(np.float32)
+        d_part, d_x = torch.as_tensor(part).to(cuda), torch.as_tensor(x0).to(cuda)
+        d_m, d_v = torch.as_tensor(m0).to(cuda), torch.as_tensor(v0).to(cuda)
+        d_g = torch.empty(P, device=cuda)
+        d_stats = torch.empty(3, device=cuda)
+        _n.check(lib.d3p_perturb_finalize_f32(_n.ptr(d_part), n_part, P, B, C.byref(lt), dp_scale, C_, obs, 1, _n.ptr(d_g),
+                                              C.byref(od), _n.ptr(d_x), _n.ptr(d_m), _n.ptr(d_v), _n.ptr(d_stats), None,
+                                              _n.stream_ptr()), "finalize")
+        # numpy restatement (float32 arithmetic in the reference's order)
+        f32 = np.float32
+        tot = part.astype(np.float64).sum(0)
+        f = f32(B) / f32(n)
+        sigma = f32(dp_scale) * (f32(C_) / f32(n))
+        noise = np.concatenate([chacha.normal(site_keys[l], (lens[l],)) for l in range(n_leaves)])
+        g = (f32(1) * (tot[:P] / B).astype(f32) + noise * sigma) * f32(obs) * f
+        got_g = d_g.cpu().numpy()
+        scale = float(np.sqrt(np.mean(g.astype(np.float64) ** 2)))
+        assert np.max(np.abs(got_g - g)) <= 2e-6 * scale + 2e-6 * np.max(np.abs(g)), (trial, P, n_part)
+        stats = d_stats.cpu().numpy()
+        assert stats[1] == n and np.isclose(stats[2], f, rtol=1e-6)
+        assert np.isclose(stats[0], tot[P] / B * f, rtol=1e-5, atol=1e-6)
+        if kind == _n.OPT_SGD:
+            want_x = x0 - f32(1e-2) * g
+        else:
+            t = step + 1
+            m1 = (1 - .9) * g + .9 * m0
+            v1 = (1 - .999) * g * g + .999 * v0
+            want_x = x0 - 1e-2 * (m1 / (1 - .9 ** t)) / (np.sqrt(v1 / (1 - .999 ** t)) + 1e-8)
+            assert np.allclose(d_m.cpu().numpy(), m1, rtol=1e-5, atol=1e-6 * scale)
+            assert np.allclose(d_v.cpu().numpy(), v1, rtol=1e-5, atol=1e-6 * scale * scale)
+        assert np.allclose(d_x.cpu().numpy(), want_x, rtol=1e-5, atol=1e-5), (trial, P, kind)
