@@ -81,10 +81,15 @@ D3P_D unsigned long long global_ns() {
 // flag, read by every later finalize kernel) and in the host-mapped mirror (read by the next d3p_* call).
 // `which`: 1 = the clipped-sum exchange of a finalize kernel, 2 = the tile counts of the sharded sampler (the host
 // mirror keeps one counter per kind at words [1], [2]: d3p_comm_timeout_detail).
+// The counters live in the window (device memory: err[0] all, err[1] exchange, err[2] sampler) and are MIRRORED into
+// the host-mapped words with plain system-scope stores: an atomic on mapped host memory needs PCIe atomics, which the
+// platform may not offer (compute-sanitizer rejects it).  Racing mirrors may land out of order, so the host copy is
+// a lower bound of the device count - and non-zero as soon as one wait has given up, which is what the host tests.
 D3P_D void comm_flag_timeout(uint32_t* err, uint32_t* err_host, int which) {
-  atomicAdd(err, 1u);
-  atomicAdd_system(err_host, 1u);
-  atomicAdd_system(err_host + which, 1u);
+  const uint32_t all = atomicAdd(err, 1u) + 1u;
+  const uint32_t kind = atomicAdd(err + which, 1u) + 1u;
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(err_host), "r"(all) : "memory");
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(err_host + which), "r"(kind) : "memory");
 }
 // wait for rank src's slot j of this epoch (spins on LOCAL memory).  A slot whose tag never matches is NOT
 // consumed: the result is NaN, which poisons this step's gradient, parameters and loss on this rank and, through

@@ -5,12 +5,21 @@ import torch
 import d3p_b200.random as rng
 from d3p_b200 import minibatch as mb, models, optimizers, svi as dsvi
 dev = torch.device("cuda", 0)
-N, d = 200_000, 1024
-X = rng.normal(rng.PRNGKey(1), (N, d)); y = (rng.uniform(rng.PRNGKey(2), (N,)) < 0.5).to(torch.int32)
-fam = models.LogisticRegression(d)
-s = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), 1.0, 1.0, num_obs_total=N)
-s.donate_state = True
-init, get = mb.poisson_batchify_data((X, y), 0.01, .99)
+VAE = "--vae" in sys.argv
+if VAE:       # the C5 workload of bench.py
+    N = 60_000
+    X = (rng.uniform(rng.PRNGKey(1), (N, 28, 28)) < 0.3).float()
+    fam = models.VAE(784, 400, 20)
+    s = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), 10.0, 1.0, num_obs_total=N)
+    s.donate_state = True
+    init, get = mb.subsample_batchify_data((X,), batch_size=4096, return_mask=True)
+else:
+    N, d = 200_000, 1024
+    X = rng.normal(rng.PRNGKey(1), (N, d)); y = (rng.uniform(rng.PRNGKey(2), (N,)) < 0.5).to(torch.int32)
+    fam = models.LogisticRegression(d)
+    s = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), 1.0, 1.0, num_obs_total=N)
+    s.donate_state = True
+    init, get = mb.poisson_batchify_data((X, y), 0.01, .99)
 key, k_init, k_fetch = rng.split(rng.PRNGKey(0), 3)
 _, bst = init(k_fetch)
 batch, mask = get(0, bst)
