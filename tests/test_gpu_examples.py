@@ -32,3 +32,25 @@ def test_example_simple_gaussian_posterior(cuda):
     assert np.max(np.abs(out["mu_loc"] - out["analytical_loc"])) < 0.1, out
     losses = [h[1] for h in out["history"]]
     assert losses[-1] < losses[0]
+
+
+def test_example_gaussian_mixture_model(cuda):
+    import gaussian_mixture_model as ex
+    out = ex.main(ex.parse(["--num-epochs", "30", "--epsilon", "4.0"]), verbose=False)
+    losses = [h[1] for h in out["history"]]
+    assert np.all(np.isfinite(losses)) and losses[-1] < losses[0]
+    # the three well-separated modes (-10, 10, -2) are found and test points are attributed to the right component
+    assert out["acc"] > 0.9, out
+    found = np.sort(out["modes"].mean(axis=1))
+    assert np.allclose(found, [-10., -2., 10.], atol=1.5), found
+
+
+def test_example_vae(cuda):
+    import vae as ex
+    out = ex.main(ex.parse(["--num-epochs", "30", "--epsilon", "8.0", "-N", "12000", "-batch-size", "256", "-lr", "3e-3"]),
+                  verbose=False)
+    losses = [h[1] for h in out["history"]]
+    assert np.all(np.isfinite(losses))
+    # per-image test loss: starts at 784 log 2 = 543 (an untrained decoder), passes the "pixel marginals only" plateau
+    # near 490 and ends near 195 once the latent code is in use (1 400 DP-SVI steps at epsilon = 8)
+    assert 500 < losses[0] < 600 and losses[-1] < 0.5 * losses[0], losses
