@@ -14,7 +14,7 @@ if VAE:       # the C5 workload of bench.py
     s.donate_state = True
     init, get = mb.subsample_batchify_data((X,), batch_size=4096, return_mask=True)
 else:
-    N, d = 200_000, 1024
+    N, d = (10_000_000, 1024) if "--c2" in sys.argv else (200_000, 1024)
     X = rng.normal(rng.PRNGKey(1), (N, d)); y = (rng.uniform(rng.PRNGKey(2), (N,)) < 0.5).to(torch.int32)
     fam = models.LogisticRegression(d)
     s = dsvi.DPSVI(fam.model, fam.guide, optimizers.Adam(1e-3), models.Trace_ELBO(), 1.0, 1.0, num_obs_total=N)
@@ -26,7 +26,7 @@ batch, mask = get(0, bst)
 st = s.init(k_init, *batch)
 st, _ = s.run_epoch(st, get, bst, 3)
 torch.cuda.synchronize()
-for K in (1, 2, 5, 20, 100):
+for K in (1, 2, 3, 5, 10, 20, 50, 100):
     ts = []
     for rep in range(5):
         torch.cuda.synchronize()
