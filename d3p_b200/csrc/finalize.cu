@@ -183,9 +183,14 @@ struct ChunkTable { uint32_t n_chunks; uint32_t chunk_start[D3P_MAX_LEAVES + 1];
 
 D3P_D void quad_qr(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) { D3P_QR(a, b, c, d) }
 
-__global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites,
-                                                            const uint32_t* __restrict__ sites_d, ChunkTable ct,
-                                                            CommDev comm) {
+// (the tables are __grid_constant__: indexing a by-value kernel parameter with a run-time leaf number otherwise makes
+// every thread copy it to local memory first)
+__global__ void __launch_bounds__(256) finalize_quad_kernel(const __grid_constant__ FinalizeArgs a,
+                                                            const __grid_constant__ LeafTable leaves,
+                                                            const __grid_constant__ SiteStates sites,
+                                                            const uint32_t* __restrict__ sites_d,
+                                                            const __grid_constant__ ChunkTable ct,
+                                                            const __grid_constant__ CommDev comm) {
   __shared__ float red[2][8];
   __shared__ float s_n, s_loss;
   const uint32_t stride = a.P + 2;
@@ -234,12 +239,22 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
     m0[i] = (ok[i] && a.opt_kind == D3P_OPT_ADAM) ? pm[jj[i]] : 0.f;
     v0[i] = (ok[i] && a.opt_kind == D3P_OPT_ADAM) ? pv[jj[i]] : 0.f;
   }
-  // the partial rows are requested before the ChaCha rounds below and 5 rows at a time (20 independent loads per
-  // thread): the row loop was one dependent round trip to L2 / HBM per row
-#pragma unroll 5
-  for (uint32_t p = 0; p < a.n_partials; ++p) {
+  // The partial rows are requested before the ChaCha rounds below.  Up to 4 rows (the VAE's concurrent wave writes 4)
+  // are only LOADED here and added after the rounds, so that the 200 dependent instructions of the rounds run under
+  // the loads' latency instead of behind it; more rows are added 5 at a time (20 independent loads per thread).
+  const bool few = a.n_partials <= 4;
+  float pre[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sum[i] += ok[i] ? __ldg(parts + (size_t)p * stride + jj[i]) : 0.f;
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      pre[p][i] = (few && (uint32_t)p < a.n_partials && ok[i]) ? __ldg(parts + (size_t)p * stride + jj[i]) : 0.f;
+  if (!few) {
+#pragma unroll 5
+    for (uint32_t p = 0; p < a.n_partials; ++p) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sum[i] += ok[i] ? __ldg(parts + (size_t)p * stride + jj[i]) : 0.f;
+    }
   }
   // column q of the state: rows 0..3
   const uint32_t* sw = sites_d ? sites_d + 16 * leaf : sites.w[leaf];
@@ -259,6 +274,10 @@ __global__ void __launch_bounds__(256) finalize_quad_kernel(FinalizeArgs a, Leaf
     x3 = __shfl_sync(0xffffffffu, x3, base + ((q + 1) & 3));
   }
   const uint32_t ks[4] = {x0 + i0, x1 + i1, x2 + i2, x3 + i3};   // keystream words q, 4 + q, 8 + q, 12 + q
+#pragma unroll
+  for (int p = 0; p < 4; ++p)                                    // rows in row order, as the loop above adds them
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sum[i] += pre[p][i];
   float n_all = s_n, loss_all = s_loss;
   if (comm.world > 1) {                                    // one-shot all-reduce over peer memory (comm.cuh)
     const float my_n = s_n, my_loss = s_loss;
