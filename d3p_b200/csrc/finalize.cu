@@ -55,8 +55,11 @@ struct SiteStates { uint32_t w[D3P_MAX_LEAVES][16]; };
 
 // `sites_d` (the *_dk entry point): the per-leaf ChaCha states live in device memory ([n_leaves][16] words, written by
 // d3p_dpsvi_keys_dk) instead of the kernel parameters.
-__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a, LeafTable leaves, SiteStates sites,
-                                                               const uint32_t* __restrict__ sites_d, CommDev comm) {
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(const __grid_constant__ FinalizeArgs a,
+                                                               const __grid_constant__ LeafTable leaves,
+                                                               const __grid_constant__ SiteStates sites,
+                                                               const uint32_t* __restrict__ sites_d,
+                                                               const __grid_constant__ CommDev comm) {
   __shared__ float red[2][kFinThreads / 32];
   __shared__ float s_n, s_loss;
   const uint32_t stride = a.P + 2;
