@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_fwd_mma_kernel(VaeArgs a)
     const float* ph1 = a.h1_hi + (size_t)rg8 * a.ldh;
     const float* pl0 = a.h1_lo + (size_t)rg * a.ldh;
     const float* pl1 = a.h1_lo + (size_t)rg8 * a.ldh;
-#pragma unroll 2
+#pragma unroll 4
     for (uint32_t ks = warp; ks < fd.ks23; ks += kMmaWarps) {
       uint32_t ah[4], al[4];
       load_a_pair(ph0, ph1, 8 * ks + 2 * t, ah);
@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_bwd_mma_kernel(VaeArgs a)
     for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
     const float* p0 = a.d4 + (size_t)rg * H;
     const float* p1 = a.d4 + (size_t)rg8 * H;
-#pragma unroll 2
+#pragma unroll 4
     for (uint32_t ks = warp; ks < fd.ks4t; ks += kMmaWarps) {
       uint32_t ah[4], al[4];
       const uint32_t k = 8 * ks + 2 * t;
@@ -950,15 +950,17 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_bwd_mma_kernel(VaeArgs a)
     const float* pl1 = a.h1_lo + (size_t)rg8 * a.ldh;
     for (uint32_t nt = warp; nt < fd.nt23t; nt += kMmaWarps) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      // h1 of this column block is requested before the MMA loop (the MMAs are opaque to the compiler, which would
+      // otherwise leave these loads behind them and expose their full latency in every iteration)
+      const uint32_t n = 8 * nt + 2 * t;
+      const float2 hh0 = __ldg(reinterpret_cast<const float2*>(ph0 + n)), hl0 = __ldg(reinterpret_cast<const float2*>(pl0 + n));
+      const float2 hh1 = __ldg(reinterpret_cast<const float2*>(ph1 + n)), hl1 = __ldg(reinterpret_cast<const float2*>(pl1 + n));
       for (uint32_t ks = 0; ks < fd.ks23t; ++ks) {
         uint32_t ah[4], al[4];
         load_a_pair(&s_dh[0][g][0], &s_dh[0][g + 8][0], 8 * ks + 2 * t, ah);
         load_a_pair(&s_dh[1][g][0], &s_dh[1][g + 8][0], 8 * ks + 2 * t, al);
         mma3(acc, ah, al, __ldg(a.wf23t + ((size_t)ks * fd.nt23t + nt) * 32 + lane));
       }
-      const uint32_t n = 8 * nt + 2 * t;
-      const float2 hh0 = *reinterpret_cast<const float2*>(ph0 + n), hl0 = *reinterpret_cast<const float2*>(pl0 + n);
-      const float2 hh1 = *reinterpret_cast<const float2*>(ph1 + n), hl1 = *reinterpret_cast<const float2*>(pl1 + n);
       const float d00 = live0 ? acc[0] * (-expm1f(-(hh0.x + hl0.x))) : 0.f;
       const float d01 = live0 ? acc[1] * (-expm1f(-(hh0.y + hl0.y))) : 0.f;
       const float d10 = live1 ? acc[2] * (-expm1f(-(hh1.x + hl1.x))) : 0.f;
