@@ -1014,10 +1014,10 @@ __global__ void __launch_bounds__(kMmaThreads) vae_mid_bwd_mma_kernel(VaeArgs a)
   __syncthreads();
   // ---- phase 5: scaled hi / lo operands of the clipped-sum GEMMs (streaming) ---------------------------------------
   const uint32_t H4 = H / 4;
-#pragma unroll 2
-  for (uint32_t i = threadIdx.x; i < kMmaRows * H4; i += kMmaThreads) {
+  const uint32_t n_stream = min((uint32_t)kMmaRows, a.Bl - r0) * H4;      // the rows of this CTA that exist
+#pragma unroll 4
+  for (uint32_t i = threadIdx.x; i < n_stream; i += kMmaThreads) {
     const uint32_t e = i / H4, h = 4 * (i - e * H4), r = r0 + e;
-    if (r >= a.Bl) continue;
     const float cc = s_cc[e];
     const float4 d1 = *reinterpret_cast<const float4*>(s_d1 + (size_t)e * H + h);
     const float4 d4 = *reinterpret_cast<const float4*>(a.d4 + (size_t)r * H + h);
