@@ -280,12 +280,12 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uin
     uint32_t s = base + (uint32_t)(higher + incl - c);   // selected records with a larger index
     if (blk >= n_blocks) continue;
     if (kSharded) {
-#pragma unroll
-      for (int i = 15; i >= 0; --i) {
-        if ((m >> i) & 1u) {
-          if (s >= pos_begin && s < lim) idx[s] = (int32_t)(blk * 16u + i);
-          ++s;
-        }
+      // walk the SET bits from the top (1 % of the records are selected: 2 - 3 iterations per warp instead of 16)
+      for (uint32_t mm = m; mm;) {
+        const int i = 31 - __clz(mm);
+        mm &= ~(1u << i);
+        if (s >= pos_begin && s < lim) idx[s] = (int32_t)(blk * 16u + i);
+        ++s;
       }
       continue;
     }
@@ -294,6 +294,19 @@ __global__ void __launch_bounds__(kPoisThreads) poisson_compact_kernel(const uin
     const bool any_sel = (m != 0) && (s < max_b);
     const bool any_unsel = total < max_b && ((n_records - 1u - min(rec_hi, n_records - 1u)) - s + total < max_b + 16u);
     if (!any_sel && !any_unsel) continue;
+    if (!any_unsel) {
+      // the common case (no padding slot can come from this block): walk the set bits from the top, 2 - 3
+      // iterations per warp instead of the 16 of the general loop below
+      for (uint32_t mm = m; mm;) {
+        const int i = 31 - __clz(mm);
+        mm &= ~(1u << i);
+        const uint32_t rec = blk * 16u + i;
+        if (rec >= n_records) continue;
+        if (s < max_b) idx[s] = (int32_t)rec;
+        ++s;
+      }
+      continue;
+    }
 #pragma unroll
     for (int i = 15; i >= 0; --i) {
       const uint32_t rec = blk * 16u + i;
