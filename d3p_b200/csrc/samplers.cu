@@ -66,17 +66,22 @@ constexpr int kPoisThreads = 256;
 constexpr uint32_t kTileRecords = kPoisThreads * 16;
 
 // 16 selectors of ChaCha block `blk`: rng_suite.uniform(key, (N,), float32) <= q  (d3p/minibatch.py:34)
+// The uniform of word w is u = k 2^-23 with k = w >> 9, exactly (jax.random._uniform: mantissa bits | 1.0f, minus 1, times
+// (1 - 0) plus 0, max with 0: every step exact), so u <= q  <=>  k <= floor(q 2^23) for 0 <= q < 1 (q 2^23 is exact in
+// float32); q >= 1 selects everything, q < 0 or NaN nothing.  One integer compare per record instead of the float path.
+D3P_D int32_t poisson_threshold(float q) {
+  return q >= 1.0f ? 0x7fffff : (q >= 0.0f ? (int32_t)floorf(q * 8388608.0f) : -1);
+}
 D3P_D uint32_t poisson_block_mask(const ChaChaState& st, float q, uint32_t n_records, uint32_t blk) {
   uint32_t ks[16];
   chacha20_block(st.w, st.w[12] + blk, ks);
+  const int32_t kq = poisson_threshold(q);
   uint32_t m = 0;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float u = fmaxf(0.0f, bits_to_unit_float(ks[i]));
-    bool sel = (u <= q) && (blk * 16u + i < n_records);
-    m |= (sel ? 1u : 0u) << i;
-  }
-  return m;
+  for (int i = 0; i < 16; ++i) m |= ((int32_t)(ks[i] >> 9) <= kq ? 1u : 0u) << i;
+  const uint32_t first = blk * 16u;                          // records past the end of the data set (last block only)
+  const uint32_t n_valid = n_records > first ? min(16u, n_records - first) : 0u;
+  return m & ((1u << n_valid) - 1u);
 }
 
 D3P_D int tile_count(uint32_t m, int* warp_c) {      // CTA total of popc(m); valid in thread 0
