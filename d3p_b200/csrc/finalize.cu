@@ -63,6 +63,41 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const __grid_cons
   __shared__ float red[2][kFinThreads / 32];
   __shared__ float s_n, s_loss;
   const uint32_t stride = a.P + 2;
+  // Launched as a programmatic dependent of the step kernel, this CTA is resident while that kernel is still running.
+  // Everything that does not depend on its partial rows happens NOW, under the producer's tail instead of behind it:
+  // the column's Gaussian draw (a ChaCha block: keys only), the Adam bias corrections and the loads of the parameter
+  // and its moments (written by the previous finalize, which completed before the step kernel started).
+  float xi_pre = 0.f, x_pre = 0.f, m_pre = 0.f, v_pre = 0.f, bc1 = 1.f, bc2 = 1.f;
+  bool have_xi = false;
+  {
+    const uint32_t jp = blockIdx.x * 32 + (threadIdx.x & 31);
+    if ((threadIdx.x >> 5) == 0 && jp < a.P) {
+      if (a.add_noise) {
+        int leaf = -1;
+#pragma unroll 1
+        for (uint32_t l = 0; l < leaves.n_leaves; ++l)
+          if (jp >= leaves.off[l] && jp < leaves.off[l] + leaves.len[l]) leaf = (int)l;
+        if (leaf >= 0) {
+          uint32_t e = jp - leaves.off[leaf];
+          uint32_t ks[16], st[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) st[i] = sites_d ? __ldg(sites_d + 16 * leaf + i) : sites.w[leaf][i];
+          chacha20_block(st, st[12] + (e >> 4), ks);
+          uint32_t bits = ks[0];
+#pragma unroll
+          for (int i = 1; i < 16; ++i) bits = ((e & 15u) == (uint32_t)i) ? ks[i] : bits;
+          xi_pre = bits_to_normal<false>(bits);
+          have_xi = true;
+        }
+      }
+      if (a.opt_kind == D3P_OPT_SGD || a.opt_kind == D3P_OPT_ADAM) x_pre = a.params[jp];
+      if (a.opt_kind == D3P_OPT_ADAM) {
+        m_pre = a.m[jp]; v_pre = a.v[jp];
+        const float t = (float)(a.step + 1);
+        bc1 = 1.0f - powf(a.b1, t); bc2 = 1.0f - powf(a.b2, t);
+      }
+    }
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");    // no-op unless launched as a programmatic dependent
   // every CTA reduces the (count, loss) columns itself: n_partials is a few hundred at most
   float cnt = 0.f, loss = 0.f;
@@ -133,35 +168,17 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const __grid_cons
   float err2 = 0.f;
   if (live) {
     float g = __fdiv_rn(sum, Bf);                                      // mean over the padded batch size
-    if (a.add_noise) {
-      int leaf = -1;
-#pragma unroll 1
-      for (uint32_t l = 0; l < leaves.n_leaves; ++l)
-        if (j >= leaves.off[l] && j < leaves.off[l] + leaves.len[l]) leaf = (int)l;
-      if (leaf >= 0) {
-        uint32_t e = j - leaves.off[leaf];
-        uint32_t ks[16], st[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) st[i] = sites_d ? __ldg(sites_d + 16 * leaf + i) : sites.w[leaf][i];
-        chacha20_block(st, st[12] + (e >> 4), ks);
-        uint32_t bits = ks[0];
-#pragma unroll
-        for (int i = 1; i < 16; ++i) bits = ((e & 15u) == (uint32_t)i) ? ks[i] : bits;
-        float xi = bits_to_normal<false>(bits);
-        g = __fadd_rn(g, __fmul_rn(xi, sigma));                        // svi.py:485-486
-      }
-    }
+    if (have_xi) g = __fadd_rn(g, __fmul_rn(xi_pre, sigma));          // svi.py:485-486 (drawn in the prologue)
     g = __fmul_rn(__fmul_rn(g, a.obs_scale), f);                       // svi.py:374-375
     if (a.grad_out) a.grad_out[j] = g;
     if (a.opt_kind == D3P_OPT_SGD) {
-      a.params[j] = a.params[j] - a.step_size * g;
+      a.params[j] = x_pre - a.step_size * g;
     } else if (a.opt_kind == D3P_OPT_ADAM) {
-      float m = (1.0f - a.b1) * g + a.b1 * a.m[j];
-      float v = (1.0f - a.b2) * (g * g) + a.b2 * a.v[j];
-      float t = (float)(a.step + 1);
-      float mhat = m / (1.0f - powf(a.b1, t));
-      float vhat = v / (1.0f - powf(a.b2, t));
-      a.params[j] = a.params[j] - a.step_size * mhat / (sqrtf(vhat) + a.eps);
+      float m = (1.0f - a.b1) * g + a.b1 * m_pre;
+      float v = (1.0f - a.b2) * (g * g) + a.b2 * v_pre;
+      float mhat = m / bc1;
+      float vhat = v / bc2;
+      a.params[j] = x_pre - a.step_size * mhat / (sqrtf(vhat) + a.eps);
       a.m[j] = m;
       a.v[j] = v;
     } else if (a.opt_kind == D3P_OPT_ADADP) {
