@@ -1355,7 +1355,7 @@ static int32_t step_vae_impl(const d3p_vae_desc* desc, const float* params_d, co
     if ((rc = check_launch()) != D3P_OK) return rc;
   }
   // The four clipped-sum GEMMs are independent: GW1 stays on the caller's stream, GW5 / GW23 / GW4 run on side streams
-  // forked from it and joined before the loss kernel (one wave of CTAs, see vae_splits).  The optional profile events
+  // forked from it and joined at the end of the step (one wave of CTAs, see vae_splits).  The optional profile events
   // (bench) bracket the whole concurrent group on the caller's stream.
   if (profile_events_h && cudaEventRecord((cudaEvent_t)profile_events_h[0], s) != cudaSuccess) return D3P_ERR_CUDA;
   std::unique_lock<std::mutex> ss_lock;
@@ -1373,6 +1373,10 @@ static int32_t step_vae_impl(const d3p_vae_desc* desc, const float* params_d, co
     EpiGrad::Args ea{a.partials, (size_t)P + 2, a.off_w2, a.off_b2, Z, H, 0, Z, a.off_w3, a.off_b3};
     if ((rc = tc::launch_tc_gemm<true, true, kThinBN, EpiGrad>(A, Bo, H + 1, 2 * Z, Bl, L.S, ea, s23, nullptr)) != D3P_OK) return rc;
   }
+  // the (loss, count) columns of the partial rows need the thin-layer kernel's per-example values only, and no GEMM
+  // epilogue touches those two columns: behind the short GW23 on its side stream, off the critical path
+  vae_loss_kernel<<<L.S, 256, 0, s23>>>(a);
+  if ((rc = check_launch()) != D3P_OK) return rc;
   // GW4: (c delta4)^T [z | 1] -> dW4^T (stored [Z, H]) and db4
   {
     tc::GemmOperand A{a.cd4_hi, a.cd4_lo, 1, H}, Bo{a.z_hi, a.z_lo, 1, a.ldz};
@@ -1398,8 +1402,7 @@ static int32_t step_vae_impl(const d3p_vae_desc* desc, const float* params_d, co
     ss_lock.unlock();
   }
   if (profile_events_h && cudaEventRecord((cudaEvent_t)profile_events_h[1], s) != cudaSuccess) return D3P_ERR_CUDA;
-  vae_loss_kernel<<<L.S, 256, 0, s>>>(a);
-  return check_launch();
+  return D3P_OK;
 }
 
 extern "C" int32_t d3p_dpsvi_step_vae(const d3p_vae_desc* desc, const float* params_d, const float* x_d,
