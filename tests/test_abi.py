@@ -105,3 +105,40 @@ def test_facade_validation_errors():
     assert models.LogisticRegression(8, guide="auto").n_params == 18
     assert models.GaussianMean(256).n_params == 512
     assert svi.full_norm([]) == 0.
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/d3p_b200.h must be consumable by a C compiler (the boundary a cgo / JNI / ctypes / XLA-FFI binding sees:
+    `extern "C"`, plain pointers and sizes, no C++ or torch types) and the library must link from a C program.  The
+    program only calls host-side entry points (no GPU needed): ABI version, error strings, a host key derivation and
+    an argument check of a device entry point."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.join(ROOT, "d3p_b200", "_lib")
+    src = tmp_path / "c_client.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "d3p_b200.h"
+int main(void) {
+  uint32_t key[16], out[2 * 16];
+  const unsigned char seed[4] = {1, 2, 3, 4};
+  if (d3p_abi_version() <= 0) return 1;
+  if (!d3p_error_string(D3P_ERR_INVALID_ARGUMENT) || !strlen(d3p_error_string(D3P_ERR_PEER_TIMEOUT))) return 2;
+  if (d3p_chacha_key_from_seed_h(seed, sizeof seed, key) != D3P_OK) return 3;
+  if (d3p_chacha_split_h(key, 2, out) != D3P_OK) return 4;
+  if (memcmp(out, out + 16, 64) == 0) return 5;                       /* two different children */
+  if (d3p_feistel_sample(NULL, 10, 0, 4, NULL, NULL) != D3P_ERR_INVALID_ARGUMENT) return 6;
+  printf("abi %d ok\n", d3p_abi_version());
+  return 0;
+}
+''')
+    exe = tmp_path / "c_client"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-ld3p_b200", f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
